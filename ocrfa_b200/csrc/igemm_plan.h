@@ -1,0 +1,109 @@
+// Host-side planning for the tcgen05 implicit-GEMM: conv geometry -> tap table, M-tile box, tensor maps.
+// Geometry follows the reference layers (/root/reference/src/ocrfa/modules/blocks.py:239-322):
+// 3x3 s1 p1, 1x1, 2x2 s(2,1) p(0,1) and 2x2 s1 p0; linear layers are 1x1 convs over a [rows,1,1] image.
+#pragma once
+#include <cmath>
+#include <cstring>
+#include "igemm_tc.cuh"
+
+namespace ocrfa {
+
+struct ConvGeom {
+  int n, h_in, w_in, cin, cout;
+  int kh, kw;  // filter
+  int sh;      // stride in H (1 or 2); stride in W is always 1 on this path
+  int ph, pw;  // zero padding
+  int h_out() const { return (h_in + 2 * ph - kh) / sh + 1; }
+  int w_out() const { return w_in + 2 * pw - kw + 1; }
+};
+
+struct TileShape {
+  int tw, th, tn;
+};
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// 128 output pixels per M tile, arranged as a {tw, th, tn} box (powers of two) that wastes the fewest
+// MMA rows on the ragged edges of (W, H, N); narrow boxes pay a small penalty (more, shorter TMA rows).
+inline TileShape choose_tile(int w, int h, int n) {
+  TileShape best{128, 1, 1};
+  double best_score = 1e30;
+  for (int tw = 1; tw <= 128; tw *= 2)
+    for (int th = 1; th * tw <= 128; th *= 2) {
+      const int tn = 128 / (tw * th);
+      const double cover = double(ceil_div(w, tw) * tw) * double(ceil_div(h, th) * th) * double(ceil_div(n, tn) * tn);
+      const double waste = cover / (double(w) * h * n) - 1.0;
+      const double penalty = tw < 8 ? 0.01 * (8.0 / tw - 1.0) : 0.0;
+      const double score = waste + penalty;
+      if (score < best_score - 1e-12 || (std::fabs(score - best_score) <= 1e-12 && tw > best.tw)) {
+        best_score = score;
+        best = TileShape{tw, th, tn};
+      }
+    }
+  return best;
+}
+
+inline int choose_block_n(int cout) {
+  if (cout % 256 == 0) return 256;
+  if (cout <= 256) return ceil_div(cout, 32) * 32;
+  if (cout % 128 == 0) return 128;
+  return 64;
+}
+
+// Fills geometry-dependent fields of `p` (maps, taps, tiles). Epilogue pointers are left to the caller.
+// `in` : NHWC bf16 [n][h_in][w_in][cin_buf] (cin_buf >= cin, multiple of 64: stem output is channel-padded)
+// `wgt`: [cout][kh*kw*cin_pad] bf16 with K ordered (tap-major, channel-minor), cin_pad = round_up(cin, 64)
+inline int plan_conv(IgemmTcParams* p, const ConvGeom& g, const void* in, int cin_buf, const void* wgt,
+                     const TileShape* forced_tile = nullptr) {
+  std::memset(p, 0, sizeof(*p));
+  const int ho = g.h_out(), wo = g.w_out();
+  const int cin_pad = ceil_div(g.cin, 64) * 64;
+  if (cin_buf % 64 != 0 || cin_buf < cin_pad) return -2;
+  if (g.sh != 1 && g.sh != 2) return -3;
+  if (g.sh == 2 && (g.h_in % 2 != 0 || g.ph != 0 || g.kh != 2)) return -4;
+  if (g.kh * g.kw > kTcMaxTaps - 1) return -5;
+  const TileShape t = forced_tile ? *forced_tile : choose_tile(wo, ho, g.n);
+  p->tw = t.tw; p->th = t.th; p->tn = t.tn;
+  p->tiles_w = ceil_div(wo, t.tw);
+  p->tiles_h = ceil_div(ho, t.th);
+  p->tiles_n = ceil_div(g.n, t.tn);
+  p->n_img = g.n; p->h_out = ho; p->w_out = wo;
+  p->block_n = choose_block_n(g.cout);
+  p->n_tiles = ceil_div(g.cout, p->block_n);
+  p->n_valid = g.cout;
+  p->kchunks = cin_pad / 64;
+  p->kchunks2 = 0;
+  igemm_tc_smem_bytes(p->block_n, &p->num_stages);
+  int nt = 0;
+  for (int r = 0; r < g.kh; ++r)
+    for (int s = 0; s < g.kw; ++s) {
+      TapDesc& d = p->taps[nt++];
+      d.src = 0;
+      d.dw = static_cast<int16_t>(s - g.pw);
+      if (g.sh == 1) { d.dr = 0; d.dh = static_cast<int16_t>(r - g.ph); }
+      else { d.dr = static_cast<int16_t>(r); d.dh = 0; }  // h_in = 2*h_out + r
+    }
+  p->num_taps = nt;
+  const int R = g.sh;
+  int rc = make_act_tmap(&p->tmA, in, cin_buf, g.w_in, R, g.h_in / R, g.n, t.tw, t.th, t.tn);
+  if (rc) return rc;
+  p->tmA2 = p->tmA;
+  rc = make_wgt_tmap(&p->tmB, wgt, g.kh * g.kw * cin_pad, g.cout, p->block_n);
+  return rc;
+}
+
+// Appends a fused 1x1 (downsample) source: extra K slabs read from `in2` [n][h_out][w_out][cin2_buf].
+// The weight matrix must carry cin2_pad extra K columns after the main taps.
+inline int plan_add_source(IgemmTcParams* p, const void* in2, int cin2, int cin2_buf, const void* wgt, int ktotal,
+                           int cout) {
+  if (p->num_taps >= kTcMaxTaps) return -6;
+  const int cin2_pad = ceil_div(cin2, 64) * 64;
+  TapDesc& d = p->taps[p->num_taps++];
+  d.src = 1; d.dw = 0; d.dr = 0; d.dh = 0;
+  p->kchunks2 = cin2_pad / 64;
+  int rc = make_act_tmap(&p->tmA2, in2, cin2_buf, p->w_out, 1, p->h_out, p->n_img, p->tw, p->th, p->tn);
+  if (rc) return rc;
+  return make_wgt_tmap(&p->tmB, wgt, ktotal, cout, p->block_n);
+}
+
+}  // namespace ocrfa
