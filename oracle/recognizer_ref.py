@@ -1,0 +1,330 @@
+"""CPU restatement of the OCR-FA recognition hot path (TEST INFRASTRUCTURE - the ORACLE).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may import this module,
+and only as the checker or the timed CPU baseline. The product path (ocrfa_b200/) never does.
+
+Parity pin: the reference has no tests or golden vectors, so this restatement is pinned
+against outputs of the reference ITSELF, produced in the dev container by oracle/gen_golden.py and committed
+under tests/golden/ (tests/test_oracle_golden.py). Floating-point stages use torch fp32 CPU ops exactly as the
+reference does (the arithmetic lives in torch/numpy/Pillow, not in the reference tree); byte/integer stages
+(CTC collapse, beam bookkeeping) are plain numpy/Python.
+
+Each function cites the reference lines it follows (paths relative to /root/reference/).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+BN_EPS = 1e-5  # nn.BatchNorm2d default, src/ocrfa/modules/blocks.py:201
+
+
+# --------------------------------------------------------------------------------------------------------------
+# a1: pre-processing  (src/ocrfa/utils.py:533-602)
+# --------------------------------------------------------------------------------------------------------------
+def adjust_contrast_grey_ref(img: np.ndarray, target: float = 0.4) -> np.ndarray:
+    """utils.py:450-463: percentile 10/90 contrast stretch when contrast < target."""
+    high = np.percentile(img, 90)
+    low = np.percentile(img, 10)
+    contrast = (high - low) / np.maximum(10, high + low)
+    if contrast < target:
+        img = img.astype(int)
+        ratio = 200.0 / np.maximum(10, high - low)
+        img = (img - low + 25) * ratio
+        img = np.maximum(np.full(img.shape, 0), np.minimum(np.full(img.shape, 255), img)).astype(np.uint8)
+    return img
+
+
+def resized_width_ref(w: int, h: int, img_h: int, img_w: int) -> int:
+    """utils.py:592-596."""
+    ratio = w / float(h)
+    return img_w if math.ceil(img_h * ratio) > img_w else math.ceil(img_h * ratio)
+
+
+def normalize_pad_ref(img_u8: np.ndarray, img_h: int, img_w: int, adjust_contrast: float = 0.0) -> np.ndarray:
+    """One line: uint8 [h, w] -> float32 [1, img_h, img_w] in [-1, 1], right-padded with the last column.
+
+    utils.py:562-564 (PIL 'L' image), :587-590 (optional contrast), :592-598 (BICUBIC resize, identity when the
+    size already matches), :542-543 (ToTensor /255 then (x-0.5)/0.5), :545-548 (replicate-last-column pad).
+    """
+    from PIL import Image
+
+    if adjust_contrast > 0:
+        img_u8 = adjust_contrast_grey_ref(img_u8, target=adjust_contrast)
+    h, w = img_u8.shape
+    rw = resized_width_ref(w, h, img_h, img_w)
+    if (rw, img_h) != (w, h):
+        img_u8 = np.asarray(Image.fromarray(img_u8, "L").resize((rw, img_h), Image.BICUBIC))
+    x = img_u8.astype(np.float32) / np.float32(255.0)
+    x = (x - np.float32(0.5)) / np.float32(0.5)
+    out = np.empty((1, img_h, img_w), dtype=np.float32)
+    out[0, :, :rw] = x
+    if rw != img_w:
+        out[0, :, rw:] = x[:, rw - 1:rw]
+    return out
+
+
+def align_collate_ref(imgs: Sequence[np.ndarray], img_h: int, img_w: int, adjust_contrast: float = 0.0) -> np.ndarray:
+    """utils.py:575-602: list of uint8 lines -> float32 [B, 1, img_h, img_w]."""
+    return np.stack([normalize_pad_ref(im, img_h, img_w, adjust_contrast) for im in imgs], 0)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# a2-a5: model forward  (src/ocrfa/modules/blocks.py:186-391, 85-102, 422-447)
+# --------------------------------------------------------------------------------------------------------------
+def _t(sd, key):
+    v = sd[key]
+    return v if isinstance(v, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(v))
+
+
+def _conv_bn(sd, x, conv, bn, stride=1, padding=0, relu=True):
+    y = F.conv2d(x, _t(sd, conv + ".weight"), None, stride=stride, padding=padding)
+    y = F.batch_norm(y, _t(sd, bn + ".running_mean"), _t(sd, bn + ".running_var"), _t(sd, bn + ".weight"),
+                     _t(sd, bn + ".bias"), False, 0.0, BN_EPS)
+    return F.relu(y) if relu else y
+
+
+def _block_b(sd, x, pre):
+    """BlockB.forward, blocks.py:219-223 (+ downsample from _make_layer, blocks.py:324-331)."""
+    residual = x
+    if pre + "downsample.0.weight" in sd:
+        residual = _conv_bn(sd, x, pre + "downsample.0", pre + "downsample.1", relu=False)
+    y = _conv_bn(sd, x, pre + "conv1", pre + "bn1", padding=1)
+    y = _conv_bn(sd, y, pre + "conv2", pre + "bn2", padding=1, relu=False)
+    return F.relu(y + residual)
+
+
+def resnet_ref(sd: Dict[str, np.ndarray], x: torch.Tensor, prefix: str = "FeatureExtraction.ConvNet.") -> torch.Tensor:
+    """ResNet.forward, blocks.py:340-391. x: [B,1,H,W] -> [B,512,H',T]."""
+    p = prefix
+    x = _conv_bn(sd, x, p + "conv0_1", p + "bn0_1", padding=1)
+    x = _conv_bn(sd, x, p + "conv0_2", p + "bn0_2", padding=1)
+    x = F.max_pool2d(x, 2, 2, 0)                                       # blocks.py:259
+    for b in range(1):
+        x = _block_b(sd, x, f"{p}layer1.{b}.")
+    x = _conv_bn(sd, x, p + "conv1", p + "bn1", padding=1)
+    x = F.max_pool2d(x, 2, 2, 0)                                       # blocks.py:271-275
+    for b in range(2):
+        x = _block_b(sd, x, f"{p}layer2.{b}.")
+    x = _conv_bn(sd, x, p + "conv2", p + "bn2", padding=1)
+    x = F.max_pool2d(x, 2, (2, 1), (0, 1))                             # blocks.py:292
+    for b in range(5):
+        x = _block_b(sd, x, f"{p}layer3.{b}.")
+    x = _conv_bn(sd, x, p + "conv3", p + "bn3", padding=1)
+    for b in range(3):
+        x = _block_b(sd, x, f"{p}layer4.{b}.")
+    x = _conv_bn(sd, x, p + "conv4_1", p + "bn4_1", stride=(2, 1), padding=(0, 1))   # blocks.py:305-313
+    x = _conv_bn(sd, x, p + "conv4_2", p + "bn4_2", stride=1, padding=0)             # blocks.py:314-322
+    return x
+
+
+def lstm_dir_ref(x: torch.Tensor, w_ih, w_hh, b_ih, b_hh, reverse: bool) -> torch.Tensor:
+    """One direction of nn.LSTM (blocks.py:89), PyTorch gate order i,f,g,o, h0=c0=0. x: [B,T,I] -> [B,T,H]."""
+    B, T, _ = x.shape
+    H = w_hh.shape[1]
+    xp = x @ w_ih.t() + b_ih + b_hh  # hoisted input projection (same math, different association than cuDNN)
+    h = x.new_zeros(B, H)
+    c = x.new_zeros(B, H)
+    out = x.new_empty(B, T, H)
+    steps = range(T - 1, -1, -1) if reverse else range(T)
+    for t in steps:
+        g = xp[:, t] + h @ w_hh.t()
+        i, f, gg, o = g.chunk(4, dim=1)
+        c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(gg)
+        h = torch.sigmoid(o) * torch.tanh(c)
+        out[:, t] = h
+    return out
+
+
+def bilstm_ref(sd, x: torch.Tensor, pre: str) -> torch.Tensor:
+    """BidirectionalLSTM.forward, blocks.py:92-102: LSTM(bidirectional) -> Linear(1024 -> 512)."""
+    fwd = lstm_dir_ref(x, _t(sd, pre + "rnn.weight_ih_l0"), _t(sd, pre + "rnn.weight_hh_l0"),
+                       _t(sd, pre + "rnn.bias_ih_l0"), _t(sd, pre + "rnn.bias_hh_l0"), False)
+    bwd = lstm_dir_ref(x, _t(sd, pre + "rnn.weight_ih_l0_reverse"), _t(sd, pre + "rnn.weight_hh_l0_reverse"),
+                       _t(sd, pre + "rnn.bias_ih_l0_reverse"), _t(sd, pre + "rnn.bias_hh_l0_reverse"), True)
+    return F.linear(torch.cat([fwd, bwd], 2), _t(sd, pre + "linear.weight"), _t(sd, pre + "linear.bias"))
+
+
+def model_forward_ref(sd: Dict[str, np.ndarray], x, return_features: bool = False):
+    """Model.forward, blocks.py:440-447. x: float32 [B,1,H,W] -> logits float32 [B,T,C]."""
+    with torch.no_grad():
+        x = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x))
+        f = resnet_ref(sd, x.float())                       # [B,512,H',T]
+        v = f.permute(0, 3, 1, 2).mean(dim=3)               # AdaptiveAvgPool2d((None,1)) + squeeze(3): [B,T,512]
+        s = bilstm_ref(sd, v, "SequenceModeling.0.")
+        s = bilstm_ref(sd, s, "SequenceModeling.1.")
+        logits = F.linear(s, _t(sd, "Prediction.weight"), _t(sd, "Prediction.bias"))
+    if return_features:
+        return logits, v
+    return logits
+
+
+# --------------------------------------------------------------------------------------------------------------
+# a6: softmax / mask / renormalise / argmax  (src/ocrfa/utils.py:628-638)
+# --------------------------------------------------------------------------------------------------------------
+def probs_ref(logits, ignore_idx: Sequence[int]) -> np.ndarray:
+    """utils.py:628-632: softmax over classes, zero the ignored classes, divide by the row sum. float32 [B,T,C]."""
+    lg = logits if isinstance(logits, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(logits))
+    p = F.softmax(lg.float(), dim=2).cpu().numpy()
+    p[:, :, list(ignore_idx)] = 0.0
+    norm = p.sum(axis=2)
+    return (p / np.expand_dims(norm, axis=-1)).astype(np.float32)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# a7: greedy CTC decode  (src/ocrfa/utils.py:1099-1115)
+# --------------------------------------------------------------------------------------------------------------
+def greedy_labels_ref(idx_row: np.ndarray, ignore: Sequence[int] = (0,)) -> List[int]:
+    """Keep t iff idx[t] != idx[t-1] (t=0 always kept) and idx[t] not in `ignore`."""
+    out = []
+    prev = None
+    for t, k in enumerate(idx_row.tolist()):
+        if (t == 0 or k != prev) and k not in ignore:
+            out.append(k)
+        prev = k
+    return out
+
+
+def greedy_decode_ref(probs: np.ndarray, character: Sequence[str], ignore: Sequence[int] = (0,)) -> List[str]:
+    """utils.py:637-639 + decode_greedy: argmax over probabilities (lowest index wins ties), collapse, map."""
+    idx = probs.argmax(axis=2)
+    return ["".join(character[k] for k in greedy_labels_ref(row, ignore)) for row in idx]
+
+
+# --------------------------------------------------------------------------------------------------------------
+# a10: confidence  (src/ocrfa/utils.py:647-660, custom_mean :446-447)
+# --------------------------------------------------------------------------------------------------------------
+def confidence_ref(probs: np.ndarray) -> List[float]:
+    values = probs.max(axis=2)
+    indices = probs.argmax(axis=2)
+    out = []
+    for v, i in zip(values, indices):
+        mp = v[i != 0]
+        if len(mp) == 0:
+            mp = np.array([0])
+        out.append(mp.prod() ** (2.0 / np.sqrt(len(mp))))
+    return out
+
+
+# --------------------------------------------------------------------------------------------------------------
+# a8: CTC prefix beam search  (src/ocrfa/utils.py:949-1038 with :824-851, :904-946; lm=None, dict_list=[])
+# --------------------------------------------------------------------------------------------------------------
+def _extend_label(lab: Tuple[int, ...], c: int, blank: int = 0) -> Tuple[int, ...]:
+    """fast_simplify_label, utils.py:904-940, for the reachable cases (a labeling never starts with blank)."""
+    if not lab:
+        return lab if c == blank else (c,)
+    if c == blank:
+        return lab if lab[-1] == blank else lab + (c,)
+    if lab[-1] == blank:
+        return lab + (c,) if lab[-2] == c else lab[:-1] + (c,)
+    return lab + (c,)
+
+
+def beam_labels_ref(mat: np.ndarray, beam_width: int, blank: int = 0) -> Tuple[int, ...]:
+    """Best raw labeling (blanks and repeats still inside) after the last timestep.
+
+    State per labeling: [prTotal, prNonBlank, prBlank], float32 arithmetic in exactly the reference's order:
+    copy-beam first (utils.py:966-990), then every class c with mat[t,c] >= float32(0.5/C) in ascending order,
+    blank included (utils.py:997-1017); equal labelings merge by += in dict insertion order; candidates for the
+    next step are the top `beam_width` by prTotal under a stable descending sort (utils.py:847-851, :964).
+    """
+    mat = np.asarray(mat, dtype=np.float32)
+    T, C = mat.shape
+    thr = np.float32(0.5 / C)
+    one, zero = np.float32(1.0), np.float32(0.0)
+    last: Dict[Tuple[int, ...], List[np.float32]] = {(): [one, zero, one]}
+    for t in range(T):
+        curr: Dict[Tuple[int, ...], List[np.float32]] = {}
+        order = sorted(last.keys(), key=lambda k: last[k][0], reverse=True)[:beam_width]
+        row = mat[t]
+        cand = np.nonzero(row >= thr)[0].tolist()
+        for lab in order:
+            p_tot, p_nb, p_b = last[lab]
+            nb = p_nb * row[lab[-1]] if lab else zero
+            bl = p_tot * row[blank]
+            e = curr.setdefault(lab, [zero, zero, zero])
+            e[1] = e[1] + nb
+            e[2] = e[2] + bl
+            e[0] = e[0] + (bl + nb)
+            for c in cand:
+                new = _extend_label(lab, c, blank)
+                pr = row[c] * (p_b if (lab and lab[-1] == c) else p_tot)
+                e2 = curr.setdefault(new, [zero, zero, zero])
+                e2[1] = e2[1] + pr
+                e2[0] = e2[0] + pr
+        last = curr
+    return sorted(last.keys(), key=lambda k: last[k][0], reverse=True)[0]
+
+
+def beam_collapse_ref(lab: Sequence[int], ignore: Sequence[int] = (0,)) -> List[int]:
+    """utils.py:1031-1035: drop ignored indices and adjacent duplicates of the RAW labeling."""
+    return [l for i, l in enumerate(lab) if l not in ignore and not (i > 0 and lab[i - 1] == lab[i])]
+
+
+def beam_decode_ref(probs: np.ndarray, character: Sequence[str], beam_width: int = 5,
+                    ignore: Sequence[int] = (0,)) -> List[str]:
+    """CTCLabelConverter.decode_beamsearch, utils.py:1117-1122."""
+    return ["".join(character[k] for k in beam_collapse_ref(beam_labels_ref(m, beam_width), ignore)) for m in probs]
+
+
+# --------------------------------------------------------------------------------------------------------------
+# a9: word beam search, no separators, empty dictionary  (src/ocrfa/utils.py:1124-1151)
+# --------------------------------------------------------------------------------------------------------------
+def word_spans_ref(argmax_row: np.ndarray, space_idx: int) -> List[List[int]]:
+    """Maximal runs of consecutive timesteps whose argmax is not the space class (utils.py:1134-1136)."""
+    spans: List[List[int]] = []
+    for t, k in enumerate(argmax_row.tolist()):
+        if k == space_idx:
+            continue
+        if spans and spans[-1][-1] == t - 1:
+            spans[-1].append(t)
+        else:
+            spans.append([t])
+    return spans
+
+
+def wordbeam_decode_ref(probs: np.ndarray, character: Sequence[str], beam_width: int = 5,
+                        ignore: Sequence[int] = (0,)) -> List[str]:
+    space_idx = list(character).index(" ")  # converter.dict[" "] == index in `character` (utils.py:1052-1056)
+    am = np.argmax(probs, axis=2)
+    out = []
+    for i in range(probs.shape[0]):
+        words = []
+        for span in word_spans_ref(am[i], space_idx):
+            sub = probs[i, span, :]
+            words.append("".join(character[k] for k in beam_collapse_ref(beam_labels_ref(sub, beam_width), ignore)))
+        out.append(" ".join(words))
+    return out
+
+
+# --------------------------------------------------------------------------------------------------------------
+# recognizer_predict restated end to end  (src/ocrfa/utils.py:605-662)
+# --------------------------------------------------------------------------------------------------------------
+def recognizer_predict_ref(sd, x: np.ndarray, character: Sequence[str], ignore_idx: Sequence[int],
+                           decoder: str = "greedy", beam_width: int = 5):
+    """x: float32 [B,1,H,W] (already collated). Returns [[str, conf], ...] like the reference."""
+    logits = model_forward_ref(sd, x)
+    probs = probs_ref(logits, ignore_idx)
+    if decoder == "greedy":
+        strs = greedy_decode_ref(probs, character)
+    elif decoder == "beamsearch":
+        strs = beam_decode_ref(probs, character, beam_width)
+    elif decoder == "wordbeamsearch":
+        strs = wordbeam_decode_ref(probs, character, beam_width)
+    else:
+        raise ValueError(decoder)
+    return [[s, c] for s, c in zip(strs, confidence_ref(probs))]
+
+
+def ignore_idx_ref(character: str, ignore_char: str) -> List[int]:
+    """get_text, utils.py:716-722: 1-based index of the FIRST occurrence of each ignored character."""
+    out = []
+    for ch in ignore_char:
+        k = character.find(ch)
+        if k >= 0:
+            out.append(k + 1)
+    return out
