@@ -1,0 +1,146 @@
+/* ocrfa_b200 - C ABI of the B200-native OCR-FA recognition hot path.
+ *
+ * The reference has no FFI layer: its boundary is a set of Python callables. Each entry
+ * point below replaces the arithmetic behind one of them; INTEGRATION.md shows the ctypes binding a reference
+ * maintainer would add. Paths are relative to /root/reference/.
+ *
+ *   ocrfa_create / ocrfa_load_weight / ocrfa_finalize_weights
+ *        <- get_recognizer(...)                         src/ocrfa/utils.py:665-695   (Model(...), load_state_dict)
+ *   ocrfa_preprocess_u8
+ *        <- AlignCollate.__call__ + NormalizePAD        src/ocrfa/utils.py:541-550, 575-602
+ *   ocrfa_forward
+ *        <- Model.forward(inputs, *args)                src/ocrfa/modules/blocks.py:440-447
+ *   ocrfa_ctc_greedy
+ *        <- recognizer_predict softmax/mask/renorm/max  src/ocrfa/utils.py:628-638
+ *           CTCLabelConverter.decode_greedy             src/ocrfa/utils.py:1099-1115
+ *           confidence + custom_mean                    src/ocrfa/utils.py:647-660, 446-447
+ *   ocrfa_ctc_beam
+ *        <- CTCLabelConverter.decode_beamsearch         src/ocrfa/utils.py:1117-1122 (ctcBeamSearch :949-1038)
+ *   ocrfa_recognize_host
+ *        <- recognizer_predict(...) for one batch       src/ocrfa/utils.py:605-662  (host buffers in, host results out)
+ *
+ * Conventions: plain pointers and sizes only; `stream` is a cudaStream_t passed as void*; device pointers are
+ * prefixed d_, host pointers h_. Every function returns 0 on success or a negative code; the message is
+ * available from ocrfa_last_error() (thread-local). Nothing here falls back to the CPU: without a CUDA device
+ * the compute entry points fail with OCRFA_ERR_CUDA.
+ * Index -> character mapping stays with the caller (converter.character), so Unicode / bidi handling is untouched.
+ */
+#ifndef OCRFA_B200_H_
+#define OCRFA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OCRFA_OK 0
+#define OCRFA_ERR_ARG (-1)
+#define OCRFA_ERR_CUDA (-2)
+#define OCRFA_ERR_WEIGHTS (-3)
+#define OCRFA_ERR_WORKSPACE (-4)
+#define OCRFA_ERR_STATE (-5)
+
+/* arithmetic of the contraction layers */
+#define OCRFA_PRECISION_FP32 0 /* CUDA-core fp32: logits within 1e-3 of the reference's fp32 path */
+#define OCRFA_PRECISION_BF16 1 /* tcgen05 bf16 inputs, fp32 accumulate: logits within 2e-2 */
+
+typedef struct ocrfa_handle ocrfa_handle;
+
+typedef struct ocrfa_config {
+  int32_t input_channel;  /* 1 (network_params of "generation1", ocr.py:180-185) */
+  int32_t output_channel; /* 512 */
+  int32_t hidden_size;    /* 512 */
+  int32_t num_class;      /* len(converter.character), 185 for the default Farsi model */
+  int32_t precision;      /* OCRFA_PRECISION_* */
+  int32_t device;         /* CUDA device ordinal */
+} ocrfa_config;
+
+int ocrfa_abi_version(void);
+const char* ocrfa_last_error(void);
+
+int ocrfa_create(const ocrfa_config* cfg, ocrfa_handle** out);
+void ocrfa_destroy(ocrfa_handle* h);
+
+/* One state-dict entry (float32, host memory, PyTorch layout); an optional "module." prefix is stripped.
+ * Integer entries (num_batches_tracked) may be skipped by the caller. */
+int ocrfa_load_weight(ocrfa_handle* h, const char* name, const float* h_data, const int64_t* shape, int32_t ndim);
+/* Folds BatchNorm into the convolutions, repacks for the kernels and uploads. Call once after all weights. */
+int ocrfa_finalize_weights(ocrfa_handle* h, void* stream);
+
+/* T = W/4 + 1 timesteps for an input width W (multiple of 4); 0 on invalid geometry. */
+int32_t ocrfa_out_timesteps(int32_t img_h, int32_t img_w);
+/* Bytes of caller-provided device scratch ocrfa_forward needs for a batch of B lines of H x W. */
+size_t ocrfa_workspace_bytes(const ocrfa_handle* h, int32_t B, int32_t H, int32_t W);
+
+/* uint8 lines already at model height -> float32 [B,1,H,W] in [-1,1]; columns >= widths[b] replicate the last
+ * valid column (widths may be NULL: all lines are W wide). in_stride = bytes between rows of d_img. */
+int ocrfa_preprocess_u8(const uint8_t* d_img, const int32_t* d_widths, int32_t B, int32_t H, int32_t W,
+                        int32_t in_stride, float* d_x, void* stream);
+
+/* d_x: float32 [B,1,H,W]; d_logits: float32 [B,T,num_class]. */
+int ocrfa_forward(ocrfa_handle* h, const float* d_x, int32_t B, int32_t H, int32_t W, float* d_logits, void* d_ws,
+                  size_t ws_bytes, void* stream);
+/* The two halves of ocrfa_forward, for stage-wise use and parity checks:
+ *   features = AdaptiveAvgPool(FeatureExtraction(x))   float32 [B,T,512]   (blocks.py:432-433, 443-446)
+ *   logits   = Prediction(SequenceModeling(features))  float32 [B,T,num_class] (blocks.py:434-438, 441-442)
+ * (H, W) always name the INPUT line geometry; T = W/4 + 1. */
+int ocrfa_forward_features(ocrfa_handle* h, const float* d_x, int32_t B, int32_t H, int32_t W, float* d_features,
+                           void* d_ws, size_t ws_bytes, void* stream);
+int ocrfa_forward_sequence(ocrfa_handle* h, const float* d_features, int32_t B, int32_t H, int32_t W, float* d_logits,
+                           void* d_ws, size_t ws_bytes, void* stream);
+
+/* Same, straight from uint8 lines (normalisation fused into the stem convolution). */
+int ocrfa_forward_u8(ocrfa_handle* h, const uint8_t* d_img, const int32_t* d_widths, int32_t B, int32_t H,
+                     int32_t W, float* d_logits, void* d_ws, size_t ws_bytes, void* stream);
+
+/* softmax over C, zero the classes with d_ignore_mask[c] != 0, renormalise, argmax, CTC collapse, confidence.
+ * Optional outputs may be NULL: d_probs [B,T,C], d_idx [B,T], d_maxp [B,T]. d_collapse_ignore [C] may be NULL
+ * (only blank is dropped). d_labels [B,T] int32 (first d_len[b] valid), d_conf [B] float64. */
+int ocrfa_ctc_greedy(const float* d_logits, int32_t B, int32_t T, int32_t C, const uint8_t* d_ignore_mask,
+                     const uint8_t* d_collapse_ignore, float* d_probs, int32_t* d_idx, float* d_maxp,
+                     int32_t* d_labels, int32_t* d_len, double* d_conf, void* stream);
+
+/* CTCLabelConverter.decode_greedy on caller-provided indices (src/ocrfa/utils.py:1099-1115): line b owns
+ * d_idx[d_offsets[b] .. d_offsets[b+1]); keeps an index iff it differs from its predecessor in the line and is
+ * neither blank (0) nor flagged in d_collapse_ignore [C] (may be NULL). d_labels uses the same offsets. */
+int ocrfa_ctc_collapse(const int32_t* d_idx, const int32_t* d_offsets, int32_t B, int32_t C,
+                       const uint8_t* d_collapse_ignore, int32_t* d_labels, int32_t* d_len, void* stream);
+
+/* np.argmax(mat, axis=-1) of a [rows, C] float32 matrix (first maximum wins) - the word segmentation input of
+ * decode_wordbeamsearch (src/ocrfa/utils.py:1126). */
+int ocrfa_argmax_rows(const float* d_mat, int64_t rows, int32_t C, int32_t* d_idx, void* stream);
+
+/* Scratch bytes for ocrfa_ctc_beam. */
+size_t ocrfa_beam_workspace_bytes(int32_t B, int32_t T, int32_t C, int32_t beam_width);
+/* CTC prefix beam search over probabilities `mat` [B,T,C] (already masked/renormalised), lm = None, empty
+ * dictionary. Bit-exact with the reference's float32 arithmetic. beam_width in [1, 64]. */
+int ocrfa_ctc_beam(const float* d_probs, int32_t B, int32_t T, int32_t C, int32_t beam_width,
+                   const uint8_t* d_collapse_ignore, int32_t* d_labels, int32_t* d_len, void* d_ws, size_t ws_bytes,
+                   void* stream);
+
+/* Beam search over ragged row spans of one [rows, C] matrix (the per-word calls of decode_wordbeamsearch,
+ * src/ocrfa/utils.py:1138-1147): span i covers rows d_span_row0[i] .. + d_span_len[i] (<= t_max).
+ * d_labels is [n_spans, t_max]; scratch = ocrfa_beam_workspace_bytes(n_spans, t_max, C, beam_width). */
+int ocrfa_ctc_beam_spans(const float* d_probs, const int32_t* d_span_row0, const int32_t* d_span_len, int32_t n_spans,
+                         int32_t t_max, int32_t C, int32_t beam_width, const uint8_t* d_collapse_ignore,
+                         int32_t* d_labels, int32_t* d_len, void* d_ws, size_t ws_bytes, void* stream);
+
+/* Whole recognizer_predict step for one batch with HOST buffers: H2D of the uint8 lines, preprocess, forward,
+ * decode (decoder 0 = greedy, 1 = beamsearch), D2H of labels/lengths/confidences, stream synchronised on return.
+ * h_ignore_mask [num_class] may be NULL. h_labels [B,T] int32, h_len [B] int32, h_conf [B] float64. */
+int ocrfa_recognize_host(ocrfa_handle* h, const uint8_t* h_img, const int32_t* h_widths, int32_t B, int32_t H,
+                         int32_t W, const uint8_t* h_ignore_mask, int32_t decoder, int32_t beam_width,
+                         int32_t* h_labels, int32_t* h_len, double* h_conf, void* d_ws, size_t ws_bytes,
+                         void* stream);
+/* Scratch bytes ocrfa_recognize_host needs (forward workspace + staging + decode scratch). */
+size_t ocrfa_recognize_workspace_bytes(const ocrfa_handle* h, int32_t B, int32_t H, int32_t W, int32_t beam_width);
+
+/* Number of kernels this library has launched on behalf of the handle since creation (bench bookkeeping). */
+int64_t ocrfa_launch_count(const ocrfa_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OCRFA_B200_H_ */

@@ -1,0 +1,88 @@
+"""ctypes binding of libocrfa_b200.so (include/ocrfa_b200.h). Plumbing only: no arithmetic lives here.
+
+The library is built in-tree by `__graft_entry__.build()` / `make -C ocrfa_b200/csrc`. There is no CPU fallback:
+if the shared object is missing, importing the compute entry points raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libocrfa_b200.so")
+
+PRECISION_FP32 = 0
+PRECISION_BF16 = 1
+
+# every symbol include/ocrfa_b200.h declares (tests/test_cabi_symbols.py checks the header against this list)
+SYMBOLS = (
+    "ocrfa_abi_version", "ocrfa_last_error", "ocrfa_create", "ocrfa_destroy", "ocrfa_load_weight",
+    "ocrfa_finalize_weights", "ocrfa_out_timesteps", "ocrfa_workspace_bytes", "ocrfa_preprocess_u8",
+    "ocrfa_forward", "ocrfa_forward_features", "ocrfa_forward_sequence", "ocrfa_forward_u8", "ocrfa_ctc_greedy", "ocrfa_ctc_collapse", "ocrfa_argmax_rows",
+    "ocrfa_beam_workspace_bytes", "ocrfa_ctc_beam", "ocrfa_ctc_beam_spans", "ocrfa_recognize_host",
+    "ocrfa_recognize_workspace_bytes", "ocrfa_launch_count",
+)
+
+
+class OcrfaConfig(C.Structure):
+    _fields_ = [("input_channel", C.c_int32), ("output_channel", C.c_int32), ("hidden_size", C.c_int32),
+                ("num_class", C.c_int32), ("precision", C.c_int32), ("device", C.c_int32)]
+
+
+class OcrfaError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Loads the shared library once; raises OcrfaError (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise OcrfaError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                         "or `make -C ocrfa_b200/csrc` (there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, sz = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t
+    lib.ocrfa_abi_version.restype = C.c_int
+    lib.ocrfa_last_error.restype = C.c_char_p
+    lib.ocrfa_create.argtypes = [C.POINTER(OcrfaConfig), C.POINTER(vp)]
+    lib.ocrfa_destroy.argtypes = [vp]
+    lib.ocrfa_destroy.restype = None
+    lib.ocrfa_load_weight.argtypes = [vp, C.c_char_p, vp, C.POINTER(i64), i32]
+    lib.ocrfa_finalize_weights.argtypes = [vp, vp]
+    lib.ocrfa_out_timesteps.argtypes = [i32, i32]
+    lib.ocrfa_out_timesteps.restype = i32
+    lib.ocrfa_workspace_bytes.argtypes = [vp, i32, i32, i32]
+    lib.ocrfa_workspace_bytes.restype = sz
+    lib.ocrfa_preprocess_u8.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp]
+    lib.ocrfa_forward.argtypes = [vp, vp, i32, i32, i32, vp, vp, sz, vp]
+    lib.ocrfa_forward_features.argtypes = [vp, vp, i32, i32, i32, vp, vp, sz, vp]
+    lib.ocrfa_forward_sequence.argtypes = [vp, vp, i32, i32, i32, vp, vp, sz, vp]
+    lib.ocrfa_forward_u8.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, sz, vp]
+    lib.ocrfa_ctc_greedy.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.ocrfa_ctc_collapse.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp]
+    lib.ocrfa_argmax_rows.argtypes = [vp, i64, i32, vp, vp]
+    lib.ocrfa_beam_workspace_bytes.argtypes = [i32, i32, i32, i32]
+    lib.ocrfa_beam_workspace_bytes.restype = sz
+    lib.ocrfa_ctc_beam.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, vp, sz, vp]
+    lib.ocrfa_ctc_beam_spans.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, sz, vp]
+    lib.ocrfa_recognize_host.argtypes = [vp, vp, vp, i32, i32, i32, vp, i32, i32, vp, vp, vp, vp, sz, vp]
+    lib.ocrfa_recognize_workspace_bytes.argtypes = [vp, i32, i32, i32, i32]
+    lib.ocrfa_recognize_workspace_bytes.restype = sz
+    lib.ocrfa_launch_count.argtypes = [vp]
+    lib.ocrfa_launch_count.restype = i64
+    for name in SYMBOLS:
+        fn = getattr(lib, name)
+        if fn.restype is C.c_int and name not in ("ocrfa_abi_version",):
+            pass
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = load().ocrfa_last_error()
+        raise OcrfaError(f"ocrfa_b200 error {rc}: {msg.decode('utf-8', 'replace') if msg else ''}")

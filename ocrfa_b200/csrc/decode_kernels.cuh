@@ -1,0 +1,422 @@
+// CTC decode kernels: softmax / mask / renormalise / argmax / collapse / confidence and the prefix beam search.
+//
+//   softmax+mask+renorm+argmax  /root/reference/src/ocrfa/utils.py:628-638
+//   greedy collapse             /root/reference/src/ocrfa/utils.py:1099-1115   (CTCLabelConverter.decode_greedy)
+//   confidence                  /root/reference/src/ocrfa/utils.py:647-660, 446-447 (custom_mean)
+//   prefix beam search          /root/reference/src/ocrfa/utils.py:949-1038 with :824-851, :904-946
+//
+// The reference does these on the host with two device<->host round trips per batch; here one CTA per text line
+// keeps the whole line on chip. The beam search reproduces the reference's float32 arithmetic order (explicit
+// __fmul_rn/__fadd_rn, no FMA contraction), its stable descending sort and its labeling quirks bit for bit.
+#pragma once
+#include "common.cuh"
+
+namespace ocrfa {
+
+// ---------------------------------------------------------------------------------------------
+// greedy: one CTA (4 warps) per line. Each warp owns timesteps t = warp, warp+4, ...; a lane holds classes
+// lane, lane+32, ... (C <= 256). Algorithmic HBM bytes per line: T*C*4 read + T*4 written (+T*C*4 if probs kept).
+// ---------------------------------------------------------------------------------------------
+constexpr int kGreedyThreads = 128;
+constexpr int kMaxClassesPerLane = 8;  // C <= 256
+
+struct GreedyParams {
+  const float* logits;      // [B][T][C]
+  const uint8_t* ignore;    // [C] 1 = class masked to probability 0 before renormalisation (never class 0)
+  const uint8_t* collapse_ignore;  // [C] 1 = index dropped by the collapse (converter.ignore_idx; class 0 always)
+  float* probs_out;         // [B][T][C] or null
+  int32_t* idx_out;         // [B][T] argmax per timestep, or null
+  float* maxp_out;          // [B][T] or null
+  int32_t* labels_out;      // [B][T] collapsed label indices (first len[b] valid)
+  int32_t* len_out;         // [B]
+  double* conf_out;         // [B]
+  int B, T, C;
+};
+
+__global__ void __launch_bounds__(kGreedyThreads) ctc_greedy_kernel(const GreedyParams p) {
+  extern __shared__ uint8_t dsm[];
+  int32_t* s_idx = reinterpret_cast<int32_t*>(dsm);           // [T]
+  float* s_maxp = reinterpret_cast<float*>(s_idx + p.T);       // [T]
+  const int b = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nwarps = kGreedyThreads / 32;
+  const float* lg = p.logits + (size_t)b * p.T * p.C;
+
+  uint32_t ign_bits = 0;  // bit k: class lane+32k is masked
+  for (int k = 0; k < kMaxClassesPerLane; ++k) {
+    const int c = lane + 32 * k;
+    if (c < p.C && p.ignore && p.ignore[c]) ign_bits |= 1u << k;
+  }
+
+  for (int t = warp; t < p.T; t += nwarps) {
+    const float* row = lg + (size_t)t * p.C;
+    float v[kMaxClassesPerLane];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < kMaxClassesPerLane; ++k) {
+      const int c = lane + 32 * k;
+      v[k] = c < p.C ? __ldg(row + c) : -INFINITY;
+      mx = fmaxf(mx, v[k]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < kMaxClassesPerLane; ++k) {
+      v[k] = (lane + 32 * k) < p.C ? expf(v[k] - mx) : 0.f;
+      sum += v[k];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    float msum = 0.f;
+#pragma unroll
+    for (int k = 0; k < kMaxClassesPerLane; ++k) {
+      v[k] = __fdiv_rn(v[k], sum);                 // softmax probability
+      if ((ign_bits >> k) & 1u) v[k] = 0.f;        // preds_prob[:, :, ignore_idx] = 0
+      msum += v[k];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) msum += __shfl_xor_sync(0xffffffffu, msum, o);
+    float best = -1.f;
+    int besti = 0x7fffffff;
+#pragma unroll
+    for (int k = 0; k < kMaxClassesPerLane; ++k) {
+      const int c = lane + 32 * k;
+      if (c < p.C) {
+        v[k] = __fdiv_rn(v[k], msum);              // renormalise
+        if (v[k] > best) { best = v[k]; besti = c; }  // ascending c within the lane: lowest index wins ties
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+      if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+    }
+    if (p.probs_out) {
+      float* po = p.probs_out + ((size_t)b * p.T + t) * p.C;
+#pragma unroll
+      for (int k = 0; k < kMaxClassesPerLane; ++k) {
+        const int c = lane + 32 * k;
+        if (c < p.C) po[c] = v[k];
+      }
+    }
+    if (lane == 0) {
+      s_idx[t] = besti;
+      s_maxp[t] = best;
+      if (p.idx_out) p.idx_out[(size_t)b * p.T + t] = besti;
+      if (p.maxp_out) p.maxp_out[(size_t)b * p.T + t] = best;
+    }
+  }
+  __syncthreads();
+
+  if (warp == 0) {
+    // collapse: keep t iff idx[t] != idx[t-1] (t = 0 always kept) and idx[t] not ignored
+    int base = 0;
+    int32_t* lo = p.labels_out + (size_t)b * p.T;
+    for (int t0 = 0; t0 < p.T; t0 += 32) {
+      const int t = t0 + lane;
+      bool keep = false;
+      int k = 0;
+      if (t < p.T) {
+        k = s_idx[t];
+        const bool fresh = (t == 0) || (k != s_idx[t - 1]);
+        const bool ign = (k == 0) || (p.collapse_ignore && p.collapse_ignore[k]);
+        keep = fresh && !ign;
+      }
+      const uint32_t m = __ballot_sync(0xffffffffu, keep);
+      if (keep) lo[base + __popc(m & ((1u << lane) - 1u))] = k;
+      base += __popc(m);
+    }
+    if (lane == 0) {
+      p.len_out[b] = base;
+      // confidence: product of the max probabilities at non-blank timesteps, ** (2 / sqrt(n))
+      float prod = 1.f;
+      int n = 0;
+      for (int t = 0; t < p.T; ++t)
+        if (s_idx[t] != 0) { prod = __fmul_rn(prod, s_maxp[t]); ++n; }
+      p.conf_out[b] = n > 0 ? pow(static_cast<double>(prod), 2.0 / sqrt(static_cast<double>(n))) : 0.0;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// prefix beam search: one warp per line, sequential over T.
+// ---------------------------------------------------------------------------------------------
+struct BeamParams {
+  const float* probs;    // [B][T][C] float32, already masked + renormalised (the reference's `mat`)
+  int32_t* labels_out;   // [B][T]
+  int32_t* len_out;      // [B]
+  int16_t* lab_ws;       // [B][2][bw][T] raw labelings of the live beams (global scratch, L2 resident)
+  const uint8_t* collapse_ignore;  // [C] or null (class 0 always dropped)
+  const int32_t* span_row0;  // optional [B]: item b reads rows span_row0[b] .. +span_len[b] of probs seen as [rows][C]
+  const int32_t* span_len;   // optional [B]: timesteps of item b (<= T); null = every item has T rows at b*T
+  int B, T, C, bw;
+  int emax;              // bw * (C + 1)
+  int hs;                // hash slots (power of two >= 2 * emax)
+};
+
+enum : int { kOpSame = 0, kOpAppend = 1, kOpReplace = 2 };
+
+__device__ __forceinline__ uint64_t beam_hash_mix(uint64_t h, int c) {
+  uint64_t x = (h + static_cast<uint64_t>(c) + 1ull) * 0x9E3779B97F4A7C15ull;
+  x ^= x >> 29;
+  return x * 0xBF58476D1CE4E5B9ull + 0x94D049BB133111EBull;
+}
+
+struct BeamSmem {
+  float* row; int16_t* cand;
+  // live beams, double buffered: [2][bw]
+  float *b_tot, *b_nb, *b_b; int32_t* b_len; int16_t *b_last, *b_last2; uint64_t *b_hash, *b_hprev;
+  // candidate entries of the current step: [emax]
+  uint64_t* e_hash; float *e_tot, *e_nb, *e_b; int32_t* e_len; int16_t* e_c; uint8_t *e_parent, *e_op, *e_valid;
+  int32_t* ht;  // [hs]
+};
+
+__host__ __device__ inline size_t beam_smem_bytes(int C, int bw, int emax, int hs) {
+  size_t n = 0;
+  n += (size_t)C * 4 + (size_t)((C * 2 + 7) & ~7);
+  n += (size_t)2 * bw * (4 * 3 + 4 + 2 * 2 + 8 * 2);
+  n = (n + 7) & ~(size_t)7;
+  n += (size_t)emax * (8 + 4 * 3 + 4 + 2 + 3);
+  n = (n + 7) & ~(size_t)7;
+  n += (size_t)hs * 4;
+  return n + 64;
+}
+
+__global__ void __launch_bounds__(32) ctc_beam_kernel(const BeamParams p) {
+  extern __shared__ __align__(16) uint8_t dsm[];
+  const int lane = threadIdx.x;
+  const int b = blockIdx.x;
+  const int C = p.C, T = p.T, bw = p.bw, emax = p.emax;
+  const int Tb = p.span_len ? min(p.span_len[b], T) : T;
+  // ---- carve shared memory (8-byte fields first)
+  uint8_t* q = dsm;
+  BeamSmem s;
+  s.b_hash = reinterpret_cast<uint64_t*>(q); q += (size_t)2 * bw * 8;
+  s.b_hprev = reinterpret_cast<uint64_t*>(q); q += (size_t)2 * bw * 8;
+  s.e_hash = reinterpret_cast<uint64_t*>(q); q += (size_t)emax * 8;
+  s.row = reinterpret_cast<float*>(q); q += (size_t)C * 4;
+  s.b_tot = reinterpret_cast<float*>(q); q += (size_t)2 * bw * 4;
+  s.b_nb = reinterpret_cast<float*>(q); q += (size_t)2 * bw * 4;
+  s.b_b = reinterpret_cast<float*>(q); q += (size_t)2 * bw * 4;
+  s.b_len = reinterpret_cast<int32_t*>(q); q += (size_t)2 * bw * 4;
+  s.e_tot = reinterpret_cast<float*>(q); q += (size_t)emax * 4;
+  s.e_nb = reinterpret_cast<float*>(q); q += (size_t)emax * 4;
+  s.e_b = reinterpret_cast<float*>(q); q += (size_t)emax * 4;
+  s.e_len = reinterpret_cast<int32_t*>(q); q += (size_t)emax * 4;
+  s.ht = reinterpret_cast<int32_t*>(q); q += (size_t)p.hs * 4;
+  s.b_last = reinterpret_cast<int16_t*>(q); q += (size_t)2 * bw * 2;
+  s.b_last2 = reinterpret_cast<int16_t*>(q); q += (size_t)2 * bw * 2;
+  s.e_c = reinterpret_cast<int16_t*>(q); q += (size_t)emax * 2;
+  s.cand = reinterpret_cast<int16_t*>(q); q += (size_t)C * 2;
+  s.e_parent = q; q += emax;
+  s.e_op = q; q += emax;
+  s.e_valid = q; q += emax;
+
+  const float thr = static_cast<float>(0.5 / static_cast<double>(C));  // np.float32(0.5 / maxC)
+  const float* mat = p.probs + (p.span_row0 ? (size_t)p.span_row0[b] * C : (size_t)b * T * C);
+  int16_t* lab = p.lab_ws + (size_t)b * 2 * bw * T;
+  const uint64_t kEmptyHash = 0x243F6A8885A308D3ull;
+
+  int cur = 0;   // which half of the double-buffered beam state holds the parents
+  int nb = 1;    // number of live beams
+  if (lane == 0) {
+    s.b_tot[0] = 1.f; s.b_nb[0] = 0.f; s.b_b[0] = 1.f; s.b_len[0] = 0;
+    s.b_last[0] = -1; s.b_last2[0] = -1; s.b_hash[0] = kEmptyHash; s.b_hprev[0] = kEmptyHash;
+  }
+  __syncwarp();
+
+  for (int t = 0; t < Tb; ++t) {
+    // ---- a. stage the probability row, list the classes above threshold in ascending order
+    const float* rowg = mat + (size_t)t * C;
+    int ncand = 0;
+    for (int c0 = 0; c0 < C; c0 += 32) {
+      const int c = c0 + lane;
+      float v = 0.f;
+      bool pred = false;
+      if (c < C) { v = __ldg(rowg + c); s.row[c] = v; pred = v >= thr; }
+      const uint32_t m = __ballot_sync(0xffffffffu, pred);
+      if (pred) s.cand[ncand + __popc(m & ((1u << lane) - 1u))] = static_cast<int16_t>(c);
+      ncand += __popc(m);
+    }
+    const int per_parent = 1 + ncand;
+    const int E = nb * per_parent;
+    int hs = 64;
+    while (hs < 2 * E) hs <<= 1;
+    for (int i = lane; i < hs; i += 32) s.ht[i] = -1;
+    for (int i = lane; i < E; i += 32) s.e_valid[i] = 0;
+    __syncwarp();
+
+    // ---- b. expand every parent in rank order; entries merge by labeling (hash, length)
+    const float* pt = s.b_tot + cur * bw; const float* pn = s.b_nb + cur * bw; const float* pb = s.b_b + cur * bw;
+    const int32_t* pl = s.b_len + cur * bw; const int16_t* pla = s.b_last + cur * bw; const int16_t* pl2 = s.b_last2 + cur * bw;
+    const uint64_t* ph = s.b_hash + cur * bw; const uint64_t* php = s.b_hprev + cur * bw;
+    for (int i = 0; i < nb; ++i) {
+      const float P_tot = pt[i], P_nb = pn[i], P_b = pb[i];
+      const int P_len = pl[i];
+      const int P_last = pla[i], P_last2 = pl2[i];
+      const uint64_t P_hash = ph[i], P_hprev = php[i];
+      // candidate k == 0 is the copy-beam, k >= 1 extends with cand[k-1]
+      for (int k0 = 0; k0 < per_parent; k0 += 32) {
+        const int k = k0 + lane;
+        // the copy-beam must land before this parent's extensions (an extension by blank may merge into it)
+        const bool active = k < per_parent;
+        int op = kOpSame, c = 0, nlen = P_len;
+        uint64_t nhash = P_hash;
+        float add_nb = 0.f, add_b = 0.f, add_tot = 0.f;
+        if (active) {
+          if (k == 0) {
+            const float nbv = P_len > 0 ? __fmul_rn(P_nb, s.row[P_last]) : 0.f;
+            const float blv = __fmul_rn(P_tot, s.row[0]);
+            add_nb = nbv; add_b = blv; add_tot = __fadd_rn(blv, nbv);
+          } else {
+            c = s.cand[k - 1];
+            if (P_len == 0) op = (c == 0) ? kOpSame : kOpAppend;
+            else if (c == 0) op = (P_last == 0) ? kOpSame : kOpAppend;
+            else if (P_last == 0) op = (P_last2 == c) ? kOpAppend : kOpReplace;
+            else op = kOpAppend;
+            if (op == kOpAppend) { nhash = beam_hash_mix(P_hash, c); nlen = P_len + 1; }
+            else if (op == kOpReplace) { nhash = beam_hash_mix(P_hprev, c); nlen = P_len; }
+            const float pr = __fmul_rn(s.row[c], (P_len > 0 && P_last == c) ? P_b : P_tot);
+            add_nb = pr; add_tot = pr;
+          }
+        }
+        // two passes so that k == 0 (lane 0 of the first chunk) is inserted strictly before the others
+        for (int pass = 0; pass < 2; ++pass) {
+          const bool mine = active && ((pass == 0) == (k == 0));
+          if (mine) {
+            const int self = i * per_parent + k;  // creation order == reference dict insertion order
+            s.e_hash[self] = nhash; s.e_len[self] = nlen; s.e_c[self] = static_cast<int16_t>(c);
+            s.e_parent[self] = static_cast<uint8_t>(i); s.e_op[self] = static_cast<uint8_t>(op);
+            s.e_tot[self] = 0.f; s.e_nb[self] = 0.f; s.e_b[self] = 0.f;
+            __threadfence_block();
+            uint32_t slot = static_cast<uint32_t>(nhash ^ (nhash >> 32)) & (hs - 1);
+            int idx;
+            while (true) {
+              const int seen = atomicCAS(&s.ht[slot], -1, self);
+              if (seen == -1) { idx = self; s.e_valid[self] = 1; break; }
+              if (s.e_hash[seen] == nhash && s.e_len[seen] == nlen) { idx = seen; break; }
+              slot = (slot + 1) & (hs - 1);
+            }
+            // within one parent all candidates are distinct labelings, so no two lanes share idx here
+            s.e_nb[idx] = __fadd_rn(s.e_nb[idx], add_nb);
+            if (k == 0) s.e_b[idx] = __fadd_rn(s.e_b[idx], add_b);
+            s.e_tot[idx] = __fadd_rn(s.e_tot[idx], add_tot);
+          }
+          __syncwarp();
+        }
+      }
+    }
+
+    // ---- c. keep the best `bw` entries: prTotal descending, creation order ascending on ties (stable sort)
+    const int nxt = cur ^ 1;
+    int n_new = 0;
+    for (int r = 0; r < bw; ++r) {
+      float best = -INFINITY;
+      int besti = 0x7fffffff;
+      for (int j = lane; j < E; j += 32)
+        if (s.e_valid[j]) {
+          const float v = s.e_tot[j];
+          if (v > best || (v == best && j < besti)) { best = v; besti = j; }
+        }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+        if (oi != 0x7fffffff && (besti == 0x7fffffff || ob > best || (ob == best && oi < besti))) { best = ob; besti = oi; }
+      }
+      if (besti == 0x7fffffff) break;
+      const int j = besti;
+      const int par = s.e_parent[j], op = s.e_op[j], c = s.e_c[j];
+      const int plen = pl[par];
+      // materialise the labeling: copy the parent's, then append / replace the last element
+      const int16_t* src = lab + ((size_t)cur * bw + par) * T;
+      int16_t* dst = lab + ((size_t)nxt * bw + r) * T;
+      for (int x = lane; x < plen; x += 32) dst[x] = src[x];
+      __syncwarp();
+      if (lane == 0) {
+        s.e_valid[j] = 0;
+        if (op == kOpAppend) dst[plen] = static_cast<int16_t>(c);
+        else if (op == kOpReplace) dst[plen - 1] = static_cast<int16_t>(c);
+        const int o = nxt * bw + r;
+        s.b_tot[o] = s.e_tot[j]; s.b_nb[o] = s.e_nb[j]; s.b_b[o] = s.e_b[j]; s.b_len[o] = s.e_len[j];
+        s.b_hash[o] = s.e_hash[j];
+        if (op == kOpSame) { s.b_last[o] = pla[par]; s.b_last2[o] = pl2[par]; s.b_hprev[o] = php[par]; }
+        else if (op == kOpAppend) { s.b_last[o] = static_cast<int16_t>(c); s.b_last2[o] = pla[par]; s.b_hprev[o] = ph[par]; }
+        else { s.b_last[o] = static_cast<int16_t>(c); s.b_last2[o] = pl2[par]; s.b_hprev[o] = php[par]; }
+      }
+      __syncwarp();
+      ++n_new;
+    }
+    nb = n_new;
+    cur = nxt;
+    __syncwarp();
+  }
+
+  // ---- best labeling -> drop ignored indices and adjacent duplicates of the RAW labeling (utils.py:1031-1035)
+  if (lane == 0) {
+    const int16_t* best = lab + ((size_t)cur * bw + 0) * T;
+    const int len = nb > 0 ? s.b_len[cur * bw] : 0;
+    int32_t* lo = p.labels_out + (size_t)b * T;
+    int n = 0;
+    for (int i = 0; i < len; ++i) {
+      const int l = best[i];
+      const bool ign = (l == 0) || (p.collapse_ignore && p.collapse_ignore[l]);
+      if (!ign && !(i > 0 && best[i - 1] == l)) lo[n++] = l;
+    }
+    p.len_out[b] = n;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// stand-alone collapse (CTCLabelConverter.decode_greedy on caller-provided indices, utils.py:1099-1115):
+// one warp per line, ragged lines given by offsets[B+1].
+// ---------------------------------------------------------------------------------------------
+__global__ void ctc_collapse_kernel(const int32_t* __restrict__ idx, const int32_t* __restrict__ offsets, int B, int C,
+                                    const uint8_t* __restrict__ collapse_ignore, int32_t* __restrict__ labels,
+                                    int32_t* __restrict__ len) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const int o0 = offsets[b], o1 = offsets[b + 1];
+  int base = 0;
+  for (int t0 = o0; t0 < o1; t0 += 32) {
+    const int t = t0 + lane;
+    bool keep = false;
+    int k = 0;
+    if (t < o1) {
+      k = idx[t];
+      const bool fresh = (t == o0) || (k != idx[t - 1]);
+      const bool ign = (k == 0) || (collapse_ignore && k > 0 && k < C && collapse_ignore[k]);
+      keep = fresh && !ign;
+    }
+    const uint32_t m = __ballot_sync(0xffffffffu, keep);
+    if (keep) labels[o0 + base + __popc(m & ((1u << lane) - 1u))] = k;
+    base += __popc(m);
+  }
+  if (lane == 0) len[b] = base;
+}
+
+// argmax over the class axis of a [rows][C] float matrix, first maximum wins (np.argmax, utils.py:1126)
+__global__ void argmax_rows_kernel(const float* __restrict__ mat, long long rows, int C, int32_t* __restrict__ out) {
+  const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const float* row = mat + r * C;
+  float best = -INFINITY;
+  int besti = 0x7fffffff;
+  for (int c = lane; c < C; c += 32) {
+    const float v = __ldg(row + c);
+    if (v > best || besti == 0x7fffffff) { best = v; besti = c; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+    if (oi != 0x7fffffff && (besti == 0x7fffffff || ob > best || (ob == best && oi < besti))) { best = ob; besti = oi; }
+  }
+  if (lane == 0) out[r] = besti;
+}
+
+}  // namespace ocrfa

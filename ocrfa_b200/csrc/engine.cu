@@ -1,0 +1,862 @@
+// libocrfa_b200.so: host-side engine + C ABI (include/ocrfa_b200.h) of the B200 recognition path.
+//
+// Holds the recognizer's weights (BatchNorm folded, repacked for the kernels), lays the activations out in a
+// caller-provided workspace (NHWC, bf16 or fp32), and issues the kernel sequence of
+//   Model.forward            /root/reference/src/ocrfa/modules/blocks.py:440-447
+//   ResNet.forward           /root/reference/src/ocrfa/modules/blocks.py:340-391
+//   BidirectionalLSTM.forward /root/reference/src/ocrfa/modules/blocks.py:92-102
+// on one stream. No CPU fallback exists: every compute entry point needs a CUDA device.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/ocrfa_b200.h"
+#include "decode_kernels.cuh"
+#include "igemm_plan.h"
+#include "simt_kernels.cuh"
+
+using namespace ocrfa;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                             \
+  do {                                                                                             \
+    cudaError_t e_ = (expr);                                                                       \
+    if (e_ != cudaSuccess) return fail(OCRFA_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
+  } while (0)
+
+struct HostTensor {
+  std::vector<float> data;
+  std::vector<int64_t> shape;
+};
+
+// One convolution with its BatchNorm folded in (and, on the bf16 path, the block's 1x1 downsample fused as
+// extra K columns). Geometry per /root/reference/src/ocrfa/modules/blocks.py:239-322.
+struct ConvW {
+  std::string name;
+  int cin = 0, cout = 0, kh = 0, kw = 0, sh = 1, ph = 0, pw = 0;
+  int cin_pad = 0;     // channels of the input buffer the tensor-core path reads (multiple of 64)
+  int ds_cin = 0;      // > 0: fused downsample source channels (bf16 path)
+  int ktotal = 0;      // K of the packed weight matrix
+  void* d_wgt = nullptr;   // bf16 [cout][ktotal] (tc) or float [cout][kh*kw*cin] (simt)
+  float* d_bias = nullptr;
+};
+
+struct LstmW {
+  void* d_wih = nullptr;    // [4096][512]  both directions, gate rows permuted to [tile][gate][16]
+  float* d_bih = nullptr;   // [4096]       b_ih + b_hh, same permutation
+  void* d_whh = nullptr;    // [4096][512]
+  void* d_wlin = nullptr;   // [512][1024]
+  float* d_blin = nullptr;  // [512]
+};
+
+struct WsLayout {
+  size_t act[4], xproj, hseq, seq[2], feat, cstate, hh, total;
+  size_t act_bytes;
+};
+
+}  // namespace
+
+struct ocrfa_handle {
+  ocrfa_config cfg;
+  int num_sms = 148;
+  bool finalized = false;
+  std::map<std::string, HostTensor> host;
+  std::map<std::string, ConvW> convs;
+  float* d_stem_w = nullptr;  // [9][32]
+  float* d_stem_b = nullptr;  // [32]
+  LstmW lstm[2];
+  void* d_pred_w = nullptr;   // [num_class][512]
+  float* d_pred_b = nullptr;
+  std::vector<void*> allocs;
+  int64_t launches = 0;
+  bool bf16() const { return cfg.precision == OCRFA_PRECISION_BF16; }
+};
+
+namespace {
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+WsLayout ws_layout(const ocrfa_handle* h, int B, int H, int W) {
+  WsLayout L;
+  const size_t es = h->bf16() ? 2 : 4;
+  const size_t T = W / 4 + 1;
+  L.act_bytes = align_up((size_t)B * H * W * 64 * es, 1024);
+  size_t off = 0;
+  for (int i = 0; i < 4; ++i) { L.act[i] = off; off += L.act_bytes; }
+  L.xproj = off; off += align_up((size_t)B * T * 4096 * 4, 1024);
+  L.hseq = off; off += align_up((size_t)B * T * 1024 * es, 1024);
+  for (int i = 0; i < 2; ++i) { L.seq[i] = off; off += align_up((size_t)B * T * 512 * es, 1024); }
+  L.feat = off; off += align_up((size_t)B * T * 512 * es, 1024);
+  L.cstate = off; off += align_up((size_t)2 * B * 512 * 4, 1024);
+  L.hh = off; off += align_up((size_t)2 * B * 2048 * 4, 1024);
+  L.total = off;
+  return L;
+}
+
+const HostTensor* find(const ocrfa_handle* h, const std::string& key) {
+  auto it = h->host.find(key);
+  return it == h->host.end() ? nullptr : &it->second;
+}
+
+template <typename T>
+int upload(ocrfa_handle* h, const std::vector<T>& v, void** out) {
+  void* d = nullptr;
+  CUDA_TRY(cudaMalloc(&d, v.size() * sizeof(T)));
+  h->allocs.push_back(d);
+  CUDA_TRY(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  *out = d;
+  return 0;
+}
+
+// BN(eval) folded into the conv: y = conv(x) * s + (beta - mean * s), s = gamma / sqrt(var + eps)
+int fold_bn(const ocrfa_handle* h, const std::string& conv, const std::string& bn, std::vector<double>* scale,
+            std::vector<double>* shift, const HostTensor** w_out) {
+  const HostTensor* w = find(h, conv + ".weight");
+  const HostTensor* g = find(h, bn + ".weight");
+  const HostTensor* b = find(h, bn + ".bias");
+  const HostTensor* m = find(h, bn + ".running_mean");
+  const HostTensor* v = find(h, bn + ".running_var");
+  if (!w || !g || !b || !m || !v) return fail(OCRFA_ERR_WEIGHTS, "missing weights for %s / %s", conv.c_str(), bn.c_str());
+  const size_t co = (size_t)w->shape[0];
+  if (g->data.size() != co || b->data.size() != co || m->data.size() != co || v->data.size() != co)
+    return fail(OCRFA_ERR_WEIGHTS, "BatchNorm size mismatch for %s", bn.c_str());
+  scale->resize(co);
+  shift->resize(co);
+  for (size_t i = 0; i < co; ++i) {
+    const double s = (double)g->data[i] / std::sqrt((double)v->data[i] + 1e-5);
+    (*scale)[i] = s;
+    (*shift)[i] = (double)b->data[i] - (double)m->data[i] * s;
+  }
+  *w_out = w;
+  return 0;
+}
+
+int prep_conv(ocrfa_handle* h, const std::string& prefix, const std::string& conv, const std::string& bn, int kh, int kw,
+              int sh, int ph, int pw, const std::string& ds_conv, const std::string& ds_bn) {
+  std::vector<double> sc, sf, dsc, dsf;
+  const HostTensor* w = nullptr;
+  const HostTensor* dw = nullptr;
+  int rc = fold_bn(h, prefix + conv, prefix + bn, &sc, &sf, &w);
+  if (rc) return rc;
+  if (w->shape.size() != 4 || w->shape[2] != kh || w->shape[3] != kw)
+    return fail(OCRFA_ERR_WEIGHTS, "unexpected shape for %s", conv.c_str());
+  ConvW c;
+  c.name = conv;
+  c.cout = (int)w->shape[0]; c.cin = (int)w->shape[1];
+  c.kh = kh; c.kw = kw; c.sh = sh; c.ph = ph; c.pw = pw;
+  const bool fuse_ds = !ds_conv.empty() && h->bf16();
+  if (fuse_ds) {
+    rc = fold_bn(h, prefix + ds_conv, prefix + ds_bn, &dsc, &dsf, &dw);
+    if (rc) return rc;
+    c.ds_cin = (int)dw->shape[1];
+  }
+  std::vector<float> bias(c.cout);
+  for (int o = 0; o < c.cout; ++o) bias[o] = (float)(sf[o] + (fuse_ds ? dsf[o] : 0.0));
+  const int taps = kh * kw;
+  if (h->bf16()) {
+    c.cin_pad = ceil_div(c.cin, 64) * 64;
+    const int ds_pad = fuse_ds ? ceil_div(c.ds_cin, 64) * 64 : 0;
+    c.ktotal = taps * c.cin_pad + ds_pad;
+    std::vector<__nv_bfloat16> pk((size_t)c.cout * c.ktotal, __float2bfloat16(0.f));
+    for (int o = 0; o < c.cout; ++o) {
+      for (int ci = 0; ci < c.cin; ++ci)
+        for (int r = 0; r < kh; ++r)
+          for (int s = 0; s < kw; ++s) {
+            const double v = (double)w->data[(((size_t)o * c.cin + ci) * kh + r) * kw + s] * sc[o];
+            pk[(size_t)o * c.ktotal + (size_t)(r * kw + s) * c.cin_pad + ci] = __float2bfloat16((float)v);
+          }
+      if (fuse_ds)
+        for (int ci = 0; ci < c.ds_cin; ++ci)
+          pk[(size_t)o * c.ktotal + (size_t)taps * c.cin_pad + ci] =
+              __float2bfloat16((float)((double)dw->data[(size_t)o * c.ds_cin + ci] * dsc[o]));
+    }
+    rc = upload(h, pk, &c.d_wgt);
+  } else {
+    c.cin_pad = c.cin;
+    c.ktotal = taps * c.cin;
+    std::vector<float> pk((size_t)c.cout * c.ktotal);
+    for (int o = 0; o < c.cout; ++o)
+      for (int ci = 0; ci < c.cin; ++ci)
+        for (int r = 0; r < kh; ++r)
+          for (int s = 0; s < kw; ++s)
+            pk[(size_t)o * c.ktotal + (size_t)(r * kw + s) * c.cin + ci] =
+                (float)((double)w->data[(((size_t)o * c.cin + ci) * kh + r) * kw + s] * sc[o]);
+    rc = upload(h, pk, &c.d_wgt);
+  }
+  if (rc) return rc;
+  void* db = nullptr;
+  rc = upload(h, bias, &db);
+  if (rc) return rc;
+  c.d_bias = (float*)db;
+  h->convs[conv] = c;
+  return 0;
+}
+
+// Linear layers as 1x1 "convs": weight [out][in] (+ optional row permutation), bias.
+int prep_linear(ocrfa_handle* h, const std::vector<float>& w, const std::vector<float>& b, int out, int in, void** d_w,
+                float** d_b) {
+  int rc;
+  if (h->bf16()) {
+    std::vector<__nv_bfloat16> pk(w.size());
+    for (size_t i = 0; i < w.size(); ++i) pk[i] = __float2bfloat16(w[i]);
+    rc = upload(h, pk, d_w);
+  } else {
+    rc = upload(h, w, d_w);
+  }
+  if (rc) return rc;
+  void* db = nullptr;
+  rc = upload(h, b, &db);
+  *d_b = (float*)db;
+  (void)out; (void)in;
+  return rc;
+}
+
+// nn.LSTM gate rows are [i(512) | f(512) | g(512) | o(512)]; the kernels want, per direction, 32 tiles of
+// [i(16) f(16) g(16) o(16)] so that one 64-column accumulator tile holds all four gates of 16 hidden units.
+inline int lstm_perm_row(int new_row) {  // new row within a direction -> PyTorch row
+  const int tile = new_row / 64, gate = (new_row % 64) / 16, u = new_row % 16;
+  return gate * 512 + tile * 16 + u;
+}
+
+int prep_lstm(ocrfa_handle* h, int li) {
+  const std::string pre = "SequenceModeling." + std::to_string(li) + ".";
+  std::vector<float> wih((size_t)4096 * 512), whh((size_t)4096 * 512), bsum(4096);
+  for (int dir = 0; dir < 2; ++dir) {
+    const std::string sfx = dir ? "_reverse" : "";
+    const HostTensor* a = find(h, pre + "rnn.weight_ih_l0" + sfx);
+    const HostTensor* b = find(h, pre + "rnn.weight_hh_l0" + sfx);
+    const HostTensor* c = find(h, pre + "rnn.bias_ih_l0" + sfx);
+    const HostTensor* d = find(h, pre + "rnn.bias_hh_l0" + sfx);
+    if (!a || !b || !c || !d) return fail(OCRFA_ERR_WEIGHTS, "missing LSTM weights for %s", pre.c_str());
+    if (a->data.size() != (size_t)2048 * 512 || b->data.size() != (size_t)2048 * 512 || c->data.size() != 2048 ||
+        d->data.size() != 2048)
+      return fail(OCRFA_ERR_WEIGHTS, "unexpected LSTM shapes for %s", pre.c_str());
+    for (int r = 0; r < 2048; ++r) {
+      const int src = lstm_perm_row(r);
+      memcpy(&wih[((size_t)dir * 2048 + r) * 512], &a->data[(size_t)src * 512], 512 * sizeof(float));
+      memcpy(&whh[((size_t)dir * 2048 + r) * 512], &b->data[(size_t)src * 512], 512 * sizeof(float));
+      bsum[dir * 2048 + r] = c->data[src] + d->data[src];
+    }
+  }
+  LstmW& L = h->lstm[li];
+  int rc = prep_linear(h, wih, bsum, 4096, 512, &L.d_wih, &L.d_bih);
+  if (rc) return rc;
+  std::vector<float> zero_b(1, 0.f);
+  float* dummy = nullptr;
+  rc = prep_linear(h, whh, zero_b, 4096, 512, &L.d_whh, &dummy);
+  if (rc) return rc;
+  const HostTensor* lw = find(h, pre + "linear.weight");
+  const HostTensor* lb = find(h, pre + "linear.bias");
+  if (!lw || !lb || lw->data.size() != (size_t)512 * 1024) return fail(OCRFA_ERR_WEIGHTS, "missing %slinear", pre.c_str());
+  return prep_linear(h, lw->data, lb->data, 512, 1024, &L.d_wlin, &L.d_blin);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// kernel issue helpers
+// ------------------------------------------------------------------------------------------------------------
+struct Act {
+  void* p; int n, h, w, c;  // NHWC view; c = channels of the buffer
+};
+
+int run_conv_tc(ocrfa_handle* h, const ConvW& cw, const Act& in, const Act* ds_src, const void* residual, void* out,
+                bool relu, bool out_f32, int ldo, cudaStream_t st) {
+  IgemmTcParams p;
+  ConvGeom g{in.n, in.h, in.w, cw.cin, cw.cout, cw.kh, cw.kw, cw.sh, cw.ph, cw.pw};
+  int rc = plan_conv(&p, g, in.p, in.c, cw.d_wgt);
+  if (rc) return fail(OCRFA_ERR_CUDA, "plan_conv(%s) failed: %d", cw.name.c_str(), rc);
+  if (cw.ds_cin) {
+    if (!ds_src) return fail(OCRFA_ERR_STATE, "%s expects a fused downsample source", cw.name.c_str());
+    rc = plan_add_source(&p, ds_src->p, cw.ds_cin, ds_src->c, cw.d_wgt, cw.ktotal, cw.cout);
+    if (rc) return fail(OCRFA_ERR_CUDA, "plan_add_source(%s) failed: %d", cw.name.c_str(), rc);
+  }
+  p.bias = cw.d_bias;
+  p.residual = (const __nv_bfloat16*)residual; p.ldr = cw.cout;
+  p.out = out; p.ldo = ldo; p.out_f32 = out_f32 ? 1 : 0; p.relu = relu ? 1 : 0;
+  CUDA_TRY(igemm_tc_launch(p, kModeStd, h->num_sms, st));
+  h->launches++;
+  return 0;
+}
+
+int run_conv_simt(ocrfa_handle* h, const float* wgt, const float* bias, const void* in, long long in_pix_stride, int n,
+                  int h_in, int w_in, int cin, int cout, int kh, int kw, int sh, int ph, int pw, const void* residual,
+                  void* out, int ldo, bool relu, cudaStream_t st) {
+  ConvSimtParams p;
+  p.in = in; p.in_pix_stride = in_pix_stride; p.wgt = wgt; p.bias = bias; p.residual = residual; p.ldr = cout;
+  p.out = out; p.ldo = ldo; p.n = n; p.h_in = h_in; p.w_in = w_in; p.cin = cin; p.cout = cout; p.kh = kh; p.kw = kw;
+  p.sh = sh; p.ph = ph; p.pw = pw;
+  p.h_out = (h_in + 2 * ph - kh) / sh + 1; p.w_out = w_in + 2 * pw - kw + 1; p.relu = relu ? 1 : 0;
+  const long long pix = (long long)n * p.h_out * p.w_out;
+  dim3 grid((unsigned)((pix + 63) / 64), (unsigned)((cout + 63) / 64));
+  conv_simt_kernel<float, float><<<grid, 256, 0, st>>>(p);
+  CUDA_TRY(cudaGetLastError());
+  h->launches++;
+  return 0;
+}
+
+template <typename T>
+int run_pool(ocrfa_handle* h, const Act& in, void* out, int sh, int sw, int pw, int* ho, int* wo, cudaStream_t st) {
+  *ho = (in.h - 2) / sh + 1;
+  *wo = (in.w + 2 * pw - 2) / sw + 1;
+  const long long total = (long long)in.n * *ho * *wo * (in.c / 8);
+  maxpool2x2_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const T*)in.p, (T*)out, in.n, in.h, in.w, in.c,
+                                                                       sh, sw, pw, *ho, *wo);
+  CUDA_TRY(cudaGetLastError());
+  h->launches++;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------------------
+struct BufPool {
+  void* buf[4];
+  bool used[4] = {false, false, false, false};
+  void* get() {
+    for (int i = 0; i < 4; ++i)
+      if (!used[i]) { used[i] = true; return buf[i]; }
+    return nullptr;
+  }
+  void put(void* p) {
+    for (int i = 0; i < 4; ++i)
+      if (buf[i] == p) used[i] = false;
+  }
+};
+
+// d_feat_out != null: also emit the visual features [B,T,512] as fp32 (and stop there when d_logits is null).
+// d_feat_in  != null: skip the conv stack and run the sequence head on caller-provided fp32 features.
+int forward_impl(ocrfa_handle* h, const float* d_x, const uint8_t* d_u8, const int32_t* d_widths, int B, int H, int W,
+                 float* d_logits, void* d_ws, size_t ws_bytes, cudaStream_t st, float* d_feat_out = nullptr,
+                 const float* d_feat_in = nullptr) {
+  if (!h || !h->finalized) return fail(OCRFA_ERR_STATE, "weights not finalized");
+  if (B <= 0 || H < 32 || H % 16 != 0 || W < 4 || W % 4 != 0) return fail(OCRFA_ERR_ARG, "unsupported geometry B=%d H=%d W=%d (H multiple of 16 >= 32, W multiple of 4)", B, H, W);
+  if ((!d_x && !d_u8 && !d_feat_in) || (!d_logits && !d_feat_out) || !d_ws) return fail(OCRFA_ERR_ARG, "null pointer");
+  const WsLayout L = ws_layout(h, B, H, W);
+  if (ws_bytes < L.total) return fail(OCRFA_ERR_WORKSPACE, "workspace too small: %zu < %zu", ws_bytes, L.total);
+  if (((uintptr_t)d_ws & 1023) != 0) return fail(OCRFA_ERR_WORKSPACE, "workspace must be 1024-byte aligned");
+  const bool bf = h->bf16();
+  uint8_t* ws = (uint8_t*)d_ws;
+  BufPool pool;
+  for (int i = 0; i < 4; ++i) pool.buf[i] = ws + L.act[i];
+  int rc;
+
+  auto conv = [&](const char* name, const Act& in, const Act* ds_src, const void* residual, void* out, bool relu) -> int {
+    auto it = h->convs.find(name);
+    if (it == h->convs.end()) return fail(OCRFA_ERR_STATE, "conv %s not prepared", name);
+    const ConvW& cw = it->second;
+    if (bf) return run_conv_tc(h, cw, in, ds_src, residual, out, relu, false, cw.cout, st);
+    return run_conv_simt(h, (const float*)cw.d_wgt, cw.d_bias, in.p, in.c, in.n, in.h, in.w, cw.cin, cw.cout, cw.kh,
+                         cw.kw, cw.sh, cw.ph, cw.pw, residual, out, cw.cout, relu, st);
+  };
+  auto out_dims = [&](const char* name, const Act& in, int* ho, int* wo, int* co) {
+    const ConvW& cw = h->convs.find(name)->second;
+    *ho = (in.h + 2 * cw.ph - cw.kh) / cw.sh + 1;
+    *wo = in.w + 2 * cw.pw - cw.kw + 1;
+    *co = cw.cout;
+  };
+  // conv + bn + relu into a fresh buffer; releases the input
+  auto conv_step = [&](const char* name, Act* a) -> int {
+    void* o = pool.get();
+    int ho, wo, co;
+    out_dims(name, *a, &ho, &wo, &co);
+    int r = conv(name, *a, nullptr, nullptr, o, true);
+    if (r) return r;
+    pool.put(a->p);
+    *a = Act{o, a->n, ho, wo, co};
+    return 0;
+  };
+  // BlockB: relu(bn2(conv2(relu(bn1(conv1(x))))) + residual), residual through 1x1 conv+bn when channels change
+  auto block = [&](const std::string& pre, bool has_ds, Act* a) -> int {
+    void* t = pool.get();
+    int ho, wo, co;
+    out_dims((pre + "conv1").c_str(), *a, &ho, &wo, &co);
+    int r = conv((pre + "conv1").c_str(), *a, nullptr, nullptr, t, true);
+    if (r) return r;
+    Act ta{t, a->n, ho, wo, co};
+    void* o = pool.get();
+    if (has_ds && !bf) {
+      void* rs = pool.get();
+      r = conv((pre + "downsample.0").c_str(), *a, nullptr, nullptr, rs, false);
+      if (r) return r;
+      r = conv((pre + "conv2").c_str(), ta, nullptr, rs, o, true);
+      pool.put(rs);
+    } else if (has_ds) {
+      r = conv((pre + "conv2").c_str(), ta, a, nullptr, o, true);  // downsample fused as extra K slabs
+    } else {
+      r = conv((pre + "conv2").c_str(), ta, nullptr, a->p, o, true);
+    }
+    if (r) return r;
+    pool.put(t);
+    pool.put(a->p);
+    *a = Act{o, a->n, ho, wo, co};
+    return 0;
+  };
+  auto pool_step = [&](int sh, int sw, int pw, Act* a) -> int {
+    void* o = pool.get();
+    int ho, wo;
+    int r = bf ? run_pool<__nv_bfloat16>(h, *a, o, sh, sw, pw, &ho, &wo, st) : run_pool<float>(h, *a, o, sh, sw, pw, &ho, &wo, st);
+    if (r) return r;
+    pool.put(a->p);
+    *a = Act{o, a->n, ho, wo, a->c};
+    return 0;
+  };
+
+  int T = W / 4 + 1;
+  void* feat = ws + L.feat;
+  if (d_feat_in) {
+    const long long total = (long long)B * T * 512;
+    if (bf) cvt_from_f32_kernel<__nv_bfloat16><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_feat_in, (__nv_bfloat16*)feat, total);
+    else cvt_from_f32_kernel<float><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_feat_in, (float*)feat, total);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+  } else {
+  // ---- stem: conv0_1 + bn0_1 + relu (blocks.py:341-347)
+  Act a{pool.get(), B, H, W, bf ? 64 : 32};
+  {
+    const long long pix = (long long)B * H * W;
+    const unsigned grid = (unsigned)((pix + 255) / 256);
+    if (bf)
+      stem_conv_kernel<__nv_bfloat16, 64><<<grid, 256, 0, st>>>(d_x, d_u8, d_widths, h->d_stem_w, h->d_stem_b,
+                                                                 (__nv_bfloat16*)a.p, B, H, W);
+    else
+      stem_conv_kernel<float, 32><<<grid, 256, 0, st>>>(d_x, d_u8, d_widths, h->d_stem_w, h->d_stem_b, (float*)a.p, B, H, W);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+  }
+  if ((rc = conv_step("conv0_2", &a))) return rc;
+  if ((rc = pool_step(2, 2, 0, &a))) return rc;                       // max_pool1, blocks.py:259
+  if ((rc = block("layer1.0.", true, &a))) return rc;
+  if ((rc = conv_step("conv1", &a))) return rc;
+  if ((rc = pool_step(2, 2, 0, &a))) return rc;                       // max_pool2, blocks.py:271-275
+  if ((rc = block("layer2.0.", true, &a))) return rc;
+  if ((rc = block("layer2.1.", false, &a))) return rc;
+  if ((rc = conv_step("conv2", &a))) return rc;
+  if ((rc = pool_step(2, 1, 1, &a))) return rc;                       // max_pool3 k2 s(2,1) p(0,1), blocks.py:292
+  if ((rc = block("layer3.0.", true, &a))) return rc;
+  for (int i = 1; i < 5; ++i)
+    if ((rc = block("layer3." + std::to_string(i) + ".", false, &a))) return rc;
+  if ((rc = conv_step("conv3", &a))) return rc;
+  for (int i = 0; i < 3; ++i)
+    if ((rc = block("layer4." + std::to_string(i) + ".", false, &a))) return rc;
+  if ((rc = conv_step("conv4_1", &a))) return rc;                      // 2x2 s(2,1) p(0,1), blocks.py:305-313
+  if ((rc = conv_step("conv4_2", &a))) return rc;                      // 2x2 s1 p0, blocks.py:314-322
+
+  // ---- AdaptiveAvgPool2d((None,1)) over H' + [B,T,512] layout (blocks.py:441-446)
+  T = a.w;
+  feat = a.p;
+  if (a.h > 1) {
+    feat = ws + L.feat;
+    const long long total = (long long)B * T * 512;
+    if (bf) mean_h_kernel<__nv_bfloat16><<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)a.p, (__nv_bfloat16*)feat, B, a.h, T, 512);
+    else mean_h_kernel<float><<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const float*)a.p, (float*)feat, B, a.h, T, 512);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+  }
+  }  // conv stack
+  if (d_feat_out) {
+    const long long total = (long long)B * T * 512;
+    if (bf) cvt_to_f32_kernel<__nv_bfloat16><<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)feat, d_feat_out, total);
+    else cvt_to_f32_kernel<float><<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const float*)feat, d_feat_out, total);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    if (!d_logits) return 0;
+  }
+
+  // ---- 2 x BidirectionalLSTM (blocks.py:92-102)
+  const int rows = B * T;
+  float* xproj = (float*)(ws + L.xproj);
+  void* hseq = ws + L.hseq;
+  float* cst = (float*)(ws + L.cstate);
+  float* hh = (float*)(ws + L.hh);
+  void* seq_in = feat;
+  for (int li = 0; li < 2; ++li) {
+    const LstmW& lw = h->lstm[li];
+    void* seq_out = ws + L.seq[li];
+    if (bf) {
+      // input projection for both directions: [rows,512] x [4096,512]^T + (b_ih + b_hh) -> fp32
+      ConvW xp; xp.name = "lstm.xproj"; xp.cin = 512; xp.cout = 4096; xp.kh = xp.kw = 1; xp.sh = 1; xp.cin_pad = 512;
+      xp.ktotal = 512; xp.d_wgt = lw.d_wih; xp.d_bias = lw.d_bih;
+      if ((rc = run_conv_tc(h, xp, Act{seq_in, 1, 1, rows, 512}, nullptr, nullptr, xproj, false, true, 4096, st))) return rc;
+      // recurrence: one launch per timestep, both directions in the launch
+      IgemmTcParams p;
+      memset(&p, 0, sizeof(p));
+      p.tw = 1; p.th = 128; p.tn = 1;
+      p.tiles_w = 1; p.tiles_h = ceil_div(B, 128); p.tiles_n = 1;
+      p.n_img = 1; p.h_out = B; p.w_out = 1;
+      p.block_n = 64; p.n_tiles = 64; p.n_valid = 4096;
+      p.kchunks = 8; p.num_taps = 1; p.taps[0] = TapDesc{0, 0, 0, 0};
+      igemm_tc_smem_bytes(p.block_n, &p.num_stages);
+      int r2 = make_act_tmap(&p.tmA, hseq, 1024, T, 1, B, 1, 1, 128, 1);
+      if (r2 == 0) r2 = make_wgt_tmap(&p.tmB, lw.d_whh, 512, 4096, 64);
+      if (r2) return fail(OCRFA_ERR_CUDA, "LSTM tensor map failed: %d", r2);
+      p.tmA2 = p.tmA;
+      p.lstm_T = T; p.lstm_xproj = xproj; p.lstm_c = cst; p.lstm_hseq = (__nv_bfloat16*)hseq;
+      for (int s = 0; s < T; ++s) {
+        p.lstm_step = s;
+        CUDA_TRY(igemm_tc_launch(p, kModeLstm, h->num_sms, st));
+        h->launches++;
+      }
+      ConvW lin; lin.name = "lstm.linear"; lin.cin = 1024; lin.cout = 512; lin.kh = lin.kw = 1; lin.sh = 1; lin.cin_pad = 1024;
+      lin.ktotal = 1024; lin.d_wgt = lw.d_wlin; lin.d_bias = lw.d_blin;
+      if ((rc = run_conv_tc(h, lin, Act{hseq, 1, 1, rows, 1024}, nullptr, nullptr, seq_out, false, false, 512, st))) return rc;
+    } else {
+      if ((rc = run_conv_simt(h, (const float*)lw.d_wih, lw.d_bih, seq_in, 512, 1, 1, rows, 512, 4096, 1, 1, 1, 0, 0,
+                              nullptr, xproj, 4096, false, st))) return rc;
+      for (int s = 0; s < T; ++s) {
+        if (s > 0)
+          for (int dir = 0; dir < 2; ++dir) {
+            const int t_prev = dir == 0 ? s - 1 : T - s;
+            const float* hin = (const float*)hseq + (size_t)t_prev * 1024 + dir * 512;
+            if ((rc = run_conv_simt(h, (const float*)lw.d_whh + (size_t)dir * 2048 * 512, nullptr, hin, (long long)T * 1024,
+                                    1, 1, B, 512, 2048, 1, 1, 1, 0, 0, nullptr, hh + (size_t)dir * B * 2048, 2048, false, st)))
+              return rc;
+          }
+        const int total = 2 * B * 512;
+        lstm_cell_f32_kernel<<<(total + 255) / 256, 256, 0, st>>>(hh, xproj, cst, (float*)hseq, B, T, s);
+        CUDA_TRY(cudaGetLastError());
+        h->launches++;
+      }
+      if ((rc = run_conv_simt(h, (const float*)lw.d_wlin, lw.d_blin, hseq, 1024, 1, 1, rows, 1024, 512, 1, 1, 1, 0, 0,
+                              nullptr, seq_out, 512, false, st))) return rc;
+    }
+    seq_in = seq_out;
+  }
+
+  // ---- Prediction: Linear(512 -> num_class) (blocks.py:438, 441)
+  const int C = h->cfg.num_class;
+  if (bf) {
+    ConvW pr; pr.name = "prediction"; pr.cin = 512; pr.cout = C; pr.kh = pr.kw = 1; pr.sh = 1; pr.cin_pad = 512; pr.ktotal = 512;
+    pr.d_wgt = h->d_pred_w; pr.d_bias = h->d_pred_b;
+    if ((rc = run_conv_tc(h, pr, Act{seq_in, 1, 1, rows, 512}, nullptr, nullptr, d_logits, false, true, C, st))) return rc;
+  } else {
+    if ((rc = run_conv_simt(h, (const float*)h->d_pred_w, h->d_pred_b, seq_in, 512, 1, 1, rows, 512, C, 1, 1, 1, 0, 0, nullptr,
+                            d_logits, C, false, st))) return rc;
+  }
+  return 0;
+}
+
+size_t beam_ws_bytes(int B, int T, int C, int bw) {
+  (void)C;
+  return align_up((size_t)B * 2 * bw * T * sizeof(int16_t), 256);
+}
+
+struct RecLayout {
+  size_t fwd, img, widths, mask, logits, probs, labels, len, conf, beam, total;
+};
+
+RecLayout rec_layout(const ocrfa_handle* h, int B, int H, int W, int bw) {
+  RecLayout R;
+  const int T = W / 4 + 1, C = h->cfg.num_class;
+  size_t off = 0;
+  R.fwd = off; off += align_up(ws_layout(h, B, H, W).total, 1024);
+  R.img = off; off += align_up((size_t)B * H * W, 1024);
+  R.widths = off; off += align_up((size_t)B * 4, 1024);
+  R.mask = off; off += align_up((size_t)C, 1024);
+  R.logits = off; off += align_up((size_t)B * T * C * 4, 1024);
+  R.probs = off; off += align_up((size_t)B * T * C * 4, 1024);
+  R.labels = off; off += align_up((size_t)B * T * 4, 1024);
+  R.len = off; off += align_up((size_t)B * 4, 1024);
+  R.conf = off; off += align_up((size_t)B * 8, 1024);
+  R.beam = off; off += align_up(beam_ws_bytes(B, T, C, bw > 0 ? bw : 1), 1024);
+  R.total = off;
+  return R;
+}
+
+}  // namespace
+
+// ==============================================================================================================
+// C ABI
+// ==============================================================================================================
+extern "C" {
+
+int ocrfa_abi_version(void) { return 1; }
+const char* ocrfa_last_error(void) { return g_err; }
+
+int ocrfa_create(const ocrfa_config* cfg, ocrfa_handle** out) {
+  if (!cfg || !out) return fail(OCRFA_ERR_ARG, "null argument");
+  if (cfg->input_channel != 1 || cfg->output_channel != 512 || cfg->hidden_size != 512)
+    return fail(OCRFA_ERR_ARG, "only the reference's generation1 network (1, 512, 512) is supported");
+  if (cfg->num_class < 2 || cfg->num_class > 256) return fail(OCRFA_ERR_ARG, "num_class must be in [2, 256]");
+  if (cfg->precision != OCRFA_PRECISION_FP32 && cfg->precision != OCRFA_PRECISION_BF16)
+    return fail(OCRFA_ERR_ARG, "unknown precision %d", cfg->precision);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= cfg->device)
+    return fail(OCRFA_ERR_CUDA, "no CUDA device %d (this library has no CPU path)", cfg->device);
+  CUDA_TRY(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10) return fail(OCRFA_ERR_CUDA, "sm_100a kernels need a Blackwell B200 (found cc %d.%d)", prop.major, prop.minor);
+  ocrfa_handle* h = new ocrfa_handle();
+  h->cfg = *cfg;
+  h->num_sms = prop.multiProcessorCount;
+  *out = h;
+  return 0;
+}
+
+void ocrfa_destroy(ocrfa_handle* h) {
+  if (!h) return;
+  for (void* p : h->allocs) cudaFree(p);
+  delete h;
+}
+
+int ocrfa_load_weight(ocrfa_handle* h, const char* name, const float* h_data, const int64_t* shape, int32_t ndim) {
+  if (!h || !name || !h_data || (ndim > 0 && !shape) || ndim < 0 || ndim > 4) return fail(OCRFA_ERR_ARG, "bad argument");
+  if (h->finalized) return fail(OCRFA_ERR_STATE, "weights already finalized");
+  std::string key(name);
+  if (key.rfind("module.", 0) == 0) key = key.substr(7);  // DataParallel prefix, utils.py:680-685
+  const std::string fe = "FeatureExtraction.ConvNet.";
+  if (key.rfind(fe, 0) == 0) key = key.substr(fe.size());
+  HostTensor t;
+  size_t n = 1;
+  for (int i = 0; i < ndim; ++i) { t.shape.push_back(shape[i]); n *= (size_t)shape[i]; }
+  t.data.assign(h_data, h_data + n);
+  h->host[key] = std::move(t);
+  return 0;
+}
+
+int ocrfa_finalize_weights(ocrfa_handle* h, void* stream) {
+  (void)stream;
+  if (!h) return fail(OCRFA_ERR_ARG, "null handle");
+  if (h->finalized) return fail(OCRFA_ERR_STATE, "weights already finalized");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  int rc;
+  // stem: conv0_1 [32][1][3][3] -> [9][32] fp32 with bn0_1 folded
+  {
+    std::vector<double> sc, sf;
+    const HostTensor* w = nullptr;
+    if ((rc = fold_bn(h, "conv0_1", "bn0_1", &sc, &sf, &w))) return rc;
+    if (w->data.size() != 32 * 9) return fail(OCRFA_ERR_WEIGHTS, "conv0_1 must be [32,1,3,3]");
+    std::vector<float> pk(9 * 32), b(32);
+    for (int o = 0; o < 32; ++o) {
+      for (int k = 0; k < 9; ++k) pk[k * 32 + o] = (float)((double)w->data[o * 9 + k] * sc[o]);
+      b[o] = (float)sf[o];
+    }
+    void* d = nullptr;
+    if ((rc = upload(h, pk, &d))) return rc;
+    h->d_stem_w = (float*)d;
+    if ((rc = upload(h, b, &d))) return rc;
+    h->d_stem_b = (float*)d;
+  }
+  if ((rc = prep_conv(h, "", "conv0_2", "bn0_2", 3, 3, 1, 1, 1, "", ""))) return rc;
+  const int blocks[4] = {1, 2, 5, 3};
+  for (int li = 1; li <= 4; ++li) {
+    for (int b = 0; b < blocks[li - 1]; ++b) {
+      const std::string pre = "layer" + std::to_string(li) + "." + std::to_string(b) + ".";
+      const bool has_ds = find(h, pre + "downsample.0.weight") != nullptr;
+      if ((rc = prep_conv(h, "", pre + "conv1", pre + "bn1", 3, 3, 1, 1, 1, "", ""))) return rc;
+      if ((rc = prep_conv(h, "", pre + "conv2", pre + "bn2", 3, 3, 1, 1, 1, has_ds ? pre + "downsample.0" : "",
+                          has_ds ? pre + "downsample.1" : "")))
+        return rc;
+      if (has_ds && !h->bf16())
+        if ((rc = prep_conv(h, "", pre + "downsample.0", pre + "downsample.1", 1, 1, 1, 0, 0, "", ""))) return rc;
+    }
+    if (li < 4) {
+      const std::string c = "conv" + std::to_string(li), bn = "bn" + std::to_string(li);
+      if ((rc = prep_conv(h, "", c, bn, 3, 3, 1, 1, 1, "", ""))) return rc;
+    }
+  }
+  if ((rc = prep_conv(h, "", "conv4_1", "bn4_1", 2, 2, 2, 0, 1, "", ""))) return rc;
+  if ((rc = prep_conv(h, "", "conv4_2", "bn4_2", 2, 2, 1, 0, 0, "", ""))) return rc;
+  // the bf16 conv0_2 reads the stem's 64-channel (32 real + 32 zero) buffer: its cin_pad is already 64
+  for (int li = 0; li < 2; ++li)
+    if ((rc = prep_lstm(h, li))) return rc;
+  const HostTensor* pw = find(h, "Prediction.weight");
+  const HostTensor* pb = find(h, "Prediction.bias");
+  if (!pw || !pb || pw->data.size() != (size_t)h->cfg.num_class * 512 || pb->data.size() != (size_t)h->cfg.num_class)
+    return fail(OCRFA_ERR_WEIGHTS, "Prediction weights missing or not [%d,512]", h->cfg.num_class);
+  if ((rc = prep_linear(h, pw->data, pb->data, h->cfg.num_class, 512, &h->d_pred_w, &h->d_pred_b))) return rc;
+  if (h->bf16()) {
+    CUDA_TRY(cudaFuncSetAttribute(igemm_tc_kernel<kModeStd>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(igemm_tc_kernel<kModeLstm>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    if (!get_tmap_encode()) return fail(OCRFA_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  }
+  CUDA_TRY(cudaDeviceSynchronize());
+  h->host.clear();
+  h->finalized = true;
+  return 0;
+}
+
+int32_t ocrfa_out_timesteps(int32_t img_h, int32_t img_w) {
+  if (img_h < 32 || img_h % 16 != 0 || img_w < 4 || img_w % 4 != 0) return 0;
+  return img_w / 4 + 1;
+}
+
+size_t ocrfa_workspace_bytes(const ocrfa_handle* h, int32_t B, int32_t H, int32_t W) {
+  if (!h || B <= 0 || H <= 0 || W <= 0) return 0;
+  return ws_layout(h, B, H, W).total;
+}
+
+int ocrfa_preprocess_u8(const uint8_t* d_img, const int32_t* d_widths, int32_t B, int32_t H, int32_t W, int32_t in_stride,
+                        float* d_x, void* stream) {
+  if (!d_img || !d_x || B <= 0 || H <= 0 || W <= 0 || in_stride < W) return fail(OCRFA_ERR_ARG, "bad argument");
+  const long long total = (long long)B * H * ((W + 15) / 16);
+  preprocess_u8_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_img, d_widths, d_x, B, H, W, in_stride);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int ocrfa_forward(ocrfa_handle* h, const float* d_x, int32_t B, int32_t H, int32_t W, float* d_logits, void* d_ws,
+                  size_t ws_bytes, void* stream) {
+  return forward_impl(h, d_x, nullptr, nullptr, B, H, W, d_logits, d_ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int ocrfa_forward_features(ocrfa_handle* h, const float* d_x, int32_t B, int32_t H, int32_t W, float* d_features,
+                           void* d_ws, size_t ws_bytes, void* stream) {
+  if (!d_x || !d_features) return fail(OCRFA_ERR_ARG, "null pointer");
+  return forward_impl(h, d_x, nullptr, nullptr, B, H, W, nullptr, d_ws, ws_bytes, (cudaStream_t)stream, d_features, nullptr);
+}
+
+int ocrfa_forward_sequence(ocrfa_handle* h, const float* d_features, int32_t B, int32_t H, int32_t W, float* d_logits,
+                           void* d_ws, size_t ws_bytes, void* stream) {
+  if (!d_features || !d_logits) return fail(OCRFA_ERR_ARG, "null pointer");
+  return forward_impl(h, nullptr, nullptr, nullptr, B, H, W, d_logits, d_ws, ws_bytes, (cudaStream_t)stream, nullptr, d_features);
+}
+
+int ocrfa_forward_u8(ocrfa_handle* h, const uint8_t* d_img, const int32_t* d_widths, int32_t B, int32_t H, int32_t W,
+                     float* d_logits, void* d_ws, size_t ws_bytes, void* stream) {
+  return forward_impl(h, nullptr, d_img, d_widths, B, H, W, d_logits, d_ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int ocrfa_ctc_greedy(const float* d_logits, int32_t B, int32_t T, int32_t C, const uint8_t* d_ignore_mask,
+                     const uint8_t* d_collapse_ignore, float* d_probs, int32_t* d_idx, float* d_maxp, int32_t* d_labels,
+                     int32_t* d_len, double* d_conf, void* stream) {
+  if (!d_logits || !d_labels || !d_len || !d_conf || B <= 0 || T <= 0 || C < 2 || C > 32 * kMaxClassesPerLane)
+    return fail(OCRFA_ERR_ARG, "bad argument (C must be <= %d)", 32 * kMaxClassesPerLane);
+  GreedyParams p{d_logits, d_ignore_mask, d_collapse_ignore, d_probs, d_idx, d_maxp, d_labels, d_len, d_conf, B, T, C};
+  const size_t smem = (size_t)T * 8;
+  if (smem > 48 * 1024) return fail(OCRFA_ERR_ARG, "T too large for the greedy kernel");
+  ctc_greedy_kernel<<<B, kGreedyThreads, smem, (cudaStream_t)stream>>>(p);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+size_t ocrfa_beam_workspace_bytes(int32_t B, int32_t T, int32_t C, int32_t beam_width) {
+  if (B <= 0 || T <= 0 || C <= 0 || beam_width <= 0) return 0;
+  return beam_ws_bytes(B, T, C, beam_width);
+}
+
+int ocrfa_ctc_collapse(const int32_t* d_idx, const int32_t* d_offsets, int32_t B, int32_t C,
+                       const uint8_t* d_collapse_ignore, int32_t* d_labels, int32_t* d_len, void* stream) {
+  if (!d_idx || !d_offsets || !d_labels || !d_len || B <= 0 || C < 1) return fail(OCRFA_ERR_ARG, "bad argument");
+  ctc_collapse_kernel<<<(B + 3) / 4, 128, 0, (cudaStream_t)stream>>>(d_idx, d_offsets, B, C, d_collapse_ignore, d_labels, d_len);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int ocrfa_argmax_rows(const float* d_mat, int64_t rows, int32_t C, int32_t* d_idx, void* stream) {
+  if (!d_mat || !d_idx || rows <= 0 || C < 1) return fail(OCRFA_ERR_ARG, "bad argument");
+  argmax_rows_kernel<<<(unsigned)((rows + 3) / 4), 128, 0, (cudaStream_t)stream>>>(d_mat, rows, C, d_idx);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+static int beam_launch(const float* d_probs, const int32_t* d_span_row0, const int32_t* d_span_len, int32_t B, int32_t T,
+                       int32_t C, int32_t beam_width, const uint8_t* d_collapse_ignore, int32_t* d_labels, int32_t* d_len,
+                       void* d_ws, size_t ws_bytes, void* stream);
+
+int ocrfa_ctc_beam_spans(const float* d_probs, const int32_t* d_span_row0, const int32_t* d_span_len, int32_t n_spans,
+                         int32_t t_max, int32_t C, int32_t beam_width, const uint8_t* d_collapse_ignore, int32_t* d_labels,
+                         int32_t* d_len, void* d_ws, size_t ws_bytes, void* stream) {
+  if (!d_span_row0 || !d_span_len) return fail(OCRFA_ERR_ARG, "null span arrays");
+  return beam_launch(d_probs, d_span_row0, d_span_len, n_spans, t_max, C, beam_width, d_collapse_ignore, d_labels, d_len,
+                     d_ws, ws_bytes, stream);
+}
+
+int ocrfa_ctc_beam(const float* d_probs, int32_t B, int32_t T, int32_t C, int32_t beam_width,
+                   const uint8_t* d_collapse_ignore, int32_t* d_labels, int32_t* d_len, void* d_ws, size_t ws_bytes,
+                   void* stream) {
+  return beam_launch(d_probs, nullptr, nullptr, B, T, C, beam_width, d_collapse_ignore, d_labels, d_len, d_ws, ws_bytes,
+                     stream);
+}
+
+static int beam_launch(const float* d_probs, const int32_t* d_span_row0, const int32_t* d_span_len, int32_t B, int32_t T,
+                       int32_t C, int32_t beam_width, const uint8_t* d_collapse_ignore, int32_t* d_labels, int32_t* d_len,
+                       void* d_ws, size_t ws_bytes, void* stream) {
+  if (!d_probs || !d_labels || !d_len || !d_ws || B <= 0 || T <= 0 || C < 2 || C > 32767)
+    return fail(OCRFA_ERR_ARG, "bad argument");
+  if (beam_width < 1 || beam_width > 64) return fail(OCRFA_ERR_ARG, "beam_width must be in [1, 64]");
+  if (ws_bytes < beam_ws_bytes(B, T, C, beam_width)) return fail(OCRFA_ERR_WORKSPACE, "beam workspace too small");
+  BeamParams p;
+  p.probs = d_probs; p.labels_out = d_labels; p.len_out = d_len; p.lab_ws = (int16_t*)d_ws;
+  p.collapse_ignore = d_collapse_ignore;
+  p.span_row0 = d_span_row0; p.span_len = d_span_len;
+  p.B = B; p.T = T; p.C = C; p.bw = beam_width;
+  p.emax = beam_width * (C + 1);
+  int hs = 64;
+  while (hs < 2 * p.emax) hs <<= 1;
+  p.hs = hs;
+  const size_t smem = beam_smem_bytes(C, beam_width, p.emax, hs);
+  if (smem > 227 * 1024) return fail(OCRFA_ERR_ARG, "beam_width * num_class too large for shared memory (%zu B)", smem);
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    CUDA_TRY(cudaFuncSetAttribute(ctc_beam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem = smem;
+  }
+  ctc_beam_kernel<<<B, 32, smem, (cudaStream_t)stream>>>(p);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+size_t ocrfa_recognize_workspace_bytes(const ocrfa_handle* h, int32_t B, int32_t H, int32_t W, int32_t beam_width) {
+  if (!h || B <= 0 || H <= 0 || W <= 0) return 0;
+  return rec_layout(h, B, H, W, beam_width).total;
+}
+
+int ocrfa_recognize_host(ocrfa_handle* h, const uint8_t* h_img, const int32_t* h_widths, int32_t B, int32_t H, int32_t W,
+                         const uint8_t* h_ignore_mask, int32_t decoder, int32_t beam_width, int32_t* h_labels,
+                         int32_t* h_len, double* h_conf, void* d_ws, size_t ws_bytes, void* stream) {
+  if (!h || !h_img || !h_labels || !h_len || !h_conf || !d_ws) return fail(OCRFA_ERR_ARG, "null pointer");
+  if (decoder != 0 && decoder != 1) return fail(OCRFA_ERR_ARG, "decoder must be 0 (greedy) or 1 (beamsearch)");
+  const int T = ocrfa_out_timesteps(H, W);
+  if (T == 0) return fail(OCRFA_ERR_ARG, "unsupported geometry");
+  const int C = h->cfg.num_class;
+  const RecLayout R = rec_layout(h, B, H, W, beam_width);
+  if (ws_bytes < R.total) return fail(OCRFA_ERR_WORKSPACE, "workspace too small: %zu < %zu", ws_bytes, R.total);
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* ws = (uint8_t*)d_ws;
+  uint8_t* d_img = ws + R.img;
+  int32_t* d_w = (int32_t*)(ws + R.widths);
+  uint8_t* d_mask = ws + R.mask;
+  float* d_logits = (float*)(ws + R.logits);
+  float* d_probs = (float*)(ws + R.probs);
+  int32_t* d_labels = (int32_t*)(ws + R.labels);
+  int32_t* d_len = (int32_t*)(ws + R.len);
+  double* d_conf = (double*)(ws + R.conf);
+  CUDA_TRY(cudaMemcpyAsync(d_img, h_img, (size_t)B * H * W, cudaMemcpyHostToDevice, st));
+  if (h_widths) CUDA_TRY(cudaMemcpyAsync(d_w, h_widths, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+  if (h_ignore_mask) CUDA_TRY(cudaMemcpyAsync(d_mask, h_ignore_mask, (size_t)C, cudaMemcpyHostToDevice, st));
+  int rc = forward_impl(h, nullptr, d_img, h_widths ? d_w : nullptr, B, H, W, d_logits, ws + R.fwd, R.img - R.fwd, st);
+  if (rc) return rc;
+  rc = ocrfa_ctc_greedy(d_logits, B, T, C, h_ignore_mask ? d_mask : nullptr, nullptr, decoder == 1 ? d_probs : nullptr,
+                        nullptr, nullptr, d_labels, d_len, d_conf, st);
+  if (rc) return rc;
+  h->launches++;
+  if (decoder == 1) {
+    rc = ocrfa_ctc_beam(d_probs, B, T, C, beam_width, nullptr, d_labels, d_len, ws + R.beam, R.total - R.beam, st);
+    if (rc) return rc;
+    h->launches++;
+  }
+  CUDA_TRY(cudaMemcpyAsync(h_labels, d_labels, (size_t)B * T * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(h_len, d_len, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(h_conf, d_conf, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int64_t ocrfa_launch_count(const ocrfa_handle* h) { return h ? h->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,334 @@
+// CUDA-core kernels of the recognition path: everything that is not a large dense contraction, plus the
+// fp32 "parity mode" contraction (CUDA-core implicit GEMM, used when logits must match the reference's fp32
+// arithmetic to 1e-3 and as the on-device cross-check of the tcgen05 path).
+//
+//   preprocess   /root/reference/src/ocrfa/utils.py:541-550, 592-602   (normalise + replicate-pad)
+//   stem         /root/reference/src/ocrfa/modules/blocks.py:239-247   (conv0_1 + bn0_1 + relu, Cin = 1)
+//   max pools    /root/reference/src/ocrfa/modules/blocks.py:259, 271-275, 292
+//   H' mean      /root/reference/src/ocrfa/modules/blocks.py:433, 441-446
+//   LSTM cell    /root/reference/src/ocrfa/modules/blocks.py:89 (nn.LSTM gate math, order i,f,g,o)
+#pragma once
+#include "common.cuh"
+
+namespace ocrfa {
+
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// ---------------------------------------------------------------------------------------------
+// preprocess: uint8 lines (already at model height) -> float32 [B,1,H,W] in [-1,1], right-padded by
+// replicating the last valid column. Memory-bound: 1 B read + 4 B written per pixel; 16 pixels/thread.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float normalize_u8(uint32_t v) {
+  // ToTensor (/255) then sub_(0.5).div_(0.5), in fp32 exactly as the reference computes it
+  return (__fdiv_rn(static_cast<float>(v), 255.0f) - 0.5f) / 0.5f;
+}
+
+__global__ void preprocess_u8_kernel(const uint8_t* __restrict__ in, const int32_t* __restrict__ widths,
+                                     float* __restrict__ out, int B, int H, int W, int in_stride) {
+  // one thread = 16 consecutive pixels of one row; W is a multiple of 4 on this path
+  const int chunks_per_row = (W + 15) / 16;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)B * H * chunks_per_row;
+  if (gid >= total) return;
+  const int ch = gid % chunks_per_row;
+  const long long row = gid / chunks_per_row;  // b*H + y
+  const int b = row / H;
+  const int wv = widths ? min(max(widths[b], 1), W) : W;
+  const uint8_t* src = in + row * in_stride;
+  float* dst = out + row * W;
+  const int x0 = ch * 16;
+  const float edge = normalize_u8(src[wv - 1]);
+  if (x0 + 16 <= wv && (in_stride & 15) == 0) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + x0));
+    const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float4 o;
+      o.x = normalize_u8(w4[q] & 0xff);
+      o.y = normalize_u8((w4[q] >> 8) & 0xff);
+      o.z = normalize_u8((w4[q] >> 16) & 0xff);
+      o.w = normalize_u8(w4[q] >> 24);
+      *reinterpret_cast<float4*>(dst + x0 + q * 4) = o;
+    }
+  } else {
+    for (int x = x0; x < min(x0 + 16, W); ++x) dst[x] = x < wv ? normalize_u8(src[x]) : edge;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// stem: conv0_1 (1 -> 32, 3x3, pad 1) + folded BN + ReLU. Input fp32 [B,H,W] or uint8 (+normalise),
+// output NHWC with OUT_C channels (32 real; the bf16 path pads to 64 so the next conv's K slab is 128 B).
+// One thread = one pixel, 32 channels in registers; weights [9][32] + bias[32] in shared memory.
+// ---------------------------------------------------------------------------------------------
+template <typename TOut, int OUT_C>
+__global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict__ x, const uint8_t* __restrict__ x_u8,
+                                                        const int32_t* __restrict__ widths,
+                                                        const float* __restrict__ wgt /*[9][32]*/,
+                                                        const float* __restrict__ bias /*[32]*/, TOut* __restrict__ out,
+                                                        int B, int H, int W) {
+  __shared__ float sw[9 * 32];
+  __shared__ float sb[32];
+  for (int i = threadIdx.x; i < 9 * 32; i += blockDim.x) sw[i] = wgt[i];
+  if (threadIdx.x < 32) sb[threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= (long long)B * H * W) return;
+  const int xw = pix % W;
+  const int y = (pix / W) % H;
+  const int b = pix / ((long long)W * H);
+  float v[9];
+  const int wv = (x_u8 && widths) ? min(max(widths[b], 1), W) : W;
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      const int yy = y + r - 1, xx = xw + s - 1;
+      float t = 0.f;
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+        if (x_u8) t = normalize_u8(x_u8[((long long)b * H + yy) * W + min(xx, wv - 1)]);
+        else t = __ldg(x + ((long long)b * H + yy) * W + xx);
+      }
+      v[r * 3 + s] = t;
+    }
+  TOut* op = out + pix * OUT_C;
+#pragma unroll
+  for (int c0 = 0; c0 < 32; c0 += 8) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float a = 0.f;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) a = fmaf(v[k], sw[k * 32 + c0 + j], a);
+      acc[j] = fmaxf(a + sb[c0 + j], 0.f);
+    }
+    if (sizeof(TOut) == 2) {
+      uint4 o;
+      o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
+      o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
+      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(op) + c0) = o;
+    } else {
+      float* fo = reinterpret_cast<float*>(op) + c0;
+      *reinterpret_cast<float4*>(fo) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      *reinterpret_cast<float4*>(fo + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+  }
+  if (OUT_C > 32) {
+    // zero channel padding (bf16 path): 32 x 2 B = 64 B
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    __nv_bfloat16* bp = reinterpret_cast<__nv_bfloat16*>(op) + 32;
+#pragma unroll
+    for (int i = 0; i < (OUT_C - 32) / 8; ++i) *reinterpret_cast<uint4*>(bp + i * 8) = z;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// generic CUDA-core implicit GEMM (fp32 accumulate): conv kh x kw, stride (sh,1), zero pad (ph,pw), NHWC.
+// 64 pixels x 64 output channels per 256-thread block, 4x4 outputs per thread, K staged 16 at a time.
+// ---------------------------------------------------------------------------------------------
+struct ConvSimtParams {
+  const void* in; long long in_pix_stride;  // elements between consecutive input pixels (>= cin)
+  const float* wgt;                          // [cout][kh*kw*cin] fp32, K = (tap-major, channel-minor)
+  const float* bias;                         // [cout] or null
+  const void* residual; int ldr;
+  void* out; int ldo;
+  int n, h_in, w_in, cin, cout, kh, kw, sh, ph, pw, h_out, w_out, relu;
+};
+
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(256) conv_simt_kernel(const ConvSimtParams p) {
+  __shared__ float As[16][64 + 4];
+  __shared__ float Bs[16][64 + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const long long total_pix = (long long)p.n * p.h_out * p.w_out;
+  const long long pix0 = (long long)blockIdx.x * 64;
+  const int co0 = blockIdx.y * 64;
+  const int ktotal = p.kh * p.kw * p.cin;
+
+  // loader role: thread loads 4 consecutive K elements of row (tid/4)
+  const int lrow = tid >> 2, lk = (tid & 3) * 4;
+  const long long lpix = pix0 + lrow;
+  const bool lpix_ok = lpix < total_pix;
+  int ln = 0, lho = 0, lwo = 0;
+  if (lpix_ok) {
+    lwo = lpix % p.w_out;
+    lho = (lpix / p.w_out) % p.h_out;
+    ln = lpix / ((long long)p.w_out * p.h_out);
+  }
+  const int lco = co0 + lrow;
+  const TIn* in = reinterpret_cast<const TIn*>(p.in);
+
+  // fp64 accumulators: products of two floats are exact in double, so the only rounding left is the final
+  // conversion - the parity mode then differs from the reference by the REFERENCE's own fp32 summation error only.
+  double acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+
+  for (int r = 0; r < p.kh; ++r)
+    for (int s = 0; s < p.kw; ++s) {
+      const int hi = lho * p.sh + r - p.ph, wi = lwo + s - p.pw;
+      const bool a_ok = lpix_ok && hi >= 0 && hi < p.h_in && wi >= 0 && wi < p.w_in;
+      const TIn* ap = in + (((long long)ln * p.h_in + hi) * p.w_in + wi) * p.in_pix_stride;
+      const float* bp = p.wgt + (long long)lco * ktotal + (r * p.kw + s) * p.cin;
+      for (int c0 = 0; c0 < p.cin; c0 += 16) {
+        float a4[4] = {0.f, 0.f, 0.f, 0.f}, b4[4] = {0.f, 0.f, 0.f, 0.f};
+        if (a_ok) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (c0 + lk + e < p.cin) a4[e] = to_f32<TIn>(ap[c0 + lk + e]);
+        }
+        if (lco < p.cout) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (c0 + lk + e < p.cin) b4[e] = __ldg(bp + c0 + lk + e);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { As[lk + e][lrow] = a4[e]; Bs[lk + e][lrow] = b4[e]; }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+          const float4 bv = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+          const double a[4] = {av.x, av.y, av.z, av.w}, b[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+        }
+      }
+    }
+
+  TOut* out = reinterpret_cast<TOut*>(p.out);
+  const TOut* res = reinterpret_cast<const TOut*>(p.residual);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long pix = pix0 + ty * 4 + i;
+    if (pix >= total_pix) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int co = co0 + tx * 4 + j;
+      if (co >= p.cout) continue;
+      double vd = acc[i][j];
+      if (p.bias) vd += (double)__ldg(p.bias + co);
+      if (res) vd += (double)to_f32<TOut>(res[pix * p.ldr + co]);
+      float v = (float)vd;
+      if (p.relu) v = fmaxf(v, 0.f);
+      out[pix * p.ldo + co] = from_f32<TOut>(v);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 2x2 max pool, stride (sh, sw), padding (0, pw) with -inf semantics, NHWC, 8 channels per thread.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void maxpool2x2_kernel(const T* __restrict__ in, T* __restrict__ out, int n, int h_in, int w_in, int c,
+                                  int sh, int sw, int pw, int h_out, int w_out) {
+  const int cv = c / 8;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)n * h_out * w_out * cv;
+  if (gid >= total) return;
+  const int cg = gid % cv;
+  const long long pix = gid / cv;
+  const int wo = pix % w_out;
+  const int ho = (pix / w_out) % h_out;
+  const int b = pix / ((long long)w_out * h_out);
+  float m[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) m[i] = -INFINITY;
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const int hi = ho * sh + r, wi = wo * sw + s - pw;
+      if (hi < h_in && wi >= 0 && wi < w_in) {
+        const T* ip = in + (((long long)b * h_in + hi) * w_in + wi) * c + cg * 8;
+        if (sizeof(T) == 2) {
+          const uint4 v = __ldg(reinterpret_cast<const uint4*>(ip));
+          m[0] = fmaxf(m[0], bf16lo_to_f32(v.x)); m[1] = fmaxf(m[1], bf16hi_to_f32(v.x));
+          m[2] = fmaxf(m[2], bf16lo_to_f32(v.y)); m[3] = fmaxf(m[3], bf16hi_to_f32(v.y));
+          m[4] = fmaxf(m[4], bf16lo_to_f32(v.z)); m[5] = fmaxf(m[5], bf16hi_to_f32(v.z));
+          m[6] = fmaxf(m[6], bf16lo_to_f32(v.w)); m[7] = fmaxf(m[7], bf16hi_to_f32(v.w));
+        } else {
+          const float4 v0 = __ldg(reinterpret_cast<const float4*>(ip));
+          const float4 v1 = __ldg(reinterpret_cast<const float4*>(ip) + 1);
+          m[0] = fmaxf(m[0], v0.x); m[1] = fmaxf(m[1], v0.y); m[2] = fmaxf(m[2], v0.z); m[3] = fmaxf(m[3], v0.w);
+          m[4] = fmaxf(m[4], v1.x); m[5] = fmaxf(m[5], v1.y); m[6] = fmaxf(m[6], v1.z); m[7] = fmaxf(m[7], v1.w);
+        }
+      }
+    }
+  T* op = out + pix * c + cg * 8;
+  if (sizeof(T) == 2) {
+    uint4 o;
+    o.x = pack_bf16x2(m[0], m[1]); o.y = pack_bf16x2(m[2], m[3]);
+    o.z = pack_bf16x2(m[4], m[5]); o.w = pack_bf16x2(m[6], m[7]);
+    *reinterpret_cast<uint4*>(op) = o;
+  } else {
+    float* fo = reinterpret_cast<float*>(op);
+    *reinterpret_cast<float4*>(fo) = make_float4(m[0], m[1], m[2], m[3]);
+    *reinterpret_cast<float4*>(fo + 4) = make_float4(m[4], m[5], m[6], m[7]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// mean over H' (AdaptiveAvgPool2d((None,1)) after the permute): [B,H',T,C] -> [B,T,C]
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void mean_h_kernel(const T* __restrict__ in, T* __restrict__ out, int b, int hp, int t, int c) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)b * t * c;
+  if (gid >= total) return;
+  const int ch = gid % c;
+  const int tt = (gid / c) % t;
+  const int bb = gid / ((long long)c * t);
+  float s = 0.f;
+  for (int h = 0; h < hp; ++h) s += to_f32<T>(in[(((long long)bb * hp + h) * t + tt) * c + ch]);
+  out[gid] = from_f32<T>(s / static_cast<float>(hp));
+}
+
+template <typename T>
+__global__ void cvt_to_f32_kernel(const T* __restrict__ in, float* __restrict__ out, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = to_f32<T>(in[i]);
+}
+template <typename T>
+__global__ void cvt_from_f32_kernel(const float* __restrict__ in, T* __restrict__ out, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = from_f32<T>(in[i]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// fp32-mode LSTM cell: gates = xproj[b,t,dir,:] + hh[dir][b][:] (both in the permuted [tile][gate][16] order)
+// ---------------------------------------------------------------------------------------------
+__global__ void lstm_cell_f32_kernel(const float* __restrict__ hh /*[2][B][2048]*/, const float* __restrict__ xproj,
+                                     float* __restrict__ c /*[2][B][512]*/, float* __restrict__ hseq /*[B][T][1024]*/,
+                                     int B, int T, int step) {
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= 2 * B * 512) return;
+  const int j = gid % 512;
+  const int b = (gid / 512) % B;
+  const int dir = gid / (512 * B);
+  const int t = dir == 0 ? step : T - 1 - step;
+  const int tile = j >> 4, u = j & 15;
+  const float* hp = hh + ((long long)dir * B + b) * 2048 + tile * 64 + u;
+  const float* xp = xproj + ((long long)b * T + t) * 4096 + dir * 2048 + tile * 64 + u;
+  const bool first = step == 0;
+  const float gi = sigmoidf_acc(xp[0] + (first ? 0.f : hp[0]));
+  const float gf = sigmoidf_acc(xp[16] + (first ? 0.f : hp[16]));
+  const float gg = tanhf(xp[32] + (first ? 0.f : hp[32]));
+  const float go = sigmoidf_acc(xp[48] + (first ? 0.f : hp[48]));
+  const float cprev = first ? 0.f : c[gid];
+  const float cn = gf * cprev + gi * gg;
+  c[gid] = cn;
+  hseq[((long long)b * T + t) * 1024 + dir * 512 + j] = go * tanhf(cn);
+}
+
+}  // namespace ocrfa

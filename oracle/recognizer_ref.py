@@ -164,6 +164,102 @@ def model_forward_ref(sd: Dict[str, np.ndarray], x, return_features: bool = Fals
 
 
 # --------------------------------------------------------------------------------------------------------------
+# bf16 emulation of the same forward: identical math, with the tensor-core path's rounding points
+# (weights with BN folded -> bf16; every stored activation -> bf16; fp32 accumulate, bias, gate math, cell state).
+# Used to check the bf16 kernels tightly: against the fp32 reference a random-weight network amplifies ANY bf16
+# evaluation's rounding noise beyond 2e-2 (tools/bf16_sensitivity.py), which says nothing about the kernels.
+# --------------------------------------------------------------------------------------------------------------
+def _bf(t: torch.Tensor) -> torch.Tensor:
+    return t.bfloat16().float()
+
+
+def _fold(sd, conv, bn):
+    w = _t(sd, conv + ".weight").double()
+    s = _t(sd, bn + ".weight").double() / torch.sqrt(_t(sd, bn + ".running_var").double() + BN_EPS)
+    b = _t(sd, bn + ".bias").double() - _t(sd, bn + ".running_mean").double() * s
+    return (w * s[:, None, None, None]).float(), b.float()
+
+
+def _conv_q(sd, x, conv, bn, stride=1, padding=0, extra=None):
+    w, b = _fold(sd, conv, bn)
+    y = F.conv2d(x, _bf(w), None, stride=stride, padding=padding)
+    if extra is not None:
+        y = y + extra
+    return _bf(F.relu(y + b[None, :, None, None]))
+
+
+def _block_q(sd, x, pre):
+    y = _conv_q(sd, x, pre + "conv1", pre + "bn1", padding=1)
+    if pre + "downsample.0.weight" in sd:  # fused into conv2's accumulator: never rounded on its own
+        wd, bd = _fold(sd, pre + "downsample.0", pre + "downsample.1")
+        extra = F.conv2d(x, _bf(wd), None) + bd[None, :, None, None]
+    else:
+        extra = x
+    return _conv_q(sd, y, pre + "conv2", pre + "bn2", padding=1, extra=extra)
+
+
+def _lstm_dir_q(x, w_ih, w_hh, b_ih, b_hh, reverse):
+    B, T, _ = x.shape
+    H = w_hh.shape[1]
+    xp = x @ _bf(w_ih).t() + (b_ih + b_hh)
+    whh = _bf(w_hh).t()
+    h = x.new_zeros(B, H)
+    c = x.new_zeros(B, H)
+    out = x.new_empty(B, T, H)
+    for t in (range(T - 1, -1, -1) if reverse else range(T)):
+        i, f, gg, o = (xp[:, t] + h @ whh).chunk(4, dim=1)
+        c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(gg)
+        h = _bf(torch.sigmoid(o) * torch.tanh(c))
+        out[:, t] = h
+    return out
+
+
+def features_bf16emu_ref(sd, x) -> torch.Tensor:
+    """float32 [B,1,H,W] -> visual features [B,T,512] (bf16-valued float32) with the kernel's rounding points."""
+    p = "FeatureExtraction.ConvNet."
+    with torch.no_grad():
+        x = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x))
+        w0, b0 = _fold(sd, p + "conv0_1", p + "bn0_1")          # stem runs in fp32, output stored as bf16
+        a = _bf(F.relu(F.conv2d(x.float(), w0, b0, padding=1)))
+        a = _conv_q(sd, a, p + "conv0_2", p + "bn0_2", padding=1)
+        a = F.max_pool2d(a, 2, 2, 0)
+        a = _block_q(sd, a, p + "layer1.0.")
+        a = _conv_q(sd, a, p + "conv1", p + "bn1", padding=1)
+        a = F.max_pool2d(a, 2, 2, 0)
+        for b in range(2):
+            a = _block_q(sd, a, f"{p}layer2.{b}.")
+        a = _conv_q(sd, a, p + "conv2", p + "bn2", padding=1)
+        a = F.max_pool2d(a, 2, (2, 1), (0, 1))
+        for b in range(5):
+            a = _block_q(sd, a, f"{p}layer3.{b}.")
+        a = _conv_q(sd, a, p + "conv3", p + "bn3", padding=1)
+        for b in range(3):
+            a = _block_q(sd, a, f"{p}layer4.{b}.")
+        a = _conv_q(sd, a, p + "conv4_1", p + "bn4_1", stride=(2, 1), padding=(0, 1))
+        a = _conv_q(sd, a, p + "conv4_2", p + "bn4_2")
+        s = a.permute(0, 3, 1, 2)
+        return _bf(s.mean(dim=3)) if s.shape[3] > 1 else s[..., 0].contiguous()
+
+
+def sequence_bf16emu_ref(sd, feat) -> torch.Tensor:
+    """features [B,T,512] -> logits [B,T,C]: 2 x BiLSTM(+Linear) + Prediction with bf16 storage, fp32 accumulate."""
+    with torch.no_grad():
+        s = feat if isinstance(feat, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(feat))
+        s = _bf(s.float())
+        for li in range(2):
+            pre = f"SequenceModeling.{li}."
+            fw = _lstm_dir_q(s, *[_t(sd, pre + "rnn." + n + "_l0") for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")], False)
+            bw = _lstm_dir_q(s, *[_t(sd, pre + "rnn." + n + "_l0_reverse") for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")], True)
+            s = _bf(F.linear(torch.cat([fw, bw], 2), _bf(_t(sd, pre + "linear.weight")), _t(sd, pre + "linear.bias")))
+        return F.linear(s, _bf(_t(sd, "Prediction.weight")), _t(sd, "Prediction.bias"))
+
+
+def model_forward_bf16emu_ref(sd, x) -> torch.Tensor:
+    """float32 [B,1,H,W] -> logits float32 [B,T,C] with bf16 storage / fp32 accumulation at the kernel's points."""
+    return sequence_bf16emu_ref(sd, features_bf16emu_ref(sd, x))
+
+
+# --------------------------------------------------------------------------------------------------------------
 # a6: softmax / mask / renormalise / argmax  (src/ocrfa/utils.py:628-638)
 # --------------------------------------------------------------------------------------------------------------
 def probs_ref(logits, ignore_idx: Sequence[int]) -> np.ndarray:

@@ -72,8 +72,8 @@ def synth_state_dict(seed: int = 0, num_class: int = 185, blank_bias: float = 3.
     for li in range(2):
         sm = prefix + f"SequenceModeling.{li}."
         for suffix in ("", "_reverse"):
-            sd[sm + "rnn.weight_ih_l0" + suffix] = normal((2048, 512), 3.0 / math.sqrt(512))
-            sd[sm + "rnn.weight_hh_l0" + suffix] = normal((2048, 512), 3.0 / math.sqrt(512))
+            sd[sm + "rnn.weight_ih_l0" + suffix] = normal((2048, 512), 1.0 / math.sqrt(512))
+            sd[sm + "rnn.weight_hh_l0" + suffix] = normal((2048, 512), 1.0 / math.sqrt(512))
             sd[sm + "rnn.bias_ih_l0" + suffix] = normal((2048,), 0.05)
             sd[sm + "rnn.bias_hh_l0" + suffix] = normal((2048,), 0.05)
         sd[sm + "linear.weight"] = normal((512, 1024), 2.0 / math.sqrt(1024))
