@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py - text lines/sec of the OCR-FA recognition hot path on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--config c2|c1|c3|c4]
+
+A step = one pass of the hot path (uint8 lines -> fused normalise+stem -> ResNet-29 -> 2xBiLSTM -> Linear -> softmax/
+mask/renorm/argmax/CTC collapse/confidence) over one batch of synthetic lines per rank. Default workload is BASELINE
+config 2 (256 lines of 32x512, greedy, bf16 tensor-core arithmetic); ranks are independent (weak scaling), NCCL is
+used only to gather timings and decoded labels after the timed region.
+
+JSON line keys: value = whole-job lines/s with inputs resident in HBM (CUDA events, max over ranks);
+e2e = the same through ocrfa_recognize_host with pinned HOST buffers (H2D + D2H inside the timed region);
+roofline = tcgen05 implicit-GEMM kernel, algorithmic FLOPs / CUDA-event kernel time vs MEASURED_PEAKS.json;
+cpu_baseline = the oracle (port of the reference's CPU path) on a bounded sample, rank 0, N=1 only.
+`--impl reference` times that CPU path alone (the reference is Python and cannot travel to the GPU box, so the
+oracle port pinned against it in tests/test_oracle_golden.py is what runs).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "text lines/sec (device-timed, max over ranks)"
+UNIT = "lines/s"
+CONFIGS = {
+    # name: (batch, H, W, decoder, beam)
+    "c1": (1, 32, 128, "greedy", 1),
+    "c2": (256, 32, 512, "greedy", 1),
+    "c3": (64, 64, 2048, "greedy", 1),
+    "c4": (128, 32, 512, "beamsearch", 8),
+}
+# algorithmic FLOPs per line (2*MAC of every conv/LSTM/Linear), SURVEY.md section 8d / BASELINE.md section 3
+FLOPS_PER_LINE = {(32, 128): 13.453e9, (32, 512): 52.788e9, (64, 2048): 411.546e9}
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"bf16_sustained": float(p.get("bf16_tflops_sustained", 1354.4)), "hbm": float(p.get("hbm_gbs", 6550.4)),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"bf16_sustained": 1400.0, "hbm": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    return rank, local_rank, world
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's CPU path (recognizer_predict on torch CPU fp32)
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_lines_per_s(cfg_name: str, sample_lines: int, repeats: int, warmup: int):
+    from oracle import recognizer_ref as R
+    from ocrfa_b200.synth import synth_lines, synth_state_dict
+    import ocrfa_b200.charset as cs
+
+    B, H, W, decoder, beam = CONFIGS[cfg_name]
+    n = min(sample_lines, B)
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    sd = {k: torch.from_numpy(v) for k, v in synth_state_dict(0).items()}
+    chars = ["[blank]"] + list(cs.default_character())
+    ign = R.ignore_idx_ref(cs.default_character(), cs.default_ignore_char())
+    imgs = synth_lines(n, H, W, seed=777)
+
+    def one_pass():
+        x = R.align_collate_ref(list(imgs), H, W)
+        return R.recognizer_predict_ref(sd, x, chars, ign, decoder, beam if decoder != "greedy" else 5)
+
+    for _ in range(warmup):
+        one_pass()
+    times = []
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        one_pass()
+        times.append(time.perf_counter() - t0)
+    return n / (sum(times) / len(times)), threads, n, sum(times) / len(times)
+
+
+def run_reference_arm(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    B, H, W, decoder, beam = CONFIGS[args.config]
+    sample = min(B, 32 if (H, W) == (32, 512) else (4 if H == 64 else B))
+    lps, threads, n, sec = cpu_lines_per_s(args.config, sample, max(1, args.steps), max(1, min(args.warmup, 1)))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": lps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.config}: {B} lines of {H}x{W}, {decoder}" + (f" beam={beam}" if decoder != "greedy" else ""),
+                   "sample": f"{n} lines per step on the host CPU"},
+        "cpu_baseline": {"value": lps, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{n} lines of {H}x{W} per step, torch CPU fp32, {threads} threads (oracle port of "
+                                   "recognizer_predict; the Python reference cannot travel to the GPU box)"},
+        "e2e": {"value": lps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------------------
+def run_gpu_arm(args):
+    import ocrfa_b200 as ob
+    from ocrfa_b200 import _lib
+    from ocrfa_b200.synth import synth_lines, synth_state_dict  # synthetic data generator (not timed)
+
+    rank, local_rank, world = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group(backend="nccl", device_id=dev)
+
+    B, H, W, decoder, beam = CONFIGS[args.config]
+    lib = _lib.load()
+    chars = ob.default_character()
+    conv = ob.CTCLabelConverter(chars)
+    Cn = len(conv.character)
+    model = ob.Model(1, 512, 512, Cn, precision=args.precision)
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in synth_state_dict(0).items()})
+    handle = model._ensure_handle(dev)
+    T = lib.ocrfa_out_timesteps(H, W)
+
+    # synthetic lines: a small seeded pool of text-like lines tiled to the batch (content does not change the work)
+    pool = synth_lines(min(B, 32), H, W, seed=1234 + rank)
+    imgs_np = np.ascontiguousarray(np.tile(pool, ((B + len(pool) - 1) // len(pool), 1, 1))[:B])
+    h_img = torch.from_numpy(imgs_np).pin_memory()
+    d_img = h_img.to(dev)
+    mask_np = np.zeros(Cn, dtype=np.uint8)
+    from ocrfa_b200.recognition import _ignore_mask
+    ign = [chars.index(ch) + 1 for ch in ob.default_ignore_char()]
+    mask_np = _ignore_mask(Cn, ign)
+    d_mask = torch.from_numpy(mask_np).to(dev)
+    bw = beam if decoder == "beamsearch" else 1
+    ws_bytes = lib.ocrfa_recognize_workspace_bytes(handle, B, H, W, bw)
+    ws = model.workspace(ws_bytes, dev)
+    d_labels = torch.empty((B, T), dtype=torch.int32, device=dev)
+    d_len = torch.empty(B, dtype=torch.int32, device=dev)
+    d_conf = torch.empty(B, dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream(dev)
+    dec = 1 if decoder == "beamsearch" else 0
+
+    def step_device():
+        _lib.check(lib.ocrfa_recognize_device(handle, C.c_void_p(d_img.data_ptr()), None, B, H, W,
+                                              C.c_void_p(d_mask.data_ptr()), dec, bw, C.c_void_p(d_labels.data_ptr()),
+                                              C.c_void_p(d_len.data_ptr()), C.c_void_p(d_conf.data_ptr()),
+                                              C.c_void_p(ws.data_ptr()), ws_bytes, C.c_void_p(stream.cuda_stream)))
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(3, args.warmup)):
+        step_device()
+    barrier()
+
+    # ---- timed region 1: device-resident inputs, CUDA events on the launching stream; tcgen05 class profiled
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.ocrfa_launch_count(handle)
+    _lib.check(lib.ocrfa_profile_begin(handle, 1 << 1))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+    e1.record(stream)
+    barrier()
+    dev_ms = e0.elapsed_time(e1)
+    ms_cls = (C.c_double * 8)()
+    fl_cls = (C.c_double * 8)()
+    n_cls = (C.c_int64 * 8)()
+    _lib.check(lib.ocrfa_profile_end(handle, ms_cls, fl_cls, n_cls))
+    launches = int(lib.ocrfa_launch_count(handle) - launches0)
+
+    # ---- timed region 2: end to end through the host-buffer C-ABI call (H2D + kernels + D2H + sync per step)
+    h_labels = torch.empty((B, T), dtype=torch.int32).pin_memory()
+    h_len = torch.empty(B, dtype=torch.int32).pin_memory()
+    h_conf = torch.empty(B, dtype=torch.float64).pin_memory()
+
+    def step_host():
+        _lib.check(lib.ocrfa_recognize_host(handle, C.c_void_p(h_img.data_ptr()), None, B, H, W,
+                                            mask_np.ctypes.data_as(C.c_void_p), dec, bw, C.c_void_p(h_labels.data_ptr()),
+                                            C.c_void_p(h_len.data_ptr()), C.c_void_p(h_conf.data_ptr()),
+                                            C.c_void_p(ws.data_ptr()), ws_bytes, C.c_void_p(stream.cuda_stream)))
+
+    step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_host()
+    torch.cuda.synchronize(dev)
+    host_s = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- extra pass (not timed): per-class kernel time shares for the record
+    _lib.check(lib.ocrfa_profile_begin(handle, 0xff))
+    step_device()
+    ms_all = (C.c_double * 8)()
+    fl_all = (C.c_double * 8)()
+    n_all = (C.c_int64 * 8)()
+    _lib.check(lib.ocrfa_profile_end(handle, ms_all, fl_all, n_all))
+
+    # ---- max over ranks; gather a checksum of the decoded labels (NCCL only after the timed regions)
+    times = torch.tensor([dev_ms, host_s * 1e3], dtype=torch.float64, device=dev)
+    label_sum = (d_labels.to(torch.int64) * (torch.arange(T, device=dev) < d_len[:, None])).sum().reshape(1)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+        gathered = [torch.zeros_like(label_sum) for _ in range(world)]
+        dist.all_gather(gathered, label_sum)
+        label_sums = [int(g.item()) for g in gathered]
+    else:
+        label_sums = [int(label_sum.item())]
+    dev_ms_max, host_ms_max = float(times[0].item()), float(times[1].item())
+
+    if rank == 0:
+        peaks = load_peaks()
+        total_lines = B * args.steps * world
+        value = total_lines / (dev_ms_max * 1e-3)
+        e2e_value = total_lines / (host_ms_max * 1e-3)
+        tc_ms, tc_flops, tc_n = float(ms_cls[1]), float(fl_cls[1]), int(n_cls[1])
+        achieved = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
+        names = ["stem", "igemm_tc", "lstm_tc", "pool_mean_cvt", "conv_simt", "lstm_cell_f32", "ctc_greedy", "ctc_beam"]
+        tot_all = sum(float(v) for v in ms_all) or 1.0
+        shares = {n: {"ms_per_step": round(float(ms_all[i]), 4), "launches": int(n_all[i]),
+                      "share": round(float(ms_all[i]) / tot_all, 4)} for i, n in enumerate(names) if n_all[i]}
+        flops_line = FLOPS_PER_LINE.get((H, W))
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "config": {"workload": f"{args.config}: {B} lines of {H}x{W} per rank per step, {decoder}"
+                                   + (f" beam={beam}" if decoder != "greedy" else "") + ", reference default model (ResNet-29 + 2xBiLSTM + Linear185), random-init weights",
+                       "l2": "per-step working set (>2 GB of activations at c2) exceeds the 126 MB L2; no explicit flush",
+                       "parallelism": f"dp{world} (independent ranks, no collective on the path)"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * H * W + Cn),
+                    "d2h_bytes_per_step": int(B * T * 4 + B * 4 + B * 8), "ms_per_step": host_ms_max / args.steps},
+            "gpu_launches": launches,
+            "roofline": {"kernel": "igemm_tc_kernel<Std> (tcgen05 implicit GEMM: all convs, xproj/linear/prediction GEMMs)",
+                         "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                         "frac": achieved / peaks["bf16_sustained"], "traffic": None,
+                         "launches_per_step": tc_n / max(1, args.steps), "kernel_ms_per_step": tc_ms / max(1, args.steps),
+                         "peak_source": peaks["source"] + ", sustained bf16",
+                         "whole_step_tflops": (flops_line * B / (dev_ms_max / args.steps * 1e-3) / 1e12) if flops_line else None},
+            "kernel_shares": shares,
+            "clocks": clocks,
+            "label_checksums": label_sums,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            sample = 32 if (H, W) == (32, 512) else (4 if H == 64 else min(B, 32))
+            lps, threads, n, sec = cpu_lines_per_s(args.config, sample, 2, 1)
+            line["cpu_baseline"] = {"value": lps, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"{n} lines of {H}x{W}, best-effort mean of 2 passes after 1 warm-up, torch CPU fp32 "
+                                              f"{threads} threads (oracle port of recognizer_predict, {decoder})"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -134,8 +134,22 @@ int ocrfa_recognize_host(ocrfa_handle* h, const uint8_t* h_img, const int32_t* h
                          int32_t W, const uint8_t* h_ignore_mask, int32_t decoder, int32_t beam_width,
                          int32_t* h_labels, int32_t* h_len, double* h_conf, void* d_ws, size_t ws_bytes,
                          void* stream);
+/* The same step on DEVICE buffers, asynchronous on `stream`: d_img uint8 [B,H,W], outputs d_labels [B,T],
+ * d_len [B], d_conf [B] stay on the device. Workspace = ocrfa_recognize_workspace_bytes. */
+int ocrfa_recognize_device(ocrfa_handle* h, const uint8_t* d_img, const int32_t* d_widths, int32_t B, int32_t H,
+                           int32_t W, const uint8_t* d_ignore_mask, int32_t decoder, int32_t beam_width,
+                           int32_t* d_labels, int32_t* d_len, double* d_conf, void* d_ws, size_t ws_bytes,
+                           void* stream);
+
 /* Scratch bytes ocrfa_recognize_host needs (forward workspace + staging + decode scratch). */
 size_t ocrfa_recognize_workspace_bytes(const ocrfa_handle* h, int32_t B, int32_t H, int32_t W, int32_t beam_width);
+
+/* CUDA-event profile per kernel class (bit c of class_mask selects class c: 0 stem, 1 tcgen05 implicit GEMM,
+ * 2 tcgen05 LSTM step, 3 pool/mean/convert, 4 CUDA-core conv, 5 fp32 LSTM cell, 6 greedy decode, 7 beam search).
+ * ocrfa_profile_end synchronises the device and returns, per class, summed kernel milliseconds, summed
+ * algorithmic FLOPs and launch counts (arrays of 8) since ocrfa_profile_begin. */
+int ocrfa_profile_begin(ocrfa_handle* h, uint32_t class_mask);
+int ocrfa_profile_end(ocrfa_handle* h, double* ms_by_class, double* flops_by_class, int64_t* launches_by_class);
 
 /* Number of kernels this library has launched on behalf of the handle since creation (bench bookkeeping). */
 int64_t ocrfa_launch_count(const ocrfa_handle* h);

@@ -20,7 +20,8 @@ SYMBOLS = (
     "ocrfa_finalize_weights", "ocrfa_out_timesteps", "ocrfa_workspace_bytes", "ocrfa_preprocess_u8",
     "ocrfa_forward", "ocrfa_forward_features", "ocrfa_forward_sequence", "ocrfa_forward_u8", "ocrfa_ctc_greedy", "ocrfa_ctc_collapse", "ocrfa_argmax_rows",
     "ocrfa_beam_workspace_bytes", "ocrfa_ctc_beam", "ocrfa_ctc_beam_spans", "ocrfa_recognize_host",
-    "ocrfa_recognize_workspace_bytes", "ocrfa_launch_count",
+    "ocrfa_recognize_device", "ocrfa_recognize_workspace_bytes", "ocrfa_profile_begin", "ocrfa_profile_end",
+    "ocrfa_launch_count",
 )
 
 
@@ -70,6 +71,9 @@ def load():
     lib.ocrfa_ctc_beam.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, vp, sz, vp]
     lib.ocrfa_ctc_beam_spans.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, sz, vp]
     lib.ocrfa_recognize_host.argtypes = [vp, vp, vp, i32, i32, i32, vp, i32, i32, vp, vp, vp, vp, sz, vp]
+    lib.ocrfa_recognize_device.argtypes = [vp, vp, vp, i32, i32, i32, vp, i32, i32, vp, vp, vp, vp, sz, vp]
+    lib.ocrfa_profile_begin.argtypes = [vp, C.c_uint32]
+    lib.ocrfa_profile_end.argtypes = [vp, vp, vp, vp]
     lib.ocrfa_recognize_workspace_bytes.argtypes = [vp, i32, i32, i32, i32]
     lib.ocrfa_recognize_workspace_bytes.restype = sz
     lib.ocrfa_launch_count.argtypes = [vp]

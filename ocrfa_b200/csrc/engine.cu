@@ -17,6 +17,7 @@
 #include "../../include/ocrfa_b200.h"
 #include "decode_kernels.cuh"
 #include "igemm_plan.h"
+#include "lstm_tc.cuh"
 #include "simt_kernels.cuh"
 
 using namespace ocrfa;
@@ -65,13 +66,37 @@ struct LstmW {
 };
 
 struct WsLayout {
-  size_t act[4], xproj, hseq, seq[2], feat, cstate, hh, total;
+  size_t act[4], xproj, hseq, seq[2], feat, cstate, hh, sync, total;
   size_t act_bytes;
 };
 
 }  // namespace
 
+// Kernel classes for launch accounting and the optional CUDA-event profile (bench.py's roofline evidence).
+enum KernelClass : int {
+  kClsStem = 0, kClsIgemmTc = 1, kClsLstmTc = 2, kClsPool = 3, kClsSimtConv = 4, kClsLstmCell = 5, kClsDecode = 6,
+  kClsBeam = 7, kNumClasses = 8
+};
+
+struct Profiler {
+  uint32_t mask = 0;  // bit c set: class c is bracketed by events
+  std::vector<cudaEvent_t> pool;
+  struct Span { int cls; size_t e0, e1; double flops; };
+  std::vector<Span> spans;
+  size_t used = 0;
+  int64_t launches[kNumClasses] = {0};
+  cudaEvent_t next() {
+    if (used == pool.size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      pool.push_back(e);
+    }
+    return pool[used++];
+  }
+};
+
 struct ocrfa_handle {
+  Profiler prof;
   ocrfa_config cfg;
   int num_sms = 148;
   bool finalized = false;
@@ -104,6 +129,7 @@ WsLayout ws_layout(const ocrfa_handle* h, int B, int H, int W) {
   L.feat = off; off += align_up((size_t)B * T * 512 * es, 1024);
   L.cstate = off; off += align_up((size_t)2 * B * 512 * 4, 1024);
   L.hh = off; off += align_up((size_t)2 * B * 2048 * 4, 1024);
+  L.sync = off; off += 4096;  // group counters of the persistent LSTM launches (zeroed once per forward)
   L.total = off;
   return L;
 }
@@ -273,6 +299,28 @@ struct Act {
   void* p; int n, h, w, c;  // NHWC view; c = channels of the buffer
 };
 
+// Counts one kernel launch of class `cls`; when that class is being profiled, brackets it with CUDA events on the
+// launching stream (begin in the constructor, end in the destructor, i.e. right after the <<<>>>).
+struct LaunchScope {
+  ocrfa_handle* h; cudaStream_t st; int cls; size_t span = (size_t)-1;
+  LaunchScope(ocrfa_handle* h_, int cls_, double flops, cudaStream_t st_) : h(h_), st(st_), cls(cls_) {
+    h->launches++;
+    h->prof.launches[cls]++;
+    if (h->prof.mask & (1u << cls)) {
+      const size_t e0 = h->prof.used;
+      cudaEventRecord(h->prof.next(), st);
+      span = h->prof.spans.size();
+      h->prof.spans.push_back({cls, e0, 0, flops});
+    }
+  }
+  ~LaunchScope() {
+    if (span != (size_t)-1) {
+      h->prof.spans[span].e1 = h->prof.used;
+      cudaEventRecord(h->prof.next(), st);
+    }
+  }
+};
+
 int run_conv_tc(ocrfa_handle* h, const ConvW& cw, const Act& in, const Act* ds_src, const void* residual, void* out,
                 bool relu, bool out_f32, int ldo, cudaStream_t st) {
   IgemmTcParams p;
@@ -287,8 +335,10 @@ int run_conv_tc(ocrfa_handle* h, const ConvW& cw, const Act& in, const Act* ds_s
   p.bias = cw.d_bias;
   p.residual = (const __nv_bfloat16*)residual; p.ldr = cw.cout;
   p.out = out; p.ldo = ldo; p.out_f32 = out_f32 ? 1 : 0; p.relu = relu ? 1 : 0;
+  // algorithmic FLOPs: 2 * output pixels * Cout * real K (channel padding and ragged-tile rows not counted)
+  const double flops = 2.0 * (double)in.n * p.h_out * p.w_out * cw.cout * ((double)cw.kh * cw.kw * cw.cin + cw.ds_cin);
+  LaunchScope ls(h, kClsIgemmTc, flops, st);
   CUDA_TRY(igemm_tc_launch(p, kModeStd, h->num_sms, st));
-  h->launches++;
   return 0;
 }
 
@@ -302,9 +352,9 @@ int run_conv_simt(ocrfa_handle* h, const float* wgt, const float* bias, const vo
   p.h_out = (h_in + 2 * ph - kh) / sh + 1; p.w_out = w_in + 2 * pw - kw + 1; p.relu = relu ? 1 : 0;
   const long long pix = (long long)n * p.h_out * p.w_out;
   dim3 grid((unsigned)((pix + 63) / 64), (unsigned)((cout + 63) / 64));
+  LaunchScope ls(h, kClsSimtConv, 2.0 * (double)pix * cout * kh * kw * cin, st);
   conv_simt_kernel<float, float><<<grid, 256, 0, st>>>(p);
   CUDA_TRY(cudaGetLastError());
-  h->launches++;
   return 0;
 }
 
@@ -313,10 +363,10 @@ int run_pool(ocrfa_handle* h, const Act& in, void* out, int sh, int sw, int pw, 
   *ho = (in.h - 2) / sh + 1;
   *wo = (in.w + 2 * pw - 2) / sw + 1;
   const long long total = (long long)in.n * *ho * *wo * (in.c / 8);
+  LaunchScope ls(h, kClsPool, 0.0, st);
   maxpool2x2_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const T*)in.p, (T*)out, in.n, in.h, in.w, in.c,
                                                                        sh, sw, pw, *ho, *wo);
   CUDA_TRY(cudaGetLastError());
-  h->launches++;
   return 0;
 }
 
@@ -419,23 +469,23 @@ int forward_impl(ocrfa_handle* h, const float* d_x, const uint8_t* d_u8, const i
   void* feat = ws + L.feat;
   if (d_feat_in) {
     const long long total = (long long)B * T * 512;
+    LaunchScope ls(h, kClsPool, 0.0, st);
     if (bf) cvt_from_f32_kernel<__nv_bfloat16><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_feat_in, (__nv_bfloat16*)feat, total);
     else cvt_from_f32_kernel<float><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_feat_in, (float*)feat, total);
     CUDA_TRY(cudaGetLastError());
-    h->launches++;
   } else {
   // ---- stem: conv0_1 + bn0_1 + relu (blocks.py:341-347)
   Act a{pool.get(), B, H, W, bf ? 64 : 32};
   {
     const long long pix = (long long)B * H * W;
     const unsigned grid = (unsigned)((pix + 255) / 256);
+    LaunchScope ls(h, kClsStem, 2.0 * (double)pix * 32 * 9, st);
     if (bf)
       stem_conv_kernel<__nv_bfloat16, 64><<<grid, 256, 0, st>>>(d_x, d_u8, d_widths, h->d_stem_w, h->d_stem_b,
                                                                  (__nv_bfloat16*)a.p, B, H, W);
     else
       stem_conv_kernel<float, 32><<<grid, 256, 0, st>>>(d_x, d_u8, d_widths, h->d_stem_w, h->d_stem_b, (float*)a.p, B, H, W);
     CUDA_TRY(cudaGetLastError());
-    h->launches++;
   }
   if ((rc = conv_step("conv0_2", &a))) return rc;
   if ((rc = pool_step(2, 2, 0, &a))) return rc;                       // max_pool1, blocks.py:259
@@ -461,22 +511,25 @@ int forward_impl(ocrfa_handle* h, const float* d_x, const uint8_t* d_u8, const i
   if (a.h > 1) {
     feat = ws + L.feat;
     const long long total = (long long)B * T * 512;
+    LaunchScope ls(h, kClsPool, 0.0, st);
     if (bf) mean_h_kernel<__nv_bfloat16><<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)a.p, (__nv_bfloat16*)feat, B, a.h, T, 512);
     else mean_h_kernel<float><<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const float*)a.p, (float*)feat, B, a.h, T, 512);
     CUDA_TRY(cudaGetLastError());
-    h->launches++;
   }
   }  // conv stack
   if (d_feat_out) {
     const long long total = (long long)B * T * 512;
+    {
+    LaunchScope ls(h, kClsPool, 0.0, st);
     if (bf) cvt_to_f32_kernel<__nv_bfloat16><<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)feat, d_feat_out, total);
     else cvt_to_f32_kernel<float><<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const float*)feat, d_feat_out, total);
     CUDA_TRY(cudaGetLastError());
-    h->launches++;
+    }
     if (!d_logits) return 0;
   }
 
   // ---- 2 x BidirectionalLSTM (blocks.py:92-102)
+  if (bf) CUDA_TRY(cudaMemsetAsync(ws + L.sync, 0, 4096, st));
   const int rows = B * T;
   float* xproj = (float*)(ws + L.xproj);
   void* hseq = ws + L.hseq;
@@ -491,24 +544,26 @@ int forward_impl(ocrfa_handle* h, const float* d_x, const uint8_t* d_u8, const i
       ConvW xp; xp.name = "lstm.xproj"; xp.cin = 512; xp.cout = 4096; xp.kh = xp.kw = 1; xp.sh = 1; xp.cin_pad = 512;
       xp.ktotal = 512; xp.d_wgt = lw.d_wih; xp.d_bias = lw.d_bih;
       if ((rc = run_conv_tc(h, xp, Act{seq_in, 1, 1, rows, 512}, nullptr, nullptr, xproj, false, true, 4096, st))) return rc;
-      // recurrence: one launch per timestep, both directions in the launch
-      IgemmTcParams p;
-      memset(&p, 0, sizeof(p));
-      p.tw = 1; p.th = 128; p.tn = 1;
-      p.tiles_w = 1; p.tiles_h = ceil_div(B, 128); p.tiles_n = 1;
-      p.n_img = 1; p.h_out = B; p.w_out = 1;
-      p.block_n = 64; p.n_tiles = 64; p.n_valid = 4096;
-      p.kchunks = 8; p.num_taps = 1; p.taps[0] = TapDesc{0, 0, 0, 0};
-      igemm_tc_smem_bytes(p.block_n, &p.num_stages);
-      int r2 = make_act_tmap(&p.tmA, hseq, 1024, T, 1, B, 1, 1, 128, 1);
-      if (r2 == 0) r2 = make_wgt_tmap(&p.tmB, lw.d_whh, 512, 4096, 64);
-      if (r2) return fail(OCRFA_ERR_CUDA, "LSTM tensor map failed: %d", r2);
-      p.tmA2 = p.tmA;
-      p.lstm_T = T; p.lstm_xproj = xproj; p.lstm_c = cst; p.lstm_hseq = (__nv_bfloat16*)hseq;
-      for (int s = 0; s < T; ++s) {
-        p.lstm_step = s;
-        CUDA_TRY(igemm_tc_launch(p, kModeLstm, h->num_sms, st));
-        h->launches++;
+      // recurrence: ONE persistent launch per 256-line slice walks all T steps of both directions (lstm_tc.cuh)
+      int slice = 0;
+      for (int b0 = 0; b0 < B; b0 += 256, ++slice) {
+        const int nb = B - b0 < 256 ? B - b0 : 256;
+        LstmTcParams lp;
+        memset(&lp, 0, sizeof(lp));
+        __nv_bfloat16* hs = (__nv_bfloat16*)hseq + (size_t)b0 * T * 1024;
+        int r2 = make_act_tmap(&lp.tmH, hs, 1024, T, 1, nb, 1, 1, 128, 1);
+        if (r2 == 0) r2 = make_wgt_tmap(&lp.tmW, lw.d_whh, 512, 4096, 64);
+        if (r2) return fail(OCRFA_ERR_CUDA, "LSTM tensor map failed: %d", r2);
+        lp.xproj = xproj + (size_t)b0 * T * 4096;
+        lp.hseq = hs;
+        lp.m_tiles = ceil_div(nb, 128);
+        const int ctr = (li * 64 + slice) * 4;
+        if (ctr + 4 > 1024) return fail(OCRFA_ERR_ARG, "batch too large for the LSTM counter table");
+        lp.sync = (unsigned int*)(ws + L.sync) + ctr;
+        lp.dbg = nullptr;
+        lp.B = nb; lp.T = T;
+        LaunchScope ls(h, kClsLstmTc, 2.0 * 2.0 * nb * 2048.0 * 512.0 * (T - 1), st);
+        CUDA_TRY(lstm_tc_launch(lp, st));
       }
       ConvW lin; lin.name = "lstm.linear"; lin.cin = 1024; lin.cout = 512; lin.kh = lin.kw = 1; lin.sh = 1; lin.cin_pad = 1024;
       lin.ktotal = 1024; lin.d_wgt = lw.d_wlin; lin.d_bias = lw.d_blin;
@@ -526,9 +581,9 @@ int forward_impl(ocrfa_handle* h, const float* d_x, const uint8_t* d_u8, const i
               return rc;
           }
         const int total = 2 * B * 512;
+        LaunchScope ls(h, kClsLstmCell, 0.0, st);
         lstm_cell_f32_kernel<<<(total + 255) / 256, 256, 0, st>>>(hh, xproj, cst, (float*)hseq, B, T, s);
         CUDA_TRY(cudaGetLastError());
-        h->launches++;
       }
       if ((rc = run_conv_simt(h, (const float*)lw.d_wlin, lw.d_blin, hseq, 1024, 1, 1, rows, 1024, 512, 1, 1, 1, 0, 0,
                               nullptr, seq_out, 512, false, st))) return rc;
@@ -576,6 +631,13 @@ RecLayout rec_layout(const ocrfa_handle* h, int B, int H, int W, int bw) {
   return R;
 }
 
+}  // namespace
+
+namespace {
+// forward + decode on device buffers, asynchronous on `st` (labels/len/conf stay on the device)
+int recognize_device_impl(ocrfa_handle* h, const uint8_t* d_img, const int32_t* d_widths, int B, int H, int W,
+                          const uint8_t* d_ignore_mask, int decoder, int beam_width, int32_t* d_labels, int32_t* d_len,
+                          double* d_conf, void* d_ws, size_t ws_bytes, cudaStream_t st);
 }  // namespace
 
 // ==============================================================================================================
@@ -682,6 +744,7 @@ int ocrfa_finalize_weights(ocrfa_handle* h, void* stream) {
   if (h->bf16()) {
     CUDA_TRY(cudaFuncSetAttribute(igemm_tc_kernel<kModeStd>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CUDA_TRY(cudaFuncSetAttribute(igemm_tc_kernel<kModeLstm>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(lstm_tc_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lstm_tc_smem_bytes()));
     if (!get_tmap_encode()) return fail(OCRFA_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
   }
   CUDA_TRY(cudaDeviceSynchronize());
@@ -811,6 +874,74 @@ static int beam_launch(const float* d_probs, const int32_t* d_span_row0, const i
   return 0;
 }
 
+}  // extern "C"
+
+namespace {
+int recognize_device_impl(ocrfa_handle* h, const uint8_t* d_img, const int32_t* d_widths, int B, int H, int W,
+                          const uint8_t* d_ignore_mask, int decoder, int beam_width, int32_t* d_labels, int32_t* d_len,
+                          double* d_conf, void* d_ws, size_t ws_bytes, cudaStream_t st) {
+  if (!h || !d_img || !d_labels || !d_len || !d_conf || !d_ws) return fail(OCRFA_ERR_ARG, "null pointer");
+  if (decoder != 0 && decoder != 1) return fail(OCRFA_ERR_ARG, "decoder must be 0 (greedy) or 1 (beamsearch)");
+  const int T = ocrfa_out_timesteps(H, W);
+  if (T == 0) return fail(OCRFA_ERR_ARG, "unsupported geometry");
+  const int C = h->cfg.num_class;
+  const RecLayout R = rec_layout(h, B, H, W, beam_width);
+  if (ws_bytes < R.total) return fail(OCRFA_ERR_WORKSPACE, "workspace too small: %zu < %zu", ws_bytes, R.total);
+  uint8_t* ws = (uint8_t*)d_ws;
+  float* d_logits = (float*)(ws + R.logits);
+  float* d_probs = (float*)(ws + R.probs);
+  int rc = forward_impl(h, nullptr, d_img, d_widths, B, H, W, d_logits, ws + R.fwd, R.img - R.fwd, st);
+  if (rc) return rc;
+  {
+    LaunchScope ls(h, kClsDecode, 0.0, st);
+    rc = ocrfa_ctc_greedy(d_logits, B, T, C, d_ignore_mask, nullptr, decoder == 1 ? d_probs : nullptr, nullptr, nullptr,
+                          d_labels, d_len, d_conf, st);
+    if (rc) return rc;
+  }
+  if (decoder == 1) {
+    LaunchScope ls(h, kClsBeam, 0.0, st);
+    rc = ocrfa_ctc_beam(d_probs, B, T, C, beam_width, nullptr, d_labels, d_len, ws + R.beam, R.total - R.beam, st);
+    if (rc) return rc;
+  }
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int ocrfa_recognize_device(ocrfa_handle* h, const uint8_t* d_img, const int32_t* d_widths, int32_t B, int32_t H, int32_t W,
+                           const uint8_t* d_ignore_mask, int32_t decoder, int32_t beam_width, int32_t* d_labels,
+                           int32_t* d_len, double* d_conf, void* d_ws, size_t ws_bytes, void* stream) {
+  return recognize_device_impl(h, d_img, d_widths, B, H, W, d_ignore_mask, decoder, beam_width, d_labels, d_len, d_conf,
+                               d_ws, ws_bytes, (cudaStream_t)stream);
+}
+
+// ---- CUDA-event profile of selected kernel classes (bench.py) -----------------------------------------------
+int ocrfa_profile_begin(ocrfa_handle* h, uint32_t class_mask) {
+  if (!h) return fail(OCRFA_ERR_ARG, "null handle");
+  h->prof.mask = class_mask;
+  h->prof.spans.clear();
+  h->prof.used = 0;
+  for (int i = 0; i < kNumClasses; ++i) h->prof.launches[i] = 0;
+  return 0;
+}
+
+int ocrfa_profile_end(ocrfa_handle* h, double* ms_by_class, double* flops_by_class, int64_t* launches_by_class) {
+  if (!h || !ms_by_class || !flops_by_class || !launches_by_class) return fail(OCRFA_ERR_ARG, "null argument");
+  CUDA_TRY(cudaDeviceSynchronize());
+  for (int i = 0; i < kNumClasses; ++i) { ms_by_class[i] = 0.0; flops_by_class[i] = 0.0; launches_by_class[i] = h->prof.launches[i]; }
+  for (const Profiler::Span& sp : h->prof.spans) {
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, h->prof.pool[sp.e0], h->prof.pool[sp.e1]));
+    ms_by_class[sp.cls] += ms;
+    flops_by_class[sp.cls] += sp.flops;
+  }
+  h->prof.mask = 0;
+  h->prof.spans.clear();
+  h->prof.used = 0;
+  return 0;
+}
+
 size_t ocrfa_recognize_workspace_bytes(const ocrfa_handle* h, int32_t B, int32_t H, int32_t W, int32_t beam_width) {
   if (!h || B <= 0 || H <= 0 || W <= 0) return 0;
   return rec_layout(h, B, H, W, beam_width).total;
@@ -839,17 +970,9 @@ int ocrfa_recognize_host(ocrfa_handle* h, const uint8_t* h_img, const int32_t* h
   CUDA_TRY(cudaMemcpyAsync(d_img, h_img, (size_t)B * H * W, cudaMemcpyHostToDevice, st));
   if (h_widths) CUDA_TRY(cudaMemcpyAsync(d_w, h_widths, (size_t)B * 4, cudaMemcpyHostToDevice, st));
   if (h_ignore_mask) CUDA_TRY(cudaMemcpyAsync(d_mask, h_ignore_mask, (size_t)C, cudaMemcpyHostToDevice, st));
-  int rc = forward_impl(h, nullptr, d_img, h_widths ? d_w : nullptr, B, H, W, d_logits, ws + R.fwd, R.img - R.fwd, st);
+  int rc = recognize_device_impl(h, d_img, h_widths ? d_w : nullptr, B, H, W, h_ignore_mask ? d_mask : nullptr, decoder,
+                                 beam_width, d_labels, d_len, d_conf, d_ws, ws_bytes, st);
   if (rc) return rc;
-  rc = ocrfa_ctc_greedy(d_logits, B, T, C, h_ignore_mask ? d_mask : nullptr, nullptr, decoder == 1 ? d_probs : nullptr,
-                        nullptr, nullptr, d_labels, d_len, d_conf, st);
-  if (rc) return rc;
-  h->launches++;
-  if (decoder == 1) {
-    rc = ocrfa_ctc_beam(d_probs, B, T, C, beam_width, nullptr, d_labels, d_len, ws + R.beam, R.total - R.beam, st);
-    if (rc) return rc;
-    h->launches++;
-  }
   CUDA_TRY(cudaMemcpyAsync(h_labels, d_labels, (size_t)B * T * 4, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaMemcpyAsync(h_len, d_len, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaMemcpyAsync(h_conf, d_conf, (size_t)B * 8, cudaMemcpyDeviceToHost, st));

@@ -10,6 +10,7 @@
 #include <random>
 #include <vector>
 #include "igemm_plan.h"
+#include "lstm_tc.cuh"
 
 using namespace ocrfa;
 
@@ -196,7 +197,8 @@ static void run_case(const Case& c) {
 // ---------------------------------------------------------------------------------------------
 // LSTM step mode against a host reference
 // ---------------------------------------------------------------------------------------------
-static void run_lstm_case(int B, int T, int steps) {
+static void run_lstm_case(int B, int T, int steps, bool persistent = false) {
+  if (persistent) steps = T;
   const int H = 512;
   std::vector<__nv_bfloat16> whh((size_t)2 * 2048 * H);  // permuted layout: row = dir*2048 + tile*64 + gate*16 + u
   std::vector<float> xproj((size_t)B * T * 4096);
@@ -224,15 +226,46 @@ static void run_lstm_case(int B, int T, int steps) {
 
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  unsigned int* d_sync = nullptr;
+  CK(cudaMalloc(&d_sync, 64));
+  LstmTcParams lp;
+  memset(&lp, 0, sizeof(lp));
+  lp.tmH = p.tmA; lp.tmW = p.tmB; lp.xproj = d_xproj; lp.hseq = d_hseq; lp.sync = d_sync;
+  lp.B = B; lp.T = T; lp.m_tiles = ceil_div(B, 128);
+  long long* d_dbg = nullptr;
+  CK(cudaMalloc(&d_dbg, 64 * 16 * 8)); CK(cudaMemset(d_dbg, 0, 64 * 16 * 8));
+  lp.dbg = (persistent && getenv("LSTM_DBG")) ? d_dbg : nullptr;
+  if (persistent) {  // warm-up launch (also exercises relaunch with a re-zeroed counter)
+    CK(cudaMemsetAsync(d_sync, 0, 64));
+    CK(lstm_tc_launch(lp, 0));
+    CK(cudaMemsetAsync(d_hseq, 0, (size_t)B * T * 1024 * 2));
+  }
   CK(cudaEventRecord(e0));
-  for (int s = 0; s < steps; ++s) {
-    p.lstm_step = s;
-    CK(igemm_tc_launch(p, kModeLstm, g_sms, 0));
+  if (persistent) {
+    CK(cudaMemsetAsync(d_sync, 0, 64));
+    CK(lstm_tc_launch(lp, 0));
+  } else {
+    for (int s = 0; s < steps; ++s) {
+      p.lstm_step = s;
+      CK(igemm_tc_launch(p, kModeLstm, g_sms, 0));
+    }
   }
   CK(cudaEventRecord(e1));
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("[lstm] kernel failed: %s\n", cudaGetErrorString(e)); exit(3); }
   float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+  if (lp.dbg) {
+    std::vector<long long> ts(64 * 16);
+    CK(cudaMemcpy(ts.data(), d_dbg, ts.size() * 8, cudaMemcpyDeviceToHost));
+    const char* nm[16] = {"prod:step_begin", "prod:poll_done", "prod:fence_done", "prod:loads_issued", "mma:first_kblock", "mma:last_kblock",
+                          "mma:committed", "", "epi:tfull", "epi:tmem_loaded", "epi:math_done", "epi:stored", "epi:threadfence", "epi:bar", "epi:released", ""};
+    for (int s = 4; s < 8 && s < T; ++s) {
+      const long long base = ts[s * 16 + 0];
+      printf("    step %d (cycles since producer step begin):", s);
+      for (int k = 0; k < 15; ++k) if (nm[k][0]) printf(" %s=%lld", nm[k], ts[s * 16 + k] - base);
+      printf(" | next step begin=%lld\n", ts[(s + 1) * 16 + 0] - base);
+    }
+  }
 
   // host reference (float math on bf16-rounded h, mirroring the device's rounding points)
   std::vector<float> hprev((size_t)2 * B * H, 0.f), cst((size_t)2 * B * H, 0.f);
@@ -285,7 +318,7 @@ static void run_lstm_case(int B, int T, int steps) {
           cnt++;
         }
       }
-  printf("[lstm] B=%d T=%d steps=%d : max_abs_err=%.4g bad=%zu/%zu %s ; %.2f us/step (launch loop, both dirs)\n", B, T,
+  printf("[lstm%s] B=%d T=%d steps=%d : max_abs_err=%.4g bad=%zu/%zu %s ; %.2f us/step (both dirs)\n", persistent ? "-persistent" : "", B, T,
          steps, max_abs, bad, cnt, bad ? "FAIL" : "ok", ms * 1000.f / steps);
   if (bad) g_fail++;
   cudaFree(d_whh); cudaFree(d_xproj); cudaFree(d_hseq); cudaFree(d_c);
@@ -293,12 +326,29 @@ static void run_lstm_case(int B, int T, int steps) {
 
 int main(int argc, char** argv) {
   bool perf = false;
-  for (int i = 1; i < argc; ++i) if (!strcmp(argv[i], "--perf")) perf = true;
+  const char* only = nullptr;  // --only NAME: run one perf case (or "lstm") alone, e.g. under ncu
+  for (int i = 1; i < argc; ++i) {
+    if (!strcmp(argv[i], "--perf")) perf = true;
+    if (!strcmp(argv[i], "--only") && i + 1 < argc) only = argv[++i];
+  }
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, 0));
   g_sms = prop.multiProcessorCount;
   printf("device: %s, %d SMs, cc %d.%d\n", prop.name, g_sms, prop.major, prop.minor);
 
+  if (only) {
+    std::vector<Case> pc = {
+        {"perf_l1_c128", {256, 16, 256, 128, 128, 3, 3, 1, 1, 1}, 1, 1, 1, 0, 0, 0, 0, 0, 2},
+        {"perf_l2_c256", {256, 8, 128, 256, 256, 3, 3, 1, 1, 1},  1, 1, 1, 0, 0, 0, 0, 0, 2},
+        {"perf_l3_c512", {256, 4, 129, 512, 512, 3, 3, 1, 1, 1},  1, 1, 1, 0, 0, 0, 0, 0, 2},
+        {"perf_c0_2",    {256, 32, 512, 64, 64, 3, 3, 1, 1, 1},   1, 1, 0, 0, 0, 0, 0, 0, 2},
+    };
+    for (const Case& c : pc) if (!strcmp(only, c.name)) run_case(c);
+    if (!strcmp(only, "lstm")) run_lstm_case(256, 129, 12);
+    if (!strcmp(only, "lstm_persistent")) run_lstm_case(256, 129, 129, true);
+    printf("%s (%d failing cases)\n", g_fail ? "FAILED" : "ALL OK", g_fail);
+    return g_fail ? 1 : 0;
+  }
   std::vector<Case> cases = {
       //  name          n  h   w   cin cout kh kw sh ph pw   relu bias res f32 fuse  tile      perf
       {"gemm_small",   {1, 1, 256, 64, 64, 1, 1, 1, 0, 0},   0, 0, 0, 1, 0, 128, 1, 1, 0},
@@ -319,6 +369,9 @@ int main(int argc, char** argv) {
   };
   for (const Case& c : cases) run_case(c);
   run_lstm_case(200, 9, 9);
+  run_lstm_case(200, 9, 9, true);
+  run_lstm_case(64, 33, 33, true);
+  run_lstm_case(256, 17, 17, true);
 
   if (perf && g_fail == 0) {
     std::vector<Case> pc = {
@@ -332,6 +385,8 @@ int main(int argc, char** argv) {
     };
     for (const Case& c : pc) run_case(c);
     run_lstm_case(256, 129, 129);
+    run_lstm_case(256, 129, 129, true);
+    run_lstm_case(64, 513, 513, true);
   }
   printf("%s (%d failing cases)\n", g_fail ? "FAILED" : "ALL OK", g_fail);
   return g_fail ? 1 : 0;
