@@ -1,0 +1,100 @@
+"""Decoded-string parity on >= 10k synthetic lines (north_star's correctness target), run on the GPU box:
+
+    python tools/parity_10k.py [--lines 10240] [--height 32] [--width 128] [--out gpurun_out/parity_10k.json]
+
+For every line: the oracle (CPU restatement of the reference, fp32) decodes greedy strings; the CUDA path decodes
+the same uint8 lines in fp32 parity mode and in bf16 tensor-core mode through ocrfa_recognize_host. Reports how
+many strings are identical, and the logit error statistics on a subsample. Test infrastructure (imports oracle/).
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import ocrfa_b200 as ob  # noqa: E402
+from ocrfa_b200.recognition import _ignore_mask  # noqa: E402
+from ocrfa_b200.synth import synth_lines, synth_state_dict  # noqa: E402
+from oracle import recognizer_ref as R  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--lines", type=int, default=10240)
+    ap.add_argument("--height", type=int, default=32)
+    ap.add_argument("--width", type=int, default=128)
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "parity_10k.json"))
+    args = ap.parse_args()
+    N, H, W = args.lines, args.height, args.width
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd_np = synth_state_dict(0)
+    sd = {k: torch.from_numpy(v) for k, v in sd_np.items()}
+    chars = ob.default_character()
+    conv = ob.CTCLabelConverter(chars)
+    ign = R.ignore_idx_ref(chars, ob.default_ignore_char())
+    mask = _ignore_mask(len(conv.character), ign)
+    dev = torch.device("cuda", 0)
+    models = {}
+    for prec in ("fp32", "bf16"):
+        m = ob.Model(1, 512, 512, len(conv.character), precision=prec)
+        m.load_state_dict(sd)
+        models[prec] = m
+
+    same = {"fp32": 0, "bf16": 0}
+    step_agree = {"fp32": [0, 0], "bf16": [0, 0]}
+    conf_err = {"fp32": 0.0, "bf16": 0.0}
+    mismatches = {"fp32": [], "bf16": []}
+    t_cpu = t_gpu = 0.0
+    for b0 in range(0, N, args.batch):
+        n = min(args.batch, N - b0)
+        imgs = synth_lines(n, H, W, seed=900000 + b0)  # disjoint from the timing set (seed 1234 + rank)
+        t0 = time.perf_counter()
+        x = R.align_collate_ref(list(imgs), H, W)
+        logits = R.model_forward_ref(sd, x)
+        probs = R.probs_ref(logits, ign)
+        ref_strs = R.greedy_decode_ref(probs, conv.character)
+        ref_conf = np.array(R.confidence_ref(probs), dtype=np.float64)
+        ref_idx = probs.argmax(2)
+        t_cpu += time.perf_counter() - t0
+        batch = ob.AlignCollate(H, W)(list(imgs))
+        for prec in ("fp32", "bf16"):
+            t0 = time.perf_counter()
+            strs, conf = ob.recognize_host(models[prec], conv, batch.images_u8, batch.widths, mask, "greedy", 5, dev)
+            t_gpu += time.perf_counter() - t0
+            for i, (a, b) in enumerate(zip(strs, ref_strs)):
+                if a == b:
+                    same[prec] += 1
+                elif len(mismatches[prec]) < 5:
+                    mismatches[prec].append({"line": b0 + i, "got": a, "ref": b})
+            ok = np.isfinite(ref_conf) & (ref_conf > 0)
+            if ok.any():
+                conf_err[prec] = max(conf_err[prec], float(np.max(np.abs(conf[ok] - ref_conf[ok]) / ref_conf[ok])))
+            lg = models[prec].forward_u8(batch.images_u8.to(dev), None).cpu().numpy()
+            idx = R.probs_ref(lg, ign).argmax(2)
+            step_agree[prec][0] += int((idx == ref_idx).sum())
+            step_agree[prec][1] += idx.size
+        print(f"{b0 + n}/{N}: identical fp32 {same['fp32']} bf16 {same['bf16']}", flush=True)
+    out = {
+        "lines": N, "shape": [H, W], "decoder": "greedy", "weights": "synthetic seed 0 (ocrfa_b200/synth.py)",
+        "identical_strings": same,
+        "identical_fraction": {k: v / N for k, v in same.items()},
+        "per_timestep_argmax_agreement": {k: v[0] / max(1, v[1]) for k, v in step_agree.items()},
+        "max_rel_confidence_error": conf_err,
+        "first_mismatches": mismatches,
+        "cpu_oracle_lines_per_s": N / t_cpu, "cpu_threads": torch.get_num_threads(),
+    }
+    os.makedirs(os.path.dirname(args.out), exist_ok=True)
+    with open(args.out, "w", encoding="utf-8") as f:
+        json.dump(out, f, ensure_ascii=False, indent=1)
+    print(json.dumps(out, ensure_ascii=False))
+
+
+if __name__ == "__main__":
+    main()
