@@ -179,6 +179,8 @@ def run_gpu_arm(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         import torch.distributed as dist
+        # stdout carries exactly one JSON line: NCCL's own banner / debug output goes to a file
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/ocrfa_nccl_%h_%p.log")
         dist.init_process_group(backend="nccl", device_id=dev)
 
     B, H, W, decoder, beam = CONFIGS[args.config]
@@ -337,7 +339,7 @@ def run_gpu_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
