@@ -79,6 +79,24 @@ size_t ocrfa_workspace_bytes(const ocrfa_handle* h, int32_t B, int32_t H, int32_
 int ocrfa_preprocess_u8(const uint8_t* d_img, const int32_t* d_widths, int32_t B, int32_t H, int32_t W,
                         int32_t in_stride, float* d_x, void* stream);
 
+/* AlignCollate for lines that are not yet at model height (src/ocrfa/utils.py:587-598): optional contrast stretch
+ * (adjust_contrast_grey, utils.py:450-463, applied when contrast_target > 0 and desc.contrast != 0) followed by
+ * Pillow's 8-bit fixed-point BICUBIC resize to img_h rows, bit-exact with PIL. Lines are packed back to back in
+ * d_src; the fixed-point coefficient tables are produced on the host (ocrfa_b200/resize.py mirrors Pillow's
+ * precompute_coeffs). d_tmp holds the horizontal-pass intermediates, d_lut is [B][256] scratch,
+ * d_out is uint8 [B, img_h, img_w] (columns >= out_w zeroed; ocrfa_preprocess_u8 / the stem replicate-pad them). */
+typedef struct ocrfa_line_desc {
+  int64_t src_off;  /* byte offset of uint8 [src_h][src_w] in d_src */
+  int64_t tmp_off;  /* byte offset of the [src_h][out_w] intermediate in d_tmp */
+  int32_t src_h, src_w, out_w;
+  int32_t kh_off, kh_size, bh_off; /* horizontal: coef int32 [out_w][kh_size], bounds int32 [out_w][2]; kh_size 0 = copy */
+  int32_t kv_off, kv_size, bv_off; /* vertical:   coef [img_h][kv_size], bounds [img_h][2];            kv_size 0 = copy */
+  int32_t contrast;
+} ocrfa_line_desc;
+int ocrfa_align_collate_u8(const uint8_t* d_src, const ocrfa_line_desc* d_desc, const int32_t* d_tables, int32_t B,
+                           int32_t img_h, int32_t img_w, double contrast_target, uint8_t* d_tmp, uint8_t* d_lut,
+                           uint8_t* d_out, void* stream);
+
 /* d_x: float32 [B,1,H,W]; d_logits: float32 [B,T,num_class]. */
 int ocrfa_forward(ocrfa_handle* h, const float* d_x, int32_t B, int32_t H, int32_t W, float* d_logits, void* d_ws,
                   size_t ws_bytes, void* stream);

@@ -17,7 +17,7 @@ PRECISION_BF16 = 1
 # every symbol include/ocrfa_b200.h declares (tests/test_cabi_symbols.py checks the header against this list)
 SYMBOLS = (
     "ocrfa_abi_version", "ocrfa_last_error", "ocrfa_create", "ocrfa_destroy", "ocrfa_load_weight",
-    "ocrfa_finalize_weights", "ocrfa_out_timesteps", "ocrfa_workspace_bytes", "ocrfa_preprocess_u8",
+    "ocrfa_finalize_weights", "ocrfa_out_timesteps", "ocrfa_workspace_bytes", "ocrfa_preprocess_u8", "ocrfa_align_collate_u8",
     "ocrfa_forward", "ocrfa_forward_features", "ocrfa_forward_sequence", "ocrfa_forward_u8", "ocrfa_ctc_greedy", "ocrfa_ctc_collapse", "ocrfa_argmax_rows",
     "ocrfa_beam_workspace_bytes", "ocrfa_ctc_beam", "ocrfa_ctc_beam_spans", "ocrfa_recognize_host",
     "ocrfa_recognize_device", "ocrfa_recognize_workspace_bytes", "ocrfa_profile_begin", "ocrfa_profile_end",
@@ -59,6 +59,7 @@ def load():
     lib.ocrfa_workspace_bytes.argtypes = [vp, i32, i32, i32]
     lib.ocrfa_workspace_bytes.restype = sz
     lib.ocrfa_preprocess_u8.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp]
+    lib.ocrfa_align_collate_u8.argtypes = [vp, vp, vp, i32, i32, i32, C.c_double, vp, vp, vp, vp]
     lib.ocrfa_forward.argtypes = [vp, vp, i32, i32, i32, vp, vp, sz, vp]
     lib.ocrfa_forward_features.argtypes = [vp, vp, i32, i32, i32, vp, vp, sz, vp]
     lib.ocrfa_forward_sequence.argtypes = [vp, vp, i32, i32, i32, vp, vp, sz, vp]

@@ -19,6 +19,7 @@
 #include "decode_kernels.cuh"
 #include "igemm_plan.h"
 #include "lstm_tc.cuh"
+#include "resize_kernels.cuh"
 #include "simt_kernels.cuh"
 
 using namespace ocrfa;
@@ -67,7 +68,7 @@ struct LstmW {
 };
 
 struct WsLayout {
-  size_t act[4], xproj, hseq, seq[2], feat, cstate, hh, sync, total;
+  size_t act[4], xproj, hseq, seq[2], feat, cstate, hh, sync, hx, total;
   size_t act_bytes;
 };
 
@@ -147,6 +148,7 @@ WsLayout ws_layout(const ocrfa_handle* h, int B, int H, int W) {
   L.cstate = off; off += align_up((size_t)2 * B * 512 * 4, 1024);
   L.hh = off; off += align_up((size_t)2 * B * 2048 * 4, 1024);
   L.sync = off; off += 4096;  // group counters of the persistent LSTM launches (zeroed once per forward)
+  L.hx = off; off += (size_t)2 * 2 * 2 * 8 * 128 * 64 * 2;  // LSTM h exchange: 2 dirs x 2 m_tiles x 2 parities x 128 KB
   L.total = off;
   return L;
 }
@@ -568,7 +570,9 @@ int forward_impl(ocrfa_handle* h, const float* d_x, const uint8_t* d_u8, const i
         LstmTcParams lp;
         memset(&lp, 0, sizeof(lp));
         __nv_bfloat16* hs = (__nv_bfloat16*)hseq + (size_t)b0 * T * 1024;
-        int r2 = make_act_tmap(&lp.tmH, hs, 1024, T, 1, nb, 1, 1, 128, 1);
+        lp.m_tiles = ceil_div(nb, 128);
+        lp.hx = (__nv_bfloat16*)(ws + L.hx);
+        int r2 = make_rows64_tmap(&lp.tmX, lp.hx, (long long)2 * lp.m_tiles * 2 * 8 * 128, 128);
         if (r2 == 0) r2 = make_wgt_tmap(&lp.tmW, lw.d_whh, 512, 4096, 64);
         if (r2) return fail(OCRFA_ERR_CUDA, "LSTM tensor map failed: %d", r2);
         lp.xproj = xproj + (size_t)b0 * T * 4096;
@@ -789,6 +793,23 @@ int ocrfa_preprocess_u8(const uint8_t* d_img, const int32_t* d_widths, int32_t B
   if (!d_img || !d_x || B <= 0 || H <= 0 || W <= 0 || in_stride < W) return fail(OCRFA_ERR_ARG, "bad argument");
   const long long total = (long long)B * H * ((W + 15) / 16);
   preprocess_u8_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_img, d_widths, d_x, B, H, W, in_stride);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int ocrfa_align_collate_u8(const uint8_t* d_src, const ocrfa_line_desc* d_desc, const int32_t* d_tables, int32_t B,
+                           int32_t img_h, int32_t img_w, double contrast_target, uint8_t* d_tmp, uint8_t* d_lut,
+                           uint8_t* d_out, void* stream) {
+  static_assert(sizeof(ocrfa_line_desc) == sizeof(LineDesc), "ocrfa_line_desc layout");
+  if (!d_src || !d_desc || !d_tables || !d_tmp || !d_lut || !d_out || B <= 0 || img_h <= 0 || img_w <= 0)
+    return fail(OCRFA_ERR_ARG, "bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const LineDesc* desc = reinterpret_cast<const LineDesc*>(d_desc);
+  contrast_lut_kernel<<<B, 256, 0, st>>>(d_src, desc, contrast_target, d_lut);
+  CUDA_TRY(cudaGetLastError());
+  resize_h_kernel<<<dim3(64, B), 256, 0, st>>>(d_src, desc, d_tables, d_lut, d_tmp);
+  CUDA_TRY(cudaGetLastError());
+  resize_v_kernel<<<dim3(64, B), 256, 0, st>>>(d_tmp, desc, d_tables, d_out, img_h, img_w);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

@@ -405,6 +405,20 @@ inline int make_wgt_tmap(CUtensorMap* tm, const void* base, int ktotal, int cout
   return rc == CUDA_SUCCESS ? 0 : -static_cast<int>(rc) - 1000;
 }
 
+// Generic row-major bf16 matrix [rows][64] as a 2-D map with {64, box_rows} boxes (LSTM h exchange slabs).
+inline int make_rows64_tmap(CUtensorMap* tm, const void* base, long long rows, int box_rows) {
+  PFN_tmapEncodeTiled enc = get_tmap_encode();
+  if (!enc) return -1;
+  cuuint64_t dims[2] = {64, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {128};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult rc = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return rc == CUDA_SUCCESS ? 0 : -static_cast<int>(rc) - 1000;
+}
+
 inline cudaError_t igemm_tc_launch(const IgemmTcParams& p, int mode, int num_sms, cudaStream_t stream) {
   static bool attr_set[2] = {false, false};
   int stages = 0;

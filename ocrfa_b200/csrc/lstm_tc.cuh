@@ -8,9 +8,11 @@
 // This kernel then walks the T dependent steps:
 //   * CTA (n_tile, m_tile) owns 16 hidden units (64 gate columns) of one direction for 128 batch rows;
 //     its W_hh slice [64 x 512] bf16 (64 KB) is loaded ONCE and stays in shared memory for all T steps;
-//   * per step the previous hidden state h_{t-1} [128 x 512] bf16 is streamed by TMA from the h-sequence tensor
-//     (the layer's output buffer, L2 resident) through an 8-deep ring, multiplied on tcgen05 (M=128, N=64) into
-//     TMEM, and the epilogue warps apply the gate math with the cell state held in REGISTERS across all steps;
+//   * per step the previous hidden state h_{t-1} [128 x 512] bf16 is streamed by TMA from a compact, parity
+//     double-buffered exchange buffer (eight contiguous 16 KB slabs, L2 resident) through an 8-deep ring,
+//     multiplied on tcgen05 (M=128, N=64) into TMEM, and the epilogue warps apply the gate math with the cell
+//     state held in REGISTERS across all steps; h_t is written both to the layer output [B][T][1024] and to the
+//     exchange buffer;
 //   * the only cross-CTA dependency is "all 32 CTAs of my (direction, m_tile) group wrote h_t": a monotonic
 //     global counter per group (release add / acquire poll), no kernel relaunch, no grid-wide barrier;
 //   * xproj rows for step s+1 are prefetched into registers while step s's peers finish, so the HBM latency
@@ -29,10 +31,11 @@ constexpr int kLstmTmemCols = 128;    // 2 accumulators x 64 columns
 constexpr int kLstmGroupCtas = 32;    // CTAs per (direction, m_tile) group = 512 hidden units / 16
 
 struct alignas(64) LstmTcParams {
-  CUtensorMap tmH;  // h sequence [B][T][1024] bf16 seen as 5-D (C=1024, W=T, 1, Ho=B, 1), box {64,1,1,128,1}
+  CUtensorMap tmX;  // h exchange buffer [2 dirs][m_tiles][2 parities][8 K-blocks][128 rows][64] bf16 as 2-D (64, rows), box {64,128}
   CUtensorMap tmW;  // permuted W_hh [4096][512] bf16, box {64, 64}
   const float* xproj;        // [B*T][4096] fp32
-  __nv_bfloat16* hseq;       // [B][T][1024] bf16 (fwd | bwd)
+  __nv_bfloat16* hseq;       // [B][T][1024] bf16 (fwd | bwd): the layer output
+  __nv_bfloat16* hx;         // exchange buffer (see tmX): h_t of the whole group, one contiguous 16 KB slab per K-block
   unsigned int* sync;        // [2 * m_tiles] group counters, zero before launch
   long long* dbg;            // optional [64 steps][16] SM-clock timestamps of CTA 0 (bring-up profiling), or null
   int B, T, m_tiles;
@@ -80,7 +83,7 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_tc_persistent_kernel(con
     mbar_init(w_full, 1);
     fence_mbar_init();
   }
-  if (warp == 0 && lane == 0) { tma_prefetch_desc(&p.tmH); tma_prefetch_desc(&p.tmW); }
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&p.tmX); tma_prefetch_desc(&p.tmW); }
   if (warp == 1) { tmem_alloc(tmem_slot, kLstmTmemCols); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
@@ -114,11 +117,14 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_tc_persistent_kernel(con
           fence_proxy_async_all();  // peers' generic-proxy stores of h -> visible to the TMA (async proxy) reads below
         }
         LSTM_TS(s, 2);
-        const int t_prev = dir == 0 ? s - 1 : T - s;  // out of bounds at s == 0: TMA zero-fills, h0 = 0
+        // slabs of h_{s-1}: parity (s-1)&1 of this group's exchange region; at s == 0 an out-of-bounds row
+        // coordinate makes the TMA zero-fill (h0 = 0)
+        const int xrow0 = s == 0 ? (2 * p.m_tiles * 2 * 8 * 128)
+                                 : (((dir * p.m_tiles + m_tile) * 2 + ((s - 1) & 1)) * 8) * 128;
         for (int kb = 0; kb < 8; ++kb) {
           mbar_wait(&a_empty[stage], phase ^ 1u, 11);
           mbar_expect_tx(&a_full[stage], 16384);
-          tma_load_5d(ring + stage * 16384, &p.tmH, &a_full[stage], dir * 512 + kb * 64, t_prev, 0, m_tile * 128, 0);
+          tma_load_2d(ring + stage * 16384, &p.tmX, &a_full[stage], 0, xrow0 + kb * 128);
           if (++stage == kLstmRing) { stage = 0; phase ^= 1u; }
         }
         LSTM_TS(s, 3);
@@ -217,6 +223,10 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_tc_persistent_kernel(con
         o1.z = pack_bf16x2(hout[12], hout[13]); o1.w = pack_bf16x2(hout[14], hout[15]);
         *reinterpret_cast<uint4*>(hp) = o0;
         *reinterpret_cast<uint4*>(hp + 8) = o1;
+        // exchange copy for the next step's MMAs (rows >= B are never read back into valid results)
+        __nv_bfloat16* xp2 = p.hx + (static_cast<size_t>((((dir * p.m_tiles + m_tile) * 2 + (s & 1)) * 8 + (j0 >> 6)) * 128 + row)) * 64 + (j0 & 63);
+        *reinterpret_cast<uint4*>(xp2) = o0;
+        *reinterpret_cast<uint4*>(xp2 + 8) = o1;
       }
       // publish: the CTA barrier orders every epilogue thread's h stores before thread 0's gpu-scope release
       // (cumulative), which the peers' acquire polls + proxy fence pair with

@@ -2,10 +2,10 @@
 `get_recognizer`, `get_text`, `recognizer_predict`, `AlignCollate`, `ListDataset`, `custom_mean` keep their names,
 argument meaning and error behaviour; the arithmetic behind them runs in libocrfa_b200.so.
 
-What stays on the host, exactly where the reference has it: list plumbing, the optional PIL BICUBIC resize of a
-line that is not yet at model height (utils.py:598; a GPU restatement of Pillow's fixed-point bicubic is the
-next item of SURVEY.md section 8f), the percentile contrast stretch of the second pass (utils.py:450-463), and
-the index -> character lookup.
+What stays on the host, exactly where the reference has it: list plumbing, packing of the ragged uint8 lines and
+the size-only coefficient tables of the resize (ocrfa_b200/resize.py), and the index -> character lookup. The
+Pillow-exact BICUBIC resize (utils.py:598) and the percentile contrast stretch of the second pass
+(utils.py:450-463) run on the GPU (ocrfa_align_collate_u8).
 """
 from __future__ import annotations
 
@@ -19,6 +19,7 @@ import torch
 from . import _lib
 from .converter import CTCLabelConverter
 from .model import Model
+from .resize import align_collate_device, resized_width
 
 
 def custom_mean(x):
@@ -82,27 +83,27 @@ class AlignCollate:
 
     def __call__(self, batch) -> LineBatch:
         images = [np.asarray(b) for b in batch if b is not None]
+        for img in images:
+            if img.ndim != 2 or img.dtype != np.uint8:
+                raise ValueError("lines must be uint8 grayscale arrays [h, w]")
+        rws = [resized_width(img.shape[1], img.shape[0], self.imgH, self.imgW) for img in images]
+        identity = self.adjust_contrast <= 0 and all(img.shape == (self.imgH, rw) for img, rw in zip(images, rws))
+        if not identity:
+            # contrast stretch and/or Pillow-exact BICUBIC resize: GPU kernels (ocrfa_align_collate_u8)
+            if not torch.cuda.is_available():
+                raise _lib.OcrfaError("AlignCollate needs a CUDA device for lines that are not at model height "
+                                      "(no CPU fallback)")
+            dev = torch.device("cuda", torch.cuda.current_device())
+            out, widths = align_collate_device(images, self.imgH, self.imgW, self.adjust_contrast, dev)
+            return LineBatch(out, widths)
         out = torch.empty((len(images), self.imgH, self.imgW), dtype=torch.uint8)
         if torch.cuda.is_available():
             out = out.pin_memory()
         out_np = out.numpy()
-        widths = np.empty(len(images), dtype=np.int32)
-        for i, img in enumerate(images):
-            if img.ndim != 2 or img.dtype != np.uint8:
-                raise ValueError("lines must be uint8 grayscale arrays [h, w]")
-            if self.adjust_contrast > 0:
-                img = adjust_contrast_grey(img, target=self.adjust_contrast)
-            h, w = img.shape
-            ratio = w / float(h)
-            rw = self.imgW if math.ceil(self.imgH * ratio) > self.imgW else math.ceil(self.imgH * ratio)
-            if (rw, self.imgH) != (w, h):
-                from PIL import Image
-
-                img = np.asarray(Image.fromarray(img, "L").resize((rw, self.imgH), Image.BICUBIC))
+        for i, (img, rw) in enumerate(zip(images, rws)):
             out_np[i, :, :rw] = img
             out_np[i, :, rw:] = 0  # overwritten on the device by the replicate pad
-            widths[i] = rw
-        return LineBatch(out, torch.from_numpy(widths))
+        return LineBatch(out, torch.tensor(rws, dtype=torch.int32))
 
 
 def _batches(dataset: ListDataset, batch_size: int, collate) -> Iterable[LineBatch]:
@@ -158,7 +159,7 @@ def recognizer_predict(model: Model, converter: CTCLabelConverter, test_loader, 
     lib = _lib.load()
     for batch in test_loader:
         if isinstance(batch, LineBatch):
-            if decoder in ("greedy", "beamsearch"):
+            if decoder in ("greedy", "beamsearch") and not batch.images_u8.is_cuda:
                 strs, conf = recognize_host(model, converter, batch.images_u8, batch.widths, mask_np, decoder, beamWidth, dev)
             else:
                 logits = model.forward_u8(batch.images_u8.to(dev, non_blocking=True), batch.widths.to(dev))

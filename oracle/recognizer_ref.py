@@ -45,6 +45,85 @@ def resized_width_ref(w: int, h: int, img_h: int, img_w: int) -> int:
     return img_w if math.ceil(img_h * ratio) > img_w else math.ceil(img_h * ratio)
 
 
+# Pillow's Image.resize(..., BICUBIC) for 8-bit images, restated (third-party arithmetic: Pillow 10.1 pinned by the
+# reference's requirements.txt:4, 12.2 in this container; src/libImaging/Resample.c: precompute_coeffs,
+# normalize_coeffs_8bpc, ImagingResampleHorizontal_8bpc / Vertical_8bpc). Two passes, horizontal first; every pass
+# rounds to uint8: out = clip8((2^21 + sum_k pixel_k * round(coef_k * 2^22)) >> 22).
+PRECISION_BITS = 32 - 8 - 2
+
+
+def _bicubic_filter(x: float) -> float:
+    a = -0.5
+    if x < 0.0:
+        x = -x
+    if x < 1.0:
+        return ((a + 2.0) * x - (a + 3.0)) * x * x + 1
+    if x < 2.0:
+        return (((x - 5) * x + 8) * x - 4) * a
+    return 0.0
+
+
+def pillow_coeffs_ref(in_size: int, out_size: int):
+    """Per output position: first input index, number of taps, fixed-point coefficients (precompute_coeffs with
+    box (0, in_size), filter support 2.0). Returns (bounds int32 [out,2], kk int32 [out,ksize], ksize)."""
+    scale = filterscale = float(in_size) / out_size
+    if filterscale < 1.0:
+        filterscale = 1.0
+    support = 2.0 * filterscale
+    ksize = int(math.ceil(support)) * 2 + 1
+    bounds = np.zeros((out_size, 2), dtype=np.int32)
+    kk = np.zeros((out_size, ksize), dtype=np.int32)
+    ss = 1.0 / filterscale
+    for xx in range(out_size):
+        center = (xx + 0.5) * scale
+        ww = 0.0
+        xmin = int(center - support + 0.5)
+        if xmin < 0:
+            xmin = 0
+        xmax = int(center + support + 0.5)
+        if xmax > in_size:
+            xmax = in_size
+        xmax -= xmin
+        k = [0.0] * ksize
+        for x in range(xmax):
+            w = _bicubic_filter((x + xmin - center + 0.5) * ss)
+            k[x] = w
+            ww += w
+        for x in range(xmax):
+            if ww != 0.0:
+                k[x] /= ww
+        for x in range(ksize):  # normalize_coeffs_8bpc
+            v = k[x] * (1 << PRECISION_BITS)
+            kk[xx, x] = int(-0.5 + v) if k[x] < 0 else int(0.5 + v)
+        bounds[xx] = (xmin, xmax)
+    return bounds, kk, ksize
+
+
+def _resample_axis_ref(img: np.ndarray, out_size: int, axis: int) -> np.ndarray:
+    in_size = img.shape[axis]
+    bounds, kk, _ = pillow_coeffs_ref(in_size, out_size)
+    src = np.moveaxis(img, axis, 0).astype(np.int64)
+    out = np.empty((out_size,) + src.shape[1:], dtype=np.uint8)
+    for xx in range(out_size):
+        xmin, n = int(bounds[xx, 0]), int(bounds[xx, 1])
+        acc = np.full(src.shape[1:], 1 << (PRECISION_BITS - 1), dtype=np.int64)
+        for x in range(n):
+            acc += src[xmin + x] * int(kk[xx, x])
+        out[xx] = np.clip(acc >> PRECISION_BITS, 0, 255).astype(np.uint8)
+    return np.moveaxis(out, 0, axis)
+
+
+def pillow_bicubic_resize_ref(img_u8: np.ndarray, out_w: int, out_h: int) -> np.ndarray:
+    """uint8 [h, w] -> uint8 [out_h, out_w], bit-exact with PIL.Image.resize((out_w, out_h), Image.BICUBIC)."""
+    h, w = img_u8.shape
+    out = img_u8
+    if out_w != w:
+        out = _resample_axis_ref(out, out_w, axis=1)
+    if out_h != h:
+        out = _resample_axis_ref(out, out_h, axis=0)
+    return np.ascontiguousarray(out)
+
+
 def normalize_pad_ref(img_u8: np.ndarray, img_h: int, img_w: int, adjust_contrast: float = 0.0) -> np.ndarray:
     """One line: uint8 [h, w] -> float32 [1, img_h, img_w] in [-1, 1], right-padded with the last column.
 

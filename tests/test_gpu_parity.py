@@ -348,3 +348,90 @@ def test_tcgen05_layers_against_naive_reference():
     out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     print(out.stdout[-3000:])
     assert out.returncode == 0 and "ALL OK" in out.stdout
+
+
+def _align_collate_u8_ref(img, img_h, img_w, adjust_contrast):
+    """The reference's AlignCollate up to (not including) ToTensor: contrast stretch (utils.py:587-590) then PIL
+    BICUBIC (utils.py:592-598). Pillow itself is the checker here (it is in the image on the GPU box too)."""
+    from PIL import Image
+    from oracle import recognizer_ref as R
+
+    if adjust_contrast > 0:
+        img = R.adjust_contrast_grey_ref(img, target=adjust_contrast)
+    h, w = img.shape
+    rw = R.resized_width_ref(w, h, img_h, img_w)
+    if (rw, img_h) != (w, h):
+        img = np.asarray(Image.fromarray(img, "L").resize((rw, img_h), Image.BICUBIC))
+    return img, rw
+
+
+@pytest.mark.parametrize("img_h,img_w", [(32, 320), (64, 600)])
+@pytest.mark.parametrize("contrast", [0.0, 0.5])
+def test_align_collate_gpu_bit_exact_with_pillow(env, img_h, img_w, contrast):
+    """Ragged lines (taller, shorter, wider than imgW, 1-pixel, low and high contrast) through the GPU AlignCollate
+    (ocrfa_align_collate_u8): bytes identical to contrast stretch + PIL BICUBIC, then the normalise/replicate-pad
+    output identical to the oracle's float32 tensor."""
+    from oracle import recognizer_ref as R
+
+    ob = env["ob"]
+    rng = np.random.default_rng(5 + img_h)
+    shapes = [(40, 333), (64, 512), (img_h, 100), (17, 90), (100, 37), (33, 77), (5, 9), (128, 64), (31, 500), (1, 7),
+              (img_h, img_w), (img_h, img_w + 50), (48, 1500), (2, 2), (img_h, 1)]
+    imgs = []
+    for i, (h, w) in enumerate(shapes):
+        if i % 3 == 0:   # low-contrast line: the stretch branch is taken when contrast > 0
+            imgs.append(rng.integers(100, 140, (h, w), dtype=np.uint8))
+        elif i % 3 == 1:
+            imgs.append(rng.integers(0, 256, (h, w), dtype=np.uint8))
+        else:            # text-like: bright background, dark strokes
+            a = np.full((h, w), 230, dtype=np.uint8)
+            a[:, :: 3] = rng.integers(0, 60, a[:, :: 3].shape, dtype=np.uint8)
+            imgs.append(a)
+    batch = ob.AlignCollate(img_h, img_w, keep_ratio_with_pad=True, adjust_contrast=contrast)(imgs)
+    assert batch.images_u8.is_cuda
+    got = batch.images_u8.cpu().numpy()
+    widths = batch.widths.cpu().numpy()
+    for i, im in enumerate(imgs):
+        ref, rw = _align_collate_u8_ref(im, img_h, img_w, contrast)
+        assert widths[i] == rw
+        assert np.array_equal(got[i, :, :rw], ref), f"line {i} shape {im.shape}"
+    # and the normalised, replicate-padded float tensor
+    from ocrfa_b200 import _lib
+
+    lib = _lib.load()
+    B = len(imgs)
+    out = torch.empty((B, 1, img_h, img_w), dtype=torch.float32, device="cuda")
+    _lib.check(lib.ocrfa_preprocess_u8(C.c_void_p(batch.images_u8.data_ptr()), C.c_void_p(batch.widths.data_ptr()), B,
+                                       img_h, img_w, img_w, C.c_void_p(out.data_ptr()), None))
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), R.align_collate_ref(imgs, img_h, img_w, contrast))
+
+
+def test_get_text_ragged_heights_fp32(env, synth_sd):
+    """get_text on lines that are NOT at model height (GPU resize + GPU contrast retry) against the oracle's
+    restatement of the same two-pass flow (PIL resize on the CPU side)."""
+    from oracle import recognizer_ref as R
+    from ocrfa_b200.synth import synth_lines
+
+    ob = env["ob"]
+    base = synth_lines(6, 48, 400, seed=5)
+    imgs = [base[0], base[1][:40, :333], base[2][:, :250], base[3][:20, :100], base[4][:32, :320], base[5][:45, :77]]
+    image_list = [([[0, 0], [1, 0], [1, 1], [0, 1]], im) for im in imgs]
+    res = ob.get_text(env["chars"], 32, 320, env["models"]["fp32"], env["conv"], image_list, ob.default_ignore_char(),
+                      "greedy", 5, 4, 0.1, 0.5, 0.003, 0, "cuda")
+    sd = synth_sd
+    exp = []
+    for im in imgs:
+        best = None
+        for contrast in (0.0, 0.5):
+            x = R.align_collate_ref([im], 32, 320, contrast)
+            r = R.recognizer_predict_ref(sd, x, env["conv"].character, env["ign"], "greedy", 5)[0]
+            if best is None:
+                best = r
+                if r[1] >= 0.1:
+                    break
+            elif r[1] > best[1]:
+                best = r
+        exp.append(best)
+    assert [r[1] for r in res] == [e[0] for e in exp]
+    np.testing.assert_allclose([r[2] for r in res], [e[1] for e in exp], rtol=5e-3, atol=1e-9)

@@ -230,8 +230,12 @@ static void run_lstm_case(int B, int T, int steps, bool persistent = false) {
   CK(cudaMalloc(&d_sync, 64));
   LstmTcParams lp;
   memset(&lp, 0, sizeof(lp));
-  lp.tmH = p.tmA; lp.tmW = p.tmB; lp.xproj = d_xproj; lp.hseq = d_hseq; lp.sync = d_sync;
   lp.B = B; lp.T = T; lp.m_tiles = ceil_div(B, 128);
+  __nv_bfloat16* d_hx = nullptr;
+  const long long hx_rows = (long long)2 * lp.m_tiles * 2 * 8 * 128;
+  CK(cudaMalloc(&d_hx, hx_rows * 128)); CK(cudaMemset(d_hx, 0xff, hx_rows * 128));  // NaN-filled: stale reads would show
+  if (make_rows64_tmap(&lp.tmX, d_hx, hx_rows, 128)) { printf("[lstm] exchange map failed\n"); g_fail++; return; }
+  lp.tmW = p.tmB; lp.xproj = d_xproj; lp.hseq = d_hseq; lp.hx = d_hx; lp.sync = d_sync;
   long long* d_dbg = nullptr;
   CK(cudaMalloc(&d_dbg, 64 * 16 * 8)); CK(cudaMemset(d_dbg, 0, 64 * 16 * 8));
   lp.dbg = (persistent && getenv("LSTM_DBG")) ? d_dbg : nullptr;
