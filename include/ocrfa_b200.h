@@ -45,6 +45,8 @@ extern "C" {
 /* arithmetic of the contraction layers */
 #define OCRFA_PRECISION_FP32 0 /* CUDA-core fp32: logits within 1e-3 of the reference's fp32 path */
 #define OCRFA_PRECISION_BF16 1 /* tcgen05 bf16 inputs, fp32 accumulate: logits within 2e-2 */
+#define OCRFA_PRECISION_F16X3 2 /* tcgen05 fp16 hi/lo split operands, 3 products per term, fp32 accumulate: fp32-grade
+                                   logits (within 1e-3 of the reference) at 1/3 of the tensor-core rate */
 
 typedef struct ocrfa_handle ocrfa_handle;
 

@@ -208,6 +208,15 @@ __host__ __device__ __forceinline__ uint32_t make_idesc_bf16(uint32_t m, uint32_
   return d;
 }
 
+// Same, fp16 A and B (format code 0): used by the hi/lo split-precision mode.
+__host__ __device__ __forceinline__ uint32_t make_idesc_f16(uint32_t m, uint32_t n) {
+  uint32_t d = 0;
+  d |= 1u << 4;
+  d |= (n >> 3) << 17;
+  d |= (m >> 4) << 24;
+  return d;
+}
+
 // ---------------------------------------------------------------------------------------------
 // numeric helpers
 // ---------------------------------------------------------------------------------------------

@@ -55,16 +55,18 @@ struct ConvW {
   int cin_pad = 0;     // channels of the input buffer the tensor-core path reads (multiple of 64)
   int ds_cin = 0;      // > 0: fused downsample source channels (bf16 path)
   int ktotal = 0;      // K of the packed weight matrix
-  void* d_wgt = nullptr;   // bf16 [cout][ktotal] (tc) or float [cout][kh*kw*cin] (simt)
+  float out_scale = 1.f;   // split path: 2^-k undoing the power-of-two pre-scale of the fp16 hi/lo weights
+  void* d_wgt = nullptr;   // bf16 [cout][ktotal] (tc), fp16 hi/lo [cout][2*ktotal'] (split) or float [cout][kh*kw*cin] (simt)
   float* d_bias = nullptr;
 };
 
 struct LstmW {
-  void* d_wih = nullptr;    // [4096][512]  both directions, gate rows permuted to [tile][gate][16]
+  void* d_wih = nullptr;    // [4096][512]  both directions, gate rows permuted to [tile][gate][16] (fp32 / split paths)
   float* d_bih = nullptr;   // [4096]       b_ih + b_hh, same permutation
-  void* d_whh = nullptr;    // [4096][512]
+  void* d_whh = nullptr;    // fp32: [4096][512]; bf16: [4096][W_ih 512 | W_hh 512]; split: [4096][W_hh hi 512 | lo 512]
   void* d_wlin = nullptr;   // [512][1024]
   float* d_blin = nullptr;  // [512]
+  float s_wih = 1.f, s_whh = 1.f, s_wlin = 1.f;  // split path: output scales (2^-k) of the pre-scaled weights
 };
 
 struct WsLayout {
@@ -128,6 +130,9 @@ struct ocrfa_handle {
   std::vector<void*> allocs;
   int64_t launches = 0;
   bool bf16() const { return cfg.precision == OCRFA_PRECISION_BF16; }
+  bool split() const { return cfg.precision == OCRFA_PRECISION_F16X3; }  // fp16 hi/lo operands, three products
+  bool tc() const { return bf16() || split(); }                          // tcgen05 path (vs the CUDA-core fp32 path)
+  float s_pred = 1.f;
 };
 
 namespace {
@@ -148,7 +153,7 @@ WsLayout ws_layout(const ocrfa_handle* h, int B, int H, int W) {
   L.cstate = off; off += align_up((size_t)2 * B * 512 * 4, 1024);
   L.hh = off; off += align_up((size_t)2 * B * 2048 * 4, 1024);
   L.sync = off; off += 4096;  // group counters of the persistent LSTM launches (zeroed once per forward)
-  L.hx = off; off += (size_t)2 * 2 * 2 * 8 * 128 * 64 * 2;  // LSTM h exchange: 2 dirs x 2 m_tiles x 2 parities x 128 KB
+  L.hx = off; off += (size_t)2 * 2 * 2 * 16 * 128 * 64 * 2;  // LSTM h exchange: 2 dirs x 2 m_tiles x 2 parities x <= 16 slabs of 16 KB
   L.total = off;
   return L;
 }
@@ -166,6 +171,21 @@ int upload(ocrfa_handle* h, const std::vector<T>& v, void** out) {
   CUDA_TRY(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
   *out = d;
   return 0;
+}
+
+// Split-precision weight packing: w * 2^k = hi + lo (fp16 pair). k puts the largest |w| in [2^12, 2^13) so that the
+// lo halves of all weights within 2^-15 of the largest stay in fp16's normal range; the kernels multiply the fp32
+// accumulators by 2^-k (exact).
+int split_scale_exp(double max_abs) {
+  if (!(max_abs > 0.0) || !std::isfinite(max_abs)) return 0;
+  int e = 0;
+  std::frexp(max_abs, &e);  // max_abs = m * 2^e, m in [0.5, 1)
+  return 13 - e;
+}
+inline void split_f16_host(double v, __half* hi, __half* lo) {
+  const __half h = __float2half_rn((float)v);
+  *hi = h;
+  *lo = __float2half_rn((float)(v - (double)__half2float(h)));
 }
 
 // BN(eval) folded into the conv: y = conv(x) * s + (beta - mean * s), s = gamma / sqrt(var + eps)
@@ -204,7 +224,7 @@ int prep_conv(ocrfa_handle* h, const std::string& prefix, const std::string& con
   c.name = conv;
   c.cout = (int)w->shape[0]; c.cin = (int)w->shape[1];
   c.kh = kh; c.kw = kw; c.sh = sh; c.ph = ph; c.pw = pw;
-  const bool fuse_ds = !ds_conv.empty() && h->bf16();
+  const bool fuse_ds = !ds_conv.empty() && h->tc();
   if (fuse_ds) {
     rc = fold_bn(h, prefix + ds_conv, prefix + ds_bn, &dsc, &dsf, &dw);
     if (rc) return rc;
@@ -213,7 +233,38 @@ int prep_conv(ocrfa_handle* h, const std::string& prefix, const std::string& con
   std::vector<float> bias(c.cout);
   for (int o = 0; o < c.cout; ++o) bias[o] = (float)(sf[o] + (fuse_ds ? dsf[o] : 0.0));
   const int taps = kh * kw;
-  if (h->bf16()) {
+  if (h->split()) {
+    // [cout][tap][hi(cin_pad) | lo(cin_pad)] (+ [hi(ds_pad) | lo(ds_pad)] for the fused downsample), fp16, pre-scaled
+    c.cin_pad = ceil_div(c.cin, 64) * 64;
+    const int ds_pad = fuse_ds ? ceil_div(c.ds_cin, 64) * 64 : 0;
+    c.ktotal = 2 * (taps * c.cin_pad + ds_pad);
+    double mx = 0.0;
+    for (int o = 0; o < c.cout; ++o) {
+      for (size_t i = 0; i < (size_t)c.cin * taps; ++i) mx = std::max(mx, std::fabs((double)w->data[(size_t)o * c.cin * taps + i] * sc[o]));
+      if (fuse_ds)
+        for (int ci = 0; ci < c.ds_cin; ++ci) mx = std::max(mx, std::fabs((double)dw->data[(size_t)o * c.ds_cin + ci] * dsc[o]));
+    }
+    const int k = split_scale_exp(mx);
+    c.out_scale = (float)std::ldexp(1.0, -k);
+    std::vector<__half> pk((size_t)c.cout * c.ktotal, __float2half(0.f));
+    for (int o = 0; o < c.cout; ++o) {
+      __half* row = &pk[(size_t)o * c.ktotal];
+      for (int ci = 0; ci < c.cin; ++ci)
+        for (int r = 0; r < kh; ++r)
+          for (int s2 = 0; s2 < kw; ++s2) {
+            const double v = std::ldexp((double)w->data[(((size_t)o * c.cin + ci) * kh + r) * kw + s2] * sc[o], k);
+            const size_t base = (size_t)(r * kw + s2) * 2 * c.cin_pad;
+            split_f16_host(v, &row[base + ci], &row[base + c.cin_pad + ci]);
+          }
+      if (fuse_ds)
+        for (int ci = 0; ci < c.ds_cin; ++ci) {
+          const double v = std::ldexp((double)dw->data[(size_t)o * c.ds_cin + ci] * dsc[o], k);
+          const size_t base = (size_t)taps * 2 * c.cin_pad;
+          split_f16_host(v, &row[base + ci], &row[base + ds_pad + ci]);
+        }
+    }
+    rc = upload(h, pk, &c.d_wgt);
+  } else if (h->bf16()) {
     c.cin_pad = ceil_div(c.cin, 64) * 64;
     const int ds_pad = fuse_ds ? ceil_div(c.ds_cin, 64) * 64 : 0;
     c.ktotal = taps * c.cin_pad + ds_pad;
@@ -254,9 +305,20 @@ int prep_conv(ocrfa_handle* h, const std::string& prefix, const std::string& con
 
 // Linear layers as 1x1 "convs": weight [out][in] (+ optional row permutation), bias.
 int prep_linear(ocrfa_handle* h, const std::vector<float>& w, const std::vector<float>& b, int out, int in, void** d_w,
-                float** d_b) {
+                float** d_b, float* out_scale = nullptr) {
   int rc;
-  if (h->bf16()) {
+  if (h->split()) {
+    // [out][hi(in) | lo(in)] fp16, pre-scaled by 2^k
+    double mx = 0.0;
+    for (float v : w) mx = std::max(mx, std::fabs((double)v));
+    const int k = split_scale_exp(mx);
+    if (out_scale) *out_scale = (float)std::ldexp(1.0, -k);
+    std::vector<__half> pk((size_t)out * 2 * in);
+    for (int o = 0; o < out; ++o)
+      for (int i = 0; i < in; ++i)
+        split_f16_host(std::ldexp((double)w[(size_t)o * in + i], k), &pk[(size_t)o * 2 * in + i], &pk[(size_t)o * 2 * in + in + i]);
+    rc = upload(h, pk, d_w);
+  } else if (h->bf16()) {
     std::vector<__nv_bfloat16> pk(w.size());
     for (size_t i = 0; i < w.size(); ++i) pk[i] = __float2bfloat16(w[i]);
     rc = upload(h, pk, d_w);
@@ -299,16 +361,28 @@ int prep_lstm(ocrfa_handle* h, int li) {
     }
   }
   LstmW& L = h->lstm[li];
-  int rc = prep_linear(h, wih, bsum, 4096, 512, &L.d_wih, &L.d_bih);
-  if (rc) return rc;
+  int rc;
   std::vector<float> zero_b(1, 0.f);
   float* dummy = nullptr;
-  rc = prep_linear(h, whh, zero_b, 4096, 512, &L.d_whh, &dummy);
-  if (rc) return rc;
+  if (h->bf16()) {
+    // fused input projection: resident weights of the persistent kernel are [W_ih | W_hh] (K = 1024)
+    std::vector<float> wcat((size_t)4096 * 1024);
+    for (int r = 0; r < 4096; ++r) {
+      memcpy(&wcat[(size_t)r * 1024], &wih[(size_t)r * 512], 512 * sizeof(float));
+      memcpy(&wcat[(size_t)r * 1024 + 512], &whh[(size_t)r * 512], 512 * sizeof(float));
+    }
+    rc = prep_linear(h, wcat, bsum, 4096, 1024, &L.d_whh, &L.d_bih);
+    if (rc) return rc;
+  } else {
+    rc = prep_linear(h, wih, bsum, 4096, 512, &L.d_wih, &L.d_bih, &L.s_wih);
+    if (rc) return rc;
+    rc = prep_linear(h, whh, zero_b, 4096, 512, &L.d_whh, &dummy, &L.s_whh);  // split: [hi 512 | lo 512] per row
+    if (rc) return rc;
+  }
   const HostTensor* lw = find(h, pre + "linear.weight");
   const HostTensor* lb = find(h, pre + "linear.bias");
   if (!lw || !lb || lw->data.size() != (size_t)512 * 1024) return fail(OCRFA_ERR_WEIGHTS, "missing %slinear", pre.c_str());
-  return prep_linear(h, lw->data, lb->data, 512, 1024, &L.d_wlin, &L.d_blin);
+  return prep_linear(h, lw->data, lb->data, 512, 1024, &L.d_wlin, &L.d_blin, &L.s_wlin);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -344,7 +418,8 @@ int run_conv_tc(ocrfa_handle* h, const ConvW& cw, const Act& in, const Act* ds_s
                 bool relu, bool out_f32, int ldo, cudaStream_t st) {
   IgemmTcParams p;
   ConvGeom g{in.n, in.h, in.w, cw.cin, cw.cout, cw.kh, cw.kw, cw.sh, cw.ph, cw.pw};
-  int rc = plan_conv(&p, g, in.p, in.c, cw.d_wgt);
+  const bool split = h->split();
+  int rc = plan_conv(&p, g, in.p, in.c, cw.d_wgt, nullptr, split);
   if (rc) return fail(OCRFA_ERR_CUDA, "plan_conv(%s) failed: %d", cw.name.c_str(), rc);
   if (cw.ds_cin) {
     if (!ds_src) return fail(OCRFA_ERR_STATE, "%s expects a fused downsample source", cw.name.c_str());
@@ -352,8 +427,14 @@ int run_conv_tc(ocrfa_handle* h, const ConvW& cw, const Act& in, const Act* ds_s
     if (rc) return fail(OCRFA_ERR_CUDA, "plan_add_source(%s) failed: %d", cw.name.c_str(), rc);
   }
   p.bias = cw.d_bias;
-  p.residual = (const __nv_bfloat16*)residual; p.ldr = cw.cout;
+  p.residual = residual; p.ldr = cw.cout;
   p.out = out; p.ldo = ldo; p.out_f32 = out_f32 ? 1 : 0; p.relu = relu ? 1 : 0;
+  if (split) {
+    // fp16 hi/lo pixels: [hi(C) | lo(C)]
+    p.out_scale = cw.out_scale;
+    p.ldr = 2 * cw.cout; p.res_lo = cw.cout;
+    if (!out_f32) { p.ldo = 2 * ldo; p.out_lo = ldo; }
+  }
   // algorithmic FLOPs: 2 * output pixels * Cout * real K (channel padding and ragged-tile rows not counted)
   const double flops = 2.0 * (double)in.n * p.h_out * p.w_out * cw.cout * ((double)cw.kh * cw.kw * cw.cin + cw.ds_cin);
   LaunchScope ls(h, kClsIgemmTc, flops, st);
@@ -389,6 +470,17 @@ int run_pool(ocrfa_handle* h, const Act& in, void* out, int sh, int sw, int pw, 
   return 0;
 }
 
+int run_pool_split(ocrfa_handle* h, const Act& in, void* out, int sh, int sw, int pw, int* ho, int* wo, cudaStream_t st) {
+  *ho = (in.h - 2) / sh + 1;
+  *wo = (in.w + 2 * pw - 2) / sw + 1;
+  const long long total = (long long)in.n * *ho * *wo * (in.c / 8);
+  LaunchScope ls(h, kClsPool, 0.0, st);
+  maxpool2x2_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const __half*)in.p, (__half*)out, in.n, in.h,
+                                                                           in.w, in.c, sh, sw, pw, *ho, *wo);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------------------
@@ -418,6 +510,8 @@ int forward_impl(ocrfa_handle* h, const float* d_x, const uint8_t* d_u8, const i
   if (ws_bytes < L.total) return fail(OCRFA_ERR_WORKSPACE, "workspace too small: %zu < %zu", ws_bytes, L.total);
   if (((uintptr_t)d_ws & 1023) != 0) return fail(OCRFA_ERR_WORKSPACE, "workspace must be 1024-byte aligned");
   const bool bf = h->bf16();
+  const bool sp = h->split();
+  const bool tc = bf || sp;
   uint8_t* ws = (uint8_t*)d_ws;
   BufPool pool;
   for (int i = 0; i < 4; ++i) pool.buf[i] = ws + L.act[i];
@@ -427,7 +521,7 @@ int forward_impl(ocrfa_handle* h, const float* d_x, const uint8_t* d_u8, const i
     auto it = h->convs.find(name);
     if (it == h->convs.end()) return fail(OCRFA_ERR_STATE, "conv %s not prepared", name);
     const ConvW& cw = it->second;
-    if (bf) return run_conv_tc(h, cw, in, ds_src, residual, out, relu, false, cw.cout, st);
+    if (tc) return run_conv_tc(h, cw, in, ds_src, residual, out, relu, false, cw.cout, st);
     return run_conv_simt(h, (const float*)cw.d_wgt, cw.d_bias, in.p, in.c, in.n, in.h, in.w, cw.cin, cw.cout, cw.kh,
                          cw.kw, cw.sh, cw.ph, cw.pw, residual, out, cw.cout, relu, st);
   };
@@ -457,7 +551,7 @@ int forward_impl(ocrfa_handle* h, const float* d_x, const uint8_t* d_u8, const i
     if (r) return r;
     Act ta{t, a->n, ho, wo, co};
     void* o = pool.get();
-    if (has_ds && !bf) {
+    if (has_ds && !tc) {
       void* rs = pool.get();
       r = conv((pre + "downsample.0").c_str(), *a, nullptr, nullptr, rs, false);
       if (r) return r;
@@ -477,7 +571,8 @@ int forward_impl(ocrfa_handle* h, const float* d_x, const uint8_t* d_u8, const i
   auto pool_step = [&](int sh, int sw, int pw, Act* a) -> int {
     void* o = pool.get();
     int ho, wo;
-    int r = bf ? run_pool<__nv_bfloat16>(h, *a, o, sh, sw, pw, &ho, &wo, st) : run_pool<float>(h, *a, o, sh, sw, pw, &ho, &wo, st);
+    int r = sp ? run_pool_split(h, *a, o, sh, sw, pw, &ho, &wo, st)
+               : bf ? run_pool<__nv_bfloat16>(h, *a, o, sh, sw, pw, &ho, &wo, st) : run_pool<float>(h, *a, o, sh, sw, pw, &ho, &wo, st);
     if (r) return r;
     pool.put(a->p);
     *a = Act{o, a->n, ho, wo, a->c};
@@ -489,17 +584,20 @@ int forward_impl(ocrfa_handle* h, const float* d_x, const uint8_t* d_u8, const i
   if (d_feat_in) {
     const long long total = (long long)B * T * 512;
     LaunchScope ls(h, kClsPool, 0.0, st);
-    if (bf) cvt_from_f32_kernel<__nv_bfloat16><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_feat_in, (__nv_bfloat16*)feat, total);
+    if (sp) cvt_f32_to_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_feat_in, (__half*)feat, (long long)B * T, 512);
+    else if (bf) cvt_from_f32_kernel<__nv_bfloat16><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_feat_in, (__nv_bfloat16*)feat, total);
     else cvt_from_f32_kernel<float><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_feat_in, (float*)feat, total);
     CUDA_TRY(cudaGetLastError());
   } else {
   // ---- stem: conv0_1 + bn0_1 + relu (blocks.py:341-347)
-  Act a{pool.get(), B, H, W, bf ? 64 : 32};
+  Act a{pool.get(), B, H, W, tc ? 64 : 32};
   {
     const long long pix = (long long)B * H * W;
     const unsigned grid = (unsigned)((pix + 255) / 256);
     LaunchScope ls(h, kClsStem, 2.0 * (double)pix * 32 * 9, st);
-    if (bf)
+    if (sp)
+      stem_conv_kernel<__half, 128><<<grid, 256, 0, st>>>(d_x, d_u8, d_widths, h->d_stem_w, h->d_stem_b, (__half*)a.p, B, H, W);
+    else if (bf)
       stem_conv_kernel<__nv_bfloat16, 64><<<grid, 256, 0, st>>>(d_x, d_u8, d_widths, h->d_stem_w, h->d_stem_b,
                                                                  (__nv_bfloat16*)a.p, B, H, W);
     else
@@ -531,7 +629,8 @@ int forward_impl(ocrfa_handle* h, const float* d_x, const uint8_t* d_u8, const i
     feat = ws + L.feat;
     const long long total = (long long)B * T * 512;
     LaunchScope ls(h, kClsPool, 0.0, st);
-    if (bf) mean_h_kernel<__nv_bfloat16><<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)a.p, (__nv_bfloat16*)feat, B, a.h, T, 512);
+    if (sp) mean_h_split_kernel<<<(unsigned)((total / 8 + 255) / 256), 256, 0, st>>>((const __half*)a.p, (__half*)feat, B, a.h, T, 512);
+    else if (bf) mean_h_kernel<__nv_bfloat16><<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)a.p, (__nv_bfloat16*)feat, B, a.h, T, 512);
     else mean_h_kernel<float><<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const float*)a.p, (float*)feat, B, a.h, T, 512);
     CUDA_TRY(cudaGetLastError());
   }
@@ -540,7 +639,8 @@ int forward_impl(ocrfa_handle* h, const float* d_x, const uint8_t* d_u8, const i
     const long long total = (long long)B * T * 512;
     {
     LaunchScope ls(h, kClsPool, 0.0, st);
-    if (bf) cvt_to_f32_kernel<__nv_bfloat16><<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)feat, d_feat_out, total);
+    if (sp) cvt_split_to_f32_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const __half*)feat, d_feat_out, (long long)B * T, 512);
+    else if (bf) cvt_to_f32_kernel<__nv_bfloat16><<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)feat, d_feat_out, total);
     else cvt_to_f32_kernel<float><<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const float*)feat, d_feat_out, total);
     CUDA_TRY(cudaGetLastError());
     }
@@ -548,7 +648,7 @@ int forward_impl(ocrfa_handle* h, const float* d_x, const uint8_t* d_u8, const i
   }
 
   // ---- 2 x BidirectionalLSTM (blocks.py:92-102)
-  if (bf) CUDA_TRY(cudaMemsetAsync(ws + L.sync, 0, 4096, st));
+  if (tc) CUDA_TRY(cudaMemsetAsync(ws + L.sync, 0, 4096, st));
   const int rows = B * T;
   float* xproj = (float*)(ws + L.xproj);
   void* hseq = ws + L.hseq;
@@ -558,36 +658,45 @@ int forward_impl(ocrfa_handle* h, const float* d_x, const uint8_t* d_u8, const i
   for (int li = 0; li < 2; ++li) {
     const LstmW& lw = h->lstm[li];
     void* seq_out = ws + L.seq[li];
-    if (bf) {
-      // input projection for both directions: [rows,512] x [4096,512]^T + (b_ih + b_hh) -> fp32
-      ConvW xp; xp.name = "lstm.xproj"; xp.cin = 512; xp.cout = 4096; xp.kh = xp.kw = 1; xp.sh = 1; xp.cin_pad = 512;
-      xp.ktotal = 512; xp.d_wgt = lw.d_wih; xp.d_bias = lw.d_bih;
-      if ((rc = run_conv_tc(h, xp, Act{seq_in, 1, 1, rows, 512}, nullptr, nullptr, xproj, false, true, 4096, st))) return rc;
-      // recurrence: ONE persistent launch per 256-line slice walks all T steps of both directions (lstm_tc.cuh)
+    if (tc) {
+      if (sp) {
+        // split path: input projection for both directions as one split igemm:
+        // [rows,512] x [4096,512]^T + (b_ih + b_hh) -> fp32 gate pre-activations
+        ConvW xp; xp.name = "lstm.xproj"; xp.cin = 512; xp.cout = 4096; xp.kh = xp.kw = 1; xp.sh = 1; xp.cin_pad = 512;
+        xp.ktotal = 1024; xp.d_wgt = lw.d_wih; xp.d_bias = lw.d_bih; xp.out_scale = lw.s_wih;
+        if ((rc = run_conv_tc(h, xp, Act{seq_in, 1, 1, rows, 512}, nullptr, nullptr, xproj, false, true, 4096, st))) return rc;
+      }
+      // recurrence: ONE persistent launch per 256-line slice walks all T steps of both directions (lstm_tc.cuh);
+      // on the bf16 path the input projection is fused into it (K = [x_t | h_{t-1}])
+      const int mode = sp ? kLstmF16Split : kLstmBf16FusedX;
+      const size_t hs_row = sp ? 2048 : 1024;  // elements per (b, t) row of the h sequence
       int slice = 0;
       for (int b0 = 0; b0 < B; b0 += 256, ++slice) {
         const int nb = B - b0 < 256 ? B - b0 : 256;
         LstmTcParams lp;
         memset(&lp, 0, sizeof(lp));
-        __nv_bfloat16* hs = (__nv_bfloat16*)hseq + (size_t)b0 * T * 1024;
         lp.m_tiles = ceil_div(nb, 128);
-        lp.hx = (__nv_bfloat16*)(ws + L.hx);
-        int r2 = make_rows64_tmap(&lp.tmX, lp.hx, (long long)2 * lp.m_tiles * 2 * 8 * 128, 128);
-        if (r2 == 0) r2 = make_wgt_tmap(&lp.tmW, lw.d_whh, 512, 4096, 64);
+        lp.hx = ws + L.hx;
+        int r2 = make_rows64_tmap(&lp.tmX, lp.hx, lstm_hx_rows(mode, lp.m_tiles), 128);
+        if (r2 == 0) r2 = make_wgt_tmap(&lp.tmW, lw.d_whh, 1024, 4096, 64);
+        if (r2 == 0 && !sp)
+          r2 = make_act_tmap(&lp.tmS, (const __nv_bfloat16*)seq_in + (size_t)b0 * T * 512, 512, T, 1, nb, 1, 1, 128, 1);
         if (r2) return fail(OCRFA_ERR_CUDA, "LSTM tensor map failed: %d", r2);
-        lp.xproj = xproj + (size_t)b0 * T * 4096;
-        lp.hseq = hs;
-        lp.m_tiles = ceil_div(nb, 128);
+        lp.xproj = sp ? xproj + (size_t)b0 * T * 4096 : nullptr;
+        lp.bias = lw.d_bih;
+        lp.hseq = (uint16_t*)hseq + (size_t)b0 * T * hs_row;
+        lp.acc_scale = lw.s_whh;
         const int ctr = (li * 64 + slice) * 4;
         if (ctr + 4 > 1024) return fail(OCRFA_ERR_ARG, "batch too large for the LSTM counter table");
         lp.sync = (unsigned int*)(ws + L.sync) + ctr;
         lp.dbg = nullptr;
         lp.B = nb; lp.T = T;
-        LaunchScope ls(h, kClsLstmTc, 2.0 * 2.0 * nb * 2048.0 * 512.0 * (T - 1), st);
-        CUDA_TRY(lstm_tc_launch(lp, st));
+        const double kx = sp ? 0.0 : 512.0 * T;  // fused input projection
+        LaunchScope ls(h, kClsLstmTc, 2.0 * 2.0 * nb * 2048.0 * (512.0 * (T - 1) + kx), st);
+        CUDA_TRY(lstm_tc_launch(lp, mode, st));
       }
       ConvW lin; lin.name = "lstm.linear"; lin.cin = 1024; lin.cout = 512; lin.kh = lin.kw = 1; lin.sh = 1; lin.cin_pad = 1024;
-      lin.ktotal = 1024; lin.d_wgt = lw.d_wlin; lin.d_bias = lw.d_blin;
+      lin.ktotal = sp ? 2048 : 1024; lin.d_wgt = lw.d_wlin; lin.d_bias = lw.d_blin; lin.out_scale = lw.s_wlin;
       if ((rc = run_conv_tc(h, lin, Act{hseq, 1, 1, rows, 1024}, nullptr, nullptr, seq_out, false, false, 512, st))) return rc;
     } else {
       if ((rc = run_conv_simt(h, (const float*)lw.d_wih, lw.d_bih, seq_in, 512, 1, 1, rows, 512, 4096, 1, 1, 1, 0, 0,
@@ -614,9 +723,9 @@ int forward_impl(ocrfa_handle* h, const float* d_x, const uint8_t* d_u8, const i
 
   // ---- Prediction: Linear(512 -> num_class) (blocks.py:438, 441)
   const int C = h->cfg.num_class;
-  if (bf) {
-    ConvW pr; pr.name = "prediction"; pr.cin = 512; pr.cout = C; pr.kh = pr.kw = 1; pr.sh = 1; pr.cin_pad = 512; pr.ktotal = 512;
-    pr.d_wgt = h->d_pred_w; pr.d_bias = h->d_pred_b;
+  if (tc) {
+    ConvW pr; pr.name = "prediction"; pr.cin = 512; pr.cout = C; pr.kh = pr.kw = 1; pr.sh = 1; pr.cin_pad = 512;
+    pr.ktotal = sp ? 1024 : 512; pr.d_wgt = h->d_pred_w; pr.d_bias = h->d_pred_b; pr.out_scale = h->s_pred;
     if ((rc = run_conv_tc(h, pr, Act{seq_in, 1, 1, rows, 512}, nullptr, nullptr, d_logits, false, true, C, st))) return rc;
   } else {
     if ((rc = run_conv_simt(h, (const float*)h->d_pred_w, h->d_pred_b, seq_in, 512, 1, 1, rows, 512, C, 1, 1, 1, 0, 0, nullptr,
@@ -674,7 +783,8 @@ int ocrfa_create(const ocrfa_config* cfg, ocrfa_handle** out) {
   if (cfg->input_channel != 1 || cfg->output_channel != 512 || cfg->hidden_size != 512)
     return fail(OCRFA_ERR_ARG, "only the reference's generation1 network (1, 512, 512) is supported");
   if (cfg->num_class < 2 || cfg->num_class > 256) return fail(OCRFA_ERR_ARG, "num_class must be in [2, 256]");
-  if (cfg->precision != OCRFA_PRECISION_FP32 && cfg->precision != OCRFA_PRECISION_BF16)
+  if (cfg->precision != OCRFA_PRECISION_FP32 && cfg->precision != OCRFA_PRECISION_BF16 &&
+      cfg->precision != OCRFA_PRECISION_F16X3)
     return fail(OCRFA_ERR_ARG, "unknown precision %d", cfg->precision);
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= cfg->device)
@@ -748,7 +858,7 @@ int ocrfa_finalize_weights(ocrfa_handle* h, void* stream) {
       if ((rc = prep_conv(h, "", pre + "conv2", pre + "bn2", 3, 3, 1, 1, 1, has_ds ? pre + "downsample.0" : "",
                           has_ds ? pre + "downsample.1" : "")))
         return rc;
-      if (has_ds && !h->bf16())
+      if (has_ds && !h->tc())
         if ((rc = prep_conv(h, "", pre + "downsample.0", pre + "downsample.1", 1, 1, 1, 0, 0, "", ""))) return rc;
     }
     if (li < 4) {
@@ -765,11 +875,12 @@ int ocrfa_finalize_weights(ocrfa_handle* h, void* stream) {
   const HostTensor* pb = find(h, "Prediction.bias");
   if (!pw || !pb || pw->data.size() != (size_t)h->cfg.num_class * 512 || pb->data.size() != (size_t)h->cfg.num_class)
     return fail(OCRFA_ERR_WEIGHTS, "Prediction weights missing or not [%d,512]", h->cfg.num_class);
-  if ((rc = prep_linear(h, pw->data, pb->data, h->cfg.num_class, 512, &h->d_pred_w, &h->d_pred_b))) return rc;
-  if (h->bf16()) {
+  if ((rc = prep_linear(h, pw->data, pb->data, h->cfg.num_class, 512, &h->d_pred_w, &h->d_pred_b, &h->s_pred))) return rc;
+  if (h->tc()) {
     CUDA_TRY(cudaFuncSetAttribute(igemm_tc_kernel<kModeStd>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CUDA_TRY(cudaFuncSetAttribute(igemm_tc_kernel<kModeLstm>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CUDA_TRY(cudaFuncSetAttribute(lstm_tc_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lstm_tc_smem_bytes()));
+    CUDA_TRY(cudaFuncSetAttribute(igemm_tc_kernel<kModeSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(lstm_tc_persistent_kernel<kLstmBf16FusedX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lstm_tc_smem_bytes()));
+    CUDA_TRY(cudaFuncSetAttribute(lstm_tc_persistent_kernel<kLstmF16Split>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lstm_tc_smem_bytes()));
     if (!get_tmap_encode()) return fail(OCRFA_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
   }
   CUDA_TRY(cudaDeviceSynchronize());
@@ -954,7 +1065,7 @@ int recognize_device_impl(ocrfa_handle* h, const uint8_t* d_img, const int32_t* 
                           const uint8_t* d_ignore_mask, int decoder, int beam_width, int32_t* d_labels, int32_t* d_len,
                           double* d_conf, void* d_ws, size_t ws_bytes, cudaStream_t st) {
   if (!h) return fail(OCRFA_ERR_ARG, "null handle");
-  if (!h->graphs_enabled || h->prof.mask != 0 || !h->bf16())
+  if (!h->graphs_enabled || h->prof.mask != 0 || !h->tc())
     return recognize_device_body(h, d_img, d_widths, B, H, W, d_ignore_mask, decoder, beam_width, d_labels, d_len, d_conf,
                                  d_ws, ws_bytes, st);
   const GraphKey key{d_img, d_widths, d_ignore_mask, d_labels, d_len, d_conf, d_ws, ws_bytes, B, H, W, decoder, beam_width};

@@ -53,8 +53,10 @@ inline int choose_block_n(int cout) {
 // Fills geometry-dependent fields of `p` (maps, taps, tiles). Epilogue pointers are left to the caller.
 // `in` : NHWC bf16 [n][h_in][w_in][cin_buf] (cin_buf >= cin, multiple of 64: stem output is channel-padded)
 // `wgt`: [cout][kh*kw*cin_pad] bf16 with K ordered (tap-major, channel-minor), cin_pad = round_up(cin, 64)
+// split = true: fp16 hi/lo operands - `in` pixels are [hi(cin_buf) | lo(cin_buf)], the weight matrix carries
+// [hi(cin_pad) | lo(cin_pad)] per tap (K doubles).
 inline int plan_conv(IgemmTcParams* p, const ConvGeom& g, const void* in, int cin_buf, const void* wgt,
-                     const TileShape* forced_tile = nullptr) {
+                     const TileShape* forced_tile = nullptr, bool split = false) {
   std::memset(p, 0, sizeof(*p));
   const int ho = g.h_out(), wo = g.w_out();
   const int cin_pad = ceil_div(g.cin, 64) * 64;
@@ -69,10 +71,14 @@ inline int plan_conv(IgemmTcParams* p, const ConvGeom& g, const void* in, int ci
   p->tiles_n = ceil_div(g.n, t.tn);
   p->n_img = g.n; p->h_out = ho; p->w_out = wo;
   p->block_n = choose_block_n(g.cout);
+  if (split) p->block_n = ceil_div(p->block_n, 64) * 64;  // the split epilogue halves a tile in 32-column groups
   p->n_tiles = ceil_div(g.cout, p->block_n);
   p->n_valid = g.cout;
   p->kchunks = cin_pad / 64;
   p->kchunks2 = 0;
+  p->split = split ? 1 : 0;
+  p->a_lo = cin_buf;
+  p->out_scale = 1.0f;
   igemm_tc_smem_bytes(p->block_n, &p->num_stages);
   int nt = 0;
   for (int r = 0; r < g.kh; ++r)
@@ -85,15 +91,17 @@ inline int plan_conv(IgemmTcParams* p, const ConvGeom& g, const void* in, int ci
     }
   p->num_taps = nt;
   const int R = g.sh;
-  int rc = make_act_tmap(&p->tmA, in, cin_buf, g.w_in, R, g.h_in / R, g.n, t.tw, t.th, t.tn);
+  const int km = split ? 2 : 1;
+  int rc = make_act_tmap(&p->tmA, in, km * cin_buf, g.w_in, R, g.h_in / R, g.n, t.tw, t.th, t.tn);
   if (rc) return rc;
   p->tmA2 = p->tmA;
-  rc = make_wgt_tmap(&p->tmB, wgt, g.kh * g.kw * cin_pad, g.cout, p->block_n);
+  rc = make_wgt_tmap(&p->tmB, wgt, km * g.kh * g.kw * cin_pad, g.cout, p->block_n);
   return rc;
 }
 
 // Appends a fused 1x1 (downsample) source: extra K slabs read from `in2` [n][h_out][w_out][cin2_buf].
-// The weight matrix must carry cin2_pad extra K columns after the main taps.
+// The weight matrix must carry cin2_pad (split: 2 * cin2_pad) extra K columns after the main taps; `ktotal` is the
+// full K of the weight matrix.
 inline int plan_add_source(IgemmTcParams* p, const void* in2, int cin2, int cin2_buf, const void* wgt, int ktotal,
                            int cout) {
   if (p->num_taps >= kTcMaxTaps) return -6;
@@ -101,7 +109,8 @@ inline int plan_add_source(IgemmTcParams* p, const void* in2, int cin2, int cin2
   TapDesc& d = p->taps[p->num_taps++];
   d.src = 1; d.dw = 0; d.dr = 0; d.dh = 0;
   p->kchunks2 = cin2_pad / 64;
-  int rc = make_act_tmap(&p->tmA2, in2, cin2_buf, p->w_out, 1, p->h_out, p->n_img, p->tw, p->th, p->tn);
+  p->a_lo2 = cin2_buf;
+  int rc = make_act_tmap(&p->tmA2, in2, (p->split ? 2 : 1) * cin2_buf, p->w_out, 1, p->h_out, p->n_img, p->tw, p->th, p->tn);
   if (rc) return rc;
   return make_wgt_tmap(&p->tmB, wgt, ktotal, cout, p->block_n);
 }

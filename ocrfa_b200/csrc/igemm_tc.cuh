@@ -13,8 +13,18 @@
 // K=16) with the accumulator in TMEM; TMEM is double-buffered so the epilogue of tile i overlaps the
 // MMAs of tile i+1. Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..5 =
 // epilogue (TMEM -> registers -> bias/residual/ReLU -> global).
+//
+// Split-precision mode (IgemmTcParams::split): every operand is an fp16 hi/lo pair (x = hi + lo, 22 significant
+// bits; activations NHWC [hi(C) | lo(C)] per pixel, weights [Cout][tap][hi(C) | lo(C)] pre-scaled by a power of
+// two) and every K chunk is multiplied three times - hi.hi + lo.hi + hi.lo: fp32-grade results (the dropped lo.lo
+// term is ~2^-22) at one third of the tensor-core rate. Because the tensor core's fp32 accumulate TRUNCATES (a bias
+// that grows with the length and magnitude of the running sum - measured: error linear in K), the split kernel
+// (kModeSplit, 8 epilogue warps) accumulates a tile in chunks: all lo.hi / hi.lo products first (small), then the
+// hi.hi K blocks two at a time into alternating TMEM buffers that the epilogue warps sum in registers with
+// round-to-nearest fp32.
 #pragma once
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace ocrfa {
@@ -23,10 +33,12 @@ constexpr int kTcBlockM = 128;
 constexpr int kTcBlockK = 64;
 constexpr int kTcMaxStages = 8;
 constexpr int kTcMaxTaps = 10;
-constexpr int kTcThreads = 192;
+constexpr int kTcThreads = 192;       // bf16 kernel: producer + MMA + 4 epilogue warps
+constexpr int kTcThreadsSplit = 320;  // split kernel: producer + MMA + 8 epilogue warps (register accumulators)
+constexpr int kTcSplitChunkKb = 2;    // split kernel: hi.hi K blocks per TMEM accumulation chunk
 constexpr int kTcTmemCols = 512;
 
-enum IgemmMode : int { kModeStd = 0, kModeLstm = 1 };
+enum IgemmMode : int { kModeStd = 0, kModeSplit = 1 };
 
 struct TapDesc {
   int16_t dw, dr, dh, src;  // coordinate offsets in W, R (row-parity dim), H; src selects tmA (0) / tmA2 (1)
@@ -51,19 +63,143 @@ struct alignas(64) IgemmTcParams {
   int out_f32;
   int ldo;       // output row stride (elements)
   int ldr;       // residual row stride (elements)
+  int split;     // 1: fp16 hi/lo operands, three products per K chunk (see the header comment)
+  int a_lo;      // split: channel offset of the lo half inside source 0's pixel (= its channel count)
+  int a_lo2;     // ... inside source 1's pixel
+  int out_lo;    // split, !out_f32: channel offset of the lo half inside the output pixel (ldo = 2 * out_lo)
+  int res_lo;    // split: channel offset of the lo half inside the residual pixel (ldr = 2 * res_lo)
+  float out_scale;  // split: accumulators are multiplied by this power of two (undoes the weight pre-scale)
   const float* bias;              // [n_valid] fp32 or nullptr
-  const __nv_bfloat16* residual;  // NHWC bf16 or nullptr
-  void* out;                      // NHWC bf16 (or fp32 when out_f32)
-  // --- LSTM step mode (kModeLstm): A = h sequence [B][T][1024] bf16, B = permuted W_hh [2*2048][512]
-  int lstm_T;
-  int lstm_step;                  // 0..T-1 (forward walks t=step, backward walks t=T-1-step)
-  const float* lstm_xproj;        // [B*T][4096] fp32, gate pre-activations from the input projection
-  float* lstm_c;                  // [2][B][512] fp32 cell state (in/out)
-  __nv_bfloat16* lstm_hseq;       // [B][T][1024] bf16 (fwd | bwd)
+  const void* residual;           // NHWC bf16 (split: fp16 hi/lo) or nullptr
+  void* out;                      // NHWC bf16 (split: fp16 hi/lo; fp32 when out_f32)
 };
 
+// Epilogue tail shared by both kernels: 32 consecutive output channels of one pixel, fp32 accumulators in f[]
+// -> (split: x out_scale) + bias + residual -> ReLU -> store (bf16 / fp16 hi|lo / fp32).
+__device__ __forceinline__ void igemm_finish32(const IgemmTcParams& p, float (&f)[32], size_t pix, int col0) {
+  const bool full = (col0 + 32 <= p.n_valid);
+  if (p.split) {
+    const float sc = p.out_scale;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] *= sc;
+  }
+  if (p.bias != nullptr) {
+    if (full) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
+        f[i] += b4.x; f[i + 1] += b4.y; f[i + 2] += b4.z; f[i + 3] += b4.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i < p.n_valid) f[i] += __ldg(p.bias + col0 + i);
+    }
+  }
+  if (p.residual != nullptr && p.split) {
+    // fp16 hi/lo residual: exact sum of the pair in fp32
+    const __half* rp = reinterpret_cast<const __half*>(p.residual) + pix * p.ldr + col0;
+    if (full) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        const uint4 rh = __ldg(reinterpret_cast<const uint4*>(rp + i));
+        const uint4 rl = __ldg(reinterpret_cast<const uint4*>(rp + p.res_lo + i));
+        const uint32_t hw[4] = {rh.x, rh.y, rh.z, rh.w}, lw[4] = {rl.x, rl.y, rl.z, rl.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 hv = __half22float2(*reinterpret_cast<const __half2*>(&hw[j]));
+          const float2 lv = __half22float2(*reinterpret_cast<const __half2*>(&lw[j]));
+          f[i + 2 * j] += hv.x + lv.x;
+          f[i + 2 * j + 1] += hv.y + lv.y;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i < p.n_valid) f[i] += __half2float(rp[i]) + __half2float(rp[p.res_lo + i]);
+    }
+  } else if (p.residual != nullptr) {
+    const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + pix * p.ldr + col0;
+    if (full) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        const uint4 r4 = __ldg(reinterpret_cast<const uint4*>(rp + i));
+        f[i] += bf16lo_to_f32(r4.x);     f[i + 1] += bf16hi_to_f32(r4.x);
+        f[i + 2] += bf16lo_to_f32(r4.y); f[i + 3] += bf16hi_to_f32(r4.y);
+        f[i + 4] += bf16lo_to_f32(r4.z); f[i + 5] += bf16hi_to_f32(r4.z);
+        f[i + 6] += bf16lo_to_f32(r4.w); f[i + 7] += bf16hi_to_f32(r4.w);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i < p.n_valid) f[i] += __bfloat162float(rp[i]);
+    }
+  }
+  if (p.relu) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.0f);
+  }
+  if (p.out_f32) {
+    float* op = reinterpret_cast<float*>(p.out) + pix * p.ldo + col0;
+    if (full && (p.ldo & 3) == 0) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 4)
+        *reinterpret_cast<float4*>(op + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i < p.n_valid) op[i] = f[i];
+    }
+  } else if (p.split) {
+    __half* op = reinterpret_cast<__half*>(p.out) + pix * p.ldo + col0;
+    float lo[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float hv = __half2float(__float2half_rn(f[i]));
+      lo[i] = f[i] - hv;
+      f[i] = hv;
+    }
+    if (full) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        uint4 o, l;
+        __half2 t;
+        t = __floats2half2_rn(f[i], f[i + 1]);       o.x = *reinterpret_cast<uint32_t*>(&t);
+        t = __floats2half2_rn(f[i + 2], f[i + 3]);   o.y = *reinterpret_cast<uint32_t*>(&t);
+        t = __floats2half2_rn(f[i + 4], f[i + 5]);   o.z = *reinterpret_cast<uint32_t*>(&t);
+        t = __floats2half2_rn(f[i + 6], f[i + 7]);   o.w = *reinterpret_cast<uint32_t*>(&t);
+        t = __floats2half2_rn(lo[i], lo[i + 1]);     l.x = *reinterpret_cast<uint32_t*>(&t);
+        t = __floats2half2_rn(lo[i + 2], lo[i + 3]); l.y = *reinterpret_cast<uint32_t*>(&t);
+        t = __floats2half2_rn(lo[i + 4], lo[i + 5]); l.z = *reinterpret_cast<uint32_t*>(&t);
+        t = __floats2half2_rn(lo[i + 6], lo[i + 7]); l.w = *reinterpret_cast<uint32_t*>(&t);
+        *reinterpret_cast<uint4*>(op + i) = o;
+        *reinterpret_cast<uint4*>(op + p.out_lo + i) = l;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i < p.n_valid) { op[i] = __float2half_rn(f[i]); op[p.out_lo + i] = __float2half_rn(lo[i]); }
+    }
+  } else {
+    __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.ldo + col0;
+    if (full) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        uint4 o;
+        o.x = pack_bf16x2(f[i], f[i + 1]);     o.y = pack_bf16x2(f[i + 2], f[i + 3]);
+        o.z = pack_bf16x2(f[i + 4], f[i + 5]); o.w = pack_bf16x2(f[i + 6], f[i + 7]);
+        *reinterpret_cast<uint4*>(op + i) = o;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i < p.n_valid) op[i] = __float2bfloat16_rn(f[i]);
+    }
+  }
+}
+
 template <int MODE>
-__global__ void __launch_bounds__(kTcThreads, 1) igemm_tc_kernel(const __grid_constant__ IgemmTcParams p) {
+__global__ void __launch_bounds__(MODE == kModeSplit ? kTcThreadsSplit : kTcThreads, 1) igemm_tc_kernel(const __grid_constant__ IgemmTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128-byte swizzle atoms (8 rows x 128 B).
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -85,8 +221,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) igemm_tc_kernel(const __grid_co
 
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
   const int total_tiles = m_tiles * p.n_tiles;
+  const int npass = MODE == kModeSplit ? 3 : 1;
   int total_kb = 0;
-  for (int t = 0; t < p.num_taps; ++t) total_kb += p.taps[t].src ? p.kchunks2 : p.kchunks;
+  for (int t = 0; t < p.num_taps; ++t) total_kb += (p.taps[t].src ? p.kchunks2 : p.kchunks) * npass;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) {
@@ -95,7 +232,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) igemm_tc_kernel(const __grid_co
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 128);
+      mbar_init(&tempty_bar[s], MODE == kModeSplit ? 256 : 128);
     }
     fence_mbar_init();
   }
@@ -125,6 +262,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) igemm_tc_kernel(const __grid_co
         const int ih = (m_tile / p.tiles_w) % p.tiles_h;
         const int in = m_tile / (p.tiles_w * p.tiles_h);
         const int w0 = iw * p.tw, h0 = ih * p.th, n0 = in * p.tn;
+        if (npass == 3) {
+          // split precision, pass-major: first every lo.hi and hi.lo product (the accumulator is still ~2^-11 of its
+          // final size, so the tensor core's truncating fp32 accumulate costs nothing there), then hi.hi.
+          // Weight K blocks of a tap are [hi chunks | lo chunks].
+          for (int pp = 0; pp < 3; ++pp) {
+            const int pass = pp == 0 ? 1 : (pp == 1 ? 2 : 0);  // 1: lo.hi, 2: hi.lo, 0: hi.hi
+            int kb_base = 0;
+            for (int t = 0; t < p.num_taps; ++t) {
+              const TapDesc tap = p.taps[t];
+              const int chunks = tap.src ? p.kchunks2 : p.kchunks;
+              const void* tm = tap.src ? static_cast<const void*>(&p.tmA2) : static_cast<const void*>(&p.tmA);
+              const int a_off = pass == 1 ? (tap.src ? p.a_lo2 : p.a_lo) : 0;
+              const int b_off = kb_base + (pass == 2 ? chunks : 0);
+              for (int cc = 0; cc < chunks; ++cc) {
+                mbar_wait(&empty_bar[stage], phase ^ 1u, 1);
+                uint8_t* sa = stage_base + static_cast<size_t>(stage) * stage_bytes;
+                mbar_expect_tx(&full_bar[stage], stage_bytes);
+                tma_load_5d(sa, tm, &full_bar[stage], a_off + cc * kTcBlockK, w0 + tap.dw, tap.dr, h0 + tap.dh, n0);
+                tma_load_2d(sa + a_bytes, &p.tmB, &full_bar[stage], (b_off + cc) * kTcBlockK, n_tile * p.block_n);
+                if (++stage == stages) { stage = 0; phase ^= 1u; }
+              }
+              kb_base += 2 * chunks;
+            }
+          }
+          continue;
+        }
         int kb_global = 0;
         for (int t = 0; t < p.num_taps; ++t) {
           const TapDesc tap = p.taps[t];
@@ -135,14 +298,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) igemm_tc_kernel(const __grid_co
             uint8_t* sa = stage_base + static_cast<size_t>(stage) * stage_bytes;
             uint8_t* sb = sa + a_bytes;
             mbar_expect_tx(&full_bar[stage], stage_bytes);
-            if (MODE == kModeLstm) {
-              // A rows = batch entries b0..b0+127 of h at the previous timestep of this direction.
-              const int dir = n_tile / (p.n_tiles >> 1);
-              const int t_prev = dir == 0 ? p.lstm_step - 1 : p.lstm_T - p.lstm_step;  // OOB at step 0 -> zeros
-              tma_load_5d(sa, tm, &full_bar[stage], dir * 512 + cc * kTcBlockK, t_prev, 0, h0, 0);
-            } else {
-              tma_load_5d(sa, tm, &full_bar[stage], cc * kTcBlockK, w0 + tap.dw, tap.dr, h0 + tap.dh, n0);
-            }
+            tma_load_5d(sa, tm, &full_bar[stage], cc * kTcBlockK, w0 + tap.dw, tap.dr, h0 + tap.dh, n0);
             tma_load_2d(sb, &p.tmB, &full_bar[stage], kb_global * kTcBlockK, n_tile * p.block_n);
             if (++stage == stages) { stage = 0; phase ^= 1u; }
           }
@@ -152,32 +308,65 @@ __global__ void __launch_bounds__(kTcThreads, 1) igemm_tc_kernel(const __grid_co
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(kTcBlockM, static_cast<uint32_t>(p.block_n));
+      const uint32_t idesc = MODE == kModeSplit ? make_idesc_f16(kTcBlockM, static_cast<uint32_t>(p.block_n))
+                                                : make_idesc_bf16(kTcBlockM, static_cast<uint32_t>(p.block_n));
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty_bar[as], aphase ^ 1u, 2);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as) * 256u;
-        for (int kb = 0; kb < total_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase, 3);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(stage_base + static_cast<size_t>(stage) * stage_bytes);
-          const uint64_t a_desc = make_sw128_kmajor_desc(sa);
-          const uint64_t b_desc = make_sw128_kmajor_desc(sa + a_bytes);
+      if (MODE == kModeSplit) {
+        // Chunked accumulation: the tensor core's fp32 accumulate truncates, and that bias grows with the length
+        // and the magnitude of the running sum. So a tile is accumulated in CHUNKS, each into a fresh TMEM buffer:
+        // chunk 0 = every lo.hi / hi.lo product (small), then the hi.hi K blocks kTcSplitChunkKb at a time; the
+        // epilogue warps add the chunks in registers with round-to-nearest fp32.
+        const int lo_kb = (total_kb / 3) * 2;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+          int kb = 0;
+          while (kb < total_kb) {
+            const int kb_end = kb < lo_kb ? lo_kb : (kb + kTcSplitChunkKb < total_kb ? kb + kTcSplitChunkKb : total_kb);
+            mbar_wait(&tempty_bar[as], aphase ^ 1u, 2);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as) * 256u;
+            for (const int k0 = kb; kb < kb_end; ++kb) {
+              mbar_wait(&full_bar[stage], phase, 3);
+              tc_fence_after();
+              const uint32_t sa = smem_u32(stage_base + static_cast<size_t>(stage) * stage_bytes);
+              const uint64_t a_desc = make_sw128_kmajor_desc(sa);
+              const uint64_t b_desc = make_sw128_kmajor_desc(sa + a_bytes);
 #pragma unroll
-          for (int k = 0; k < kTcBlockK / 16; ++k) {
-            // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in 16-byte units
-            umma_bf16(d_tmem, a_desc + static_cast<uint64_t>(2 * k), b_desc + static_cast<uint64_t>(2 * k), idesc,
-                      (kb > 0 || k > 0) ? 1u : 0u);
+              for (int k = 0; k < kTcBlockK / 16; ++k)
+                umma_bf16(d_tmem, a_desc + static_cast<uint64_t>(2 * k), b_desc + static_cast<uint64_t>(2 * k), idesc,
+                          (kb > k0 || k > 0) ? 1u : 0u);
+              umma_commit(&empty_bar[stage]);
+              if (++stage == stages) { stage = 0; phase ^= 1u; }
+            }
+            umma_commit(&tfull_bar[as]);
+            if (++as == 2) { as = 0; aphase ^= 1u; }
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
-          if (++stage == stages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(&tfull_bar[as]);  // accumulator complete -> epilogue
-        if (++as == 2) { as = 0; aphase ^= 1u; }
+      } else {
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+          mbar_wait(&tempty_bar[as], aphase ^ 1u, 2);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as) * 256u;
+          for (int kb = 0; kb < total_kb; ++kb) {
+            mbar_wait(&full_bar[stage], phase, 3);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(stage_base + static_cast<size_t>(stage) * stage_bytes);
+            const uint64_t a_desc = make_sw128_kmajor_desc(sa);
+            const uint64_t b_desc = make_sw128_kmajor_desc(sa + a_bytes);
+  #pragma unroll
+            for (int k = 0; k < kTcBlockK / 16; ++k) {
+              // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in 16-byte units
+              umma_bf16(d_tmem, a_desc + static_cast<uint64_t>(2 * k), b_desc + static_cast<uint64_t>(2 * k), idesc,
+                        (kb > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+            if (++stage == stages) { stage = 0; phase ^= 1u; }
+          }
+          umma_commit(&tfull_bar[as]);  // accumulator complete -> epilogue
+          if (++as == 2) { as = 0; aphase ^= 1u; }
+        }
       }
     }
   } else {
@@ -186,6 +375,58 @@ __global__ void __launch_bounds__(kTcThreads, 1) igemm_tc_kernel(const __grid_co
     const int row = q * 32 + lane;
     int as = 0;
     uint32_t aphase = 0;
+    if (MODE == kModeSplit) {
+      // 8 warps: warp (q, half) owns rows q*32.. of column half `half`; fp32 register accumulators over the chunks
+      const int half = (warp - 2) >> 2;
+      const int half_cols = p.block_n >> 1;  // multiple of 32 (block_n is a multiple of 64 on this path)
+      const int nchunks = 1 + (total_kb / 3 + kTcSplitChunkKb - 1) / kTcSplitChunkKb;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.n_tiles;
+        const int m_tile = tile / p.n_tiles;
+        const int iw = m_tile % p.tiles_w;
+        const int ih = (m_tile / p.tiles_w) % p.tiles_h;
+        const int in = m_tile / (p.tiles_w * p.tiles_h);
+        const int ww = row % p.tw;
+        const int hh = (row / p.tw) % p.th;
+        const int nn = row / (p.tw * p.th);
+        const int w = iw * p.tw + ww, h = ih * p.th + hh, n = in * p.tn + nn;
+        const bool valid = (w < p.w_out) && (h < p.h_out) && (n < p.n_img);
+        const size_t pix = (static_cast<size_t>(n) * p.h_out + h) * p.w_out + w;
+        const int n_off = n_tile * p.block_n + half * half_cols;
+        float racc[128];
+#pragma unroll
+        for (int i = 0; i < 128; ++i) racc[i] = 0.f;
+        for (int ch = 0; ch < nchunks; ++ch) {
+          mbar_wait(&tfull_bar[as], aphase, 4);
+          tc_fence_after();
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as) * 256u +
+                                 static_cast<uint32_t>(half * half_cols);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (g * 32 < half_cols) {
+              uint32_t v[32];
+              tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(g * 32), v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) racc[g * 32 + i] += __uint_as_float(v[i]);
+            }
+          }
+          tc_fence_before();
+          mbar_arrive(&tempty_bar[as]);
+          if (++as == 2) { as = 0; aphase ^= 1u; }
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int col0 = n_off + g * 32;
+          if (g * 32 < half_cols && valid && col0 < p.n_valid) {
+            float f[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = racc[g * 32 + i];
+            igemm_finish32(p, f, pix, col0);
+          }
+        }
+      }
+    } else
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int n_tile = tile % p.n_tiles;
       const int m_tile = tile / p.n_tiles;
@@ -204,54 +445,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) igemm_tc_kernel(const __grid_co
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as) * 256u;
 
-      if (MODE == kModeLstm) {
-        // block_n == 64: columns are [gate i,f,g,o][16 hidden units] of one direction.
-        uint32_t v0[32], v1[32];
-        tmem_ld_32x32b_x32(taddr, v0);
-        tmem_ld_32x32b_x32(taddr + 32u, v1);
-        tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(&tempty_bar[as]);
-        if (valid) {
-          const int b = h;
-          const int tiles_per_dir = p.n_tiles >> 1;
-          const int dir = n_tile / tiles_per_dir;
-          const int t_cur = dir == 0 ? p.lstm_step : p.lstm_T - 1 - p.lstm_step;
-          const int j0 = (n_tile % tiles_per_dir) * 16;
-          const float* xp = p.lstm_xproj + (static_cast<size_t>(b) * p.lstm_T + t_cur) * 4096 + n_off;
-          float* cptr = p.lstm_c + (static_cast<size_t>(dir) * p.h_out + b) * 512 + j0;
-          __nv_bfloat16* hptr = p.lstm_hseq + (static_cast<size_t>(b) * p.lstm_T + t_cur) * 1024 + dir * 512 + j0;
-          float hout[16];
-#pragma unroll
-          for (int u = 0; u < 16; u += 4) {
-            const float4 xi = __ldg(reinterpret_cast<const float4*>(xp + u));
-            const float4 xf = __ldg(reinterpret_cast<const float4*>(xp + 16 + u));
-            const float4 xg = __ldg(reinterpret_cast<const float4*>(xp + 32 + u));
-            const float4 xo = __ldg(reinterpret_cast<const float4*>(xp + 48 + u));
-            float4 c = p.lstm_step == 0 ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(cptr + u);
-            const float xiv[4] = {xi.x, xi.y, xi.z, xi.w}, xfv[4] = {xf.x, xf.y, xf.z, xf.w};
-            const float xgv[4] = {xg.x, xg.y, xg.z, xg.w}, xov[4] = {xo.x, xo.y, xo.z, xo.w};
-            float cv[4] = {c.x, c.y, c.z, c.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float gi = sigmoidf_acc(__uint_as_float(v0[u + e]) + xiv[e]);
-              const float gf = sigmoidf_acc(__uint_as_float(v0[16 + u + e]) + xfv[e]);
-              const float gg = tanhf(__uint_as_float(v1[u + e]) + xgv[e]);
-              const float go = sigmoidf_acc(__uint_as_float(v1[16 + u + e]) + xov[e]);
-              cv[e] = gf * cv[e] + gi * gg;
-              hout[u + e] = go * tanhf(cv[e]);
-            }
-            *reinterpret_cast<float4*>(cptr + u) = make_float4(cv[0], cv[1], cv[2], cv[3]);
-          }
-          uint4 o0, o1;
-          o0.x = pack_bf16x2(hout[0], hout[1]);   o0.y = pack_bf16x2(hout[2], hout[3]);
-          o0.z = pack_bf16x2(hout[4], hout[5]);   o0.w = pack_bf16x2(hout[6], hout[7]);
-          o1.x = pack_bf16x2(hout[8], hout[9]);   o1.y = pack_bf16x2(hout[10], hout[11]);
-          o1.z = pack_bf16x2(hout[12], hout[13]); o1.w = pack_bf16x2(hout[14], hout[15]);
-          *reinterpret_cast<uint4*>(hptr) = o0;
-          *reinterpret_cast<uint4*>(hptr + 8) = o1;
-        }
-      } else {
+      {
         for (int c0 = 0; c0 < p.block_n; c0 += 32) {
           uint32_t v[32];
           tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c0), v);
@@ -266,68 +460,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) igemm_tc_kernel(const __grid_co
             float f[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-            const bool full = (col0 + 32 <= p.n_valid);
-            if (p.bias != nullptr) {
-              if (full) {
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
-                  f[i] += b4.x; f[i + 1] += b4.y; f[i + 2] += b4.z; f[i + 3] += b4.w;
-                }
-              } else {
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                  if (col0 + i < p.n_valid) f[i] += __ldg(p.bias + col0 + i);
-              }
-            }
-            if (p.residual != nullptr) {
-              const __nv_bfloat16* rp = p.residual + pix * p.ldr + col0;
-              if (full) {
-#pragma unroll
-                for (int i = 0; i < 32; i += 8) {
-                  const uint4 r4 = __ldg(reinterpret_cast<const uint4*>(rp + i));
-                  f[i] += bf16lo_to_f32(r4.x);     f[i + 1] += bf16hi_to_f32(r4.x);
-                  f[i + 2] += bf16lo_to_f32(r4.y); f[i + 3] += bf16hi_to_f32(r4.y);
-                  f[i + 4] += bf16lo_to_f32(r4.z); f[i + 5] += bf16hi_to_f32(r4.z);
-                  f[i + 6] += bf16lo_to_f32(r4.w); f[i + 7] += bf16hi_to_f32(r4.w);
-                }
-              } else {
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                  if (col0 + i < p.n_valid) f[i] += __bfloat162float(rp[i]);
-              }
-            }
-            if (p.relu) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.0f);
-            }
-            if (p.out_f32) {
-              float* op = reinterpret_cast<float*>(p.out) + pix * p.ldo + col0;
-              if (full && (p.ldo & 3) == 0) {
-#pragma unroll
-                for (int i = 0; i < 32; i += 4)
-                  *reinterpret_cast<float4*>(op + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
-              } else {
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                  if (col0 + i < p.n_valid) op[i] = f[i];
-              }
-            } else {
-              __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.ldo + col0;
-              if (full) {
-#pragma unroll
-                for (int i = 0; i < 32; i += 8) {
-                  uint4 o;
-                  o.x = pack_bf16x2(f[i], f[i + 1]);     o.y = pack_bf16x2(f[i + 2], f[i + 3]);
-                  o.z = pack_bf16x2(f[i + 4], f[i + 5]); o.w = pack_bf16x2(f[i + 6], f[i + 7]);
-                  *reinterpret_cast<uint4*>(op + i) = o;
-                }
-              } else {
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                  if (col0 + i < p.n_valid) op[i] = __float2bfloat16_rn(f[i]);
-              }
-            }
+            igemm_finish32(p, f, pix, col0);
           }
         }
       }
@@ -419,23 +552,23 @@ inline int make_rows64_tmap(CUtensorMap* tm, const void* base, long long rows, i
   return rc == CUDA_SUCCESS ? 0 : -static_cast<int>(rc) - 1000;
 }
 
-inline cudaError_t igemm_tc_launch(const IgemmTcParams& p, int mode, int num_sms, cudaStream_t stream) {
+inline cudaError_t igemm_tc_launch(const IgemmTcParams& p, int /*mode*/, int num_sms, cudaStream_t stream) {
   static bool attr_set[2] = {false, false};
+  const int mode = p.split ? kModeSplit : kModeStd;
   int stages = 0;
   const size_t smem = igemm_tc_smem_bytes(p.block_n, &stages);
   if (!attr_set[mode]) {
-    cudaError_t e = mode == kModeLstm
-                        ? cudaFuncSetAttribute(igemm_tc_kernel<kModeLstm>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               227 * 1024)
-                        : cudaFuncSetAttribute(igemm_tc_kernel<kModeStd>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               227 * 1024);
+    cudaError_t e = mode == kModeSplit
+                        ? cudaFuncSetAttribute(igemm_tc_kernel<kModeSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
+                        : cudaFuncSetAttribute(igemm_tc_kernel<kModeStd>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     attr_set[mode] = true;
   }
+  if (p.split && (p.block_n & 63) != 0) return cudaErrorInvalidValue;  // the split epilogue halves the tile in 32-column groups
   const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
   const int grid = total_tiles < num_sms ? total_tiles : num_sms;
-  if (mode == kModeLstm)
-    igemm_tc_kernel<kModeLstm><<<grid, kTcThreads, smem, stream>>>(p);
+  if (mode == kModeSplit)
+    igemm_tc_kernel<kModeSplit><<<grid, kTcThreadsSplit, smem, stream>>>(p);
   else
     igemm_tc_kernel<kModeStd><<<grid, kTcThreads, smem, stream>>>(p);
   return cudaGetLastError();

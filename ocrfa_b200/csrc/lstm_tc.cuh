@@ -3,41 +3,59 @@
 // reference: nn.LSTM(bidirectional=True, batch_first=True) inside BidirectionalLSTM,
 //            /root/reference/src/ocrfa/modules/blocks.py:85-102 (gate order i,f,g,o; h0 = c0 = 0)
 //
-// The input projection x.W_ih^T + b_ih + b_hh is hoisted into one GEMM (igemm_tc) that leaves fp32 gate
-// pre-activations `xproj` [B*T][4096] in HBM (both directions, gate rows permuted to [32 tiles][i,f,g,o][16 units]).
-// This kernel then walks the T dependent steps:
-//   * CTA (n_tile, m_tile) owns 16 hidden units (64 gate columns) of one direction for 128 batch rows;
-//     its W_hh slice [64 x 512] bf16 (64 KB) is loaded ONCE and stays in shared memory for all T steps;
-//   * per step the previous hidden state h_{t-1} [128 x 512] bf16 is streamed by TMA from a compact, parity
-//     double-buffered exchange buffer (eight contiguous 16 KB slabs, L2 resident) through an 8-deep ring,
-//     multiplied on tcgen05 (M=128, N=64) into TMEM, and the epilogue warps apply the gate math with the cell
-//     state held in REGISTERS across all steps; h_t is written both to the layer output [B][T][1024] and to the
-//     exchange buffer;
-//   * the only cross-CTA dependency is "all 32 CTAs of my (direction, m_tile) group wrote h_t": a monotonic
-//     global counter per group (release add / acquire poll), no kernel relaunch, no grid-wide barrier;
-//   * xproj rows for step s+1 are prefetched into registers while step s's peers finish, so the HBM latency
-//     of the 4 MB/step xproj stream is off the critical path.
-// All CTAs must be co-resident (<= 128 CTAs, 1 per SM): the host uses a cooperative launch, and every spin is
-// bounded (trap on timeout) so a scheduling surprise surfaces as an error, not a hung GPU.
+// CTA (n_tile, m_tile) owns 16 hidden units (64 gate columns, rows permuted to [32 tiles][i,f,g,o][16 units]) of
+// one direction for 128 batch rows. Sixteen 8 KB weight slabs (64 gate columns x 64 K) are loaded ONCE and stay in
+// shared memory for all T steps; per step sixteen 16 KB activation slabs (128 rows x 64 K) stream through a TMA
+// ring into tcgen05.mma (M=128, N=64, fp32 accumulators double-buffered in TMEM); the epilogue warps apply the gate
+// math with the cell state held in REGISTERS across all steps and write h_t to the layer output and to a compact,
+// parity double-buffered exchange buffer (contiguous 16 KB slabs, L2 resident) that feeds the next step.
+//
+// Two arithmetic modes share the pipeline:
+//   kLstmBf16FusedX  bf16 operands. K = [x_t | h_{t-1}] (1024): the input projection is FUSED - the resident
+//                    weights are [W_ih | W_hh], the eight x_t slabs come straight from the layer input [B][T][512]
+//                    and do not depend on the recurrence, so they are fetched and multiplied while the group is
+//                    still converging on h_{t-1}; no xproj tensor ever reaches HBM. Bias from shared memory.
+//   kLstmF16Split    fp16 hi/lo split operands (fp32-grade): h = h_hi + h_lo, W_hh = W_hi + W_lo (pre-scaled by a
+//                    power of two), three products h_hi.W_hi + h_hi.W_lo + h_lo.W_hi per K block; the resident
+//                    weights are [W_hi | W_lo]; the input projection (fp32, bias included) comes from the split
+//                    igemm; accurate expf/tanhf gate math.
+//
+// The only cross-CTA dependency is "all 32 CTAs of my (direction, m_tile) group wrote h_t": a monotonic global
+// counter per group (release add / acquire poll), no kernel relaunch, no grid-wide barrier. All CTAs must be
+// co-resident (<= 128 CTAs, 1 per SM): the host uses a cooperative launch, and every spin is bounded (trap on
+// timeout) so a scheduling surprise surfaces as an error, not a hung GPU.
 #pragma once
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace ocrfa {
 
 constexpr int kLstmThreads = 192;
-constexpr int kLstmRing = 8;          // A-ring stages (one per K block of a step)
+constexpr int kLstmRing = 6;          // A-ring stages of 16 KB
 constexpr int kLstmTmemCols = 128;    // 2 accumulators x 64 columns
 constexpr int kLstmGroupCtas = 32;    // CTAs per (direction, m_tile) group = 512 hidden units / 16
+constexpr int kLstmWSlabs = 16;       // resident weight slabs (8 KB each) = 128 KB
+
+enum LstmMode : int { kLstmBf16FusedX = 0, kLstmF16Split = 1 };
+
+// slabs of the exchange buffer per (direction, m_tile, parity): 8 K-blocks of h (bf16) or 8 hi + 8 lo (split)
+__host__ __device__ constexpr int lstm_hx_slabs(int mode) { return mode == kLstmF16Split ? 16 : 8; }
+__host__ __device__ inline long long lstm_hx_rows(int mode, int m_tiles) {
+  return static_cast<long long>(2) * m_tiles * 2 * lstm_hx_slabs(mode) * 128;
+}
 
 struct alignas(64) LstmTcParams {
-  CUtensorMap tmX;  // h exchange buffer [2 dirs][m_tiles][2 parities][8 K-blocks][128 rows][64] bf16 as 2-D (64, rows), box {64,128}
-  CUtensorMap tmW;  // permuted W_hh [4096][512] bf16, box {64, 64}
-  const float* xproj;        // [B*T][4096] fp32
-  __nv_bfloat16* hseq;       // [B][T][1024] bf16 (fwd | bwd): the layer output
-  __nv_bfloat16* hx;         // exchange buffer (see tmX): h_t of the whole group, one contiguous 16 KB slab per K-block
+  CUtensorMap tmX;  // exchange buffer [2 dirs][m_tiles][2 parities][slabs][128 rows][64] as 2-D (64, rows), box {64,128}
+  CUtensorMap tmW;  // resident weights [4096][1024] (bf16: [W_ih | W_hh]; split: [W_hi | W_lo]), box {64, 64}
+  CUtensorMap tmS;  // bf16 mode: layer input [B][T][512] bf16 as the 5-D activation map, box {64,1,1,128,1}
+  const float* xproj;        // split mode: [B*T][4096] fp32 gate pre-activations (bias included)
+  const float* bias;         // bf16 mode: [4096] b_ih + b_hh in the permuted order
+  void* hseq;                // layer output: bf16 [B][T][1024] (fwd | bwd), or fp16 [B][T][hi 1024 | lo 1024]
+  void* hx;                  // exchange buffer (see tmX)
   unsigned int* sync;        // [2 * m_tiles] group counters, zero before launch
   long long* dbg;            // optional [64 steps][16] SM-clock timestamps of CTA 0 (bring-up profiling), or null
+  float acc_scale;           // split mode: 2^-k undoing the power-of-two pre-scale of W_hh
   int B, T, m_tiles;
 };
 
@@ -55,6 +73,25 @@ __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.pr
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float tanh_fast(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
 
+template <int MODE> __device__ __forceinline__ float lstm_sigmoid(float x) {
+  return MODE == kLstmF16Split ? sigmoidf_acc(x) : sigmoid_fast(x);
+}
+template <int MODE> __device__ __forceinline__ float lstm_tanh(float x) {
+  return MODE == kLstmF16Split ? tanhf(x) : tanh_fast(x);
+}
+
+__device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
+  __half2 v = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+// x = hi + lo with hi = fp16(x), lo = fp16(x - hi): 22 significant bits for |x| in the fp16 normal range
+__device__ __forceinline__ void split_f16(float x, float* hi, float* lo) {
+  const float h = __half2float(__float2half_rn(x));
+  *hi = h;
+  *lo = x - h;
+}
+
+template <int MODE>
 __global__ void __launch_bounds__(kLstmThreads, 1) lstm_tc_persistent_kernel(const __grid_constant__ LstmTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -65,9 +102,11 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_tc_persistent_kernel(con
   uint64_t* tempty = tfull + 2;                           // [2]
   uint64_t* w_full = tempty + 2;                          // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
-  uint8_t* w_smem = smem + 1024;                          // 8 K-blocks x (64 rows x 128 B) = 64 KB
-  uint8_t* ring = w_smem + 8 * 8192;                      // kLstmRing x 16 KB
+  float* sbias = reinterpret_cast<float*>(smem + 512);    // [64] (bf16 mode)
+  uint8_t* w_smem = smem + 1024;                          // kLstmWSlabs x (64 rows x 128 B) = 128 KB
+  uint8_t* ring = w_smem + kLstmWSlabs * 8192;            // kLstmRing x 16 KB
 
+  constexpr int kHxSlabs = lstm_hx_slabs(MODE);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tile = blockIdx.x % 64;
   const int m_tile = blockIdx.x / 64;
@@ -83,8 +122,14 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_tc_persistent_kernel(con
     mbar_init(w_full, 1);
     fence_mbar_init();
   }
-  if (warp == 0 && lane == 0) { tma_prefetch_desc(&p.tmX); tma_prefetch_desc(&p.tmW); }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmX);
+    tma_prefetch_desc(&p.tmW);
+    if (MODE == kLstmBf16FusedX) tma_prefetch_desc(&p.tmS);
+  }
   if (warp == 1) { tmem_alloc(tmem_slot, kLstmTmemCols); tmem_relinquish(); }
+  if (MODE == kLstmBf16FusedX && threadIdx.x >= 64 && threadIdx.x < 128)
+    sbias[threadIdx.x - 64] = __ldg(p.bias + n_tile * 64 + (threadIdx.x - 64));
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -93,12 +138,23 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_tc_persistent_kernel(con
   if (warp == 0) {
     // ===================================== TMA producer =====================================
     if (lane == 0) {
-      mbar_expect_tx(w_full, 8 * 8192);
-      for (int kb = 0; kb < 8; ++kb) tma_load_2d(w_smem + kb * 8192, &p.tmW, w_full, kb * 64, n_tile * 64);
+      mbar_expect_tx(w_full, kLstmWSlabs * 8192);
+      for (int i = 0; i < kLstmWSlabs; ++i) tma_load_2d(w_smem + i * 8192, &p.tmW, w_full, i * 64, n_tile * 64);
       int stage = 0;
       uint32_t phase = 0;
+      const int oob_row = static_cast<int>(lstm_hx_rows(MODE, p.m_tiles));
       for (int s = 0; s < T; ++s) {
         LSTM_TS(s, 0);
+        if (MODE == kLstmBf16FusedX) {
+          // x_t slabs: independent of the recurrence, so they are in flight (and multiplied) while the group converges
+          const int t_cur = dir == 0 ? s : T - 1 - s;
+          for (int kb = 0; kb < 8; ++kb) {
+            mbar_wait(&a_empty[stage], phase ^ 1u, 10);
+            mbar_expect_tx(&a_full[stage], 16384);
+            tma_load_5d(ring + stage * 16384, &p.tmS, &a_full[stage], kb * 64, t_cur, 0, m_tile * 128, 0);
+            if (++stage == kLstmRing) { stage = 0; phase ^= 1u; }
+          }
+        }
         if (s > 0) {
           // wait until every CTA of this (direction, m_tile) group has published h of step s-1
           const unsigned int need = static_cast<unsigned int>(kLstmGroupCtas) * static_cast<unsigned int>(s);
@@ -119,12 +175,11 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_tc_persistent_kernel(con
         LSTM_TS(s, 2);
         // slabs of h_{s-1}: parity (s-1)&1 of this group's exchange region; at s == 0 an out-of-bounds row
         // coordinate makes the TMA zero-fill (h0 = 0)
-        const int xrow0 = s == 0 ? (2 * p.m_tiles * 2 * 8 * 128)
-                                 : (((dir * p.m_tiles + m_tile) * 2 + ((s - 1) & 1)) * 8) * 128;
-        for (int kb = 0; kb < 8; ++kb) {
+        const int xrow0 = s == 0 ? oob_row : (((dir * p.m_tiles + m_tile) * 2 + ((s - 1) & 1)) * kHxSlabs) * 128;
+        for (int i = 0; i < kHxSlabs; ++i) {
           mbar_wait(&a_empty[stage], phase ^ 1u, 11);
           mbar_expect_tx(&a_full[stage], 16384);
-          tma_load_2d(ring + stage * 16384, &p.tmX, &a_full[stage], 0, xrow0 + kb * 128);
+          tma_load_2d(ring + stage * 16384, &p.tmX, &a_full[stage], 0, xrow0 + i * 128);
           if (++stage == kLstmRing) { stage = 0; phase ^= 1u; }
         }
         LSTM_TS(s, 3);
@@ -133,7 +188,7 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_tc_persistent_kernel(con
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, 64);
+      const uint32_t idesc = MODE == kLstmF16Split ? make_idesc_f16(128, 64) : make_idesc_bf16(128, 64);
       mbar_wait(w_full, 0, 12);
       tc_fence_after();
       int stage = 0, as = 0;
@@ -142,17 +197,25 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_tc_persistent_kernel(con
         mbar_wait(&tempty[as], aphase ^ 1u, 13);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as) * 64u;
-        for (int kb = 0; kb < 8; ++kb) {
+        uint32_t accumulate = 0;
+        for (int i = 0; i < 16; ++i) {
           mbar_wait(&a_full[stage], phase, 14);
-          if (kb == 0) LSTM_TS(s, 4);
-          if (kb == 7) LSTM_TS(s, 5);
+          if (i == 8) LSTM_TS(s, 4);
+          if (i == 15) LSTM_TS(s, 5);
           tc_fence_after();
           const uint64_t a_desc = make_sw128_kmajor_desc(smem_u32(ring + stage * 16384));
-          const uint64_t b_desc = make_sw128_kmajor_desc(smem_u32(w_smem + kb * 8192));
+          // bf16: A slab i (x K-blocks 0..7, then h K-blocks 0..7) x weight slab i ([W_ih | W_hh]).
+          // split: slabs 0..7 = h_hi x (W_hi, W_lo); slabs 8..15 = h_lo x W_hi.
+          const int w0 = MODE == kLstmF16Split ? (i & 7) : i;
+          const int nw = (MODE == kLstmF16Split && i < 8) ? 2 : 1;
+          for (int j = 0; j < nw; ++j) {
+            const uint64_t b_desc = make_sw128_kmajor_desc(smem_u32(w_smem + (w0 + 8 * j) * 8192));
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(d_tmem, a_desc + static_cast<uint64_t>(2 * k), b_desc + static_cast<uint64_t>(2 * k), idesc,
-                      (kb > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) {
+              umma_bf16(d_tmem, a_desc + static_cast<uint64_t>(2 * k), b_desc + static_cast<uint64_t>(2 * k), idesc, accumulate);
+              accumulate = 1u;
+            }
+          }
           umma_commit(&a_empty[stage]);
           if (++stage == kLstmRing) { stage = 0; phase ^= 1u; }
         }
@@ -173,13 +236,15 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_tc_persistent_kernel(con
     float c[16];
 #pragma unroll
     for (int u = 0; u < 16; ++u) c[u] = 0.f;
-    float4 xr[16];  // xproj row slice for the CURRENT step: [i(16) f(16) g(16) o(16)]
-    {
+    float4 xr[16];  // split mode: xproj row slice for the CURRENT step: [i(16) f(16) g(16) o(16)]
+    if (MODE == kLstmF16Split) {
       const int t0 = dir == 0 ? 0 : T - 1;
       const float4* xp = reinterpret_cast<const float4*>(p.xproj + (static_cast<size_t>(valid ? b : 0) * T + t0) * 4096 + n_tile * 64);
 #pragma unroll
       for (int i = 0; i < 16; ++i) xr[i] = valid ? __ldg(xp + i) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    const float acc_scale = p.acc_scale;
+    const size_t hx_region = static_cast<size_t>(dir * p.m_tiles + m_tile) * 2;
     int as = 0;
     uint32_t aphase = 0;
     for (int s = 0; s < T; ++s) {
@@ -198,37 +263,65 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_tc_persistent_kernel(con
       float hout[16];
 #pragma unroll
       for (int g4 = 0; g4 < 4; ++g4) {
-        const float xi[4] = {xr[g4].x, xr[g4].y, xr[g4].z, xr[g4].w};
-        const float xf[4] = {xr[4 + g4].x, xr[4 + g4].y, xr[4 + g4].z, xr[4 + g4].w};
-        const float xg[4] = {xr[8 + g4].x, xr[8 + g4].y, xr[8 + g4].z, xr[8 + g4].w};
-        const float xo[4] = {xr[12 + g4].x, xr[12 + g4].y, xr[12 + g4].z, xr[12 + g4].w};
+        float4 ai, af, ag, ao;
+        if (MODE == kLstmF16Split) {
+          ai = xr[g4]; af = xr[4 + g4]; ag = xr[8 + g4]; ao = xr[12 + g4];
+        } else {
+          const float4* sb = reinterpret_cast<const float4*>(sbias);
+          ai = sb[g4]; af = sb[4 + g4]; ag = sb[8 + g4]; ao = sb[12 + g4];
+        }
+        const float xi[4] = {ai.x, ai.y, ai.z, ai.w}, xf[4] = {af.x, af.y, af.z, af.w};
+        const float xg[4] = {ag.x, ag.y, ag.z, ag.w}, xo[4] = {ao.x, ao.y, ao.z, ao.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int u = g4 * 4 + e;
-          const float gi = sigmoid_fast(__uint_as_float(v0[u]) + xi[e]);
-          const float gf = sigmoid_fast(__uint_as_float(v0[16 + u]) + xf[e]);
-          const float gg = tanh_fast(__uint_as_float(v1[u]) + xg[e]);
-          const float go = sigmoid_fast(__uint_as_float(v1[16 + u]) + xo[e]);
+          float pi = __uint_as_float(v0[u]), pf = __uint_as_float(v0[16 + u]);
+          float pg = __uint_as_float(v1[u]), po = __uint_as_float(v1[16 + u]);
+          if (MODE == kLstmF16Split) { pi *= acc_scale; pf *= acc_scale; pg *= acc_scale; po *= acc_scale; }
+          const float gi = lstm_sigmoid<MODE>(pi + xi[e]);
+          const float gf = lstm_sigmoid<MODE>(pf + xf[e]);
+          const float gg = lstm_tanh<MODE>(pg + xg[e]);
+          const float go = lstm_sigmoid<MODE>(po + xo[e]);
           c[u] = gf * c[u] + gi * gg;
-          hout[u] = go * tanh_fast(c[u]);
+          hout[u] = go * lstm_tanh<MODE>(c[u]);
         }
       }
       if (et == 0) LSTM_TS(s, 10);
-      if (valid) {
-        __nv_bfloat16* hp = p.hseq + (static_cast<size_t>(b) * T + t_cur) * 1024 + dir * 512 + j0;
-        uint4 o0, o1;
+      // pack h_t; the exchange copy goes out first (it is what the peers wait for), the layer output after the release
+      uint4 o0, o1, l0, l1;
+      if (MODE == kLstmF16Split) {
+        float hi[16], lo[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) split_f16(hout[u], &hi[u], &lo[u]);
+        o0.x = pack_f16x2(hi[0], hi[1]);   o0.y = pack_f16x2(hi[2], hi[3]);
+        o0.z = pack_f16x2(hi[4], hi[5]);   o0.w = pack_f16x2(hi[6], hi[7]);
+        o1.x = pack_f16x2(hi[8], hi[9]);   o1.y = pack_f16x2(hi[10], hi[11]);
+        o1.z = pack_f16x2(hi[12], hi[13]); o1.w = pack_f16x2(hi[14], hi[15]);
+        l0.x = pack_f16x2(lo[0], lo[1]);   l0.y = pack_f16x2(lo[2], lo[3]);
+        l0.z = pack_f16x2(lo[4], lo[5]);   l0.w = pack_f16x2(lo[6], lo[7]);
+        l1.x = pack_f16x2(lo[8], lo[9]);   l1.y = pack_f16x2(lo[10], lo[11]);
+        l1.z = pack_f16x2(lo[12], lo[13]); l1.w = pack_f16x2(lo[14], lo[15]);
+      } else {
         o0.x = pack_bf16x2(hout[0], hout[1]);   o0.y = pack_bf16x2(hout[2], hout[3]);
         o0.z = pack_bf16x2(hout[4], hout[5]);   o0.w = pack_bf16x2(hout[6], hout[7]);
         o1.x = pack_bf16x2(hout[8], hout[9]);   o1.y = pack_bf16x2(hout[10], hout[11]);
         o1.z = pack_bf16x2(hout[12], hout[13]); o1.w = pack_bf16x2(hout[14], hout[15]);
-        *reinterpret_cast<uint4*>(hp) = o0;
-        *reinterpret_cast<uint4*>(hp + 8) = o1;
-        // exchange copy for the next step's MMAs (rows >= B are never read back into valid results)
-        __nv_bfloat16* xp2 = p.hx + (static_cast<size_t>((((dir * p.m_tiles + m_tile) * 2 + (s & 1)) * 8 + (j0 >> 6)) * 128 + row)) * 64 + (j0 & 63);
+        l0 = o0; l1 = o1;
+      }
+      if (valid) {
+        // rows >= B of the exchange buffer are never read back into valid results
+        uint16_t* hx = reinterpret_cast<uint16_t*>(p.hx);
+        const size_t slab = (hx_region + (s & 1)) * kHxSlabs + (j0 >> 6);
+        uint16_t* xp2 = hx + (slab * 128 + row) * 64 + (j0 & 63);
         *reinterpret_cast<uint4*>(xp2) = o0;
         *reinterpret_cast<uint4*>(xp2 + 8) = o1;
+        if (MODE == kLstmF16Split) {
+          uint16_t* xp3 = xp2 + static_cast<size_t>(8) * 128 * 64;  // lo slabs follow the 8 hi slabs
+          *reinterpret_cast<uint4*>(xp3) = l0;
+          *reinterpret_cast<uint4*>(xp3 + 8) = l1;
+        }
       }
-      // publish: the CTA barrier orders every epilogue thread's h stores before thread 0's gpu-scope release
+      // publish: the CTA barrier orders every epilogue thread's exchange stores before thread 0's gpu-scope release
       // (cumulative), which the peers' acquire polls + proxy fence pair with
       if (et == 0) LSTM_TS(s, 11);
       asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -237,8 +330,22 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_tc_persistent_kernel(con
         red_release_gpu_add(group_ctr, 1u);
         LSTM_TS(s, 14);
       }
-      // prefetch the next step's xproj slice while the group converges and the next MMAs run
-      if (s + 1 < T) {
+      if (valid) {
+        uint16_t* hs = reinterpret_cast<uint16_t*>(p.hseq);
+        if (MODE == kLstmF16Split) {
+          uint16_t* hp = hs + (static_cast<size_t>(b) * T + t_cur) * 2048 + dir * 512 + j0;
+          *reinterpret_cast<uint4*>(hp) = o0;
+          *reinterpret_cast<uint4*>(hp + 8) = o1;
+          *reinterpret_cast<uint4*>(hp + 1024) = l0;
+          *reinterpret_cast<uint4*>(hp + 1032) = l1;
+        } else {
+          uint16_t* hp = hs + (static_cast<size_t>(b) * T + t_cur) * 1024 + dir * 512 + j0;
+          *reinterpret_cast<uint4*>(hp) = o0;
+          *reinterpret_cast<uint4*>(hp + 8) = o1;
+        }
+      }
+      // split mode: prefetch the next step's xproj slice while the group converges and the next MMAs run
+      if (MODE == kLstmF16Split && s + 1 < T) {
         const int t_next = dir == 0 ? s + 1 : T - 2 - s;
         const float4* xp = reinterpret_cast<const float4*>(p.xproj + (static_cast<size_t>(valid ? b : 0) * T + t_next) * 4096 + n_tile * 64);
 #pragma unroll
@@ -248,6 +355,7 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_tc_persistent_kernel(con
       if (as == 0) aphase ^= 1u;
     }
   }
+#undef LSTM_TS
 
   tc_fence_before();
   __syncthreads();
@@ -258,20 +366,21 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_tc_persistent_kernel(con
   }
 }
 
-inline size_t lstm_tc_smem_bytes() { return 2048 + 8 * 8192 + static_cast<size_t>(kLstmRing) * 16384; }
+inline size_t lstm_tc_smem_bytes() { return 2048 + kLstmWSlabs * 8192 + static_cast<size_t>(kLstmRing) * 16384; }
 
 // Cooperative launch (all CTAs co-resident). `sync` must hold 2*m_tiles zeroed counters.
-inline cudaError_t lstm_tc_launch(const LstmTcParams& p, cudaStream_t stream) {
-  static bool attr_set = false;
+inline cudaError_t lstm_tc_launch(const LstmTcParams& p, int mode, cudaStream_t stream) {
+  static bool attr_set[2] = {false, false};
   const size_t smem = lstm_tc_smem_bytes();
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(lstm_tc_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  void* fn = mode == kLstmF16Split ? reinterpret_cast<void*>(lstm_tc_persistent_kernel<kLstmF16Split>)
+                                   : reinterpret_cast<void*>(lstm_tc_persistent_kernel<kLstmBf16FusedX>);
+  if (!attr_set[mode]) {
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    attr_set[mode] = true;
   }
   void* args[] = {const_cast<LstmTcParams*>(&p)};
-  return cudaLaunchCooperativeKernel(reinterpret_cast<void*>(lstm_tc_persistent_kernel), dim3(64 * p.m_tiles), dim3(kLstmThreads),
-                                     args, smem, stream);
+  return cudaLaunchCooperativeKernel(fn, dim3(64 * p.m_tiles), dim3(kLstmThreads), args, smem, stream);
 }
 
 }  // namespace ocrfa

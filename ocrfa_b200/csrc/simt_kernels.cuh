@@ -8,6 +8,7 @@
 //   H' mean      /root/reference/src/ocrfa/modules/blocks.py:433, 441-446
 //   LSTM cell    /root/reference/src/ocrfa/modules/blocks.py:89 (nn.LSTM gate math, order i,f,g,o)
 #pragma once
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace ocrfa {
@@ -71,6 +72,7 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict_
                                                         const float* __restrict__ wgt /*[9][32]*/,
                                                         const float* __restrict__ bias /*[32]*/, TOut* __restrict__ out,
                                                         int B, int H, int W) {
+  constexpr bool kSplit = OUT_C == 128;  // TOut = __half, split-precision activations
   __shared__ float sw[9 * 32];
   __shared__ float sb[32];
   for (int i = threadIdx.x; i < 9 * 32; i += blockDim.x) sw[i] = wgt[i];
@@ -106,7 +108,21 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict_
       for (int k = 0; k < 9; ++k) a = fmaf(v[k], sw[k * 32 + c0 + j], a);
       acc[j] = fmaxf(a + sb[c0 + j], 0.f);
     }
-    if (sizeof(TOut) == 2) {
+    if (kSplit) {
+      // fp16 hi/lo pair per channel: pixel = [hi(64) | lo(64)], channels 32..63 of both halves are zero padding
+      uint32_t hw[4], lw[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const __half2 hv = __floats2half2_rn(acc[2 * j], acc[2 * j + 1]);
+        const float2 hf = __half22float2(hv);
+        const __half2 lv = __floats2half2_rn(acc[2 * j] - hf.x, acc[2 * j + 1] - hf.y);
+        hw[j] = *reinterpret_cast<const uint32_t*>(&hv);
+        lw[j] = *reinterpret_cast<const uint32_t*>(&lv);
+      }
+      __half* hp = reinterpret_cast<__half*>(op);
+      *reinterpret_cast<uint4*>(hp + c0) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+      *reinterpret_cast<uint4*>(hp + 64 + c0) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+    } else if (sizeof(TOut) == 2) {
       uint4 o;
       o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
       o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
@@ -117,7 +133,15 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict_
       *reinterpret_cast<float4*>(fo + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
     }
   }
-  if (OUT_C > 32) {
+  if (kSplit) {
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    uint16_t* bp = reinterpret_cast<uint16_t*>(op);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      *reinterpret_cast<uint4*>(bp + 32 + i * 8) = z;
+      *reinterpret_cast<uint4*>(bp + 96 + i * 8) = z;
+    }
+  } else if (OUT_C > 32) {
     // zero channel padding (bf16 path): 32 x 2 B = 64 B
     const uint4 z = make_uint4(0, 0, 0, 0);
     __nv_bfloat16* bp = reinterpret_cast<__nv_bfloat16*>(op) + 32;
@@ -303,6 +327,106 @@ template <typename T>
 __global__ void cvt_from_f32_kernel(const float* __restrict__ in, T* __restrict__ out, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = from_f32<T>(in[i]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// split-precision (fp16 hi/lo) variants: a pixel is [hi(c) | lo(c)]; hi + lo is exact in fp32.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_split8(const __half* px, int c, int ch, float (&v)[8]) {
+  const uint4 h = __ldg(reinterpret_cast<const uint4*>(px + ch));
+  const uint4 l = __ldg(reinterpret_cast<const uint4*>(px + c + ch));
+  const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[j]));
+    const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[j]));
+    v[2 * j] = hf.x + lf.x;
+    v[2 * j + 1] = hf.y + lf.y;
+  }
+}
+__device__ __forceinline__ void store_split8(__half* px, int c, int ch, const float (&v)[8]) {
+  uint32_t hw[4], lw[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const __half2 hv = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+    const float2 hf = __half22float2(hv);
+    const __half2 lv = __floats2half2_rn(v[2 * j] - hf.x, v[2 * j + 1] - hf.y);
+    hw[j] = *reinterpret_cast<const uint32_t*>(&hv);
+    lw[j] = *reinterpret_cast<const uint32_t*>(&lv);
+  }
+  *reinterpret_cast<uint4*>(px + ch) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+  *reinterpret_cast<uint4*>(px + c + ch) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+}
+
+__global__ void maxpool2x2_split_kernel(const __half* __restrict__ in, __half* __restrict__ out, int n, int h_in, int w_in,
+                                        int c, int sh, int sw, int pw, int h_out, int w_out) {
+  const int cv = c / 8;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)n * h_out * w_out * cv;
+  if (gid >= total) return;
+  const int cg = gid % cv;
+  const long long pix = gid / cv;
+  const int wo = pix % w_out;
+  const int ho = (pix / w_out) % h_out;
+  const int b = pix / ((long long)w_out * h_out);
+  float m[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) m[i] = -INFINITY;
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const int hi = ho * sh + r, wi = wo * sw + s - pw;
+      if (hi < h_in && wi >= 0 && wi < w_in) {
+        float v[8];
+        load_split8(in + (((long long)b * h_in + hi) * w_in + wi) * 2 * c, c, cg * 8, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], v[i]);
+      }
+    }
+  store_split8(out + pix * 2 * c, c, cg * 8, m);
+}
+
+// [B,H',T,C] split -> [B,T,C] split; the sum of H' <= 4 values and the division are fp32 like the reference's
+__global__ void mean_h_split_kernel(const __half* __restrict__ in, __half* __restrict__ out, int b, int hp, int t, int c) {
+  const int cv = c / 8;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)b * t * cv;
+  if (gid >= total) return;
+  const int cg = gid % cv;
+  const int tt = (gid / cv) % t;
+  const int bb = gid / ((long long)cv * t);
+  float s[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = 0.f;
+  for (int h = 0; h < hp; ++h) {
+    float v[8];
+    load_split8(in + (((long long)bb * hp + h) * t + tt) * 2 * c, c, cg * 8, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] += v[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = s[i] / static_cast<float>(hp);
+  store_split8(out + ((long long)bb * t + tt) * 2 * c, c, cg * 8, s);
+}
+
+// rows of [hi(c) | lo(c)] fp16 <-> rows of c fp32
+__global__ void cvt_split_to_f32_kernel(const __half* __restrict__ in, float* __restrict__ out, long long rows, int c) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * c) return;
+  const long long r = i / c;
+  const int ch = i % c;
+  out[i] = __half2float(in[r * 2 * c + ch]) + __half2float(in[r * 2 * c + c + ch]);
+}
+__global__ void cvt_f32_to_split_kernel(const float* __restrict__ in, __half* __restrict__ out, long long rows, int c) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * c) return;
+  const long long r = i / c;
+  const int ch = i % c;
+  const float v = in[i];
+  const __half h = __float2half_rn(v);
+  out[r * 2 * c + ch] = h;
+  out[r * 2 * c + c + ch] = __float2half_rn(v - __half2float(h));
 }
 
 // ---------------------------------------------------------------------------------------------

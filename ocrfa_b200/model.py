@@ -64,8 +64,8 @@ class Model(nn.Module):
 
     def __init__(self, input_channel, output_channel, hidden_size, num_class, precision: str = "bf16"):
         super().__init__()
-        if precision not in ("bf16", "fp32"):
-            raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
+        if precision not in _lib.PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(_lib.PRECISIONS)}, got {precision!r}")
         self.precision = precision
         self.num_class = int(num_class)
         self._cfg = (int(input_channel), int(output_channel), int(hidden_size))
@@ -110,7 +110,7 @@ class Model(nn.Module):
         self._release()
         lib = _lib.load()
         cfg = _lib.OcrfaConfig(self._cfg[0], self._cfg[1], self._cfg[2], self.num_class,
-                               _lib.PRECISION_BF16 if self.precision == "bf16" else _lib.PRECISION_FP32, idx)
+                               _lib.PRECISIONS[self.precision], idx)
         handle = C.c_void_p()
         _lib.check(lib.ocrfa_create(C.byref(cfg), C.byref(handle)))
         try:

@@ -23,7 +23,7 @@ def env(synth_sd, charset):
     chars = str(charset["character"])
     conv = ob.CTCLabelConverter(chars)
     models = {}
-    for prec in ("fp32", "bf16"):
+    for prec in ("fp32", "bf16", "f16x3"):
         m = ob.Model(1, 512, 512, len(conv.character), precision=prec)
         m.load_state_dict({"module." + k: torch.from_numpy(v) for k, v in synth_sd.items()})
         models[prec] = m
@@ -46,6 +46,36 @@ def test_fp32_logits_match_reference_golden(env, name):
     print(f"{name} fp32: scaled logit err {err:.3g}, max abs {np.abs(logits - g['logits']).max():.3g}")
     assert err <= TOL["fp32"]
     assert np.array_equal(logits.argmax(2), g["logits"].argmax(2))
+
+
+@pytest.mark.parametrize("name", FWD + ["c3_64x2048"])
+def test_f16x3_logits_match_reference_golden(env, name):
+    """Split-precision tensor-core mode (fp16 hi/lo operands, three tcgen05 products per term, fp32 accumulate)
+    against the reference's own fp32 logits: the fp32 tolerance of north_star (allclose rtol = atol = 1e-3),
+    identical argmax at every timestep."""
+    g = load_golden(name)
+    x = torch.from_numpy(g["x"]).cuda()
+    logits = env["models"]["f16x3"](x, None).cpu().numpy()
+    assert logits.shape == g["logits"].shape and np.isfinite(logits).all()
+    err = _logit_err(logits, g["logits"])
+    print(f"{name} f16x3: scaled logit err {err:.3g}, max abs {np.abs(logits - g['logits']).max():.3g}")
+    assert err <= TOL["fp32"]
+    assert np.array_equal(logits.argmax(2), g["logits"].argmax(2))
+
+
+@pytest.mark.parametrize("name", FWD)
+@pytest.mark.parametrize("decoder,bw", [("greedy", 5), ("beamsearch", 8), ("wordbeamsearch", 8)])
+def test_recognizer_predict_end_to_end_f16x3(env, name, decoder, bw):
+    """Images -> strings through the public API on the split-precision TENSOR-CORE path against the reference's
+    own results: identical strings."""
+    g = load_golden(name)
+    ob = env["ob"]
+    imgs = g["images"]
+    loader = [ob.AlignCollate(imgs.shape[1], imgs.shape[2])(list(imgs))]
+    res = ob.recognizer_predict(env["models"]["f16x3"], env["conv"], loader, int(imgs.shape[2] / 10), env["ign"], {},
+                                decoder, bw, "cuda")
+    assert [r[0] for r in res] == g[f"str_{decoder}_{bw}"].tolist()
+    np.testing.assert_allclose([r[1] for r in res], g[f"conf_{decoder}_{bw}"], rtol=5e-3, atol=1e-9)
 
 
 @pytest.mark.parametrize("name", FWD)
@@ -269,7 +299,7 @@ def test_bf16_strings_vs_fp32_at_config2_size(env):
     assert s16r[::-1] == s16
 
 
-@pytest.mark.parametrize("prec", ["bf16", "fp32"])
+@pytest.mark.parametrize("prec", ["bf16", "fp32", "f16x3"])
 def test_batch_composition_independence(env, prec):
     """Lines are independent: 300 lines in one call (two LSTM slices, ragged last tile) must decode exactly like
     the same lines in calls of 1, 99 and 200 - bit-identical labels and confidences (size-independent property)."""
@@ -277,7 +307,7 @@ def test_batch_composition_independence(env, prec):
     from ocrfa_b200.recognition import _ignore_mask
 
     ob = env["ob"]
-    n = 300 if prec == "bf16" else 40
+    n = 40 if prec == "fp32" else 300
     imgs = synth_lines(n, 32, 128, seed=31337)
     batch = ob.AlignCollate(32, 128)(list(imgs))
     mask = _ignore_mask(len(env["conv"].character), env["ign"])
@@ -285,7 +315,7 @@ def test_batch_composition_independence(env, prec):
     m = env["models"][prec]
     s_all, c_all = ob.recognize_host(m, env["conv"], batch.images_u8, batch.widths, mask, "greedy", 5, dev)
     parts_s, parts_c = [], []
-    cuts = [0, 1, 100, n] if prec == "bf16" else [0, 1, 17, n]
+    cuts = [0, 1, 17, n] if prec == "fp32" else [0, 1, 100, n]
     for a, b in zip(cuts, cuts[1:]):
         s, c = ob.recognize_host(m, env["conv"], batch.images_u8[a:b].contiguous(), batch.widths[a:b].contiguous(), mask,
                                  "greedy", 5, dev)
@@ -293,6 +323,25 @@ def test_batch_composition_independence(env, prec):
         parts_c.append(c)
     assert parts_s == s_all
     assert np.array_equal(np.concatenate(parts_c), c_all)
+
+
+def test_f16x3_strings_vs_fp32_at_config2_size(env):
+    """BASELINE config 2 shape (256 lines of 32x512): the split-precision tensor-core path must decode every line
+    exactly like the fp32 parity path (CUDA-core, fp64 accumulate) on the same device."""
+    from oracle.synth import synth_lines
+    from ocrfa_b200.recognition import _ignore_mask
+
+    ob = env["ob"]
+    imgs = synth_lines(256, 32, 512, seed=4242)
+    batch = ob.AlignCollate(32, 512)(list(imgs))
+    mask = _ignore_mask(len(env["conv"].character), env["ign"])
+    dev = torch.device("cuda", 0)
+    s3, c3 = ob.recognize_host(env["models"]["f16x3"], env["conv"], batch.images_u8, batch.widths, mask, "greedy", 5, dev)
+    s32, c32 = ob.recognize_host(env["models"]["fp32"], env["conv"], batch.images_u8, batch.widths, mask, "greedy", 5, dev)
+    same = sum(a == b for a, b in zip(s3, s32))
+    print(f"f16x3 vs fp32 greedy strings identical: {same}/256; max rel conf diff {np.abs(c3 / c32 - 1).max():.3g}")
+    assert s3 == s32
+    np.testing.assert_allclose(c3, c32, rtol=5e-3, atol=1e-12)
 
 
 def test_long_line_config3_shape_bf16_vs_fp32(env):

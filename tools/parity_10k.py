@@ -3,7 +3,8 @@
     python tools/parity_10k.py [--lines 10240] [--height 32] [--width 128] [--out gpurun_out/parity_10k.json]
 
 For every line: the oracle (CPU restatement of the reference, fp32) decodes greedy strings; the CUDA path decodes
-the same uint8 lines in fp32 parity mode and in bf16 tensor-core mode through ocrfa_recognize_host. Reports how
+the same uint8 lines in fp32 parity mode, in split-precision (f16x3) tensor-core mode and in bf16 tensor-core mode
+through ocrfa_recognize_host. Reports how
 many strings are identical, and the logit error statistics on a subsample. Test infrastructure (imports oracle/).
 """
 import argparse
@@ -30,6 +31,7 @@ def main():
     ap.add_argument("--height", type=int, default=32)
     ap.add_argument("--width", type=int, default=128)
     ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--precisions", default="fp32,f16x3,bf16")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "parity_10k.json"))
     args = ap.parse_args()
     N, H, W = args.lines, args.height, args.width
@@ -42,15 +44,17 @@ def main():
     mask = _ignore_mask(len(conv.character), ign)
     dev = torch.device("cuda", 0)
     models = {}
-    for prec in ("fp32", "bf16"):
+    precs = tuple(args.precisions.split(","))
+    for prec in precs:
         m = ob.Model(1, 512, 512, len(conv.character), precision=prec)
         m.load_state_dict(sd)
         models[prec] = m
 
-    same = {"fp32": 0, "bf16": 0}
-    step_agree = {"fp32": [0, 0], "bf16": [0, 0]}
-    conf_err = {"fp32": 0.0, "bf16": 0.0}
-    mismatches = {"fp32": [], "bf16": []}
+    same = {k: 0 for k in precs}
+    step_agree = {k: [0, 0] for k in precs}
+    conf_err = {k: 0.0 for k in precs}
+    logit_err = {k: 0.0 for k in precs}
+    mismatches = {k: [] for k in precs}
     t_cpu = t_gpu = 0.0
     for b0 in range(0, N, args.batch):
         n = min(args.batch, N - b0)
@@ -64,7 +68,8 @@ def main():
         ref_idx = probs.argmax(2)
         t_cpu += time.perf_counter() - t0
         batch = ob.AlignCollate(H, W)(list(imgs))
-        for prec in ("fp32", "bf16"):
+        ref_logits = logits.numpy() if hasattr(logits, "numpy") else np.asarray(logits)
+        for prec in precs:
             t0 = time.perf_counter()
             strs, conf = ob.recognize_host(models[prec], conv, batch.images_u8, batch.widths, mask, "greedy", 5, dev)
             t_gpu += time.perf_counter() - t0
@@ -77,16 +82,18 @@ def main():
             if ok.any():
                 conf_err[prec] = max(conf_err[prec], float(np.max(np.abs(conf[ok] - ref_conf[ok]) / ref_conf[ok])))
             lg = models[prec].forward_u8(batch.images_u8.to(dev), None).cpu().numpy()
+            logit_err[prec] = max(logit_err[prec], float((np.abs(lg - ref_logits) / (1.0 + np.abs(ref_logits))).max()))
             idx = R.probs_ref(lg, ign).argmax(2)
             step_agree[prec][0] += int((idx == ref_idx).sum())
             step_agree[prec][1] += idx.size
-        print(f"{b0 + n}/{N}: identical fp32 {same['fp32']} bf16 {same['bf16']}", flush=True)
+        print(f"{b0 + n}/{N}: identical " + " ".join(f"{k} {v}" for k, v in same.items()), flush=True)
     out = {
         "lines": N, "shape": [H, W], "decoder": "greedy", "weights": "synthetic seed 0 (ocrfa_b200/synth.py)",
         "identical_strings": same,
         "identical_fraction": {k: v / N for k, v in same.items()},
         "per_timestep_argmax_agreement": {k: v[0] / max(1, v[1]) for k, v in step_agree.items()},
         "max_rel_confidence_error": conf_err,
+        "max_scaled_logit_error": logit_err,  # max |got - ref| / (1 + |ref|): compare with rtol = atol
         "first_mismatches": mismatches,
         "cpu_oracle_lines_per_s": N / t_cpu, "cpu_threads": torch.get_num_threads(),
     }

@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <cuda_fp16.h>
 #include <random>
 #include <vector>
 #include "igemm_plan.h"
@@ -195,65 +196,253 @@ static void run_case(const Case& c) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// LSTM step mode against a host reference
+// split-precision (fp16 hi/lo, three products) cases against a float64 reference of the SAME operand values
 // ---------------------------------------------------------------------------------------------
-static void run_lstm_case(int B, int T, int steps, bool persistent = false) {
-  if (persistent) steps = T;
-  const int H = 512;
-  std::vector<__nv_bfloat16> whh((size_t)2 * 2048 * H);  // permuted layout: row = dir*2048 + tile*64 + gate*16 + u
-  std::vector<float> xproj((size_t)B * T * 4096);
-  fill_bf16(whh, 1.f / std::sqrt((float)H));
-  fill_f32(xproj, 1.0f);
-  __nv_bfloat16* d_whh = to_dev(whh);
-  float* d_xproj = to_dev(xproj);
-  __nv_bfloat16* d_hseq; float* d_c;
-  CK(cudaMalloc(&d_hseq, (size_t)B * T * 1024 * 2)); CK(cudaMemset(d_hseq, 0, (size_t)B * T * 1024 * 2));
-  CK(cudaMalloc(&d_c, (size_t)2 * B * 512 * 4)); CK(cudaMemset(d_c, 0, (size_t)2 * B * 512 * 4));
+struct RefSplitParams {
+  const float* in; int cin_pad;        // effective activations (hi + lo), [pix][cin_pad]
+  const float* in2; int cin2_pad;
+  const float* wgt; int ktotal;        // effective weights [cout][taps*cin_pad + cin2_pad]
+  const float* bias; const float* residual;
+  float* out;
+  int n, h_in, w_in, cout, kh, kw, sh, ph, pw, ho, wo, relu;
+};
+
+__global__ void ref_split_kernel(RefSplitParams p) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)p.n * p.ho * p.wo * p.cout;
+  if (idx >= total) return;
+  const int co = idx % p.cout;
+  const long long pix = idx / p.cout;
+  const int w = pix % p.wo;
+  const int h = (pix / p.wo) % p.ho;
+  const int n = pix / ((long long)p.wo * p.ho);
+  double acc = 0.0;
+  int k = 0;
+  for (int r = 0; r < p.kh; ++r)
+    for (int s = 0; s < p.kw; ++s) {
+      const int hi = h * p.sh + r - p.ph, wi = w + s - p.pw;
+      const bool ok = hi >= 0 && hi < p.h_in && wi >= 0 && wi < p.w_in;
+      const float* ip = p.in + (((long long)n * p.h_in + hi) * p.w_in + wi) * p.cin_pad;
+      const float* wp = p.wgt + (long long)co * p.ktotal + k;
+      if (ok)
+        for (int c = 0; c < p.cin_pad; ++c) acc += (double)ip[c] * (double)wp[c];
+      k += p.cin_pad;
+    }
+  if (p.in2) {
+    const float* ip = p.in2 + pix * p.cin2_pad;
+    const float* wp = p.wgt + (long long)co * p.ktotal + k;
+    for (int c = 0; c < p.cin2_pad; ++c) acc += (double)ip[c] * (double)wp[c];
+  }
+  if (p.bias) acc += p.bias[co];
+  if (p.residual) acc += p.residual[pix * p.cout + co];
+  if (p.relu) acc = acc > 0.0 ? acc : 0.0;
+  p.out[idx] = (float)acc;
+}
+
+// effective value v -> fp16 pair; returns hi + lo as float (exact)
+static float split_pair(float v, __half* hi, __half* lo) {
+  const __half h = __float2half_rn(v);
+  const __half l = __float2half_rn(v - __half2float(h));
+  *hi = h; *lo = l;
+  return __half2float(h) + __half2float(l);
+}
+
+// activations: [pix][hi(c) | lo(c)]; eff gets hi + lo
+static void make_split_act(size_t npix, int c, int c_real, float scale, std::vector<__half>& packed, std::vector<float>& eff) {
+  std::uniform_real_distribution<float> d(-1.f, 1.f);
+  packed.assign(npix * 2 * c, __float2half(0.f));
+  eff.assign(npix * c, 0.f);
+  for (size_t px = 0; px < npix; ++px)
+    for (int ch = 0; ch < c_real; ++ch)
+      eff[px * c + ch] = split_pair(d(rng) * scale, &packed[px * 2 * c + ch], &packed[px * 2 * c + c + ch]);
+}
+
+static void run_split_case(const Case& c) {
+  const ConvGeom& g = c.g;
+  const int ho = g.h_out(), wo = g.w_out();
+  const int cin_pad = ceil_div(g.cin, 64) * 64;
+  const int cin2_pad = c.fuse_cin2 ? ceil_div(c.fuse_cin2, 64) * 64 : 0;
+  const int taps = g.kh * g.kw;
+  const int keff = taps * cin_pad + cin2_pad;   // effective K
+  const int ktotal = 2 * keff;                  // packed K (hi | lo per tap)
+  const size_t npix_in = (size_t)g.n * g.h_in * g.w_in, npix_out = (size_t)g.n * ho * wo;
+  std::vector<__half> h_in, h_in2, h_res;
+  std::vector<float> e_in, e_in2, e_res;
+  make_split_act(npix_in, cin_pad, g.cin, 1.f, h_in, e_in);
+  if (c.fuse_cin2) make_split_act(npix_out, cin2_pad, c.fuse_cin2, 1.f, h_in2, e_in2);
+  if (c.use_res) make_split_act(npix_out, g.cout, g.cout, 1.f, h_res, e_res);
+  // weights: effective = (hi + lo) * 2^-k with k = 13 - exponent(max|w|), as the engine packs them
+  std::vector<float> w_raw((size_t)g.cout * keff);
+  fill_f32(w_raw, 1.f / std::sqrt((float)keff));
+  float mx = 0.f;
+  for (float v : w_raw) mx = std::max(mx, std::fabs(v));
+  int ex = 0; std::frexp(mx, &ex);
+  const int kexp = 13 - ex;
+  std::vector<__half> h_w((size_t)g.cout * ktotal, __float2half(0.f));
+  std::vector<float> e_w((size_t)g.cout * keff);
+  for (int o = 0; o < g.cout; ++o) {
+    for (int t = 0; t < taps; ++t)
+      for (int ch = 0; ch < cin_pad; ++ch) {
+        const size_t ie = (size_t)o * keff + (size_t)t * cin_pad + ch;
+        const size_t ip = (size_t)o * ktotal + (size_t)t * 2 * cin_pad + ch;
+        e_w[ie] = std::ldexp(split_pair(std::ldexp(w_raw[ie], kexp), &h_w[ip], &h_w[ip + cin_pad]), -kexp);
+      }
+    for (int ch = 0; ch < cin2_pad; ++ch) {
+      const size_t ie = (size_t)o * keff + (size_t)taps * cin_pad + ch;
+      const size_t ip = (size_t)o * ktotal + (size_t)taps * 2 * cin_pad + ch;
+      e_w[ie] = std::ldexp(split_pair(std::ldexp(w_raw[ie], kexp), &h_w[ip], &h_w[ip + cin2_pad]), -kexp);
+    }
+  }
+  std::vector<float> h_bias(g.cout);
+  fill_f32(h_bias, 0.5f);
+  __half *d_in = to_dev(h_in), *d_w = to_dev(h_w);
+  __half* d_in2 = c.fuse_cin2 ? to_dev(h_in2) : nullptr;
+  __half* d_res = c.use_res ? to_dev(h_res) : nullptr;
+  float *d_ein = to_dev(e_in), *d_ew = to_dev(e_w), *d_bias = to_dev(h_bias);
+  float* d_ein2 = c.fuse_cin2 ? to_dev(e_in2) : nullptr;
+  float* d_eres = c.use_res ? to_dev(e_res) : nullptr;
+  const size_t out_elems = npix_out * g.cout;
+  void* d_out;
+  CK(cudaMalloc(&d_out, out_elems * 4));
+  CK(cudaMemset(d_out, 0xff, out_elems * 4));
+  float* d_ref;
+  CK(cudaMalloc(&d_ref, out_elems * 4));
 
   IgemmTcParams p;
-  memset(&p, 0, sizeof(p));
-  p.tw = 1; p.th = 128; p.tn = 1;
-  p.tiles_w = 1; p.tiles_h = ceil_div(B, 128); p.tiles_n = 1;
-  p.n_img = 1; p.h_out = B; p.w_out = 1;
-  p.block_n = 64; p.n_tiles = 64; p.n_valid = 4096;
-  p.kchunks = H / 64; p.num_taps = 1; p.taps[0] = TapDesc{0, 0, 0, 0};
-  igemm_tc_smem_bytes(p.block_n, &p.num_stages);
-  int rc = make_act_tmap(&p.tmA, d_hseq, 1024, T, 1, B, 1, 1, 128, 1);
-  p.tmA2 = p.tmA;
-  if (rc == 0) rc = make_wgt_tmap(&p.tmB, d_whh, H, 4096, 64);
-  if (rc) { printf("[lstm] plan failed %d\n", rc); g_fail++; return; }
-  p.lstm_T = T; p.lstm_xproj = d_xproj; p.lstm_c = d_c; p.lstm_hseq = d_hseq;
+  TileShape forced{c.tw, c.th, c.tn};
+  int rc = plan_conv(&p, g, d_in, cin_pad, d_w, c.tw ? &forced : nullptr, true);
+  if (rc == 0 && c.fuse_cin2) rc = plan_add_source(&p, d_in2, c.fuse_cin2, cin2_pad, d_w, ktotal, g.cout);
+  if (rc) { printf("[split %s] plan failed rc=%d\n", c.name, rc); g_fail++; return; }
+  p.bias = c.use_bias ? d_bias : nullptr;
+  p.residual = d_res; p.ldr = 2 * g.cout; p.res_lo = g.cout;
+  p.out = d_out; p.out_f32 = c.out_f32; p.relu = c.relu;
+  p.out_scale = std::ldexp(1.f, -kexp);
+  if (c.out_f32) { p.ldo = g.cout; } else { p.ldo = 2 * g.cout; p.out_lo = g.cout; }
+  CK(igemm_tc_launch(p, kModeStd, g_sms, 0));
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("[split %s] kernel failed: %s\n", c.name, cudaGetErrorString(e)); exit(3); }
 
-  cudaEvent_t e0, e1;
-  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  RefSplitParams r{d_ein, cin_pad, d_ein2, cin2_pad, d_ew, keff, c.use_bias ? d_bias : nullptr, d_eres, d_ref,
+                   g.n, g.h_in, g.w_in, g.cout, g.kh, g.kw, g.sh, g.ph, g.pw, ho, wo, c.relu};
+  ref_split_kernel<<<(unsigned)((out_elems + 255) / 256), 256>>>(r);
+  CK(cudaDeviceSynchronize());
+  std::vector<float> ref(out_elems), got(out_elems);
+  CK(cudaMemcpy(ref.data(), d_ref, out_elems * 4, cudaMemcpyDeviceToHost));
+  if (c.out_f32) {
+    CK(cudaMemcpy(got.data(), d_out, out_elems * 4, cudaMemcpyDeviceToHost));
+  } else {
+    std::vector<__half> tmp(out_elems * 2);
+    CK(cudaMemcpy(tmp.data(), d_out, out_elems * 4, cudaMemcpyDeviceToHost));
+    for (size_t px = 0; px < npix_out; ++px)
+      for (int co = 0; co < g.cout; ++co)
+        got[px * g.cout + co] = __half2float(tmp[px * 2 * g.cout + co]) + __half2float(tmp[px * 2 * g.cout + g.cout + co]);
+  }
+  double max_abs = 0, max_ref = 0;
+  size_t bad = 0;
+  for (size_t i = 0; i < out_elems; ++i) {
+    const float d = std::fabs(got[i] - ref[i]);
+    if (!(d <= 2e-5f + 2e-5f * std::fabs(ref[i]))) {
+      if (bad < 4) printf("    bad pix=%zu co=%zu got=%.8f ref=%.8f\n", i / g.cout, i % g.cout, got[i], ref[i]);
+      bad++;
+    }
+    if (d > max_abs || std::isnan(d)) max_abs = d;
+    max_ref = std::max(max_ref, (double)std::fabs(ref[i]));
+  }
+  printf("[split %s] n=%d in=%dx%d cin=%d cout=%d k=%dx%d sh=%d bn=%d : max_abs_err=%.3g (max|ref|=%.3g) bad=%zu/%zu %s\n",
+         c.name, g.n, g.h_in, g.w_in, g.cin, g.cout, g.kh, g.kw, g.sh, p.block_n, max_abs, max_ref, bad, out_elems,
+         bad ? "FAIL" : "ok");
+  if (bad) g_fail++;
+  if (c.perf_iters > 0 && !bad) {
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    for (int i = 0; i < 3; ++i) CK(igemm_tc_launch(p, kModeStd, g_sms, 0));
+    CK(cudaEventRecord(e0));
+    for (int i = 0; i < c.perf_iters; ++i) CK(igemm_tc_launch(p, kModeStd, g_sms, 0));
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    ms /= c.perf_iters;
+    const double flops = 2.0 * npix_out * g.cout * (double)(taps * g.cin + c.fuse_cin2);
+    printf("    perf: %.3f ms/launch  %.1f TFLOP/s algorithmic (x3 products executed)\n", ms, flops / ms * 1e-9);
+  }
+  cudaFree(d_in); cudaFree(d_w); cudaFree(d_bias); cudaFree(d_out); cudaFree(d_ref); cudaFree(d_ein); cudaFree(d_ew);
+  if (d_res) { cudaFree(d_res); cudaFree(d_eres); }
+  if (d_in2) { cudaFree(d_in2); cudaFree(d_ein2); }
+}
+
+// ---------------------------------------------------------------------------------------------
+// persistent LSTM recurrence (both arithmetic modes) against a host reference
+// ---------------------------------------------------------------------------------------------
+static void run_lstm_case(int B, int T, int mode) {
+  const int H = 512;
+  const bool sp = mode == kLstmF16Split;
+  std::uniform_real_distribution<float> ud(-1.f, 1.f);
+  // effective weights (float) in the permuted layout: row = dir*2048 + tile*64 + gate*16 + u
+  std::vector<float> wih((size_t)4096 * H), whh((size_t)4096 * H), bias(4096);
+  std::vector<float> xeff((size_t)B * T * H);         // bf16 mode: layer input
+  std::vector<float> xproj((size_t)B * T * 4096);     // split mode: gate pre-activations
+  fill_f32(bias, 0.3f);
+  fill_f32(xproj, 1.0f);
+  void* d_w = nullptr;
+  float acc_scale = 1.f;
+  __nv_bfloat16* d_x = nullptr;
+  if (!sp) {
+    std::vector<__nv_bfloat16> wcat((size_t)4096 * 1024), xb(xeff.size());
+    for (int r = 0; r < 4096; ++r)
+      for (int k = 0; k < H; ++k) {
+        const __nv_bfloat16 a = __float2bfloat16(ud(rng) / std::sqrt((float)H)), b = __float2bfloat16(ud(rng) / std::sqrt((float)H));
+        wcat[(size_t)r * 1024 + k] = a; wcat[(size_t)r * 1024 + 512 + k] = b;
+        wih[(size_t)r * H + k] = __bfloat162float(a); whh[(size_t)r * H + k] = __bfloat162float(b);
+      }
+    for (size_t i = 0; i < xeff.size(); ++i) { xb[i] = __float2bfloat16(ud(rng)); xeff[i] = __bfloat162float(xb[i]); }
+    d_w = to_dev(wcat);
+    d_x = to_dev(xb);
+  } else {
+    std::vector<float> raw((size_t)4096 * H);
+    fill_f32(raw, 1.f / std::sqrt((float)H));
+    float mx = 0.f;
+    for (float v : raw) mx = std::max(mx, std::fabs(v));
+    int ex = 0; std::frexp(mx, &ex);
+    const int kexp = 13 - ex;
+    acc_scale = std::ldexp(1.f, -kexp);
+    std::vector<__half> wp((size_t)4096 * 1024);
+    for (int r = 0; r < 4096; ++r)
+      for (int k = 0; k < H; ++k)
+        whh[(size_t)r * H + k] = std::ldexp(split_pair(std::ldexp(raw[(size_t)r * H + k], kexp), &wp[(size_t)r * 1024 + k], &wp[(size_t)r * 1024 + 512 + k]), -kexp);
+    d_w = to_dev(wp);
+  }
+  float* d_xproj = to_dev(xproj);
+  float* d_bias = to_dev(bias);
+  const size_t hs_row = sp ? 2048 : 1024;
+  uint16_t* d_hseq;
+  CK(cudaMalloc(&d_hseq, (size_t)B * T * hs_row * 2)); CK(cudaMemset(d_hseq, 0, (size_t)B * T * hs_row * 2));
   unsigned int* d_sync = nullptr;
   CK(cudaMalloc(&d_sync, 64));
   LstmTcParams lp;
   memset(&lp, 0, sizeof(lp));
   lp.B = B; lp.T = T; lp.m_tiles = ceil_div(B, 128);
-  __nv_bfloat16* d_hx = nullptr;
-  const long long hx_rows = (long long)2 * lp.m_tiles * 2 * 8 * 128;
+  uint16_t* d_hx = nullptr;
+  const long long hx_rows = lstm_hx_rows(mode, lp.m_tiles);
   CK(cudaMalloc(&d_hx, hx_rows * 128)); CK(cudaMemset(d_hx, 0xff, hx_rows * 128));  // NaN-filled: stale reads would show
-  if (make_rows64_tmap(&lp.tmX, d_hx, hx_rows, 128)) { printf("[lstm] exchange map failed\n"); g_fail++; return; }
-  lp.tmW = p.tmB; lp.xproj = d_xproj; lp.hseq = d_hseq; lp.hx = d_hx; lp.sync = d_sync;
+  int rc = make_rows64_tmap(&lp.tmX, d_hx, hx_rows, 128);
+  if (rc == 0) rc = make_wgt_tmap(&lp.tmW, d_w, 1024, 4096, 64);
+  if (rc == 0 && !sp) rc = make_act_tmap(&lp.tmS, d_x, 512, T, 1, B, 1, 1, 128, 1);
+  if (rc) { printf("[lstm] tensor map failed %d\n", rc); g_fail++; return; }
+  lp.xproj = sp ? d_xproj : nullptr; lp.bias = d_bias; lp.hseq = d_hseq; lp.hx = d_hx; lp.sync = d_sync;
+  lp.acc_scale = acc_scale;
   long long* d_dbg = nullptr;
   CK(cudaMalloc(&d_dbg, 64 * 16 * 8)); CK(cudaMemset(d_dbg, 0, 64 * 16 * 8));
-  lp.dbg = (persistent && getenv("LSTM_DBG")) ? d_dbg : nullptr;
-  if (persistent) {  // warm-up launch (also exercises relaunch with a re-zeroed counter)
-    CK(cudaMemsetAsync(d_sync, 0, 64));
-    CK(lstm_tc_launch(lp, 0));
-    CK(cudaMemsetAsync(d_hseq, 0, (size_t)B * T * 1024 * 2));
-  }
+  lp.dbg = getenv("LSTM_DBG") ? d_dbg : nullptr;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  // warm-up launch (also exercises relaunch with a re-zeroed counter)
+  CK(cudaMemsetAsync(d_sync, 0, 64));
+  CK(lstm_tc_launch(lp, mode, 0));
+  CK(cudaMemsetAsync(d_hseq, 0, (size_t)B * T * hs_row * 2));
+  CK(cudaMemsetAsync(d_sync, 0, 64));
   CK(cudaEventRecord(e0));
-  if (persistent) {
-    CK(cudaMemsetAsync(d_sync, 0, 64));
-    CK(lstm_tc_launch(lp, 0));
-  } else {
-    for (int s = 0; s < steps; ++s) {
-      p.lstm_step = s;
-      CK(igemm_tc_launch(p, kModeLstm, g_sms, 0));
-    }
-  }
+  CK(lstm_tc_launch(lp, mode, 0));
   CK(cudaEventRecord(e1));
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("[lstm] kernel failed: %s\n", cudaGetErrorString(e)); exit(3); }
@@ -261,8 +450,8 @@ static void run_lstm_case(int B, int T, int steps, bool persistent = false) {
   if (lp.dbg) {
     std::vector<long long> ts(64 * 16);
     CK(cudaMemcpy(ts.data(), d_dbg, ts.size() * 8, cudaMemcpyDeviceToHost));
-    const char* nm[16] = {"prod:step_begin", "prod:poll_done", "prod:fence_done", "prod:loads_issued", "mma:first_kblock", "mma:last_kblock",
-                          "mma:committed", "", "epi:tfull", "epi:tmem_loaded", "epi:math_done", "epi:stored", "epi:threadfence", "epi:bar", "epi:released", ""};
+    const char* nm[16] = {"prod:step_begin", "prod:poll_done", "prod:fence_done", "prod:loads_issued", "mma:first_h_slab", "mma:last_slab",
+                          "mma:committed", "", "epi:tfull", "epi:tmem_loaded", "epi:math_done", "epi:hx_stored", "", "epi:bar", "epi:released", ""};
     for (int s = 4; s < 8 && s < T; ++s) {
       const long long base = ts[s * 16 + 0];
       printf("    step %d (cycles since producer step begin):", s);
@@ -271,61 +460,79 @@ static void run_lstm_case(int B, int T, int steps, bool persistent = false) {
     }
   }
 
-  // host reference (float math on bf16-rounded h, mirroring the device's rounding points)
-  std::vector<float> hprev((size_t)2 * B * H, 0.f), cst((size_t)2 * B * H, 0.f);
+  // host reference in double on the same operand values; h is rounded like the device rounds it (bf16, or the
+  // fp16 hi+lo pair) before it feeds the next step
+  auto round_h = [&](float v) -> float {
+    if (!sp) return __bfloat162float(__float2bfloat16(v));
+    __half a, b;
+    return split_pair(v, &a, &b);
+  };
+  std::vector<float> hprev((size_t)2 * B * H, 0.f);
+  std::vector<double> cst((size_t)2 * B * H, 0.0);
   std::vector<float> href((size_t)B * T * 1024, 0.f);
-  std::vector<float> wf(whh.size());
-  for (size_t i = 0; i < whh.size(); ++i) wf[i] = __bfloat162float(whh[i]);
   const int bcheck = std::min(B, 3);  // reference only a few batch rows (rows are independent)
-  for (int s = 0; s < steps; ++s)
+  for (int s = 0; s < T; ++s)
     for (int dir = 0; dir < 2; ++dir) {
       const int t = dir == 0 ? s : T - 1 - s;
       for (int b = 0; b < bcheck; ++b) {
-        std::vector<float> hn(H), cn(H);
+        std::vector<float> hn(H);
         for (int j = 0; j < H; ++j) {
           const int tile = j / 16, u = j % 16;
-          float gate[4];
+          double gate[4];
           for (int gq = 0; gq < 4; ++gq) {
             const int row = dir * 2048 + tile * 64 + gq * 16 + u;
-            float acc = 0.f;
-            const float* wr = &wf[(size_t)row * H];
+            double acc = 0.0;
+            const float* wr = &whh[(size_t)row * H];
             const float* hp = &hprev[((size_t)dir * B + b) * H];
-            for (int k = 0; k < H; ++k) acc += wr[k] * hp[k];
-            gate[gq] = acc + xproj[((size_t)b * T + t) * 4096 + row];
+            for (int k = 0; k < H; ++k) acc += (double)wr[k] * hp[k];
+            if (sp) {
+              acc += xproj[((size_t)b * T + t) * 4096 + row];
+            } else {
+              const float* wi = &wih[(size_t)row * H];
+              const float* xp = &xeff[((size_t)b * T + t) * H];
+              for (int k = 0; k < H; ++k) acc += (double)wi[k] * xp[k];
+              acc += bias[row];
+            }
+            gate[gq] = acc;
           }
-          const float gi = 1.f / (1.f + std::exp(-gate[0])), gf = 1.f / (1.f + std::exp(-gate[1]));
-          const float gg = std::tanh(gate[2]), go = 1.f / (1.f + std::exp(-gate[3]));
-          const float cc = gf * cst[((size_t)dir * B + b) * H + j] + gi * gg;
-          cn[j] = cc;
-          hn[j] = go * std::tanh(cc);
+          const double gi = 1.0 / (1.0 + std::exp(-gate[0])), gf = 1.0 / (1.0 + std::exp(-gate[1]));
+          const double gg = std::tanh(gate[2]), go = 1.0 / (1.0 + std::exp(-gate[3]));
+          double& cc = cst[((size_t)dir * B + b) * H + j];
+          cc = gf * cc + gi * gg;
+          hn[j] = (float)(go * std::tanh(cc));
         }
         for (int j = 0; j < H; ++j) {
-          cst[((size_t)dir * B + b) * H + j] = cn[j];
-          const float hb = __bfloat162float(__float2bfloat16(hn[j]));
+          const float hb = round_h(hn[j]);
           hprev[((size_t)dir * B + b) * H + j] = hb;
           href[((size_t)b * T + t) * 1024 + dir * 512 + j] = hb;
         }
       }
     }
-  std::vector<__nv_bfloat16> hgot((size_t)B * T * 1024);
+  std::vector<uint16_t> hgot((size_t)B * T * hs_row);
   CK(cudaMemcpy(hgot.data(), d_hseq, hgot.size() * 2, cudaMemcpyDeviceToHost));
+  auto got_at = [&](int b, int t, int col) -> float {
+    if (!sp) { __nv_bfloat16 v; memcpy(&v, &hgot[((size_t)b * T + t) * 1024 + col], 2); return __bfloat162float(v); }
+    __half hi, lo;
+    memcpy(&hi, &hgot[((size_t)b * T + t) * 2048 + col], 2);
+    memcpy(&lo, &hgot[((size_t)b * T + t) * 2048 + 1024 + col], 2);
+    return __half2float(hi) + __half2float(lo);
+  };
+  const float tol = sp ? 2e-5f : 2e-2f;
   double max_abs = 0; size_t bad = 0, cnt = 0;
   for (int b = 0; b < bcheck; ++b)
-    for (int s = 0; s < steps; ++s)
-      for (int dir = 0; dir < 2; ++dir) {
-        const int t = dir == 0 ? s : T - 1 - s;
-        for (int j = 0; j < H; ++j) {
-          const size_t i = ((size_t)b * T + t) * 1024 + dir * 512 + j;
-          const float d = std::fabs(__bfloat162float(hgot[i]) - href[i]);
-          max_abs = std::max(max_abs, (double)d);
-          if (!(d <= 2e-2f)) { if (bad < 5) printf("    lstm bad b=%d t=%d dir=%d j=%d got=%f ref=%f\n", b, t, dir, j, __bfloat162float(hgot[i]), href[i]); bad++; }
-          cnt++;
-        }
+    for (int t = 0; t < T; ++t)
+      for (int col = 0; col < 1024; ++col) {
+        const float g = got_at(b, t, col), r = href[((size_t)b * T + t) * 1024 + col];
+        const float d = std::fabs(g - r);
+        max_abs = std::max(max_abs, (double)d);
+        if (!(d <= tol)) { if (bad < 5) printf("    lstm bad b=%d t=%d col=%d got=%f ref=%f\n", b, t, col, g, r); bad++; }
+        cnt++;
       }
-  printf("[lstm%s] B=%d T=%d steps=%d : max_abs_err=%.4g bad=%zu/%zu %s ; %.2f us/step (both dirs)\n", persistent ? "-persistent" : "", B, T,
-         steps, max_abs, bad, cnt, bad ? "FAIL" : "ok", ms * 1000.f / steps);
+  printf("[lstm-persistent %s] B=%d T=%d : max_abs_err=%.4g bad=%zu/%zu %s ; %.2f us/step (both dirs)\n",
+         sp ? "f16-split" : "bf16-fused-x", B, T, max_abs, bad, cnt, bad ? "FAIL" : "ok", ms * 1000.f / T);
   if (bad) g_fail++;
-  cudaFree(d_whh); cudaFree(d_xproj); cudaFree(d_hseq); cudaFree(d_c);
+  cudaFree(d_w); cudaFree(d_xproj); cudaFree(d_bias); cudaFree(d_hseq); cudaFree(d_hx); cudaFree(d_sync); cudaFree(d_dbg);
+  if (d_x) cudaFree(d_x);
 }
 
 int main(int argc, char** argv) {
@@ -348,8 +555,9 @@ int main(int argc, char** argv) {
         {"perf_c0_2",    {256, 32, 512, 64, 64, 3, 3, 1, 1, 1},   1, 1, 0, 0, 0, 0, 0, 0, 2},
     };
     for (const Case& c : pc) if (!strcmp(only, c.name)) run_case(c);
-    if (!strcmp(only, "lstm")) run_lstm_case(256, 129, 12);
-    if (!strcmp(only, "lstm_persistent")) run_lstm_case(256, 129, 129, true);
+    if (!strcmp(only, "lstm_persistent")) run_lstm_case(256, 129, kLstmBf16FusedX);
+    if (!strcmp(only, "lstm_split")) run_lstm_case(256, 129, kLstmF16Split);
+    if (!strcmp(only, "split_l3")) run_split_case({"perf_l3_c512", {256, 4, 129, 512, 512, 3, 3, 1, 1, 1}, 1, 1, 1, 0, 0, 0, 0, 0, 2});
     printf("%s (%d failing cases)\n", g_fail ? "FAILED" : "ALL OK", g_fail);
     return g_fail ? 1 : 0;
   }
@@ -372,10 +580,13 @@ int main(int argc, char** argv) {
       {"c1x1_ds",      {3, 8, 128, 128, 256, 1, 1, 1, 0, 0},  0, 1, 0, 0, 0, 0, 0, 0, 0},
   };
   for (const Case& c : cases) run_case(c);
-  run_lstm_case(200, 9, 9);
-  run_lstm_case(200, 9, 9, true);
-  run_lstm_case(64, 33, 33, true);
-  run_lstm_case(256, 17, 17, true);
+  for (const Case& c : cases) run_split_case(c);
+  for (int mode : {kLstmBf16FusedX, kLstmF16Split}) {
+    run_lstm_case(200, 9, mode);
+    run_lstm_case(64, 33, mode);
+    run_lstm_case(256, 17, mode);
+    run_lstm_case(3, 1, mode);
+  }
 
   if (perf && g_fail == 0) {
     std::vector<Case> pc = {
@@ -388,9 +599,11 @@ int main(int argc, char** argv) {
         {"perf_xproj",   {1, 1, 33024, 512, 4096, 1, 1, 1, 0, 0}, 0, 1, 0, 1, 0, 0, 0, 0, 20},
     };
     for (const Case& c : pc) run_case(c);
-    run_lstm_case(256, 129, 129);
-    run_lstm_case(256, 129, 129, true);
-    run_lstm_case(64, 513, 513, true);
+    run_split_case(pc[2]);
+    run_split_case(pc[5]);
+    run_lstm_case(256, 129, kLstmBf16FusedX);
+    run_lstm_case(256, 129, kLstmF16Split);
+    run_lstm_case(64, 513, kLstmBf16FusedX);
   }
   printf("%s (%d failing cases)\n", g_fail ? "FAILED" : "ALL OK", g_fail);
   return g_fail ? 1 : 0;
