@@ -57,6 +57,17 @@ def load_peaks():
     return {"bf16_sustained": 1400.0, "hbm": 6650.0, "source": "fallback (B200_PROFILING.md)"}
 
 
+def load_traffic(config: str, precision: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the igemm launches of ONE step, per launch (mean), from the
+    committed `ncu --set full` capture of this bench command (profiles/*_traffic.json, written by tools/ncu_summary.py);
+    None when no capture exists for this config/precision."""
+    path = os.path.join(ROOT, "profiles", f"igemm_traffic_{config}_{precision}.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        return json.load(f).get("dram_bytes_per_launch")
+
+
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons sampled every 200 ms while the timed region runs."""
 
@@ -305,7 +316,8 @@ def run_gpu_arm(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "dtype": {"bf16": "bf16", "f16x3": "f16x3 (fp16 hi/lo split operands, 3 tensor-core products per MAC, fp32 accumulate)",
+                      "fp32": "f32"}[args.precision], "data": "synthetic",
             "config": {"workload": f"{args.config}: {B} lines of {H}x{W} per rank per step, {decoder}"
                                    + (f" beam={beam}" if decoder != "greedy" else "") + ", reference default model (ResNet-29 + 2xBiLSTM + Linear185), random-init weights",
                        "l2": "per-step working set (>2 GB of activations at c2) exceeds the 126 MB L2; no explicit flush",
@@ -313,9 +325,11 @@ def run_gpu_arm(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * H * W + Cn),
                     "d2h_bytes_per_step": int(B * T * 4 + B * 4 + B * 8), "ms_per_step": host_ms_max / args.steps},
             "gpu_launches": launches,
-            "roofline": {"kernel": "igemm_tc_kernel<Std> (tcgen05 implicit GEMM: all convs, xproj/linear/prediction GEMMs)",
+            "roofline": {"kernel": ("igemm_tc_kernel<Split> (tcgen05 implicit GEMM, fp16 hi/lo split: executes 3 products per algorithmic MAC)"
+                                    if args.precision == "f16x3" else
+                                    "igemm_tc_kernel<Std> (tcgen05 implicit GEMM: 28 convs + the 3 linear GEMMs; the LSTM input projection is fused into lstm_tc)"),
                          "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                         "frac": achieved / peaks["bf16_sustained"], "traffic": None,
+                         "frac": achieved / peaks["bf16_sustained"], "traffic": load_traffic(args.config, args.precision),
                          "launches_per_step": tc_n / max(1, args.steps), "kernel_ms_per_step": tc_ms / max(1, args.steps),
                          "peak_source": peaks["source"] + ", sustained bf16",
                          "whole_step_tflops": (flops_line * B / (dev_ms_max / args.steps * 1e-3) / 1e12) if flops_line else None},
@@ -343,7 +357,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "f16x3", "fp32"],
+                    help="bf16: tcgen05 bf16 (headline); f16x3: tcgen05 fp16 hi/lo split, fp32-grade logits; fp32: CUDA-core parity mode")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

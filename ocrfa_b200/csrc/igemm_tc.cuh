@@ -37,6 +37,8 @@ constexpr int kTcThreads = 192;       // bf16 kernel: producer + MMA + 4 epilogu
 constexpr int kTcThreadsSplit = 320;  // split kernel: producer + MMA + 8 epilogue warps (register accumulators)
 constexpr int kTcSplitChunkKb = 2;    // split kernel: hi.hi K blocks per TMEM accumulation chunk
 constexpr int kTcTmemCols = 512;
+constexpr int kTcSmemHeader = 8192;                   // barriers (256 B) + K-block schedule, then the 1024-aligned stages
+constexpr int kTcMaxKb = (kTcSmemHeader - 256) / 32;  // K blocks per tile the schedule table can hold (248)
 
 enum IgemmMode : int { kModeStd = 0, kModeSplit = 1 };
 
@@ -210,11 +212,13 @@ __global__ void __launch_bounds__(MODE == kModeSplit ? kTcThreadsSplit : kTcThre
   uint64_t* tfull_bar = empty_bar + kTcMaxStages;          // [2]
   uint64_t* tempty_bar = tfull_bar + 2;                    // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  uint8_t* stage_base = smem + 1024;
+  int4* kb_table = reinterpret_cast<int4*>(smem + 256);    // [total_kb][2]: per K block {a_c, dw, dr, dh}, {src, b_k, -, -}
+  uint8_t* stage_base = smem + kTcSmemHeader;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int stages = p.num_stages;
+  const int block_n = p.block_n;
   const uint32_t a_bytes = kTcBlockM * kTcBlockK * 2;
   const uint32_t b_bytes = static_cast<uint32_t>(p.block_n) * kTcBlockK * 2;
   const uint32_t stage_bytes = a_bytes + b_bytes;
@@ -241,6 +245,29 @@ __global__ void __launch_bounds__(MODE == kModeSplit ? kTcThreadsSplit : kTcThre
     tma_prefetch_desc(&p.tmB);
     tma_prefetch_desc(&p.tmA2);
   }
+  // K-block schedule: the single producer thread's inner loop must stay a handful of instructions (measured: with
+  // the tap/pass bookkeeping inside the loop the producer, not the tensor pipe, set the pace at ~550 cycles per K
+  // block), so every thread precomputes one entry of the schedule here.
+  for (int kb = threadIdx.x; kb < total_kb; kb += blockDim.x) {
+    const int per_pass = total_kb / npass;
+    const int pp = kb / per_pass;
+    int rem = kb - pp * per_pass;
+    // split precision, pass-major: first every lo.hi and hi.lo product (the accumulator is still ~2^-11 of its final
+    // size there), then hi.hi. Weight K blocks of a tap are [hi chunks | lo chunks].
+    const int pass = npass == 1 ? 0 : (pp == 0 ? 1 : (pp == 1 ? 2 : 0));  // 1: lo.hi, 2: hi.lo, 0: hi.hi
+    int kb_base = 0, t = 0, chunks = 0;
+    for (; t < p.num_taps; ++t) {
+      chunks = p.taps[t].src ? p.kchunks2 : p.kchunks;
+      if (rem < chunks) break;
+      rem -= chunks;
+      kb_base += npass == 1 ? chunks : 2 * chunks;
+    }
+    const TapDesc tap = p.taps[t];
+    const int a_c = (pass == 1 ? (tap.src ? p.a_lo2 : p.a_lo) : 0) + rem * kTcBlockK;
+    const int b_k = (kb_base + (pass == 2 ? chunks : 0) + rem) * kTcBlockK;
+    kb_table[2 * kb] = make_int4(a_c, tap.dw, tap.dr, tap.dh);
+    kb_table[2 * kb + 1] = make_int4(tap.src, b_k, 0, 0);
+  }
   if (warp == 1) {
     tmem_alloc(tmem_slot, kTcTmemCols);
     tmem_relinquish();
@@ -252,7 +279,7 @@ __global__ void __launch_bounds__(MODE == kModeSplit ? kTcThreadsSplit : kTcThre
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -262,52 +289,23 @@ __global__ void __launch_bounds__(MODE == kModeSplit ? kTcThreadsSplit : kTcThre
         const int ih = (m_tile / p.tiles_w) % p.tiles_h;
         const int in = m_tile / (p.tiles_w * p.tiles_h);
         const int w0 = iw * p.tw, h0 = ih * p.th, n0 = in * p.tn;
-        if (npass == 3) {
-          // split precision, pass-major: first every lo.hi and hi.lo product (the accumulator is still ~2^-11 of its
-          // final size, so the tensor core's truncating fp32 accumulate costs nothing there), then hi.hi.
-          // Weight K blocks of a tap are [hi chunks | lo chunks].
-          for (int pp = 0; pp < 3; ++pp) {
-            const int pass = pp == 0 ? 1 : (pp == 1 ? 2 : 0);  // 1: lo.hi, 2: hi.lo, 0: hi.hi
-            int kb_base = 0;
-            for (int t = 0; t < p.num_taps; ++t) {
-              const TapDesc tap = p.taps[t];
-              const int chunks = tap.src ? p.kchunks2 : p.kchunks;
-              const void* tm = tap.src ? static_cast<const void*>(&p.tmA2) : static_cast<const void*>(&p.tmA);
-              const int a_off = pass == 1 ? (tap.src ? p.a_lo2 : p.a_lo) : 0;
-              const int b_off = kb_base + (pass == 2 ? chunks : 0);
-              for (int cc = 0; cc < chunks; ++cc) {
-                mbar_wait(&empty_bar[stage], phase ^ 1u, 1);
-                uint8_t* sa = stage_base + static_cast<size_t>(stage) * stage_bytes;
-                mbar_expect_tx(&full_bar[stage], stage_bytes);
-                tma_load_5d(sa, tm, &full_bar[stage], a_off + cc * kTcBlockK, w0 + tap.dw, tap.dr, h0 + tap.dh, n0);
-                tma_load_2d(sa + a_bytes, &p.tmB, &full_bar[stage], (b_off + cc) * kTcBlockK, n_tile * p.block_n);
-                if (++stage == stages) { stage = 0; phase ^= 1u; }
-              }
-              kb_base += 2 * chunks;
-            }
-          }
-          continue;
-        }
-        int kb_global = 0;
-        for (int t = 0; t < p.num_taps; ++t) {
-          const TapDesc tap = p.taps[t];
-          const int chunks = tap.src ? p.kchunks2 : p.kchunks;
-          const void* tm = tap.src ? static_cast<const void*>(&p.tmA2) : static_cast<const void*>(&p.tmA);
-          for (int cc = 0; cc < chunks; ++cc, ++kb_global) {
-            mbar_wait(&empty_bar[stage], phase ^ 1u, 1);
-            uint8_t* sa = stage_base + static_cast<size_t>(stage) * stage_bytes;
-            uint8_t* sb = sa + a_bytes;
-            mbar_expect_tx(&full_bar[stage], stage_bytes);
-            tma_load_5d(sa, tm, &full_bar[stage], cc * kTcBlockK, w0 + tap.dw, tap.dr, h0 + tap.dh, n0);
-            tma_load_2d(sb, &p.tmB, &full_bar[stage], kb_global * kTcBlockK, n_tile * p.block_n);
-            if (++stage == stages) { stage = 0; phase ^= 1u; }
-          }
+        const int b_col = n_tile * block_n;
+        for (int kb = 0; kb < total_kb; ++kb) {
+          const int4 e0 = kb_table[2 * kb];
+          const int4 e1 = kb_table[2 * kb + 1];
+          mbar_wait(&empty_bar[stage], phase ^ 1u, 1);
+          uint8_t* sa = stage_base + static_cast<size_t>(stage) * stage_bytes;
+          mbar_expect_tx(&full_bar[stage], stage_bytes);
+          tma_load_5d(sa, e1.x ? static_cast<const void*>(&p.tmA2) : static_cast<const void*>(&p.tmA), &full_bar[stage],
+                      e0.x, w0 + e0.y, e0.z, h0 + e0.w, n0);
+          tma_load_2d(sa + a_bytes, &p.tmB, &full_bar[stage], e1.y, b_col);
+          if (++stage == stages) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc = MODE == kModeSplit ? make_idesc_f16(kTcBlockM, static_cast<uint32_t>(p.block_n))
                                                 : make_idesc_bf16(kTcBlockM, static_cast<uint32_t>(p.block_n));
       int stage = 0;
@@ -482,11 +480,12 @@ __global__ void __launch_bounds__(MODE == kModeSplit ? kTcThreadsSplit : kTcThre
 // ---------------------------------------------------------------------------------------------
 inline size_t igemm_tc_smem_bytes(int block_n, int* stages_out) {
   const size_t stage = static_cast<size_t>(kTcBlockM) * kTcBlockK * 2 + static_cast<size_t>(block_n) * kTcBlockK * 2;
-  const size_t budget = 227 * 1024 - 2048;  // alignment slack + barrier header
+  const size_t header = 1024 + kTcSmemHeader;  // alignment slack + barriers + K-block schedule
+  const size_t budget = 227 * 1024 - header;
   int stages = static_cast<int>(budget / stage);
   if (stages > kTcMaxStages) stages = kTcMaxStages;
   if (stages_out) *stages_out = stages;
-  return 2048 + stages * stage;
+  return header + stages * stage;
 }
 
 // cuTensorMapEncodeTiled resolved through the runtime so the library does not link libcuda directly.
@@ -565,6 +564,9 @@ inline cudaError_t igemm_tc_launch(const IgemmTcParams& p, int /*mode*/, int num
     attr_set[mode] = true;
   }
   if (p.split && (p.block_n & 63) != 0) return cudaErrorInvalidValue;  // the split epilogue halves the tile in 32-column groups
+  int total_kb = 0;
+  for (int t = 0; t < p.num_taps; ++t) total_kb += (p.taps[t].src ? p.kchunks2 : p.kchunks) * (p.split ? 3 : 1);
+  if (total_kb > kTcMaxKb) return cudaErrorInvalidValue;
   const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
   const int grid = total_tiles < num_sms ? total_tiles : num_sms;
   if (mode == kModeSplit)

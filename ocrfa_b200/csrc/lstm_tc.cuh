@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_tc_persistent_kernel(con
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_expect_tx(w_full, kLstmWSlabs * 8192);
       for (int i = 0; i < kLstmWSlabs; ++i) tma_load_2d(w_smem + i * 8192, &p.tmW, w_full, i * 64, n_tile * 64);
       int stage = 0;
@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_tc_persistent_kernel(con
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc = MODE == kLstmF16Split ? make_idesc_f16(128, 64) : make_idesc_bf16(128, 64);
       mbar_wait(w_full, 0, 12);
       tc_fence_after();
