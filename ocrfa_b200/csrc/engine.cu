@@ -879,6 +879,7 @@ int ocrfa_finalize_weights(ocrfa_handle* h, void* stream) {
   if (h->tc()) {
     CUDA_TRY(cudaFuncSetAttribute(igemm_tc_kernel<kModeStd>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CUDA_TRY(cudaFuncSetAttribute(igemm_tc_kernel<kModeSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(igemm_tc_kernel<kModePair>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CUDA_TRY(cudaFuncSetAttribute(lstm_tc_persistent_kernel<kLstmBf16FusedX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lstm_tc_smem_bytes()));
     CUDA_TRY(cudaFuncSetAttribute(lstm_tc_persistent_kernel<kLstmF16Split>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lstm_tc_smem_bytes()));
     if (!get_tmap_encode()) return fail(OCRFA_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");

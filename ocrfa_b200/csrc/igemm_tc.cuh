@@ -40,7 +40,7 @@ constexpr int kTcTmemCols = 512;
 constexpr int kTcSmemHeader = 8192;                   // barriers (256 B) + K-block schedule, then the 1024-aligned stages
 constexpr int kTcMaxKb = (kTcSmemHeader - 256) / 32;  // K blocks per tile the schedule table can hold (248)
 
-enum IgemmMode : int { kModeStd = 0, kModeSplit = 1 };
+enum IgemmMode : int { kModeStd = 0, kModeSplit = 1, kModePair = 2 };
 
 struct TapDesc {
   int16_t dw, dr, dh, src;  // coordinate offsets in W, R (row-parity dim), H; src selects tmA (0) / tmA2 (1)
@@ -65,6 +65,7 @@ struct alignas(64) IgemmTcParams {
   int out_f32;
   int ldo;       // output row stride (elements)
   int ldr;       // residual row stride (elements)
+  int pair;      // 1: CTA-pair kernel (kModePair): M = 256 across two SMs, each CTA holds half of the weight tile
   int split;     // 1: fp16 hi/lo operands, three products per K chunk (see the header comment)
   int a_lo;      // split: channel offset of the lo half inside source 0's pixel (= its channel count)
   int a_lo2;     // ... inside source 1's pixel
@@ -215,28 +216,36 @@ __global__ void __launch_bounds__(MODE == kModeSplit ? kTcThreadsSplit : kTcThre
   int4* kb_table = reinterpret_cast<int4*>(smem + 256);    // [total_kb][2]: per K block {a_c, dw, dr, dh}, {src, b_k, -, -}
   uint8_t* stage_base = smem + kTcSmemHeader;
 
+  // CTA pair (kModePair): the two CTAs of a cluster work on two consecutive M tiles and the same weight tile; CTA r
+  // keeps rows [r * block_n/2, (r+1) * block_n/2) of the weight tile. The leader (rank 0) issues the M = 256 MMAs.
+  constexpr bool kPair = MODE == kModePair;
+  const uint32_t cta_rank = kPair ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int stages = p.num_stages;
   const int block_n = p.block_n;
+  const int b_rows = kPair ? block_n >> 1 : block_n;  // weight rows in THIS CTA's shared memory
   const uint32_t a_bytes = kTcBlockM * kTcBlockK * 2;
-  const uint32_t b_bytes = static_cast<uint32_t>(p.block_n) * kTcBlockK * 2;
+  const uint32_t b_bytes = static_cast<uint32_t>(b_rows) * kTcBlockK * 2;
   const uint32_t stage_bytes = a_bytes + b_bytes;
 
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
-  const int total_tiles = m_tiles * p.n_tiles;
+  const int total_tiles = (kPair ? (m_tiles + 1) >> 1 : m_tiles) * p.n_tiles;
+  const int worker = kPair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int num_workers = kPair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   const int npass = MODE == kModeSplit ? 3 : 1;
   int total_kb = 0;
   for (int t = 0; t < p.num_taps; ++t) total_kb += (p.taps[t].src ? p.kchunks2 : p.kchunks) * npass;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], kPair ? 2 : 1);  // pair: the leader's expect_tx arrive + the peer's remote arrive
       mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], MODE == kModeSplit ? 256 : 128);
+      mbar_init(&tempty_bar[s], MODE == kModeStd ? 128 : 256);  // split: 8 epilogue warps; pair: both CTAs' 4 warps
     }
     fence_mbar_init();
   }
@@ -269,11 +278,11 @@ __global__ void __launch_bounds__(MODE == kModeSplit ? kTcThreadsSplit : kTcThre
     kb_table[2 * kb + 1] = make_int4(tap.src, b_k, 0, 0);
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, kTcTmemCols);
-    tmem_relinquish();
+    if (kPair) { tmem_alloc_pair(tmem_slot, kTcTmemCols); tmem_relinquish_pair(); }
+    else { tmem_alloc(tmem_slot, kTcTmemCols); tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  if (kPair) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -282,32 +291,42 @@ __global__ void __launch_bounds__(MODE == kModeSplit ? kTcThreadsSplit : kTcThre
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = worker; tile < total_tiles; tile += num_workers) {
         const int n_tile = tile % p.n_tiles;
-        const int m_tile = tile / p.n_tiles;
+        // pair: an odd tail leaves the peer with m_tile == m_tiles: its image coordinate is out of range, so TMA
+        // zero-fills and the epilogue stores nothing
+        const int m_tile = kPair ? ((tile / p.n_tiles) << 1) + static_cast<int>(cta_rank) : tile / p.n_tiles;
         const int iw = m_tile % p.tiles_w;
         const int ih = (m_tile / p.tiles_w) % p.tiles_h;
         const int in = m_tile / (p.tiles_w * p.tiles_h);
         const int w0 = iw * p.tw, h0 = ih * p.th, n0 = in * p.tn;
-        const int b_col = n_tile * block_n;
+        const int b_col = n_tile * block_n + static_cast<int>(cta_rank) * b_rows;
         for (int kb = 0; kb < total_kb; ++kb) {
           const int4 e0 = kb_table[2 * kb];
           const int4 e1 = kb_table[2 * kb + 1];
           mbar_wait(&empty_bar[stage], phase ^ 1u, 1);
           uint8_t* sa = stage_base + static_cast<size_t>(stage) * stage_bytes;
-          mbar_expect_tx(&full_bar[stage], stage_bytes);
-          tma_load_5d(sa, e1.x ? static_cast<const void*>(&p.tmA2) : static_cast<const void*>(&p.tmA), &full_bar[stage],
-                      e0.x, w0 + e0.y, e0.z, h0 + e0.w, n0);
-          tma_load_2d(sa + a_bytes, &p.tmB, &full_bar[stage], e1.y, b_col);
+          const void* tm = e1.x ? static_cast<const void*>(&p.tmA2) : static_cast<const void*>(&p.tmA);
+          if (kPair) {
+            // both CTAs' loads complete on the LEADER's barrier, which expects the bytes of both
+            if (leader) mbar_expect_tx(&full_bar[stage], 2u * stage_bytes);
+            tma_load_5d_pair(sa, tm, &full_bar[stage], e0.x, w0 + e0.y, e0.z, h0 + e0.w, n0);
+            tma_load_2d_pair(sa + a_bytes, &p.tmB, &full_bar[stage], e1.y, b_col);
+            if (!leader) mbar_arrive_remote(&full_bar[stage], 0u);
+          } else {
+            mbar_expect_tx(&full_bar[stage], stage_bytes);
+            tma_load_5d(sa, tm, &full_bar[stage], e0.x, w0 + e0.y, e0.z, h0 + e0.w, n0);
+            tma_load_2d(sa + a_bytes, &p.tmB, &full_bar[stage], e1.y, b_col);
+          }
           if (++stage == stages) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================================== MMA issuer =======================================
-    if (elect_one()) {
+    // ===================================== MMA issuer (pair: leader CTA only) ===============
+    if (leader && elect_one()) {
       const uint32_t idesc = MODE == kModeSplit ? make_idesc_f16(kTcBlockM, static_cast<uint32_t>(p.block_n))
-                                                : make_idesc_bf16(kTcBlockM, static_cast<uint32_t>(p.block_n));
+                                                : make_idesc_bf16(kPair ? 2 * kTcBlockM : kTcBlockM, static_cast<uint32_t>(p.block_n));
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -343,7 +362,7 @@ __global__ void __launch_bounds__(MODE == kModeSplit ? kTcThreadsSplit : kTcThre
           }
         }
       } else {
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int tile = worker; tile < total_tiles; tile += num_workers) {
           mbar_wait(&tempty_bar[as], aphase ^ 1u, 2);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as) * 256u;
@@ -353,16 +372,22 @@ __global__ void __launch_bounds__(MODE == kModeSplit ? kTcThreadsSplit : kTcThre
             const uint32_t sa = smem_u32(stage_base + static_cast<size_t>(stage) * stage_bytes);
             const uint64_t a_desc = make_sw128_kmajor_desc(sa);
             const uint64_t b_desc = make_sw128_kmajor_desc(sa + a_bytes);
-  #pragma unroll
+#pragma unroll
             for (int k = 0; k < kTcBlockK / 16; ++k) {
               // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in 16-byte units
-              umma_bf16(d_tmem, a_desc + static_cast<uint64_t>(2 * k), b_desc + static_cast<uint64_t>(2 * k), idesc,
-                        (kb > 0 || k > 0) ? 1u : 0u);
+              if (kPair)
+                umma_bf16_pair(d_tmem, a_desc + static_cast<uint64_t>(2 * k), b_desc + static_cast<uint64_t>(2 * k), idesc,
+                               (kb > 0 || k > 0) ? 1u : 0u);
+              else
+                umma_bf16(d_tmem, a_desc + static_cast<uint64_t>(2 * k), b_desc + static_cast<uint64_t>(2 * k), idesc,
+                          (kb > 0 || k > 0) ? 1u : 0u);
             }
-            umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+            // frees the smem slot (pair: in both CTAs) once these MMAs have read it
+            if (kPair) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
             if (++stage == stages) { stage = 0; phase ^= 1u; }
           }
-          umma_commit(&tfull_bar[as]);  // accumulator complete -> epilogue
+          // accumulator complete -> epilogue (pair: the epilogue warps of both CTAs)
+          if (kPair) umma_commit_pair(&tfull_bar[as]); else umma_commit(&tfull_bar[as]);
           if (++as == 2) { as = 0; aphase ^= 1u; }
         }
       }
@@ -425,9 +450,9 @@ __global__ void __launch_bounds__(MODE == kModeSplit ? kTcThreadsSplit : kTcThre
         }
       }
     } else
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = worker; tile < total_tiles; tile += num_workers) {
       const int n_tile = tile % p.n_tiles;
-      const int m_tile = tile / p.n_tiles;
+      const int m_tile = kPair ? ((tile / p.n_tiles) << 1) + static_cast<int>(cta_rank) : tile / p.n_tiles;
       const int iw = m_tile % p.tiles_w;
       const int ih = (m_tile / p.tiles_w) % p.tiles_h;
       const int in = m_tile / (p.tiles_w * p.tiles_h);
@@ -449,9 +474,11 @@ __global__ void __launch_bounds__(MODE == kModeSplit ? kTcThreadsSplit : kTcThre
           tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c0), v);
           tmem_ld_wait();
           if (c0 + 32 >= p.block_n) {
-            // last read of this accumulator: hand the TMEM buffer back before the global stores
+            // last read of this accumulator: hand the TMEM buffer back before the global stores (pair: to the
+            // leader's barrier, which counts the epilogue threads of both CTAs)
             tc_fence_before();
-            mbar_arrive(&tempty_bar[as]);
+            if (kPair && !leader) mbar_arrive_remote(&tempty_bar[as], 0u);
+            else mbar_arrive(&tempty_bar[as]);
           }
           const int col0 = n_off + c0;
           if (valid && col0 < p.n_valid) {
@@ -467,19 +494,19 @@ __global__ void __launch_bounds__(MODE == kModeSplit ? kTcThreadsSplit : kTcThre
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (kPair) cluster_sync_all(); else __syncthreads();  // pair: the peer's smem/TMEM stay live until the leader's MMAs are done
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTcTmemCols);
+    if (kPair) tmem_dealloc_pair(tmem_base, kTcTmemCols); else tmem_dealloc(tmem_base, kTcTmemCols);
   }
 }
 
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-inline size_t igemm_tc_smem_bytes(int block_n, int* stages_out) {
-  const size_t stage = static_cast<size_t>(kTcBlockM) * kTcBlockK * 2 + static_cast<size_t>(block_n) * kTcBlockK * 2;
+inline size_t igemm_tc_smem_bytes(int block_n, int* stages_out, int pair = 0) {
+  const size_t stage = static_cast<size_t>(kTcBlockM) * kTcBlockK * 2 + static_cast<size_t>(pair ? block_n / 2 : block_n) * kTcBlockK * 2;
   const size_t header = 1024 + kTcSmemHeader;  // alignment slack + barriers + K-block schedule
   const size_t budget = 227 * 1024 - header;
   int stages = static_cast<int>(budget / stage);
@@ -552,22 +579,42 @@ inline int make_rows64_tmap(CUtensorMap* tm, const void* base, long long rows, i
 }
 
 inline cudaError_t igemm_tc_launch(const IgemmTcParams& p, int /*mode*/, int num_sms, cudaStream_t stream) {
-  static bool attr_set[2] = {false, false};
-  const int mode = p.split ? kModeSplit : kModeStd;
+  static bool attr_set[3] = {false, false, false};
+  const int mode = p.split ? kModeSplit : (p.pair ? kModePair : kModeStd);
   int stages = 0;
-  const size_t smem = igemm_tc_smem_bytes(p.block_n, &stages);
+  const size_t smem = igemm_tc_smem_bytes(p.block_n, &stages, p.pair);
+  if (stages != p.num_stages) return cudaErrorInvalidValue;
   if (!attr_set[mode]) {
-    cudaError_t e = mode == kModeSplit
-                        ? cudaFuncSetAttribute(igemm_tc_kernel<kModeSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
-                        : cudaFuncSetAttribute(igemm_tc_kernel<kModeStd>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    const void* fn = mode == kModeSplit  ? reinterpret_cast<const void*>(igemm_tc_kernel<kModeSplit>)
+                     : mode == kModePair ? reinterpret_cast<const void*>(igemm_tc_kernel<kModePair>)
+                                         : reinterpret_cast<const void*>(igemm_tc_kernel<kModeStd>);
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     attr_set[mode] = true;
   }
   if (p.split && (p.block_n & 63) != 0) return cudaErrorInvalidValue;  // the split epilogue halves the tile in 32-column groups
+  if (p.pair && (p.split || (p.block_n & 15) != 0)) return cudaErrorInvalidValue;
   int total_kb = 0;
   for (int t = 0; t < p.num_taps; ++t) total_kb += (p.taps[t].src ? p.kchunks2 : p.kchunks) * (p.split ? 3 : 1);
   if (total_kb > kTcMaxKb) return cudaErrorInvalidValue;
-  const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  if (mode == kModePair) {
+    // clusters of 2 CTAs (one TPC): 74 pairs on a 148-SM part, persistent over (M-tile pair, N tile) work items
+    const int pair_tiles = ((m_tiles + 1) / 2) * p.n_tiles;
+    const int pairs = pair_tiles < num_sms / 2 ? pair_tiles : num_sms / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(kTcThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, igemm_tc_kernel<kModePair>, p);
+  }
+  const int total_tiles = m_tiles * p.n_tiles;
   const int grid = total_tiles < num_sms ? total_tiles : num_sms;
   if (mode == kModeSplit)
     igemm_tc_kernel<kModeSplit><<<grid, kTcThreadsSplit, smem, stream>>>(p);
