@@ -119,11 +119,13 @@ struct ocrfa_handle {
   Profiler prof;
   ocrfa_config cfg;
   int num_sms = 148;
+  int halo_level = 2;  // OCRFA_HALO: 0 = igemm_tc only, 1 = halo-staged kernel for Cout <= 128, 2 = wherever it tiles well
   bool finalized = false;
   std::map<std::string, HostTensor> host;
   std::map<std::string, ConvW> convs;
   float* d_stem_w = nullptr;  // [9][32]
   float* d_stem_b = nullptr;  // [32]
+  StemWeights stem_host;      // the same, passed by value to the bf16 stem kernel (constant-bank operands)
   LstmW lstm[2];
   void* d_pred_w = nullptr;   // [num_class][512]
   float* d_pred_b = nullptr;
@@ -414,11 +416,42 @@ struct LaunchScope {
   }
 };
 
+// Halo-staged kernel (igemm_halo.cuh) for the 3x3/s1/p1 convs of the bf16 path, optionally with the following 2x2
+// max pool fused. Returns 1 when the layer is not a candidate (the caller falls back to igemm_tc [+ pool kernel]).
+bool halo_wanted(const ocrfa_handle* h, const ConvW& cw, const Act& in, bool pool) {
+  if (!h->bf16() || h->halo_level <= 0) return false;
+  const ConvGeom g{in.n, in.h, in.w, cw.cin, cw.cout, cw.kh, cw.kw, cw.sh, cw.ph, cw.pw};
+  if (!halo_eligible(g, pool) || (long long)in.n * in.h * in.w >= (1ll << 31)) return false;
+  if (cw.cout > 128 && h->halo_level < 2) return false;
+  int tw = 0, th = 0;
+  halo_choose_tile(in.w, in.h, pool, &tw, &th);
+  const double cover = double(ceil_div(in.w, tw) * tw) * double(ceil_div(in.h, th) * th) / (double(in.w) * in.h);
+  return cover <= 1.06;  // e.g. 4 x 129 feature maps tile better as {4, 4, 8} boxes across images (igemm_tc)
+}
+
+int run_conv_halo(ocrfa_handle* h, const ConvW& cw, const Act& in, const Act* ds_src, const void* residual, void* out,
+                  bool relu, bool pool, cudaStream_t st) {
+  IgemmHaloParams p;
+  const ConvGeom g{in.n, in.h, in.w, cw.cin, cw.cout, cw.kh, cw.kw, cw.sh, cw.ph, cw.pw};
+  if (cw.ds_cin && !ds_src) return fail(OCRFA_ERR_STATE, "%s expects a fused downsample source", cw.name.c_str());
+  int rc = plan_halo(&p, g, in.p, in.c, cw.d_wgt, pool, cw.ds_cin ? ds_src->p : nullptr, cw.ds_cin, cw.ds_cin ? ds_src->c : 0);
+  if (rc) return fail(OCRFA_ERR_CUDA, "plan_halo(%s) failed: %d", cw.name.c_str(), rc);
+  p.bias = cw.d_bias;
+  p.residual = residual; p.ldr = cw.cout;
+  p.out = out; p.ldo = cw.cout; p.relu = relu ? 1 : 0;
+  const double flops = 2.0 * (double)in.n * in.h * in.w * cw.cout * (9.0 * cw.cin + cw.ds_cin);
+  LaunchScope ls(h, kClsIgemmTc, flops, st);
+  CUDA_TRY(igemm_halo_launch(p, h->num_sms, st));
+  return 0;
+}
+
 int run_conv_tc(ocrfa_handle* h, const ConvW& cw, const Act& in, const Act* ds_src, const void* residual, void* out,
                 bool relu, bool out_f32, int ldo, cudaStream_t st) {
   IgemmTcParams p;
   ConvGeom g{in.n, in.h, in.w, cw.cin, cw.cout, cw.kh, cw.kw, cw.sh, cw.ph, cw.pw};
   const bool split = h->split();
+  if (!out_f32 && ldo == cw.cout && halo_wanted(h, cw, in, false))
+    return run_conv_halo(h, cw, in, ds_src, residual, out, relu, false, st);
   int rc = plan_conv(&p, g, in.p, in.c, cw.d_wgt, nullptr, split);
   if (rc) return fail(OCRFA_ERR_CUDA, "plan_conv(%s) failed: %d", cw.name.c_str(), rc);
   if (cw.ds_cin) {
@@ -579,6 +612,23 @@ int forward_impl(ocrfa_handle* h, const float* d_x, const uint8_t* d_u8, const i
     return 0;
   };
 
+  // conv + bn + relu + 2x2/2 max pool: one halo-staged launch when the layer qualifies, else conv then pool
+  auto conv_pool_step = [&](const char* name, Act* a) -> int {
+    auto it = h->convs.find(name);
+    if (it == h->convs.end()) return fail(OCRFA_ERR_STATE, "conv %s not prepared", name);
+    if (halo_wanted(h, it->second, *a, true)) {
+      void* o = pool.get();
+      int r = run_conv_halo(h, it->second, *a, nullptr, nullptr, o, true, true, st);
+      if (r) return r;
+      pool.put(a->p);
+      *a = Act{o, a->n, a->h / 2, a->w / 2, it->second.cout};
+      return 0;
+    }
+    int r = conv_step(name, a);
+    if (r) return r;
+    return pool_step(2, 2, 0, a);
+  };
+
   int T = W / 4 + 1;
   void* feat = ws + L.feat;
   if (d_feat_in) {
@@ -590,12 +640,16 @@ int forward_impl(ocrfa_handle* h, const float* d_x, const uint8_t* d_u8, const i
     CUDA_TRY(cudaGetLastError());
   } else {
   // ---- stem: conv0_1 + bn0_1 + relu (blocks.py:341-347)
-  Act a{pool.get(), B, H, W, tc ? 64 : 32};
+  const bool stem32 = bf && h->halo_level > 0 && (long long)B * H * W < (1ll << 31) && halo_wanted(h, h->convs.find("conv0_2")->second, Act{nullptr, B, H, W, 32}, false);
+  Act a{pool.get(), B, H, W, (tc && !stem32) ? 64 : 32};
   {
     const long long pix = (long long)B * H * W;
     const unsigned grid = (unsigned)((pix + 255) / 256);
     LaunchScope ls(h, kClsStem, 2.0 * (double)pix * 32 * 9, st);
-    if (sp)
+    if (stem32)
+      stem_conv32_kernel<<<(unsigned)((pix + 255) / 256), 256, 0, st>>>(d_x, d_u8, d_widths, h->stem_host,
+                                                                             (__nv_bfloat16*)a.p, B, H, W);
+    else if (sp)
       stem_conv_kernel<__half, 128><<<grid, 256, 0, st>>>(d_x, d_u8, d_widths, h->d_stem_w, h->d_stem_b, (__half*)a.p, B, H, W);
     else if (bf)
       stem_conv_kernel<__nv_bfloat16, 64><<<grid, 256, 0, st>>>(d_x, d_u8, d_widths, h->d_stem_w, h->d_stem_b,
@@ -604,11 +658,9 @@ int forward_impl(ocrfa_handle* h, const float* d_x, const uint8_t* d_u8, const i
       stem_conv_kernel<float, 32><<<grid, 256, 0, st>>>(d_x, d_u8, d_widths, h->d_stem_w, h->d_stem_b, (float*)a.p, B, H, W);
     CUDA_TRY(cudaGetLastError());
   }
-  if ((rc = conv_step("conv0_2", &a))) return rc;
-  if ((rc = pool_step(2, 2, 0, &a))) return rc;                       // max_pool1, blocks.py:259
+  if ((rc = conv_pool_step("conv0_2", &a))) return rc;                 // + max_pool1, blocks.py:259
   if ((rc = block("layer1.0.", true, &a))) return rc;
-  if ((rc = conv_step("conv1", &a))) return rc;
-  if ((rc = pool_step(2, 2, 0, &a))) return rc;                       // max_pool2, blocks.py:271-275
+  if ((rc = conv_pool_step("conv1", &a))) return rc;                   // + max_pool2, blocks.py:271-275
   if ((rc = block("layer2.0.", true, &a))) return rc;
   if ((rc = block("layer2.1.", false, &a))) return rc;
   if ((rc = conv_step("conv2", &a))) return rc;
@@ -796,6 +848,7 @@ int ocrfa_create(const ocrfa_config* cfg, ocrfa_handle** out) {
   ocrfa_handle* h = new ocrfa_handle();
   h->cfg = *cfg;
   h->num_sms = prop.multiProcessorCount;
+  if (const char* hl = getenv("OCRFA_HALO")) h->halo_level = atoi(hl);
   const char* g = getenv("OCRFA_GRAPHS");
   if (g && g[0] == '0') h->graphs_enabled = 0;
   *out = h;
@@ -842,6 +895,8 @@ int ocrfa_finalize_weights(ocrfa_handle* h, void* stream) {
       for (int k = 0; k < 9; ++k) pk[k * 32 + o] = (float)((double)w->data[o * 9 + k] * sc[o]);
       b[o] = (float)sf[o];
     }
+    memcpy(h->stem_host.w, pk.data(), sizeof(h->stem_host.w));
+    memcpy(h->stem_host.b, b.data(), sizeof(h->stem_host.b));
     void* d = nullptr;
     if ((rc = upload(h, pk, &d))) return rc;
     h->d_stem_w = (float*)d;

@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include "igemm_tc.cuh"
+#include "igemm_halo.cuh"
 
 namespace ocrfa {
 
@@ -118,6 +119,71 @@ inline int plan_add_source(IgemmTcParams* p, const void* in2, int cin2, int cin2
   int rc = make_act_tmap(&p->tmA2, in2, (p->split ? 2 : 1) * cin2_buf, p->w_out, 1, p->h_out, p->n_img, p->tw, p->th, p->tn);
   if (rc) return rc;
   return make_wgt_tmap(&p->tmB, wgt, ktotal, cout, p->pair ? p->block_n / 2 : p->block_n);
+}
+
+// ---------------------------------------------------------------------------------------------
+// halo-staged kernel (igemm_halo.cuh): 3x3 / stride 1 / pad 1, Cout a multiple of 32
+// ---------------------------------------------------------------------------------------------
+inline bool halo_eligible(const ConvGeom& g, bool pool) {
+  if (g.kh != 3 || g.kw != 3 || g.sh != 1 || g.ph != 1 || g.pw != 1) return false;
+  if (g.cout % 32 != 0) return false;
+  if (pool && ((g.h_in & 1) || (g.w_in & 1))) return false;
+  return true;
+}
+
+// M tile = tw x th pixels of ONE image, tw a multiple of 8 (tap offsets stay swizzle-atom aligned); fewest wasted
+// MMA rows first, then the smallest halo overhead (th + 2) / th. The fused pool needs the 2x2 window inside a warp.
+inline void halo_choose_tile(int w, int h, bool pool, int* tw_out, int* th_out) {
+  double best = 1e30;
+  for (int tw = 8; tw <= (pool ? 16 : 128); tw *= 2) {
+    const int th = 128 / tw;
+    const double cover = double(ceil_div(w, tw) * tw) * double(ceil_div(h, th) * th) / (double(w) * h);
+    const double score = cover * 100.0 + double(th + 2) / th;
+    if (score < best) { best = score; *tw_out = tw; *th_out = th; }
+  }
+}
+
+// `in`: NHWC bf16 [n][h][w][cin_buf]; cin_buf is a multiple of 64 or, for the 32-channel stem output, 32 (the box
+// still asks for 64 channels: TMA zero-fills the out-of-range half, the weights carry zeros there).
+// `in2` (optional): fused 1x1 source [n][h][w][cin2_buf]; the weight matrix then has cin2_pad extra K columns.
+inline int plan_halo(IgemmHaloParams* p, const ConvGeom& g, const void* in, int cin_buf, const void* wgt, bool pool,
+                     const void* in2 = nullptr, int cin2 = 0, int cin2_buf = 0) {
+  std::memset(p, 0, sizeof(*p));
+  if (!halo_eligible(g, pool)) return -20;
+  const int cin_pad = ceil_div(g.cin, 64) * 64;
+  if (!(cin_buf == 32 && cin_pad == 64) && (cin_buf % 64 != 0 || cin_buf < cin_pad)) return -21;
+  const int cin2_pad = in2 ? ceil_div(cin2, 64) * 64 : 0;
+  if (in2 && (cin2_buf % 64 != 0 || cin2_buf < cin2_pad)) return -22;
+  halo_choose_tile(g.w_in, g.h_in, pool, &p->tw, &p->th);
+  p->tiles_w = ceil_div(g.w_in, p->tw);
+  p->tiles_h = ceil_div(g.h_in, p->th);
+  p->n_img = g.n; p->h_out = g.h_in; p->w_out = g.w_in;
+  p->block_n = g.cout <= 256 ? g.cout : (g.cout % 256 == 0 ? 256 : (g.cout % 128 == 0 ? 128 : 64));
+  if (g.cout % p->block_n != 0) return -23;
+  p->n_tiles = g.cout / p->block_n;
+  p->n_valid = g.cout;
+  p->kchunks = cin_pad / 64;
+  p->kchunks2 = cin2_pad / 64;
+  p->pool = pool ? 1 : 0;
+  const int total_kb = 9 * p->kchunks + p->kchunks2;
+  igemm_halo_smem_bytes(p->block_n, p->tw, p->th, total_kb, p->n_tiles, &p->num_stages, &p->b_resident);
+  if (p->num_stages < 2) return -24;
+  if (const char* e = std::getenv("OCRFA_HALO_RESIDENT")) {
+    if (e[0] == '0' && p->b_resident) {  // debugging aid: force the streamed-weights layout
+      const size_t budget = 227 * 1024 - 1024 - kHaloHeader;
+      const size_t st = static_cast<size_t>(p->th + 2) * p->tw * 128 + 3 * static_cast<size_t>(p->block_n / 2) * 128;
+      p->b_resident = 0;
+      p->num_stages = static_cast<int>(budget / st) > kTcMaxStages ? kTcMaxStages : static_cast<int>(budget / st);
+    }
+  }
+  int rc = make_act_tmap(&p->tmA, in, cin_buf, g.w_in, 1, g.h_in, g.n, p->tw, p->th + 2, 1);
+  if (rc) return rc;
+  p->tmA2 = p->tmA;
+  if (in2) {
+    rc = make_act_tmap(&p->tmA2, in2, cin2_buf, g.w_in, 1, g.h_in, g.n, p->tw, p->th, 1);
+    if (rc) return rc;
+  }
+  return make_wgt_tmap(&p->tmB, wgt, 9 * cin_pad + cin2_pad, g.cout, p->block_n / 2);
 }
 
 }  // namespace ocrfa

@@ -151,6 +151,83 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------------
+// stem, bf16 tensor-core path: same arithmetic, 32-channel NHWC bf16 output (64 B per pixel, no channel padding:
+// conv0_2's TMA box zero-fills channels 32..63). One thread = one pixel; the 9 x 32 weights and 32 biases are
+// a kernel argument, i.e. constant-bank FFMA operands (288 FFMA per pixel and no weight loads); uint8 inputs are
+// normalised through a 256-entry table built with the reference's fp32 ops; each warp transposes its 32 pixels
+// x 64 B through shared memory so that every store instruction writes 512 contiguous bytes.
+// HBM bound on paper (1 B read + 64 B written per pixel); in practice FFMA-issue bound.
+// ---------------------------------------------------------------------------------------------
+struct StemWeights {
+  float w[9 * 32];  // [tap][channel], BN scale folded
+  float b[32];      // BN shift
+};
+
+__global__ void __launch_bounds__(256) stem_conv32_kernel(const float* __restrict__ x, const uint8_t* __restrict__ x_u8,
+                                                          const int32_t* __restrict__ widths,
+                                                          const __grid_constant__ StemWeights sw,
+                                                          __nv_bfloat16* __restrict__ out, int B, int H, int W) {
+  __shared__ float lut[256];
+  __shared__ uint4 stg[8][32 * 4];  // per warp: 32 pixels x 4 pieces of 16 B, piece index XOR-swizzled by (pixel >> 1) & 3
+  lut[threadIdx.x] = normalize_u8(threadIdx.x);
+  __syncthreads();
+  const unsigned total = static_cast<unsigned>(B) * H * W;  // < 2^31 (checked by the caller)
+  const unsigned pix = blockIdx.x * 256u + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float acc[32];
+#pragma unroll
+  for (int c = 0; c < 32; ++c) acc[c] = 0.f;
+  if (pix < total) {
+    const unsigned rowi = pix / static_cast<unsigned>(W);  // b * H + y
+    const int xw = static_cast<int>(pix - rowi * W);
+    const int b = static_cast<int>(rowi / static_cast<unsigned>(H));
+    const int y = static_cast<int>(rowi - static_cast<unsigned>(b) * H);
+    const int wv = (x_u8 && widths) ? min(max(__ldg(widths + b), 1), W) : W;
+    float v[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int yy = y + r - 1;
+      const bool row_ok = yy >= 0 && yy < H;
+      const size_t roff = (static_cast<size_t>(b) * H + (row_ok ? yy : y)) * W;
+#pragma unroll
+      for (int s2 = 0; s2 < 3; ++s2) {
+        const int xx = xw + s2 - 1;
+        float t = 0.f;
+        if (row_ok && xx >= 0 && xx < W) {
+          if (x_u8) t = lut[__ldg(x_u8 + roff + min(xx, wv - 1))];
+          else t = __ldg(x + roff + xx);
+        }
+        v[r * 3 + s2] = t;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      float a = 0.f;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) a = fmaf(v[k], sw.w[k * 32 + c], a);
+      acc[c] = fmaxf(a + sw.b[c], 0.f);
+    }
+  }
+  const int swz = (lane >> 1) & 3;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint4 o;
+    o.x = pack_bf16x2(acc[8 * j], acc[8 * j + 1]);     o.y = pack_bf16x2(acc[8 * j + 2], acc[8 * j + 3]);
+    o.z = pack_bf16x2(acc[8 * j + 4], acc[8 * j + 5]); o.w = pack_bf16x2(acc[8 * j + 6], acc[8 * j + 7]);
+    stg[warp][lane * 4 + (j ^ swz)] = o;
+  }
+  __syncwarp();
+  // instruction k writes pixels 8k .. 8k+7 of this warp, 64 B each: 512 contiguous bytes
+  const unsigned warp_pix0 = blockIdx.x * 256u + warp * 32u;
+  uint4* op = reinterpret_cast<uint4*>(out + static_cast<size_t>(warp_pix0) * 32);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int pr = 8 * k + (lane >> 2);  // pixel of the warp, piece lane & 3
+    if (warp_pix0 + pr < total) op[pr * 4 + (lane & 3)] = stg[warp][pr * 4 + ((lane & 3) ^ ((pr >> 1) & 3))];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // generic CUDA-core implicit GEMM (fp32 accumulate): conv kh x kw, stride (sh,1), zero pad (ph,pw), NHWC.
 // 64 pixels x 64 output channels per 256-thread block, 4x4 outputs per thread, K staged 16 at a time.
 // ---------------------------------------------------------------------------------------------

@@ -535,18 +535,199 @@ static void run_lstm_case(int B, int T, int mode) {
   if (d_x) cudaFree(d_x);
 }
 
+// ---------------------------------------------------------------------------------------------
+// halo-staged kernel (igemm_halo.cuh): 3x3 s1 p1, optional fused 1x1 source / residual / 2x2 max pool,
+// optional 32-channel input buffer (TMA zero-fills channels 32..63 of the box)
+// ---------------------------------------------------------------------------------------------
+struct HaloCase {
+  const char* name;
+  int n, h, w, cin, cout;
+  int cin_buf;    // 32 or a multiple of 64
+  int fuse_cin2;  // extra 1x1 source channels
+  int use_res, pool;
+  int perf_iters;
+};
+
+__global__ void ref_halo_kernel(const __nv_bfloat16* in, int cin_buf, int cin_loop, int cin_pad, const __nv_bfloat16* in2,
+                                int cin2_pad, const __nv_bfloat16* wgt, int ktotal, const float* bias,
+                                const __nv_bfloat16* residual, float* out, int n, int h, int w, int cout) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)n * h * w * cout;
+  if (idx >= total) return;
+  const int co = idx % cout;
+  const long long pix = idx / cout;
+  const int x = pix % w;
+  const int y = (pix / w) % h;
+  const int b = pix / ((long long)w * h);
+  float acc = 0.f;
+  for (int r = 0; r < 3; ++r)
+    for (int s = 0; s < 3; ++s) {
+      const int yy = y + r - 1, xx = x + s - 1;
+      if (yy < 0 || yy >= h || xx < 0 || xx >= w) continue;
+      const __nv_bfloat16* ip = in + (((long long)b * h + yy) * w + xx) * cin_buf;
+      const __nv_bfloat16* wp = wgt + (long long)co * ktotal + (r * 3 + s) * cin_pad;
+      for (int c = 0; c < cin_loop; ++c) acc += __bfloat162float(ip[c]) * __bfloat162float(wp[c]);
+    }
+  if (in2) {
+    const __nv_bfloat16* ip = in2 + pix * cin2_pad;
+    const __nv_bfloat16* wp = wgt + (long long)co * ktotal + 9 * cin_pad;
+    for (int c = 0; c < cin2_pad; ++c) acc += __bfloat162float(ip[c]) * __bfloat162float(wp[c]);
+  }
+  acc += bias[co];
+  if (residual) acc += __bfloat162float(residual[pix * cout + co]);
+  out[idx] = fmaxf(acc, 0.f);
+}
+
+static void run_halo_case(const HaloCase& c) {
+  const int cin_pad = ceil_div(c.cin, 64) * 64;
+  const int cin2_pad = c.fuse_cin2 ? ceil_div(c.fuse_cin2, 64) * 64 : 0;
+  const int ktotal = 9 * cin_pad + cin2_pad;
+  const size_t npix = (size_t)c.n * c.h * c.w;
+  std::vector<__nv_bfloat16> h_in(npix * c.cin_buf), h_w((size_t)c.cout * ktotal), h_res, h_in2;
+  std::vector<float> h_bias(c.cout);
+  fill_bf16(h_in, 1.f);
+  fill_bf16(h_w, 1.f / std::sqrt((float)ktotal));
+  fill_f32(h_bias, 0.5f);
+  if (c.use_res) { h_res.resize(npix * c.cout); fill_bf16(h_res, 1.f); }
+  if (c.fuse_cin2) { h_in2.resize(npix * cin2_pad); fill_bf16(h_in2, 1.f); }
+  __nv_bfloat16 *d_in = to_dev(h_in), *d_w = to_dev(h_w);
+  __nv_bfloat16* d_res = c.use_res ? to_dev(h_res) : nullptr;
+  __nv_bfloat16* d_in2 = c.fuse_cin2 ? to_dev(h_in2) : nullptr;
+  float* d_bias = to_dev(h_bias);
+  const int ho = c.pool ? c.h / 2 : c.h, wo = c.pool ? c.w / 2 : c.w;
+  const size_t out_elems = (size_t)c.n * ho * wo * c.cout;
+  __nv_bfloat16* d_out;
+  CK(cudaMalloc(&d_out, out_elems * 2));
+  CK(cudaMemset(d_out, 0xff, out_elems * 2));
+  float* d_ref;
+  CK(cudaMalloc(&d_ref, npix * c.cout * 4));
+
+  IgemmHaloParams p;
+  ConvGeom g{c.n, c.h, c.w, c.cin, c.cout, 3, 3, 1, 1, 1};
+  int rc = plan_halo(&p, g, d_in, c.cin_buf, d_w, c.pool != 0, d_in2, c.fuse_cin2, cin2_pad);
+  if (rc) { printf("[%s] plan_halo failed rc=%d\n", c.name, rc); g_fail++; return; }
+  p.bias = d_bias; p.residual = d_res; p.ldr = c.cout; p.out = d_out; p.ldo = c.cout; p.relu = 1;
+  cudaError_t e = igemm_halo_launch(p, g_sms, 0);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("[%s] halo kernel failed: %s\n", c.name, cudaGetErrorString(e)); exit(3); }
+
+  const long long total = (long long)npix * c.cout;
+  ref_halo_kernel<<<(unsigned)((total + 255) / 256), 256>>>(d_in, c.cin_buf, std::min(c.cin_buf, cin_pad), cin_pad, d_in2, cin2_pad,
+                                                           d_w, ktotal, d_bias, d_res, d_ref, c.n, c.h, c.w, c.cout);
+  CK(cudaDeviceSynchronize());
+  std::vector<float> ref_full(npix * c.cout), ref(out_elems);
+  CK(cudaMemcpy(ref_full.data(), d_ref, ref_full.size() * 4, cudaMemcpyDeviceToHost));
+  if (c.pool) {
+    for (int b = 0; b < c.n; ++b)
+      for (int y = 0; y < ho; ++y)
+        for (int x = 0; x < wo; ++x)
+          for (int co = 0; co < c.cout; ++co) {
+            float m = -INFINITY;
+            for (int r = 0; r < 2; ++r)
+              for (int s = 0; s < 2; ++s)
+                m = std::max(m, ref_full[((((size_t)b * c.h + 2 * y + r) * c.w) + 2 * x + s) * c.cout + co]);
+            ref[(((size_t)b * ho + y) * wo + x) * c.cout + co] = m;
+          }
+  } else {
+    ref = ref_full;
+  }
+  std::vector<__nv_bfloat16> tmp(out_elems);
+  CK(cudaMemcpy(tmp.data(), d_out, out_elems * 2, cudaMemcpyDeviceToHost));
+  double max_abs = 0, max_ref = 0;
+  size_t bad = 0, first_bad = 0;
+  for (size_t i = 0; i < out_elems; ++i) {
+    const float gv = __bfloat162float(tmp[i]);
+    const float d = std::fabs(gv - ref[i]);
+    if (!(d <= 2e-2f + 1e-2f * std::fabs(ref[i]))) { if (!bad) first_bad = i; bad++; }
+    if (d > max_abs || std::isnan(d)) max_abs = d;
+    max_ref = std::max(max_ref, (double)std::fabs(ref[i]));
+  }
+  printf("[halo %s] n=%d %dx%d cin=%d(buf %d) cout=%d ds=%d res=%d pool=%d tile=(%d,%d) bn=%d stages=%d resident=%d : max_abs_err=%.4g (max|ref|=%.3g) bad=%zu/%zu %s\n",
+         c.name, c.n, c.h, c.w, c.cin, c.cin_buf, c.cout, c.fuse_cin2, c.use_res, c.pool, p.tw, p.th, p.block_n, p.num_stages,
+         p.b_resident, max_abs, max_ref, bad, out_elems, bad ? "FAIL" : "ok");
+  if (bad) {
+    g_fail++;
+    size_t shown = 0;
+    for (size_t j = first_bad; j < out_elems && shown < 6; ++j) {
+      const float gv = __bfloat162float(tmp[j]);
+      if (!(std::fabs(gv - ref[j]) <= 2e-2f + 1e-2f * std::fabs(ref[j]))) {
+        const size_t pix = j / c.cout;
+        printf("    bad pix=%zu (n=%zu y=%zu x=%zu) co=%zu got=%f ref=%f\n", pix, pix / ((size_t)ho * wo), (pix / wo) % ho, pix % wo,
+               j % c.cout, gv, ref[j]);
+        shown++;
+      }
+    }
+  }
+  if (c.perf_iters > 0 && !bad) {
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    for (int i = 0; i < 3; ++i) CK(igemm_halo_launch(p, g_sms, 0));
+    CK(cudaEventRecord(e0));
+    for (int i = 0; i < c.perf_iters; ++i) CK(igemm_halo_launch(p, g_sms, 0));
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    ms /= c.perf_iters;
+    const double flops = 2.0 * npix * c.cout * (double)(9 * c.cin + c.fuse_cin2);
+    printf("    perf: %.3f ms/launch  %.1f TFLOP/s (algorithmic)\n", ms, flops / ms * 1e-9);
+  }
+  cudaFree(d_in); cudaFree(d_w); cudaFree(d_bias); cudaFree(d_out); cudaFree(d_ref);
+  if (d_res) cudaFree(d_res);
+  if (d_in2) cudaFree(d_in2);
+}
+
+static void run_halo_suite(bool perf) {
+  std::vector<HaloCase> cases = {
+      //  name            n  h   w    cin cout buf  ds  res pool perf
+      {"c0_2_buf64",      2, 32, 512, 32, 64,  64,  0,  0, 0, 0},
+      {"c0_2_buf32",      2, 32, 512, 32, 64,  32,  0,  0, 0, 0},
+      {"c0_2_pool",       3, 32, 128, 32, 64,  32,  0,  0, 1, 0},
+      {"l1_c1",           2, 16, 256, 64, 128, 64,  0,  0, 0, 0},
+      {"l1_c2_ds",        3, 16, 64,  128, 128, 128, 64, 0, 0, 0},
+      {"conv1_pool",      2, 16, 256, 128, 128, 128, 0, 0, 1, 0},
+      {"l2_c1",           3, 8, 128, 128, 256, 128, 0,  0, 0, 0},
+      {"l2_c2_ds",        2, 8, 128, 256, 256, 256, 128, 0, 0, 0},
+      {"l2_res",          3, 8, 128, 256, 256, 256, 0,  1, 0, 0},
+      {"odd_tail",        1, 8, 40,  64, 64,  64,  0,  1, 0, 0},
+      {"ragged_w",        3, 16, 100, 64, 128, 64,  0,  0, 0, 0},
+      {"l3_h8_n512",      2, 8, 513, 256, 512, 256, 0,  1, 0, 0},
+  };
+  for (const HaloCase& c : cases) run_halo_case(c);
+  if (perf && g_fail == 0) {
+    std::vector<HaloCase> pc = {
+        {"perf_c0_2_pool", 256, 32, 512, 32, 64,  32,  0,  0, 1, 10},
+        {"perf_c0_2_b64",  256, 32, 512, 32, 64,  64,  0,  0, 0, 10},
+        {"perf_l1_c1",     256, 16, 256, 64, 128, 64,  0,  0, 0, 20},
+        {"perf_l1_c2_ds",  256, 16, 256, 128, 128, 128, 64, 0, 0, 20},
+        {"perf_conv1_pool",256, 16, 256, 128, 128, 128, 0, 0, 1, 20},
+        {"perf_l2_c1",     256, 8, 128, 128, 256, 128, 0,  0, 0, 20},
+        {"perf_l2_c2_ds",  256, 8, 128, 256, 256, 256, 128, 0, 0, 20},
+        {"perf_l2_res",    256, 8, 128, 256, 256, 256, 0,  1, 0, 20},
+    };
+    for (const HaloCase& c : pc) run_halo_case(c);
+  }
+}
+
 int main(int argc, char** argv) {
   bool perf = false;
+  bool halo_only = false;
   const char* only = nullptr;  // --only NAME: run one perf case (or "lstm") alone, e.g. under ncu
   for (int i = 1; i < argc; ++i) {
     if (!strcmp(argv[i], "--perf")) perf = true;
     if (!strcmp(argv[i], "--only") && i + 1 < argc) only = argv[++i];
+    if (!strcmp(argv[i], "--halo")) halo_only = true;
   }
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, 0));
   g_sms = prop.multiProcessorCount;
   printf("device: %s, %d SMs, cc %d.%d\n", prop.name, g_sms, prop.major, prop.minor);
 
+  if (halo_only) {
+    run_halo_suite(perf);
+    printf("%s (%d failing cases)\n", g_fail ? "FAILED" : "ALL OK", g_fail);
+    return g_fail ? 1 : 0;
+  }
   if (only) {
     std::vector<Case> pc = {
         {"perf_l1_c128", {256, 16, 256, 128, 128, 3, 3, 1, 1, 1}, 1, 1, 1, 0, 0, 0, 0, 0, 2},
@@ -580,6 +761,7 @@ int main(int argc, char** argv) {
       {"c1x1_ds",      {3, 8, 128, 128, 256, 1, 1, 1, 0, 0},  0, 1, 0, 0, 0, 0, 0, 0, 0},
   };
   for (const Case& c : cases) run_case(c);
+  run_halo_suite(false);
   for (const Case& c : cases) run_split_case(c);
   for (int mode : {kLstmBf16FusedX, kLstmF16Split}) {
     run_lstm_case(200, 9, mode);
