@@ -17,7 +17,7 @@ namespace ocrfa {
 // greedy: one CTA (4 warps) per line. Each warp owns timesteps t = warp, warp+4, ...; a lane holds classes
 // lane, lane+32, ... (C <= 256). Algorithmic HBM bytes per line: T*C*4 read + T*4 written (+T*C*4 if probs kept).
 // ---------------------------------------------------------------------------------------------
-constexpr int kGreedyThreads = 128;
+constexpr int kGreedyThreads = 512;  // 16 warps per line: the per-row softmax chain is latency bound, rows are independent
 constexpr int kMaxClassesPerLane = 8;  // C <= 256
 
 struct GreedyParams {
@@ -141,13 +141,15 @@ __global__ void __launch_bounds__(kGreedyThreads) ctc_greedy_kernel(const Greedy
 }
 
 // ---------------------------------------------------------------------------------------------
-// prefix beam search: one warp per line, sequential over T.
+// prefix beam search (ctcBeamSearch, /root/reference/src/ocrfa/utils.py:949-1038): one warp per line, sequential
+// over T. Labelings are never materialised inside the time loop: every step records, per surviving beam, a
+// back-pointer (parent rank, edit op, class) in a trellis; the best labeling is rebuilt once at the end.
 // ---------------------------------------------------------------------------------------------
 struct BeamParams {
   const float* probs;    // [B][T][C] float32, already masked + renormalised (the reference's `mat`)
   int32_t* labels_out;   // [B][T]
   int32_t* len_out;      // [B]
-  int16_t* lab_ws;       // [B][2][bw][T] raw labelings of the live beams (global scratch, L2 resident)
+  uint32_t* trellis;     // [B][T][bw] back-pointers: parent | op << 8 | class << 16 (global scratch, write-only in the loop)
   const uint8_t* collapse_ignore;  // [C] or null (class 0 always dropped)
   const int32_t* span_row0;  // optional [B]: item b reads rows span_row0[b] .. +span_len[b] of probs seen as [rows][C]
   const int32_t* span_len;   // optional [B]: timesteps of item b (<= T); null = every item has T rows at b*T
@@ -157,6 +159,7 @@ struct BeamParams {
 };
 
 enum : int { kOpSame = 0, kOpAppend = 1, kOpReplace = 2 };
+constexpr int kBeamRankMaxE = 128;  // rank-based top-bw selection up to this many candidate entries, iterative above
 
 __device__ __forceinline__ uint64_t beam_hash_mix(uint64_t h, int c) {
   uint64_t x = (h + static_cast<uint64_t>(c) + 1ull) * 0x9E3779B97F4A7C15ull;
@@ -168,12 +171,15 @@ struct BeamSmem {
   float* row; int16_t* cand;
   // live beams, double buffered: [2][bw]
   float *b_tot, *b_nb, *b_b; int32_t* b_len; int16_t *b_last, *b_last2; uint64_t *b_hash, *b_hprev;
-  // candidate entries of the current step: [emax]
+  // candidate entries of the current step: [emax]; the first five arrays are contiguous (24 B per entry) and are
+  // reused after the time loop as the staging area of the trellis
   uint64_t* e_hash; float *e_tot, *e_nb, *e_b; int32_t* e_len; int16_t* e_c; uint8_t *e_parent, *e_op, *e_valid;
-  int32_t* ht;  // [hs]
+  int32_t* ht;       // [hs]
+  uint32_t* chain;   // [T] back-pointers of the winning path
+  int16_t* raw;      // [T] its raw labeling
 };
 
-__host__ __device__ inline size_t beam_smem_bytes(int C, int bw, int emax, int hs) {
+__host__ __device__ inline size_t beam_smem_bytes(int C, int bw, int emax, int hs, int T) {
   size_t n = 0;
   n += (size_t)C * 4 + (size_t)((C * 2 + 7) & ~7);
   n += (size_t)2 * bw * (4 * 3 + 4 + 2 * 2 + 8 * 2);
@@ -181,6 +187,7 @@ __host__ __device__ inline size_t beam_smem_bytes(int C, int bw, int emax, int h
   n += (size_t)emax * (8 + 4 * 3 + 4 + 2 + 3);
   n = (n + 7) & ~(size_t)7;
   n += (size_t)hs * 4;
+  n += (size_t)T * 4 + (size_t)((T * 2 + 7) & ~7);
   return n + 64;
 }
 
@@ -193,30 +200,33 @@ __global__ void __launch_bounds__(32) ctc_beam_kernel(const BeamParams p) {
   // ---- carve shared memory (8-byte fields first)
   uint8_t* q = dsm;
   BeamSmem s;
+  s.e_hash = reinterpret_cast<uint64_t*>(q); q += (size_t)emax * 8;
+  s.e_tot = reinterpret_cast<float*>(q); q += (size_t)emax * 4;
+  s.e_nb = reinterpret_cast<float*>(q); q += (size_t)emax * 4;
+  s.e_b = reinterpret_cast<float*>(q); q += (size_t)emax * 4;
+  s.e_len = reinterpret_cast<int32_t*>(q); q += (size_t)emax * 4;
+  q = dsm + (((size_t)emax * 24 + 7) & ~(size_t)7);
   s.b_hash = reinterpret_cast<uint64_t*>(q); q += (size_t)2 * bw * 8;
   s.b_hprev = reinterpret_cast<uint64_t*>(q); q += (size_t)2 * bw * 8;
-  s.e_hash = reinterpret_cast<uint64_t*>(q); q += (size_t)emax * 8;
   s.row = reinterpret_cast<float*>(q); q += (size_t)C * 4;
   s.b_tot = reinterpret_cast<float*>(q); q += (size_t)2 * bw * 4;
   s.b_nb = reinterpret_cast<float*>(q); q += (size_t)2 * bw * 4;
   s.b_b = reinterpret_cast<float*>(q); q += (size_t)2 * bw * 4;
   s.b_len = reinterpret_cast<int32_t*>(q); q += (size_t)2 * bw * 4;
-  s.e_tot = reinterpret_cast<float*>(q); q += (size_t)emax * 4;
-  s.e_nb = reinterpret_cast<float*>(q); q += (size_t)emax * 4;
-  s.e_b = reinterpret_cast<float*>(q); q += (size_t)emax * 4;
-  s.e_len = reinterpret_cast<int32_t*>(q); q += (size_t)emax * 4;
   s.ht = reinterpret_cast<int32_t*>(q); q += (size_t)p.hs * 4;
+  s.chain = reinterpret_cast<uint32_t*>(q); q += (size_t)T * 4;
   s.b_last = reinterpret_cast<int16_t*>(q); q += (size_t)2 * bw * 2;
   s.b_last2 = reinterpret_cast<int16_t*>(q); q += (size_t)2 * bw * 2;
   s.e_c = reinterpret_cast<int16_t*>(q); q += (size_t)emax * 2;
   s.cand = reinterpret_cast<int16_t*>(q); q += (size_t)C * 2;
+  s.raw = reinterpret_cast<int16_t*>(q); q += (size_t)T * 2;
   s.e_parent = q; q += emax;
   s.e_op = q; q += emax;
   s.e_valid = q; q += emax;
 
   const float thr = static_cast<float>(0.5 / static_cast<double>(C));  // np.float32(0.5 / maxC)
   const float* mat = p.probs + (p.span_row0 ? (size_t)p.span_row0[b] * C : (size_t)b * T * C);
-  int16_t* lab = p.lab_ws + (size_t)b * 2 * bw * T;
+  uint32_t* trel = p.trellis + (size_t)b * T * bw;
   const uint64_t kEmptyHash = 0x243F6A8885A308D3ull;
 
   int cur = 0;   // which half of the double-buffered beam state holds the parents
@@ -225,20 +235,52 @@ __global__ void __launch_bounds__(32) ctc_beam_kernel(const BeamParams p) {
     s.b_tot[0] = 1.f; s.b_nb[0] = 0.f; s.b_b[0] = 1.f; s.b_len[0] = 0;
     s.b_last[0] = -1; s.b_last2[0] = -1; s.b_hash[0] = kEmptyHash; s.b_hprev[0] = kEmptyHash;
   }
+  // the probability row of the NEXT step is fetched while the current one is processed (C <= 256; larger class
+  // counts read the row in place)
+  const bool prefetch = C <= 32 * kMaxClassesPerLane;
+  float nxt_v[kMaxClassesPerLane];
+#pragma unroll
+  for (int k = 0; k < kMaxClassesPerLane; ++k) {
+    const int c = lane + 32 * k;
+    nxt_v[k] = (prefetch && Tb > 0 && c < C) ? __ldg(mat + c) : 0.f;
+  }
   __syncwarp();
 
   for (int t = 0; t < Tb; ++t) {
     // ---- a. stage the probability row, list the classes above threshold in ascending order
-    const float* rowg = mat + (size_t)t * C;
     int ncand = 0;
-    for (int c0 = 0; c0 < C; c0 += 32) {
-      const int c = c0 + lane;
-      float v = 0.f;
-      bool pred = false;
-      if (c < C) { v = __ldg(rowg + c); s.row[c] = v; pred = v >= thr; }
-      const uint32_t m = __ballot_sync(0xffffffffu, pred);
-      if (pred) s.cand[ncand + __popc(m & ((1u << lane) - 1u))] = static_cast<int16_t>(c);
-      ncand += __popc(m);
+    if (prefetch) {
+#pragma unroll
+      for (int k = 0; k < kMaxClassesPerLane; ++k) {
+        const int c = lane + 32 * k;
+        if (32 * k < C) {  // uniform
+          const float v = nxt_v[k];
+          bool pred = false;
+          if (c < C) { s.row[c] = v; pred = v >= thr; }
+          const uint32_t m = __ballot_sync(0xffffffffu, pred);
+          if (pred) s.cand[ncand + __popc(m & ((1u << lane) - 1u))] = static_cast<int16_t>(c);
+          ncand += __popc(m);
+        }
+      }
+    } else {
+      const float* rowg = mat + (size_t)t * C;
+      for (int c0 = 0; c0 < C; c0 += 32) {
+        const int c = c0 + lane;
+        float v = 0.f;
+        bool pred = false;
+        if (c < C) { v = __ldg(rowg + c); s.row[c] = v; pred = v >= thr; }
+        const uint32_t m = __ballot_sync(0xffffffffu, pred);
+        if (pred) s.cand[ncand + __popc(m & ((1u << lane) - 1u))] = static_cast<int16_t>(c);
+        ncand += __popc(m);
+      }
+    }
+    if (prefetch && t + 1 < Tb) {
+      const float* rown = mat + (size_t)(t + 1) * C;
+#pragma unroll
+      for (int k = 0; k < kMaxClassesPerLane; ++k) {
+        const int c = lane + 32 * k;
+        nxt_v[k] = c < C ? __ldg(rown + c) : 0.f;
+      }
     }
     const int per_parent = 1 + ncand;
     const int E = nb * per_parent;
@@ -247,8 +289,11 @@ __global__ void __launch_bounds__(32) ctc_beam_kernel(const BeamParams p) {
     for (int i = lane; i < hs; i += 32) s.ht[i] = -1;
     for (int i = lane; i < E; i += 32) s.e_valid[i] = 0;
     __syncwarp();
+    const bool blank_cand = ncand > 0 && s.cand[0] == 0;  // blank passes the threshold: its extension is the parent's own labeling
 
-    // ---- b. expand every parent in rank order; entries merge by labeling (hash, length)
+    // ---- b. expand every parent in rank order; entries merge by labeling (hash, length). Within one parent the
+    // candidates are distinct labelings except "extend by blank", which IS the copy-beam's labeling: lane 0 adds
+    // that contribution right after the copy-beam's own (the reference's order), so one insertion pass suffices.
     const float* pt = s.b_tot + cur * bw; const float* pn = s.b_nb + cur * bw; const float* pb = s.b_b + cur * bw;
     const int32_t* pl = s.b_len + cur * bw; const int16_t* pla = s.b_last + cur * bw; const int16_t* pl2 = s.b_last2 + cur * bw;
     const uint64_t* ph = s.b_hash + cur * bw; const uint64_t* php = s.b_hprev + cur * bw;
@@ -260,110 +305,156 @@ __global__ void __launch_bounds__(32) ctc_beam_kernel(const BeamParams p) {
       // candidate k == 0 is the copy-beam, k >= 1 extends with cand[k-1]
       for (int k0 = 0; k0 < per_parent; k0 += 32) {
         const int k = k0 + lane;
-        // the copy-beam must land before this parent's extensions (an extension by blank may merge into it)
-        const bool active = k < per_parent;
+        bool active = k < per_parent;
         int op = kOpSame, c = 0, nlen = P_len;
         uint64_t nhash = P_hash;
-        float add_nb = 0.f, add_b = 0.f, add_tot = 0.f;
+        float add_nb = 0.f, add_b = 0.f, add_tot = 0.f, add_nb2 = 0.f;
+        bool second = false;
         if (active) {
           if (k == 0) {
             const float nbv = P_len > 0 ? __fmul_rn(P_nb, s.row[P_last]) : 0.f;
             const float blv = __fmul_rn(P_tot, s.row[0]);
             add_nb = nbv; add_b = blv; add_tot = __fadd_rn(blv, nbv);
+            if (blank_cand) {
+              // extension by blank (class 0): op Same unless the parent already ends in blank... which is Same too
+              // when P_len == 0 or P_last == 0; otherwise it appends a blank and is handled by lane 1 below
+              const bool same = (P_len == 0) || (P_last == 0);
+              if (same) { second = true; add_nb2 = __fmul_rn(s.row[0], (P_len > 0 && P_last == 0) ? P_b : P_tot); }
+            }
           } else {
             c = s.cand[k - 1];
             if (P_len == 0) op = (c == 0) ? kOpSame : kOpAppend;
             else if (c == 0) op = (P_last == 0) ? kOpSame : kOpAppend;
             else if (P_last == 0) op = (P_last2 == c) ? kOpAppend : kOpReplace;
             else op = kOpAppend;
+            if (op == kOpSame) active = false;  // folded into the copy-beam by lane 0
             if (op == kOpAppend) { nhash = beam_hash_mix(P_hash, c); nlen = P_len + 1; }
             else if (op == kOpReplace) { nhash = beam_hash_mix(P_hprev, c); nlen = P_len; }
             const float pr = __fmul_rn(s.row[c], (P_len > 0 && P_last == c) ? P_b : P_tot);
             add_nb = pr; add_tot = pr;
           }
         }
-        // two passes so that k == 0 (lane 0 of the first chunk) is inserted strictly before the others
-        for (int pass = 0; pass < 2; ++pass) {
-          const bool mine = active && ((pass == 0) == (k == 0));
-          if (mine) {
-            const int self = i * per_parent + k;  // creation order == reference dict insertion order
-            s.e_hash[self] = nhash; s.e_len[self] = nlen; s.e_c[self] = static_cast<int16_t>(c);
-            s.e_parent[self] = static_cast<uint8_t>(i); s.e_op[self] = static_cast<uint8_t>(op);
-            s.e_tot[self] = 0.f; s.e_nb[self] = 0.f; s.e_b[self] = 0.f;
-            __threadfence_block();
-            uint32_t slot = static_cast<uint32_t>(nhash ^ (nhash >> 32)) & (hs - 1);
-            int idx;
-            while (true) {
-              const int seen = atomicCAS(&s.ht[slot], -1, self);
-              if (seen == -1) { idx = self; s.e_valid[self] = 1; break; }
-              if (s.e_hash[seen] == nhash && s.e_len[seen] == nlen) { idx = seen; break; }
-              slot = (slot + 1) & (hs - 1);
-            }
-            // within one parent all candidates are distinct labelings, so no two lanes share idx here
-            s.e_nb[idx] = __fadd_rn(s.e_nb[idx], add_nb);
-            if (k == 0) s.e_b[idx] = __fadd_rn(s.e_b[idx], add_b);
-            s.e_tot[idx] = __fadd_rn(s.e_tot[idx], add_tot);
-          }
-          __syncwarp();
+        const int self = i * per_parent + k;  // creation order == reference dict insertion order
+        if (active) {
+          s.e_hash[self] = nhash; s.e_len[self] = nlen; s.e_c[self] = static_cast<int16_t>(c);
+          s.e_parent[self] = static_cast<uint8_t>(i); s.e_op[self] = static_cast<uint8_t>(op);
+          s.e_tot[self] = 0.f; s.e_nb[self] = 0.f; s.e_b[self] = 0.f;
         }
+        __syncwarp();
+        if (active) {
+          uint32_t slot = static_cast<uint32_t>(nhash ^ (nhash >> 32)) & (hs - 1);
+          int idx;
+          while (true) {
+            const int seen = atomicCAS(&s.ht[slot], -1, self);
+            if (seen == -1) { idx = self; s.e_valid[self] = 1; break; }
+            if (s.e_hash[seen] == nhash && s.e_len[seen] == nlen) { idx = seen; break; }
+            slot = (slot + 1) & (hs - 1);
+          }
+          // no two lanes share idx here (distinct labelings within one parent)
+          s.e_nb[idx] = __fadd_rn(s.e_nb[idx], add_nb);
+          if (k == 0) s.e_b[idx] = __fadd_rn(s.e_b[idx], add_b);
+          s.e_tot[idx] = __fadd_rn(s.e_tot[idx], add_tot);
+          if (second) {
+            s.e_nb[idx] = __fadd_rn(s.e_nb[idx], add_nb2);
+            s.e_tot[idx] = __fadd_rn(s.e_tot[idx], add_nb2);
+          }
+        }
+        __syncwarp();
       }
     }
 
     // ---- c. keep the best `bw` entries: prTotal descending, creation order ascending on ties (stable sort)
     const int nxt = cur ^ 1;
+    uint32_t* trow = trel + (size_t)t * bw;
     int n_new = 0;
-    for (int r = 0; r < bw; ++r) {
-      float best = -INFINITY;
-      int besti = 0x7fffffff;
-      for (int j = lane; j < E; j += 32)
-        if (s.e_valid[j]) {
-          const float v = s.e_tot[j];
-          if (v > best || (v == best && j < besti)) { best = v; besti = j; }
-        }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
-        if (oi != 0x7fffffff && (besti == 0x7fffffff || ob > best || (ob == best && oi < besti))) { best = ob; besti = oi; }
-      }
-      if (besti == 0x7fffffff) break;
-      const int j = besti;
+    auto emit = [&](int j, int r) {
+      // entry j becomes beam r of the next step
       const int par = s.e_parent[j], op = s.e_op[j], c = s.e_c[j];
-      const int plen = pl[par];
-      // materialise the labeling: copy the parent's, then append / replace the last element
-      const int16_t* src = lab + ((size_t)cur * bw + par) * T;
-      int16_t* dst = lab + ((size_t)nxt * bw + r) * T;
-      for (int x = lane; x < plen; x += 32) dst[x] = src[x];
-      __syncwarp();
-      if (lane == 0) {
-        s.e_valid[j] = 0;
-        if (op == kOpAppend) dst[plen] = static_cast<int16_t>(c);
-        else if (op == kOpReplace) dst[plen - 1] = static_cast<int16_t>(c);
-        const int o = nxt * bw + r;
-        s.b_tot[o] = s.e_tot[j]; s.b_nb[o] = s.e_nb[j]; s.b_b[o] = s.e_b[j]; s.b_len[o] = s.e_len[j];
-        s.b_hash[o] = s.e_hash[j];
-        if (op == kOpSame) { s.b_last[o] = pla[par]; s.b_last2[o] = pl2[par]; s.b_hprev[o] = php[par]; }
-        else if (op == kOpAppend) { s.b_last[o] = static_cast<int16_t>(c); s.b_last2[o] = pla[par]; s.b_hprev[o] = ph[par]; }
-        else { s.b_last[o] = static_cast<int16_t>(c); s.b_last2[o] = pl2[par]; s.b_hprev[o] = php[par]; }
+      const int o = nxt * bw + r;
+      s.b_tot[o] = s.e_tot[j]; s.b_nb[o] = s.e_nb[j]; s.b_b[o] = s.e_b[j]; s.b_len[o] = s.e_len[j];
+      s.b_hash[o] = s.e_hash[j];
+      if (op == kOpSame) { s.b_last[o] = pla[par]; s.b_last2[o] = pl2[par]; s.b_hprev[o] = php[par]; }
+      else if (op == kOpAppend) { s.b_last[o] = static_cast<int16_t>(c); s.b_last2[o] = pla[par]; s.b_hprev[o] = ph[par]; }
+      else { s.b_last[o] = static_cast<int16_t>(c); s.b_last2[o] = pl2[par]; s.b_hprev[o] = php[par]; }
+      trow[r] = static_cast<uint32_t>(par) | (static_cast<uint32_t>(op) << 8) | (static_cast<uint32_t>(c) << 16);
+    };
+    if (E <= kBeamRankMaxE) {
+      // every valid entry counts the entries that sort before it; rank < bw survives as beam `rank`
+      int nvalid = 0;
+      for (int j0 = 0; j0 < E; j0 += 32) {
+        const int j = j0 + lane;
+        const bool v = j < E && s.e_valid[j];
+        nvalid += __popc(__ballot_sync(0xffffffffu, v));
+        if (v) {
+          const float mine = s.e_tot[j];
+          int rank = 0;
+          for (int x = 0; x < E; ++x)
+            if (s.e_valid[x]) {
+              const float ov = s.e_tot[x];
+              rank += (ov > mine || (ov == mine && x < j)) ? 1 : 0;
+            }
+          if (rank < bw) emit(j, rank);
+        }
       }
-      __syncwarp();
-      ++n_new;
+      n_new = nvalid < bw ? nvalid : bw;
+    } else {
+      for (int r = 0; r < bw; ++r) {
+        float best = -INFINITY;
+        int besti = 0x7fffffff;
+        for (int j = lane; j < E; j += 32)
+          if (s.e_valid[j]) {
+            const float v = s.e_tot[j];
+            if (v > best || (v == best && j < besti)) { best = v; besti = j; }
+          }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+          if (oi != 0x7fffffff && (besti == 0x7fffffff || ob > best || (ob == best && oi < besti))) { best = ob; besti = oi; }
+        }
+        if (besti == 0x7fffffff) break;
+        if (lane == 0) { s.e_valid[besti] = 0; emit(besti, r); }
+        __syncwarp();
+        ++n_new;
+      }
     }
     nb = n_new;
     cur = nxt;
     __syncwarp();
   }
 
-  // ---- best labeling -> drop ignored indices and adjacent duplicates of the RAW labeling (utils.py:1031-1035)
+  // ---- rebuild the best labeling from the trellis, then drop ignored indices and adjacent duplicates of the RAW
+  // labeling (utils.py:1031-1035). The trellis of this line is staged in the (now dead) entry arrays when it fits.
+  const size_t trel_words = (size_t)Tb * bw;
+  const uint32_t* tsrc = trel;
+  if (trel_words * 4 <= (size_t)emax * 24) {
+    uint32_t* stg = reinterpret_cast<uint32_t*>(s.e_hash);
+    for (size_t i = lane; i < trel_words; i += 32) stg[i] = trel[i];
+    tsrc = stg;
+  }
+  __syncwarp();
   if (lane == 0) {
-    const int16_t* best = lab + ((size_t)cur * bw + 0) * T;
-    const int len = nb > 0 ? s.b_len[cur * bw] : 0;
+    int len = 0;
+    if (nb > 0) {
+      int r = 0;
+      for (int t = Tb - 1; t >= 0; --t) {
+        const uint32_t e = tsrc[(size_t)t * bw + r];
+        s.chain[t] = e;
+        r = static_cast<int>(e & 0xffu);
+      }
+      for (int t = 0; t < Tb; ++t) {
+        const uint32_t e = s.chain[t];
+        const int op = (e >> 8) & 0xff, c = static_cast<int>(e >> 16);
+        if (op == kOpAppend) s.raw[len++] = static_cast<int16_t>(c);
+        else if (op == kOpReplace) s.raw[len - 1] = static_cast<int16_t>(c);
+      }
+    }
     int32_t* lo = p.labels_out + (size_t)b * T;
     int n = 0;
     for (int i = 0; i < len; ++i) {
-      const int l = best[i];
+      const int l = s.raw[i];
       const bool ign = (l == 0) || (p.collapse_ignore && p.collapse_ignore[l]);
-      if (!ign && !(i > 0 && best[i - 1] == l)) lo[n++] = l;
+      if (!ign && !(i > 0 && s.raw[i - 1] == l)) lo[n++] = l;
     }
     p.len_out[b] = n;
   }

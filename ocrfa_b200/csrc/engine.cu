@@ -1063,7 +1063,7 @@ static int beam_launch(const float* d_probs, const int32_t* d_span_row0, const i
   if (beam_width < 1 || beam_width > 64) return fail(OCRFA_ERR_ARG, "beam_width must be in [1, 64]");
   if (ws_bytes < beam_ws_bytes(B, T, C, beam_width)) return fail(OCRFA_ERR_WORKSPACE, "beam workspace too small");
   BeamParams p;
-  p.probs = d_probs; p.labels_out = d_labels; p.len_out = d_len; p.lab_ws = (int16_t*)d_ws;
+  p.probs = d_probs; p.labels_out = d_labels; p.len_out = d_len; p.trellis = (uint32_t*)d_ws;
   p.collapse_ignore = d_collapse_ignore;
   p.span_row0 = d_span_row0; p.span_len = d_span_len;
   p.B = B; p.T = T; p.C = C; p.bw = beam_width;
@@ -1071,7 +1071,7 @@ static int beam_launch(const float* d_probs, const int32_t* d_span_row0, const i
   int hs = 64;
   while (hs < 2 * p.emax) hs <<= 1;
   p.hs = hs;
-  const size_t smem = beam_smem_bytes(C, beam_width, p.emax, hs);
+  const size_t smem = beam_smem_bytes(C, beam_width, p.emax, hs, T);
   if (smem > 227 * 1024) return fail(OCRFA_ERR_ARG, "beam_width * num_class too large for shared memory (%zu B)", smem);
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
