@@ -70,8 +70,19 @@ __device__ __forceinline__ void red_release_gpu_add(unsigned int* p, unsigned in
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 // ex2.approx-based gate activations (abs error ~1e-6, far below the bf16 rounding of h); saturate cleanly at +-inf.
+#ifdef OCRFA_LSTM_TANH_APPROX
+// one MUFU op per activation (tanh.approx.f32, rel. error 2^-11) instead of two (ex2 + rcp): the gate math of a
+// step is MUFU-throughput bound (16 units x 5 activations x 128 rows per CTA)
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(tanh_fast(0.5f * x), 0.5f, 0.5f); }
+#else
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float tanh_fast(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
+#endif
 
 template <int MODE> __device__ __forceinline__ float lstm_sigmoid(float x) {
   return MODE == kLstmF16Split ? sigmoidf_acc(x) : sigmoid_fast(x);

@@ -25,6 +25,8 @@ KEEP = {
     "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed": "dram_throughput_pct",
     "dram__throughput.avg.pct_of_peak_sustained_elapsed": "dram_throughput_pct",
     "lts__t_sector_hit_rate.pct": "l2_hit_rate_pct",
+    "lts__throughput.avg.pct_of_peak_sustained_elapsed": "l2_throughput_pct",
+    "l1tex__throughput.avg.pct_of_peak_sustained_elapsed": "l1tex_throughput_pct",
     "launch__registers_per_thread": "registers_per_thread",
     "sm__warps_active.avg.pct_of_peak_sustained_active": "achieved_occupancy_pct",
     "smsp__cycles_active.avg": "smsp_cycles_active_avg",
@@ -69,7 +71,7 @@ def main():
     args = ap.parse_args()
     recs = parse(args.raw_csv)
     summary = {"source": args.raw_csv, "note": args.note, "launches": recs}
-    sel = [r for r in recs if args.kernel in r["kernel"] and "dram_read_bytes" in r]
+    sel = [r for r in recs if any(k in r["kernel"] for k in args.kernel.split(",")) and "dram_read_bytes" in r]
     if sel:
         tot_b = sum(r["dram_read_bytes"] + r["dram_write_bytes"] for r in sel)
         tot_us = sum(r.get("duration_us", 0.0) for r in sel)
