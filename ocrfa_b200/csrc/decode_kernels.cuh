@@ -159,7 +159,6 @@ struct BeamParams {
 };
 
 enum : int { kOpSame = 0, kOpAppend = 1, kOpReplace = 2 };
-constexpr int kBeamRankMaxE = 128;  // rank-based top-bw selection up to this many candidate entries, iterative above
 
 __device__ __forceinline__ uint64_t beam_hash_mix(uint64_t h, int c) {
   uint64_t x = (h + static_cast<uint64_t>(c) + 1ull) * 0x9E3779B97F4A7C15ull;
@@ -171,26 +170,43 @@ struct BeamSmem {
   float* row; int16_t* cand;
   // live beams, double buffered: [2][bw]
   float *b_tot, *b_nb, *b_b; int32_t* b_len; int16_t *b_last, *b_last2; uint64_t *b_hash, *b_hprev;
-  // candidate entries of the current step: [emax]; the first five arrays are contiguous (24 B per entry) and are
-  // reused after the time loop as the staging area of the trellis
-  uint64_t* e_hash; float *e_tot, *e_nb, *e_b; int32_t* e_len; int16_t* e_c; uint8_t *e_parent, *e_op, *e_valid;
-  int32_t* ht;       // [hs]
+  // candidate entries of the current step: [emax]. e_hash .. e_first are contiguous (28 B per entry) and are reused
+  // after the time loop as the staging area of the trellis.
+  uint64_t* e_hash;
+  float *a_tot, *a_nb, *a_b;           // accumulated probabilities of the labeling this entry REPRESENTS
+  float* x_nb;                         // this entry's own prNonBlank contribution
+  float *xp_b, *xp_2;                  // [bw] per parent: the copy-beam's prBlank contribution / its "extend by blank" one
+  int32_t* e_first;                    // creation order of the labeling (min member entry index)
+  int16_t *e_len, *e_rep;              // labeling length; representative entry of this entry's labeling
+  int16_t* e_c; uint8_t *e_parent, *e_op, *e_flags;
+  uint16_t* ht;      // [hs], 0xffff = empty
   uint32_t* chain;   // [T] back-pointers of the winning path
   int16_t* raw;      // [T] its raw labeling
 };
+enum : int { kEfActive = 1, kEfSecond = 2 };
+constexpr int kBeamEntryBytes = 8 + 4 * 3 + 4 + 4 + 2 * 3 + 3;  // 37
+constexpr int kBeamRegChunks = 8;  // register-resident top-bw selection up to 32 * 8 candidate entries
 
 __host__ __device__ inline size_t beam_smem_bytes(int C, int bw, int emax, int hs, int T) {
   size_t n = 0;
   n += (size_t)C * 4 + (size_t)((C * 2 + 7) & ~7);
-  n += (size_t)2 * bw * (4 * 3 + 4 + 2 * 2 + 8 * 2);
+  n += (size_t)2 * bw * (4 * 3 + 4 + 2 * 2 + 8 * 2) + (size_t)bw * 8;
   n = (n + 7) & ~(size_t)7;
-  n += (size_t)emax * (8 + 4 * 3 + 4 + 2 + 3);
+  n += (size_t)emax * kBeamEntryBytes;
   n = (n + 7) & ~(size_t)7;
-  n += (size_t)hs * 4;
+  n += (size_t)hs * 2;
   n += (size_t)T * 4 + (size_t)((T * 2 + 7) & ~7);
   return n + 64;
 }
 
+// One warp per line. Per timestep:
+//   1. every (parent, candidate) entry is built IN PARALLEL (32 entries per pass): labeling hash/length, edit op,
+//      its probability contribution; entries of equal labeling find one representative through a shared-memory
+//      hash table and record the labeling's creation order (min entry index = the reference's dict insertion order);
+//   2. the contributions are accumulated into the representatives parent by parent, in rank order - exactly the
+//      reference's sequence of float32 `+=` (utils.py:1004-1026), so the sums are bit-identical;
+//   3. the best `bw` labelings (prTotal descending, creation order ascending on ties = Python's stable sort) are
+//      picked with warp redux operations over register-resident keys.
 __global__ void __launch_bounds__(32) ctc_beam_kernel(const BeamParams p) {
   extern __shared__ __align__(16) uint8_t dsm[];
   const int lane = threadIdx.x;
@@ -201,11 +217,12 @@ __global__ void __launch_bounds__(32) ctc_beam_kernel(const BeamParams p) {
   uint8_t* q = dsm;
   BeamSmem s;
   s.e_hash = reinterpret_cast<uint64_t*>(q); q += (size_t)emax * 8;
-  s.e_tot = reinterpret_cast<float*>(q); q += (size_t)emax * 4;
-  s.e_nb = reinterpret_cast<float*>(q); q += (size_t)emax * 4;
-  s.e_b = reinterpret_cast<float*>(q); q += (size_t)emax * 4;
-  s.e_len = reinterpret_cast<int32_t*>(q); q += (size_t)emax * 4;
-  q = dsm + (((size_t)emax * 24 + 7) & ~(size_t)7);
+  s.a_tot = reinterpret_cast<float*>(q); q += (size_t)emax * 4;
+  s.a_nb = reinterpret_cast<float*>(q); q += (size_t)emax * 4;
+  s.a_b = reinterpret_cast<float*>(q); q += (size_t)emax * 4;
+  s.x_nb = reinterpret_cast<float*>(q); q += (size_t)emax * 4;
+  s.e_first = reinterpret_cast<int32_t*>(q); q += (size_t)emax * 4;
+  q = dsm + (((size_t)emax * 28 + 7) & ~(size_t)7);
   s.b_hash = reinterpret_cast<uint64_t*>(q); q += (size_t)2 * bw * 8;
   s.b_hprev = reinterpret_cast<uint64_t*>(q); q += (size_t)2 * bw * 8;
   s.row = reinterpret_cast<float*>(q); q += (size_t)C * 4;
@@ -213,8 +230,12 @@ __global__ void __launch_bounds__(32) ctc_beam_kernel(const BeamParams p) {
   s.b_nb = reinterpret_cast<float*>(q); q += (size_t)2 * bw * 4;
   s.b_b = reinterpret_cast<float*>(q); q += (size_t)2 * bw * 4;
   s.b_len = reinterpret_cast<int32_t*>(q); q += (size_t)2 * bw * 4;
-  s.ht = reinterpret_cast<int32_t*>(q); q += (size_t)p.hs * 4;
+  s.xp_b = reinterpret_cast<float*>(q); q += (size_t)bw * 4;
+  s.xp_2 = reinterpret_cast<float*>(q); q += (size_t)bw * 4;
   s.chain = reinterpret_cast<uint32_t*>(q); q += (size_t)T * 4;
+  s.ht = reinterpret_cast<uint16_t*>(q); q += (size_t)p.hs * 2;
+  s.e_len = reinterpret_cast<int16_t*>(q); q += (size_t)emax * 2;
+  s.e_rep = reinterpret_cast<int16_t*>(q); q += (size_t)emax * 2;
   s.b_last = reinterpret_cast<int16_t*>(q); q += (size_t)2 * bw * 2;
   s.b_last2 = reinterpret_cast<int16_t*>(q); q += (size_t)2 * bw * 2;
   s.e_c = reinterpret_cast<int16_t*>(q); q += (size_t)emax * 2;
@@ -222,7 +243,7 @@ __global__ void __launch_bounds__(32) ctc_beam_kernel(const BeamParams p) {
   s.raw = reinterpret_cast<int16_t*>(q); q += (size_t)T * 2;
   s.e_parent = q; q += emax;
   s.e_op = q; q += emax;
-  s.e_valid = q; q += emax;
+  s.e_flags = q; q += emax;
 
   const float thr = static_cast<float>(0.5 / static_cast<double>(C));  // np.float32(0.5 / maxC)
   const float* mat = p.probs + (p.span_row0 ? (size_t)p.span_row0[b] * C : (size_t)b * T * C);
@@ -286,134 +307,150 @@ __global__ void __launch_bounds__(32) ctc_beam_kernel(const BeamParams p) {
     const int E = nb * per_parent;
     int hs = 64;
     while (hs < 2 * E) hs <<= 1;
-    for (int i = lane; i < hs; i += 32) s.ht[i] = -1;
-    for (int i = lane; i < E; i += 32) s.e_valid[i] = 0;
+    for (int i = lane; i < hs; i += 32) s.ht[i] = 0xffffu;
     __syncwarp();
-    const bool blank_cand = ncand > 0 && s.cand[0] == 0;  // blank passes the threshold: its extension is the parent's own labeling
+    const bool blank_cand = ncand > 0 && s.cand[0] == 0;  // blank passes the threshold
 
-    // ---- b. expand every parent in rank order; entries merge by labeling (hash, length). Within one parent the
-    // candidates are distinct labelings except "extend by blank", which IS the copy-beam's labeling: lane 0 adds
-    // that contribution right after the copy-beam's own (the reference's order), so one insertion pass suffices.
     const float* pt = s.b_tot + cur * bw; const float* pn = s.b_nb + cur * bw; const float* pb = s.b_b + cur * bw;
     const int32_t* pl = s.b_len + cur * bw; const int16_t* pla = s.b_last + cur * bw; const int16_t* pl2 = s.b_last2 + cur * bw;
     const uint64_t* ph = s.b_hash + cur * bw; const uint64_t* php = s.b_hprev + cur * bw;
-    for (int i = 0; i < nb; ++i) {
+
+    // ---- b1. build all entries. Entry index self = parent * per_parent + k is the reference's creation order
+    // (k == 0: copy-beam, k >= 1: extension by cand[k-1]). "Extend by blank" of a parent that is empty or already
+    // ends in blank IS the parent's own labeling: it has no entry of its own, the copy-beam entry carries it as a
+    // second contribution (added right after its own, the reference's order).
+    for (int e0 = 0; e0 < E; e0 += 32) {
+      const int self = e0 + lane;
+      bool active = self < E;
+      int i = 0, k = 0;
+      if (active) { i = self / per_parent; k = self - i * per_parent; }
       const float P_tot = pt[i], P_nb = pn[i], P_b = pb[i];
       const int P_len = pl[i];
       const int P_last = pla[i], P_last2 = pl2[i];
       const uint64_t P_hash = ph[i], P_hprev = php[i];
-      // candidate k == 0 is the copy-beam, k >= 1 extends with cand[k-1]
-      for (int k0 = 0; k0 < per_parent; k0 += 32) {
-        const int k = k0 + lane;
-        bool active = k < per_parent;
-        int op = kOpSame, c = 0, nlen = P_len;
-        uint64_t nhash = P_hash;
-        float add_nb = 0.f, add_b = 0.f, add_tot = 0.f, add_nb2 = 0.f;
-        bool second = false;
-        if (active) {
-          if (k == 0) {
-            const float nbv = P_len > 0 ? __fmul_rn(P_nb, s.row[P_last]) : 0.f;
-            const float blv = __fmul_rn(P_tot, s.row[0]);
-            add_nb = nbv; add_b = blv; add_tot = __fadd_rn(blv, nbv);
-            if (blank_cand) {
-              // extension by blank (class 0): op Same unless the parent already ends in blank... which is Same too
-              // when P_len == 0 or P_last == 0; otherwise it appends a blank and is handled by lane 1 below
-              const bool same = (P_len == 0) || (P_last == 0);
-              if (same) { second = true; add_nb2 = __fmul_rn(s.row[0], (P_len > 0 && P_last == 0) ? P_b : P_tot); }
-            }
-          } else {
-            c = s.cand[k - 1];
-            if (P_len == 0) op = (c == 0) ? kOpSame : kOpAppend;
-            else if (c == 0) op = (P_last == 0) ? kOpSame : kOpAppend;
-            else if (P_last == 0) op = (P_last2 == c) ? kOpAppend : kOpReplace;
-            else op = kOpAppend;
-            if (op == kOpSame) active = false;  // folded into the copy-beam by lane 0
-            if (op == kOpAppend) { nhash = beam_hash_mix(P_hash, c); nlen = P_len + 1; }
-            else if (op == kOpReplace) { nhash = beam_hash_mix(P_hprev, c); nlen = P_len; }
-            const float pr = __fmul_rn(s.row[c], (P_len > 0 && P_last == c) ? P_b : P_tot);
-            add_nb = pr; add_tot = pr;
+      int op = kOpSame, c = 0, nlen = P_len;
+      uint64_t nhash = P_hash;
+      float add_nb = 0.f, add_b = 0.f, add_tot = 0.f, add_2 = 0.f;
+      bool second = false;
+      if (active) {
+        if (k == 0) {
+          const float nbv = P_len > 0 ? __fmul_rn(P_nb, s.row[P_last]) : 0.f;
+          const float blv = __fmul_rn(P_tot, s.row[0]);
+          add_nb = nbv; add_b = blv; add_tot = __fadd_rn(blv, nbv);
+          if (blank_cand && ((P_len == 0) || (P_last == 0))) {
+            second = true;
+            add_2 = __fmul_rn(s.row[0], (P_len > 0 && P_last == 0) ? P_b : P_tot);
           }
+        } else {
+          c = s.cand[k - 1];
+          if (P_len == 0) op = (c == 0) ? kOpSame : kOpAppend;
+          else if (c == 0) op = (P_last == 0) ? kOpSame : kOpAppend;
+          else if (P_last == 0) op = (P_last2 == c) ? kOpAppend : kOpReplace;
+          else op = kOpAppend;
+          if (op == kOpSame) active = false;  // carried by the copy-beam entry
+          if (op == kOpAppend) { nhash = beam_hash_mix(P_hash, c); nlen = P_len + 1; }
+          else if (op == kOpReplace) { nhash = beam_hash_mix(P_hprev, c); nlen = P_len; }
+          const float pr = __fmul_rn(s.row[c], (P_len > 0 && P_last == c) ? P_b : P_tot);
+          add_nb = pr; add_tot = pr;
         }
-        const int self = i * per_parent + k;  // creation order == reference dict insertion order
-        if (active) {
-          s.e_hash[self] = nhash; s.e_len[self] = nlen; s.e_c[self] = static_cast<int16_t>(c);
-          s.e_parent[self] = static_cast<uint8_t>(i); s.e_op[self] = static_cast<uint8_t>(op);
-          s.e_tot[self] = 0.f; s.e_nb[self] = 0.f; s.e_b[self] = 0.f;
-        }
-        __syncwarp();
-        if (active) {
-          uint32_t slot = static_cast<uint32_t>(nhash ^ (nhash >> 32)) & (hs - 1);
-          int idx;
-          while (true) {
-            const int seen = atomicCAS(&s.ht[slot], -1, self);
-            if (seen == -1) { idx = self; s.e_valid[self] = 1; break; }
-            if (s.e_hash[seen] == nhash && s.e_len[seen] == nlen) { idx = seen; break; }
-            slot = (slot + 1) & (hs - 1);
-          }
-          // no two lanes share idx here (distinct labelings within one parent)
-          s.e_nb[idx] = __fadd_rn(s.e_nb[idx], add_nb);
-          if (k == 0) s.e_b[idx] = __fadd_rn(s.e_b[idx], add_b);
-          s.e_tot[idx] = __fadd_rn(s.e_tot[idx], add_tot);
-          if (second) {
-            s.e_nb[idx] = __fadd_rn(s.e_nb[idx], add_nb2);
-            s.e_tot[idx] = __fadd_rn(s.e_tot[idx], add_nb2);
-          }
-        }
-        __syncwarp();
       }
+      if (self < E) {
+        s.e_hash[self] = nhash; s.e_len[self] = static_cast<int16_t>(nlen); s.e_c[self] = static_cast<int16_t>(c);
+        s.e_parent[self] = static_cast<uint8_t>(i); s.e_op[self] = static_cast<uint8_t>(op);
+        s.e_flags[self] = static_cast<uint8_t>((active ? kEfActive : 0) | (second ? kEfSecond : 0));
+        s.x_nb[self] = add_nb;
+        if (k == 0) { s.xp_b[i] = add_b; s.xp_2[i] = add_2; }
+        s.a_tot[self] = 0.f; s.a_nb[self] = 0.f; s.a_b[self] = 0.f;
+        s.e_first[self] = 0x7fffffff; s.e_rep[self] = -1;
+      }
+      __syncwarp();
+      if (active) {
+        uint32_t slot = static_cast<uint32_t>(nhash ^ (nhash >> 32)) & (hs - 1);
+        int rep;
+        while (true) {
+          const int seen = atomicCAS(&s.ht[slot], static_cast<unsigned short>(0xffffu), static_cast<unsigned short>(self));
+          if (seen == 0xffff) { rep = self; break; }
+          if (s.e_hash[seen] == nhash && s.e_len[seen] == nlen) { rep = seen; break; }
+          slot = (slot + 1) & (hs - 1);
+        }
+        s.e_rep[self] = static_cast<int16_t>(rep);
+        atomicMin(&s.e_first[rep], self);
+      }
+      __syncwarp();
     }
 
-    // ---- c. keep the best `bw` entries: prTotal descending, creation order ascending on ties (stable sort)
+    // ---- b2. ordered accumulation: parent by parent (no two entries of one parent share a labeling)
+    for (int i = 0; i < nb; ++i) {
+      for (int k = lane; k < per_parent; k += 32) {
+        const int self = i * per_parent + k;
+        const int fl = s.e_flags[self];
+        if (fl & kEfActive) {
+          const int r = s.e_rep[self];
+          const float xnb = s.x_nb[self];
+          float vnb = __fadd_rn(s.a_nb[r], xnb);
+          // prTotal contribution: the copy-beam adds (prBlank + prNonBlank), an extension its prNonBlank
+          float vtot = __fadd_rn(s.a_tot[r], k == 0 ? __fadd_rn(s.xp_b[i], xnb) : xnb);
+          if (k == 0) s.a_b[r] = __fadd_rn(s.a_b[r], s.xp_b[i]);
+          if (fl & kEfSecond) { vnb = __fadd_rn(vnb, s.xp_2[i]); vtot = __fadd_rn(vtot, s.xp_2[i]); }
+          s.a_nb[r] = vnb; s.a_tot[r] = vtot;
+        }
+      }
+      __syncwarp();
+    }
+
+    // ---- c. keep the best `bw` labelings: prTotal descending, creation order ascending on ties (stable sort)
     const int nxt = cur ^ 1;
     uint32_t* trow = trel + (size_t)t * bw;
     int n_new = 0;
     auto emit = [&](int j, int r) {
-      // entry j becomes beam r of the next step
+      // labeling represented by entry j becomes beam r of the next step
       const int par = s.e_parent[j], op = s.e_op[j], c = s.e_c[j];
       const int o = nxt * bw + r;
-      s.b_tot[o] = s.e_tot[j]; s.b_nb[o] = s.e_nb[j]; s.b_b[o] = s.e_b[j]; s.b_len[o] = s.e_len[j];
+      s.b_tot[o] = s.a_tot[j]; s.b_nb[o] = s.a_nb[j]; s.b_b[o] = s.a_b[j]; s.b_len[o] = s.e_len[j];
       s.b_hash[o] = s.e_hash[j];
       if (op == kOpSame) { s.b_last[o] = pla[par]; s.b_last2[o] = pl2[par]; s.b_hprev[o] = php[par]; }
       else if (op == kOpAppend) { s.b_last[o] = static_cast<int16_t>(c); s.b_last2[o] = pla[par]; s.b_hprev[o] = ph[par]; }
       else { s.b_last[o] = static_cast<int16_t>(c); s.b_last2[o] = pl2[par]; s.b_hprev[o] = php[par]; }
       trow[r] = static_cast<uint32_t>(par) | (static_cast<uint32_t>(op) << 8) | (static_cast<uint32_t>(c) << 16);
     };
-    if (E <= kBeamRankMaxE) {
-      // every valid entry counts the entries that sort before it; rank < bw survives as beam `rank`
-      int nvalid = 0;
-      for (int j0 = 0; j0 < E; j0 += 32) {
-        const int j = j0 + lane;
-        const bool v = j < E && s.e_valid[j];
-        nvalid += __popc(__ballot_sync(0xffffffffu, v));
-        if (v) {
-          const float mine = s.e_tot[j];
-          int rank = 0;
-          for (int x = 0; x < E; ++x)
-            if (s.e_valid[x]) {
-              const float ov = s.e_tot[x];
-              rank += (ov > mine || (ov == mine && x < j)) ? 1 : 0;
-            }
-          if (rank < bw) emit(j, rank);
-        }
-      }
-      n_new = nvalid < bw ? nvalid : bw;
-    } else {
-      for (int r = 0; r < bw; ++r) {
-        float best = -INFINITY;
-        int besti = 0x7fffffff;
-        for (int j = lane; j < E; j += 32)
-          if (s.e_valid[j]) {
-            const float v = s.e_tot[j];
-            if (v > best || (v == best && j < besti)) { best = v; besti = j; }
-          }
+    // key of a representative: float bits of prTotal (non-negative, so integer order = float order) + 1; 0 = not a candidate
+    if (E <= 32 * kBeamRegChunks) {
+      uint32_t key[kBeamRegChunks];
+      int first[kBeamRegChunks];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-          const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
-          if (oi != 0x7fffffff && (besti == 0x7fffffff || ob > best || (ob == best && oi < besti))) { best = ob; besti = oi; }
-        }
-        if (besti == 0x7fffffff) break;
-        if (lane == 0) { s.e_valid[besti] = 0; emit(besti, r); }
+      for (int m = 0; m < kBeamRegChunks; ++m) {
+        const int j = lane + 32 * m;
+        key[m] = 0u; first[m] = 0x7fffffff;
+        if (j < E && s.e_rep[j] == j) { key[m] = __float_as_uint(s.a_tot[j]) + 1u; first[m] = s.e_first[j]; }
+      }
+      for (int r = 0; r < bw; ++r) {
+        uint32_t lmax = 0u;
+#pragma unroll
+        for (int m = 0; m < kBeamRegChunks; ++m) lmax = key[m] > lmax ? key[m] : lmax;
+        const uint32_t wmax = __reduce_max_sync(0xffffffffu, lmax);
+        if (wmax == 0u) break;
+        int lfirst = 0x7fffffff;
+#pragma unroll
+        for (int m = 0; m < kBeamRegChunks; ++m) lfirst = (key[m] == wmax && first[m] < lfirst) ? first[m] : lfirst;
+        const int wfirst = __reduce_min_sync(0xffffffffu, lfirst);
+#pragma unroll
+        for (int m = 0; m < kBeamRegChunks; ++m)
+          if (key[m] == wmax && first[m] == wfirst) { emit(lane + 32 * m, r); key[m] = 0u; }
+        ++n_new;
+      }
+    } else {
+      // many candidates (flat distributions): scan shared memory each round
+      for (int r = 0; r < bw; ++r) {
+        uint32_t lmax = 0u;
+        for (int j = lane; j < E; j += 32)
+          if (s.e_rep[j] == j) { const uint32_t kx = __float_as_uint(s.a_tot[j]) + 1u; lmax = kx > lmax ? kx : lmax; }
+        const uint32_t wmax = __reduce_max_sync(0xffffffffu, lmax);
+        if (wmax == 0u) break;
+        int lfirst = 0x7fffffff, lj = -1;
+        for (int j = lane; j < E; j += 32)
+          if (s.e_rep[j] == j && __float_as_uint(s.a_tot[j]) + 1u == wmax && s.e_first[j] < lfirst) { lfirst = s.e_first[j]; lj = j; }
+        const int wfirst = __reduce_min_sync(0xffffffffu, lfirst);
+        if (lj >= 0 && lfirst == wfirst) { emit(lj, r); s.e_rep[lj] = -1; }
         __syncwarp();
         ++n_new;
       }
@@ -427,7 +464,7 @@ __global__ void __launch_bounds__(32) ctc_beam_kernel(const BeamParams p) {
   // labeling (utils.py:1031-1035). The trellis of this line is staged in the (now dead) entry arrays when it fits.
   const size_t trel_words = (size_t)Tb * bw;
   const uint32_t* tsrc = trel;
-  if (trel_words * 4 <= (size_t)emax * 24) {
+  if (trel_words * 4 <= (size_t)emax * 28) {
     uint32_t* stg = reinterpret_cast<uint32_t*>(s.e_hash);
     for (size_t i = lane; i < trel_words; i += 32) stg[i] = trel[i];
     tsrc = stg;
