@@ -325,6 +325,7 @@ def run_gpu_arm(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"bf16": "bf16", "f16x3": "f16x3 (fp16 hi/lo split operands, 3 tensor-core products per MAC, fp32 accumulate)",
+                      "f16": "f16 (fp16 operands/activations, fp32 accumulate: the bf16 kernels, 3 more mantissa bits)",
                       "fp32": "f32"}[args.precision], "data": "synthetic",
             "config": {"workload": f"{args.config}: {B} lines of {H}x{W} per rank per step, {decoder}"
                                    + (f" beam={beam}" if decoder != "greedy" else "") + ", reference default model (ResNet-29 + 2xBiLSTM + Linear185), random-init weights",
@@ -370,8 +371,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "f16x3", "fp32"],
-                    help="bf16: tcgen05 bf16 (headline); f16x3: tcgen05 fp16 hi/lo split, fp32-grade logits; fp32: CUDA-core parity mode")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "f16", "f16x3", "fp32"],
+                    help="bf16: tcgen05 bf16 (headline); f16: same kernels with fp16 operands/activations; f16x3: tcgen05 fp16 hi/lo split, fp32-grade logits; fp32: CUDA-core parity mode")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

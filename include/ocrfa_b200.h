@@ -47,6 +47,8 @@ extern "C" {
 #define OCRFA_PRECISION_BF16 1 /* tcgen05 bf16 inputs, fp32 accumulate: logits within 2e-2 */
 #define OCRFA_PRECISION_F16X3 2 /* tcgen05 fp16 hi/lo split operands, 3 products per term, fp32 accumulate: fp32-grade
                                    logits (within 1e-3 of the reference) at 1/3 of the tensor-core rate */
+#define OCRFA_PRECISION_F16 3 /* tcgen05 fp16 inputs/activations, fp32 accumulate: the bf16 kernels with 3 more mantissa bits
+                                (same rate and bytes); activations saturate at +-65504 */
 
 typedef struct ocrfa_handle ocrfa_handle;
 

@@ -14,7 +14,8 @@ LIB_PATH = os.path.join(_HERE, "libocrfa_b200.so")
 PRECISION_FP32 = 0
 PRECISION_BF16 = 1
 PRECISION_F16X3 = 2
-PRECISIONS = {"fp32": PRECISION_FP32, "bf16": PRECISION_BF16, "f16x3": PRECISION_F16X3}
+PRECISION_F16 = 3
+PRECISIONS = {"fp32": PRECISION_FP32, "bf16": PRECISION_BF16, "f16x3": PRECISION_F16X3, "f16": PRECISION_F16}
 
 # every symbol include/ocrfa_b200.h declares (tests/test_cabi_symbols.py checks the header against this list)
 SYMBOLS = (

@@ -301,6 +301,30 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float bf16lo_to_f32(uint32_t packed) { return __uint_as_float(packed << 16); }
 __device__ __forceinline__ float bf16hi_to_f32(uint32_t packed) { return __uint_as_float(packed & 0xffff0000u); }
 
+// 16-bit storage format of the single-pass tensor-core path: bf16 (OCRFA_PRECISION_BF16) or fp16
+// (OCRFA_PRECISION_F16: same tensor-core rate and bytes, 3 more mantissa bits; values saturate at +-65504).
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float lo, float hi) {
+  lo = fminf(fmaxf(lo, -65504.f), 65504.f);
+  hi = fminf(fmaxf(hi, -65504.f), 65504.f);
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack16x2(float lo, float hi, bool f16) {
+  return f16 ? pack_f16x2_sat(lo, hi) : pack_bf16x2(lo, hi);
+}
+__device__ __forceinline__ float f16bits_to_f32(uint32_t h16) {
+  float r;
+  asm("{\n\t.reg .b16 t;\n\tcvt.u16.u32 t, %1;\n\tcvt.f32.f16 %0, t;\n\t}" : "=f"(r) : "r"(h16));
+  return r;
+}
+__device__ __forceinline__ float lo16_to_f32(uint32_t packed, bool f16) {
+  return f16 ? f16bits_to_f32(packed & 0xffffu) : bf16lo_to_f32(packed);
+}
+__device__ __forceinline__ float hi16_to_f32(uint32_t packed, bool f16) {
+  return f16 ? f16bits_to_f32(packed >> 16) : bf16hi_to_f32(packed);
+}
+
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 }  // namespace ocrfa

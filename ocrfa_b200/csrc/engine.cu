@@ -131,7 +131,9 @@ struct ocrfa_handle {
   float* d_pred_b = nullptr;
   std::vector<void*> allocs;
   int64_t launches = 0;
-  bool bf16() const { return cfg.precision == OCRFA_PRECISION_BF16; }
+  // single-pass 16-bit tensor-core path: bf16 or fp16 operands/activations (same kernels, one format flag)
+  bool bf16() const { return cfg.precision == OCRFA_PRECISION_BF16 || cfg.precision == OCRFA_PRECISION_F16; }
+  bool f16() const { return cfg.precision == OCRFA_PRECISION_F16; }
   bool split() const { return cfg.precision == OCRFA_PRECISION_F16X3; }  // fp16 hi/lo operands, three products
   bool tc() const { return bf16() || split(); }                          // tcgen05 path (vs the CUDA-core fp32 path)
   float s_pred = 1.f;
@@ -178,6 +180,15 @@ int upload(ocrfa_handle* h, const std::vector<T>& v, void** out) {
 // Split-precision weight packing: w * 2^k = hi + lo (fp16 pair). k puts the largest |w| in [2^12, 2^13) so that the
 // lo halves of all weights within 2^-15 of the largest stay in fp16's normal range; the kernels multiply the fp32
 // accumulators by 2^-k (exact).
+// float -> the 16-bit storage format of the single-pass path, returned as raw bits in a bf16-typed vector element
+inline __nv_bfloat16 to_16(const ocrfa_handle* h, float v) {
+  if (!h->f16()) return __float2bfloat16(v);
+  const __half hv = __float2half_rn(std::max(-65504.f, std::min(65504.f, v)));
+  __nv_bfloat16 r;
+  memcpy(&r, &hv, 2);
+  return r;
+}
+
 int split_scale_exp(double max_abs) {
   if (!(max_abs > 0.0) || !std::isfinite(max_abs)) return 0;
   int e = 0;
@@ -276,12 +287,12 @@ int prep_conv(ocrfa_handle* h, const std::string& prefix, const std::string& con
         for (int r = 0; r < kh; ++r)
           for (int s = 0; s < kw; ++s) {
             const double v = (double)w->data[(((size_t)o * c.cin + ci) * kh + r) * kw + s] * sc[o];
-            pk[(size_t)o * c.ktotal + (size_t)(r * kw + s) * c.cin_pad + ci] = __float2bfloat16((float)v);
+            pk[(size_t)o * c.ktotal + (size_t)(r * kw + s) * c.cin_pad + ci] = to_16(h, (float)v);
           }
       if (fuse_ds)
         for (int ci = 0; ci < c.ds_cin; ++ci)
           pk[(size_t)o * c.ktotal + (size_t)taps * c.cin_pad + ci] =
-              __float2bfloat16((float)((double)dw->data[(size_t)o * c.ds_cin + ci] * dsc[o]));
+              to_16(h, (float)((double)dw->data[(size_t)o * c.ds_cin + ci] * dsc[o]));
     }
     rc = upload(h, pk, &c.d_wgt);
   } else {
@@ -322,7 +333,7 @@ int prep_linear(ocrfa_handle* h, const std::vector<float>& w, const std::vector<
     rc = upload(h, pk, d_w);
   } else if (h->bf16()) {
     std::vector<__nv_bfloat16> pk(w.size());
-    for (size_t i = 0; i < w.size(); ++i) pk[i] = __float2bfloat16(w[i]);
+    for (size_t i = 0; i < w.size(); ++i) pk[i] = to_16(h, w[i]);
     rc = upload(h, pk, d_w);
   } else {
     rc = upload(h, w, d_w);
@@ -439,6 +450,7 @@ int run_conv_halo(ocrfa_handle* h, const ConvW& cw, const Act& in, const Act* ds
   p.bias = cw.d_bias;
   p.residual = residual; p.ldr = cw.cout;
   p.out = out; p.ldo = cw.cout; p.relu = relu ? 1 : 0;
+  p.f16 = h->f16() ? 1 : 0;
   const double flops = 2.0 * (double)in.n * in.h * in.w * cw.cout * (9.0 * cw.cin + cw.ds_cin);
   LaunchScope ls(h, kClsIgemmTc, flops, st);
   CUDA_TRY(igemm_halo_launch(p, h->num_sms, st));
@@ -462,6 +474,7 @@ int run_conv_tc(ocrfa_handle* h, const ConvW& cw, const Act& in, const Act* ds_s
   p.bias = cw.d_bias;
   p.residual = residual; p.ldr = cw.cout;
   p.out = out; p.ldo = ldo; p.out_f32 = out_f32 ? 1 : 0; p.relu = relu ? 1 : 0;
+  p.f16 = h->f16() ? 1 : 0;
   if (split) {
     // fp16 hi/lo pixels: [hi(C) | lo(C)]
     p.out_scale = cw.out_scale;
@@ -605,6 +618,7 @@ int forward_impl(ocrfa_handle* h, const float* d_x, const uint8_t* d_u8, const i
     void* o = pool.get();
     int ho, wo;
     int r = sp ? run_pool_split(h, *a, o, sh, sw, pw, &ho, &wo, st)
+               : (bf && h->f16()) ? run_pool<__half>(h, *a, o, sh, sw, pw, &ho, &wo, st)
                : bf ? run_pool<__nv_bfloat16>(h, *a, o, sh, sw, pw, &ho, &wo, st) : run_pool<float>(h, *a, o, sh, sw, pw, &ho, &wo, st);
     if (r) return r;
     pool.put(a->p);
@@ -635,6 +649,7 @@ int forward_impl(ocrfa_handle* h, const float* d_x, const uint8_t* d_u8, const i
     const long long total = (long long)B * T * 512;
     LaunchScope ls(h, kClsPool, 0.0, st);
     if (sp) cvt_f32_to_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_feat_in, (__half*)feat, (long long)B * T, 512);
+    else if (bf && h->f16()) cvt_from_f32_kernel<__half><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_feat_in, (__half*)feat, total);
     else if (bf) cvt_from_f32_kernel<__nv_bfloat16><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_feat_in, (__nv_bfloat16*)feat, total);
     else cvt_from_f32_kernel<float><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_feat_in, (float*)feat, total);
     CUDA_TRY(cudaGetLastError());
@@ -648,9 +663,11 @@ int forward_impl(ocrfa_handle* h, const float* d_x, const uint8_t* d_u8, const i
     LaunchScope ls(h, kClsStem, 2.0 * (double)pix * 32 * 9, st);
     if (stem32)
       stem_conv32_kernel<<<(unsigned)((pix + 255) / 256), 256, 0, st>>>(d_x, d_u8, d_widths, h->stem_host,
-                                                                             (__nv_bfloat16*)a.p, B, H, W);
+                                                                             (__nv_bfloat16*)a.p, B, H, W, h->f16() ? 1 : 0);
     else if (sp)
       stem_conv_kernel<__half, 128><<<grid, 256, 0, st>>>(d_x, d_u8, d_widths, h->d_stem_w, h->d_stem_b, (__half*)a.p, B, H, W);
+    else if (bf && h->f16())
+      stem_conv_kernel<__half, 64><<<grid, 256, 0, st>>>(d_x, d_u8, d_widths, h->d_stem_w, h->d_stem_b, (__half*)a.p, B, H, W);
     else if (bf)
       stem_conv_kernel<__nv_bfloat16, 64><<<grid, 256, 0, st>>>(d_x, d_u8, d_widths, h->d_stem_w, h->d_stem_b,
                                                                  (__nv_bfloat16*)a.p, B, H, W);
@@ -682,6 +699,7 @@ int forward_impl(ocrfa_handle* h, const float* d_x, const uint8_t* d_u8, const i
     const long long total = (long long)B * T * 512;
     LaunchScope ls(h, kClsPool, 0.0, st);
     if (sp) mean_h_split_kernel<<<(unsigned)((total / 8 + 255) / 256), 256, 0, st>>>((const __half*)a.p, (__half*)feat, B, a.h, T, 512);
+    else if (bf && h->f16()) mean_h_kernel<__half><<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const __half*)a.p, (__half*)feat, B, a.h, T, 512);
     else if (bf) mean_h_kernel<__nv_bfloat16><<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)a.p, (__nv_bfloat16*)feat, B, a.h, T, 512);
     else mean_h_kernel<float><<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const float*)a.p, (float*)feat, B, a.h, T, 512);
     CUDA_TRY(cudaGetLastError());
@@ -692,6 +710,7 @@ int forward_impl(ocrfa_handle* h, const float* d_x, const uint8_t* d_u8, const i
     {
     LaunchScope ls(h, kClsPool, 0.0, st);
     if (sp) cvt_split_to_f32_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const __half*)feat, d_feat_out, (long long)B * T, 512);
+    else if (bf && h->f16()) cvt_to_f32_kernel<__half><<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const __half*)feat, d_feat_out, total);
     else if (bf) cvt_to_f32_kernel<__nv_bfloat16><<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)feat, d_feat_out, total);
     else cvt_to_f32_kernel<float><<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const float*)feat, d_feat_out, total);
     CUDA_TRY(cudaGetLastError());
@@ -720,7 +739,7 @@ int forward_impl(ocrfa_handle* h, const float* d_x, const uint8_t* d_u8, const i
       }
       // recurrence: ONE persistent launch per 256-line slice walks all T steps of both directions (lstm_tc.cuh);
       // on the bf16 path the input projection is fused into it (K = [x_t | h_{t-1}])
-      const int mode = sp ? kLstmF16Split : kLstmBf16FusedX;
+      const int mode = sp ? kLstmF16Split : (h->f16() ? kLstmF16FusedX : kLstmBf16FusedX);
       const size_t hs_row = sp ? 2048 : 1024;  // elements per (b, t) row of the h sequence
       int slice = 0;
       for (int b0 = 0; b0 < B; b0 += 256, ++slice) {
@@ -836,7 +855,7 @@ int ocrfa_create(const ocrfa_config* cfg, ocrfa_handle** out) {
     return fail(OCRFA_ERR_ARG, "only the reference's generation1 network (1, 512, 512) is supported");
   if (cfg->num_class < 2 || cfg->num_class > 256) return fail(OCRFA_ERR_ARG, "num_class must be in [2, 256]");
   if (cfg->precision != OCRFA_PRECISION_FP32 && cfg->precision != OCRFA_PRECISION_BF16 &&
-      cfg->precision != OCRFA_PRECISION_F16X3)
+      cfg->precision != OCRFA_PRECISION_F16X3 && cfg->precision != OCRFA_PRECISION_F16)
     return fail(OCRFA_ERR_ARG, "unknown precision %d", cfg->precision);
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= cfg->device)
@@ -937,6 +956,7 @@ int ocrfa_finalize_weights(ocrfa_handle* h, void* stream) {
     CUDA_TRY(cudaFuncSetAttribute(igemm_tc_kernel<kModePair>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CUDA_TRY(cudaFuncSetAttribute(lstm_tc_persistent_kernel<kLstmBf16FusedX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lstm_tc_smem_bytes()));
     CUDA_TRY(cudaFuncSetAttribute(lstm_tc_persistent_kernel<kLstmF16Split>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lstm_tc_smem_bytes()));
+    CUDA_TRY(cudaFuncSetAttribute(lstm_tc_persistent_kernel<kLstmF16FusedX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lstm_tc_smem_bytes()));
     if (!get_tmap_encode()) return fail(OCRFA_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
   }
   CUDA_TRY(cudaDeviceSynchronize());

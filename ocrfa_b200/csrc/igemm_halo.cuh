@@ -42,6 +42,7 @@ struct alignas(64) IgemmHaloParams {
   int b_resident;    // 1: whole weight matrix resident in shared memory (requires n_tiles == 1)
   int relu;
   int pool;          // 1: fused 2x2 stride-2 max pool, output is [N][H/2][W/2][ldo]
+  int f16;           // 1: operands / outputs are fp16 instead of bf16
   int ldo, ldr;
   const float* bias;
   const void* residual;  // NHWC bf16 or nullptr (not with pool)
@@ -57,18 +58,20 @@ __device__ __forceinline__ void halo_store8(const IgemmHaloParams& p, float (&g)
   }
   if (p.residual != nullptr) {
     const uint4 r4 = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.residual) + pix * p.ldr + col));
-    g[0] += bf16lo_to_f32(r4.x); g[1] += bf16hi_to_f32(r4.x);
-    g[2] += bf16lo_to_f32(r4.y); g[3] += bf16hi_to_f32(r4.y);
-    g[4] += bf16lo_to_f32(r4.z); g[5] += bf16hi_to_f32(r4.z);
-    g[6] += bf16lo_to_f32(r4.w); g[7] += bf16hi_to_f32(r4.w);
+    const bool h = p.f16 != 0;
+    g[0] += lo16_to_f32(r4.x, h); g[1] += hi16_to_f32(r4.x, h);
+    g[2] += lo16_to_f32(r4.y, h); g[3] += hi16_to_f32(r4.y, h);
+    g[4] += lo16_to_f32(r4.z, h); g[5] += hi16_to_f32(r4.z, h);
+    g[6] += lo16_to_f32(r4.w, h); g[7] += hi16_to_f32(r4.w, h);
   }
   if (p.relu) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) g[i] = fmaxf(g[i], 0.0f);
   }
   uint4 o;
-  o.x = pack_bf16x2(g[0], g[1]); o.y = pack_bf16x2(g[2], g[3]);
-  o.z = pack_bf16x2(g[4], g[5]); o.w = pack_bf16x2(g[6], g[7]);
+  const bool h16 = p.f16 != 0;
+  o.x = pack16x2(g[0], g[1], h16); o.y = pack16x2(g[2], g[3], h16);
+  o.z = pack16x2(g[4], g[5], h16); o.w = pack16x2(g[6], g[7], h16);
   *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.ldo + col) = o;
 }
 
@@ -192,7 +195,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) igemm_halo_kernel(const __gri
   } else if (warp == 1) {
     // ===================================== MMA issuer (leader CTA only) =====================
     if (leader && elect_one()) {
-      const uint32_t idesc = make_idesc_bf16(2 * kTcBlockM, static_cast<uint32_t>(block_n));
+      const uint32_t idesc = p.f16 ? make_idesc_f16(2 * kTcBlockM, static_cast<uint32_t>(block_n))
+                                   : make_idesc_bf16(2 * kTcBlockM, static_cast<uint32_t>(block_n));
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -288,6 +292,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) igemm_halo_kernel(const __gri
           // that every global access covers 64 contiguous bytes of 8 pixels (a 16-byte access per pixel costs one
           // L1 wavefront per lane: measured, the stores - not the MMAs - paced the Cout <= 128 layers)
           float f[32];
+          const bool h16 = p.f16 != 0;
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
           const int pc = lane & 3;                      // piece this lane moves in the transposed mapping
@@ -314,10 +319,10 @@ __global__ void __launch_bounds__(kHaloThreads, 1) igemm_halo_kernel(const __gri
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const uint4 r4 = *reinterpret_cast<const uint4*>(stg + lane * 64 + ((j ^ swz_own) << 4));
-              f[8 * j] += bf16lo_to_f32(r4.x);     f[8 * j + 1] += bf16hi_to_f32(r4.x);
-              f[8 * j + 2] += bf16lo_to_f32(r4.y); f[8 * j + 3] += bf16hi_to_f32(r4.y);
-              f[8 * j + 4] += bf16lo_to_f32(r4.z); f[8 * j + 5] += bf16hi_to_f32(r4.z);
-              f[8 * j + 6] += bf16lo_to_f32(r4.w); f[8 * j + 7] += bf16hi_to_f32(r4.w);
+              f[8 * j] += lo16_to_f32(r4.x, h16);     f[8 * j + 1] += hi16_to_f32(r4.x, h16);
+              f[8 * j + 2] += lo16_to_f32(r4.y, h16); f[8 * j + 3] += hi16_to_f32(r4.y, h16);
+              f[8 * j + 4] += lo16_to_f32(r4.z, h16); f[8 * j + 5] += hi16_to_f32(r4.z, h16);
+              f[8 * j + 6] += lo16_to_f32(r4.w, h16); f[8 * j + 7] += hi16_to_f32(r4.w, h16);
             }
             __syncwarp();
           }
@@ -328,8 +333,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) igemm_halo_kernel(const __gri
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             uint4 o;
-            o.x = pack_bf16x2(f[8 * j], f[8 * j + 1]);     o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
-            o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]); o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+            o.x = pack16x2(f[8 * j], f[8 * j + 1], h16);     o.y = pack16x2(f[8 * j + 2], f[8 * j + 3], h16);
+            o.z = pack16x2(f[8 * j + 4], f[8 * j + 5], h16); o.w = pack16x2(f[8 * j + 6], f[8 * j + 7], h16);
             *reinterpret_cast<uint4*>(stg + lane * 64 + ((j ^ swz_own) << 4)) = o;
           }
           __syncwarp();

@@ -67,6 +67,7 @@ struct alignas(64) IgemmTcParams {
   int ldr;       // residual row stride (elements)
   int pair;      // 1: CTA-pair kernel (kModePair): M = 256 across two SMs, each CTA holds half of the weight tile
   int split;     // 1: fp16 hi/lo operands, three products per K chunk (see the header comment)
+  int f16;       // 1 (non-split): operands and 16-bit outputs are fp16 instead of bf16
   int a_lo;      // split: channel offset of the lo half inside source 0's pixel (= its channel count)
   int a_lo2;     // ... inside source 1's pixel
   int out_lo;    // split, !out_f32: channel offset of the lo half inside the output pixel (ldo = 2 * out_lo)
@@ -127,15 +128,17 @@ __device__ __forceinline__ void igemm_finish32(const IgemmTcParams& p, float (&f
 #pragma unroll
       for (int i = 0; i < 32; i += 8) {
         const uint4 r4 = __ldg(reinterpret_cast<const uint4*>(rp + i));
-        f[i] += bf16lo_to_f32(r4.x);     f[i + 1] += bf16hi_to_f32(r4.x);
-        f[i + 2] += bf16lo_to_f32(r4.y); f[i + 3] += bf16hi_to_f32(r4.y);
-        f[i + 4] += bf16lo_to_f32(r4.z); f[i + 5] += bf16hi_to_f32(r4.z);
-        f[i + 6] += bf16lo_to_f32(r4.w); f[i + 7] += bf16hi_to_f32(r4.w);
+        const bool h = p.f16 != 0;
+        f[i] += lo16_to_f32(r4.x, h);     f[i + 1] += hi16_to_f32(r4.x, h);
+        f[i + 2] += lo16_to_f32(r4.y, h); f[i + 3] += hi16_to_f32(r4.y, h);
+        f[i + 4] += lo16_to_f32(r4.z, h); f[i + 5] += hi16_to_f32(r4.z, h);
+        f[i + 6] += lo16_to_f32(r4.w, h); f[i + 7] += hi16_to_f32(r4.w, h);
       }
     } else {
 #pragma unroll
       for (int i = 0; i < 32; ++i)
-        if (col0 + i < p.n_valid) f[i] += __bfloat162float(rp[i]);
+        if (col0 + i < p.n_valid)
+          f[i] += p.f16 ? f16bits_to_f32(reinterpret_cast<const uint16_t*>(rp)[i]) : __bfloat162float(rp[i]);
     }
   }
   if (p.relu) {
@@ -189,14 +192,18 @@ __device__ __forceinline__ void igemm_finish32(const IgemmTcParams& p, float (&f
 #pragma unroll
       for (int i = 0; i < 32; i += 8) {
         uint4 o;
-        o.x = pack_bf16x2(f[i], f[i + 1]);     o.y = pack_bf16x2(f[i + 2], f[i + 3]);
-        o.z = pack_bf16x2(f[i + 4], f[i + 5]); o.w = pack_bf16x2(f[i + 6], f[i + 7]);
+        const bool h = p.f16 != 0;
+        o.x = pack16x2(f[i], f[i + 1], h);     o.y = pack16x2(f[i + 2], f[i + 3], h);
+        o.z = pack16x2(f[i + 4], f[i + 5], h); o.w = pack16x2(f[i + 6], f[i + 7], h);
         *reinterpret_cast<uint4*>(op + i) = o;
       }
     } else {
 #pragma unroll
       for (int i = 0; i < 32; ++i)
-        if (col0 + i < p.n_valid) op[i] = __float2bfloat16_rn(f[i]);
+        if (col0 + i < p.n_valid) {
+          if (p.f16) reinterpret_cast<uint16_t*>(op)[i] = static_cast<uint16_t>(pack_f16x2_sat(f[i], 0.f) & 0xffffu);
+          else op[i] = __float2bfloat16_rn(f[i]);
+        }
     }
   }
 }
@@ -326,7 +333,8 @@ __global__ void __launch_bounds__(MODE == kModeSplit ? kTcThreadsSplit : kTcThre
     // ===================================== MMA issuer (pair: leader CTA only) ===============
     if (leader && elect_one()) {
       const uint32_t idesc = MODE == kModeSplit ? make_idesc_f16(kTcBlockM, static_cast<uint32_t>(p.block_n))
-                                                : make_idesc_bf16(kPair ? 2 * kTcBlockM : kTcBlockM, static_cast<uint32_t>(p.block_n));
+                             : p.f16           ? make_idesc_f16(kPair ? 2 * kTcBlockM : kTcBlockM, static_cast<uint32_t>(p.block_n))
+                                               : make_idesc_bf16(kPair ? 2 * kTcBlockM : kTcBlockM, static_cast<uint32_t>(p.block_n));
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;

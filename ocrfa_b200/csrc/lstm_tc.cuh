@@ -37,7 +37,7 @@ constexpr int kLstmTmemCols = 128;    // 2 accumulators x 64 columns
 constexpr int kLstmGroupCtas = 32;    // CTAs per (direction, m_tile) group = 512 hidden units / 16
 constexpr int kLstmWSlabs = 16;       // resident weight slabs (8 KB each) = 128 KB
 
-enum LstmMode : int { kLstmBf16FusedX = 0, kLstmF16Split = 1 };
+enum LstmMode : int { kLstmBf16FusedX = 0, kLstmF16Split = 1, kLstmF16FusedX = 2 };  // FusedX modes differ only in the 16-bit format
 
 // slabs of the exchange buffer per (direction, m_tile, parity): 8 K-blocks of h (bf16) or 8 hi + 8 lo (split)
 __host__ __device__ constexpr int lstm_hx_slabs(int mode) { return mode == kLstmF16Split ? 16 : 8; }
@@ -102,8 +102,11 @@ __device__ __forceinline__ void split_f16(float x, float* hi, float* lo) {
   *lo = x - h;
 }
 
-template <int MODE>
+template <int MODE_T>
 __global__ void __launch_bounds__(kLstmThreads, 1) lstm_tc_persistent_kernel(const __grid_constant__ LstmTcParams p) {
+  // the fused-x modes share every code path except the operand format (bf16 / fp16)
+  constexpr int MODE = MODE_T == kLstmF16FusedX ? kLstmBf16FusedX : MODE_T;
+  constexpr bool kHalf16 = MODE_T == kLstmF16FusedX;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -199,7 +202,7 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_tc_persistent_kernel(con
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
     if (elect_one()) {
-      const uint32_t idesc = MODE == kLstmF16Split ? make_idesc_f16(128, 64) : make_idesc_bf16(128, 64);
+      const uint32_t idesc = (MODE == kLstmF16Split || kHalf16) ? make_idesc_f16(128, 64) : make_idesc_bf16(128, 64);
       mbar_wait(w_full, 0, 12);
       tc_fence_after();
       int stage = 0, as = 0;
@@ -313,10 +316,10 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_tc_persistent_kernel(con
         l1.x = pack_f16x2(lo[8], lo[9]);   l1.y = pack_f16x2(lo[10], lo[11]);
         l1.z = pack_f16x2(lo[12], lo[13]); l1.w = pack_f16x2(lo[14], lo[15]);
       } else {
-        o0.x = pack_bf16x2(hout[0], hout[1]);   o0.y = pack_bf16x2(hout[2], hout[3]);
-        o0.z = pack_bf16x2(hout[4], hout[5]);   o0.w = pack_bf16x2(hout[6], hout[7]);
-        o1.x = pack_bf16x2(hout[8], hout[9]);   o1.y = pack_bf16x2(hout[10], hout[11]);
-        o1.z = pack_bf16x2(hout[12], hout[13]); o1.w = pack_bf16x2(hout[14], hout[15]);
+        o0.x = pack16x2(hout[0], hout[1], kHalf16);   o0.y = pack16x2(hout[2], hout[3], kHalf16);
+        o0.z = pack16x2(hout[4], hout[5], kHalf16);   o0.w = pack16x2(hout[6], hout[7], kHalf16);
+        o1.x = pack16x2(hout[8], hout[9], kHalf16);   o1.y = pack16x2(hout[10], hout[11], kHalf16);
+        o1.z = pack16x2(hout[12], hout[13], kHalf16); o1.w = pack16x2(hout[14], hout[15], kHalf16);
         l0 = o0; l1 = o1;
       }
       if (valid) {
@@ -381,10 +384,11 @@ inline size_t lstm_tc_smem_bytes() { return 2048 + kLstmWSlabs * 8192 + static_c
 
 // Cooperative launch (all CTAs co-resident). `sync` must hold 2*m_tiles zeroed counters.
 inline cudaError_t lstm_tc_launch(const LstmTcParams& p, int mode, cudaStream_t stream) {
-  static bool attr_set[2] = {false, false};
+  static bool attr_set[3] = {false, false, false};
   const size_t smem = lstm_tc_smem_bytes();
-  void* fn = mode == kLstmF16Split ? reinterpret_cast<void*>(lstm_tc_persistent_kernel<kLstmF16Split>)
-                                   : reinterpret_cast<void*>(lstm_tc_persistent_kernel<kLstmBf16FusedX>);
+  void* fn = mode == kLstmF16Split    ? reinterpret_cast<void*>(lstm_tc_persistent_kernel<kLstmF16Split>)
+             : mode == kLstmF16FusedX ? reinterpret_cast<void*>(lstm_tc_persistent_kernel<kLstmF16FusedX>)
+                                      : reinterpret_cast<void*>(lstm_tc_persistent_kernel<kLstmBf16FusedX>);
   if (!attr_set[mode]) {
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

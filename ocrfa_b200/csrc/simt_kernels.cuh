@@ -19,6 +19,10 @@ template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16
 template <typename T> __device__ __forceinline__ T from_f32(float v);
 template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f)); }
+template <typename T> struct Is16F16 { static constexpr bool value = false; };
+template <> struct Is16F16<__half> { static constexpr bool value = true; };
 
 // ---------------------------------------------------------------------------------------------
 // preprocess: uint8 lines (already at model height) -> float32 [B,1,H,W] in [-1,1], right-padded by
@@ -124,8 +128,9 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict_
       *reinterpret_cast<uint4*>(hp + 64 + c0) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
     } else if (sizeof(TOut) == 2) {
       uint4 o;
-      o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
-      o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
+      constexpr bool h16 = Is16F16<TOut>::value;  // (the split path's __half output took the branch above)
+      o.x = pack16x2(acc[0], acc[1], h16); o.y = pack16x2(acc[2], acc[3], h16);
+      o.z = pack16x2(acc[4], acc[5], h16); o.w = pack16x2(acc[6], acc[7], h16);
       *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(op) + c0) = o;
     } else {
       float* fo = reinterpret_cast<float*>(op) + c0;
@@ -166,7 +171,7 @@ struct StemWeights {
 __global__ void __launch_bounds__(256) stem_conv32_kernel(const float* __restrict__ x, const uint8_t* __restrict__ x_u8,
                                                           const int32_t* __restrict__ widths,
                                                           const __grid_constant__ StemWeights sw,
-                                                          __nv_bfloat16* __restrict__ out, int B, int H, int W) {
+                                                          __nv_bfloat16* __restrict__ out, int B, int H, int W, int f16) {
   __shared__ float lut[256];
   __shared__ uint4 stg[8][32 * 4];  // per warp: 32 pixels x 4 pieces of 16 B, piece index XOR-swizzled by (pixel >> 1) & 3
   lut[threadIdx.x] = normalize_u8(threadIdx.x);
@@ -212,8 +217,9 @@ __global__ void __launch_bounds__(256) stem_conv32_kernel(const float* __restric
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     uint4 o;
-    o.x = pack_bf16x2(acc[8 * j], acc[8 * j + 1]);     o.y = pack_bf16x2(acc[8 * j + 2], acc[8 * j + 3]);
-    o.z = pack_bf16x2(acc[8 * j + 4], acc[8 * j + 5]); o.w = pack_bf16x2(acc[8 * j + 6], acc[8 * j + 7]);
+    const bool h16 = f16 != 0;
+    o.x = pack16x2(acc[8 * j], acc[8 * j + 1], h16);     o.y = pack16x2(acc[8 * j + 2], acc[8 * j + 3], h16);
+    o.z = pack16x2(acc[8 * j + 4], acc[8 * j + 5], h16); o.w = pack16x2(acc[8 * j + 6], acc[8 * j + 7], h16);
     stg[warp][lane * 4 + (j ^ swz)] = o;
   }
   __syncwarp();
@@ -354,10 +360,11 @@ __global__ void maxpool2x2_kernel(const T* __restrict__ in, T* __restrict__ out,
         const T* ip = in + (((long long)b * h_in + hi) * w_in + wi) * c + cg * 8;
         if (sizeof(T) == 2) {
           const uint4 v = __ldg(reinterpret_cast<const uint4*>(ip));
-          m[0] = fmaxf(m[0], bf16lo_to_f32(v.x)); m[1] = fmaxf(m[1], bf16hi_to_f32(v.x));
-          m[2] = fmaxf(m[2], bf16lo_to_f32(v.y)); m[3] = fmaxf(m[3], bf16hi_to_f32(v.y));
-          m[4] = fmaxf(m[4], bf16lo_to_f32(v.z)); m[5] = fmaxf(m[5], bf16hi_to_f32(v.z));
-          m[6] = fmaxf(m[6], bf16lo_to_f32(v.w)); m[7] = fmaxf(m[7], bf16hi_to_f32(v.w));
+          constexpr bool h16 = Is16F16<T>::value;
+          m[0] = fmaxf(m[0], lo16_to_f32(v.x, h16)); m[1] = fmaxf(m[1], hi16_to_f32(v.x, h16));
+          m[2] = fmaxf(m[2], lo16_to_f32(v.y, h16)); m[3] = fmaxf(m[3], hi16_to_f32(v.y, h16));
+          m[4] = fmaxf(m[4], lo16_to_f32(v.z, h16)); m[5] = fmaxf(m[5], hi16_to_f32(v.z, h16));
+          m[6] = fmaxf(m[6], lo16_to_f32(v.w, h16)); m[7] = fmaxf(m[7], hi16_to_f32(v.w, h16));
         } else {
           const float4 v0 = __ldg(reinterpret_cast<const float4*>(ip));
           const float4 v1 = __ldg(reinterpret_cast<const float4*>(ip) + 1);
@@ -369,8 +376,9 @@ __global__ void maxpool2x2_kernel(const T* __restrict__ in, T* __restrict__ out,
   T* op = out + pix * c + cg * 8;
   if (sizeof(T) == 2) {
     uint4 o;
-    o.x = pack_bf16x2(m[0], m[1]); o.y = pack_bf16x2(m[2], m[3]);
-    o.z = pack_bf16x2(m[4], m[5]); o.w = pack_bf16x2(m[6], m[7]);
+    constexpr bool h16 = Is16F16<T>::value;
+    o.x = pack16x2(m[0], m[1], h16); o.y = pack16x2(m[2], m[3], h16);
+    o.z = pack16x2(m[4], m[5], h16); o.w = pack16x2(m[6], m[7], h16);
     *reinterpret_cast<uint4*>(op) = o;
   } else {
     float* fo = reinterpret_cast<float*>(op);

@@ -23,7 +23,7 @@ def env(synth_sd, charset):
     chars = str(charset["character"])
     conv = ob.CTCLabelConverter(chars)
     models = {}
-    for prec in ("fp32", "bf16", "f16x3"):
+    for prec in ("fp32", "bf16", "f16x3", "f16"):
         m = ob.Model(1, 512, 512, len(conv.character), precision=prec)
         m.load_state_dict({"module." + k: torch.from_numpy(v) for k, v in synth_sd.items()})
         models[prec] = m
@@ -274,6 +274,40 @@ def test_get_text_two_pass_matches_reference(env):
     np.testing.assert_allclose([r[2] for r in res], g["conf"], rtol=5e-3, atol=1e-9)
 
 
+@pytest.mark.parametrize("name", FWD + ["c3_64x2048"])
+def test_f16_logits_vs_fp32_reference(env, name):
+    """fp16 single-pass tensor-core mode (the bf16 kernels with fp16 operands/activations, same speed) against the
+    reference's fp32 logits: 8x less rounding noise than bf16, so the bound relative to the logit range is 4e-3
+    (bf16: 2e-2) and the elementwise allclose(2e-2) fraction is reported."""
+    g = load_golden(name)
+    ref = g["logits"]
+    logits = env["models"]["f16"](torch.from_numpy(g["x"]).cuda(), None).cpu().numpy()
+    assert np.isfinite(logits).all()
+    d = np.abs(logits - ref)
+    frac = float((d <= 2e-2 + 2e-2 * np.abs(ref)).mean())
+    print(f"{name} f16 vs fp32 reference: max abs {d.max():.3g} / max|ref| {np.abs(ref).max():.3g} = "
+          f"{d.max() / np.abs(ref).max():.3g}; elementwise allclose(2e-2) fraction {frac:.4f}; "
+          f"argmax agreement {(logits.argmax(2) == ref.argmax(2)).mean():.4f}")
+    assert d.max() <= 4e-3 * np.abs(ref).max()
+
+
+def test_f16_strings_vs_fp32_at_config2_size(env):
+    """BASELINE config 2 shape: fp16 single-pass path against the fp32 parity path - string agreement reported."""
+    from oracle.synth import synth_lines
+    from ocrfa_b200.recognition import _ignore_mask
+
+    ob = env["ob"]
+    imgs = synth_lines(256, 32, 512, seed=4242)
+    batch = ob.AlignCollate(32, 512)(list(imgs))
+    mask = _ignore_mask(len(env["conv"].character), env["ign"])
+    dev = torch.device("cuda", 0)
+    s16, c16 = ob.recognize_host(env["models"]["f16"], env["conv"], batch.images_u8, batch.widths, mask, "greedy", 5, dev)
+    s32, c32 = ob.recognize_host(env["models"]["fp32"], env["conv"], batch.images_u8, batch.widths, mask, "greedy", 5, dev)
+    same = sum(a == b for a, b in zip(s16, s32))
+    print(f"f16 vs fp32 greedy strings identical: {same}/256")
+    assert same >= 150  # near-ties (top-2 margin < 0.03) flip under any 16-bit evaluation of this random-weight network
+
+
 def test_bf16_strings_vs_fp32_at_config2_size(env):
     """BASELINE config 2 shape (256 lines of 32x512): bf16 tensor-core path against the fp32 parity path on the
     same device - string agreement is reported and must be high; per-timestep argmax flips only where the fp32
@@ -299,7 +333,7 @@ def test_bf16_strings_vs_fp32_at_config2_size(env):
     assert s16r[::-1] == s16
 
 
-@pytest.mark.parametrize("prec", ["bf16", "fp32", "f16x3"])
+@pytest.mark.parametrize("prec", ["bf16", "f16", "fp32", "f16x3"])
 def test_batch_composition_independence(env, prec):
     """Lines are independent: 300 lines in one call (two LSTM slices, ragged last tile) must decode exactly like
     the same lines in calls of 1, 99 and 200 - bit-identical labels and confidences (size-independent property)."""
