@@ -3,7 +3,7 @@
     from ocrfa_b200 import get_recognizer, get_text, recognizer_predict, Model, CTCLabelConverter
 
 mirrors /root/reference/src/ocrfa/utils.py (get_recognizer :665, get_text :698, recognizer_predict :605,
-CTCLabelConverter :1041) and /root/reference/src/ocrfa/modules/blocks.py (Model :422). The arithmetic is in
+CTCLabelConverter :1041, get_image_list :1375) and /root/reference/src/ocrfa/modules/blocks.py (Model :422). The arithmetic is in
 libocrfa_b200.so (include/ocrfa_b200.h); there is no CPU fallback.
 """
 from . import _lib
@@ -11,6 +11,7 @@ from ._lib import OcrfaError
 from .charset import (ARABIC_G1_CHARACTERS, ARABIC_G1_SYMBOLS, default_character, default_ignore_char,
                       default_lang_char)
 from .converter import CTCLabelConverter
+from .crops import calculate_ratio, get_image_list
 from .model import Model
 from .recognition import (AlignCollate, LineBatch, ListDataset, adjust_contrast_grey, contrast_grey, custom_mean,
                           get_recognizer, get_text, recognize_host, recognizer_predict)
@@ -19,5 +20,5 @@ __all__ = [
     "Model", "CTCLabelConverter", "get_recognizer", "get_text", "recognizer_predict", "recognize_host",
     "AlignCollate", "ListDataset", "LineBatch", "custom_mean", "contrast_grey", "adjust_contrast_grey",
     "default_character", "default_lang_char", "default_ignore_char", "ARABIC_G1_CHARACTERS", "ARABIC_G1_SYMBOLS",
-    "OcrfaError",
+    "OcrfaError", "get_image_list", "calculate_ratio",
 ]

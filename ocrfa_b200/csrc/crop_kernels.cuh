@@ -1,0 +1,76 @@
+// Crop + resize of text boxes out of a page image: the step that feeds the recognizer
+//   reference: get_image_list / compute_ratio_and_resize, /root/reference/src/ocrfa/utils.py:1361-1418
+// The reference calls cv2.resize(..., interpolation=Image.Resampling.LANCZOS): the PIL enum has value 1, which cv2
+// reads as INTER_LINEAR, so this is OpenCV's 8-bit bilinear resize, reproduced bit for bit:
+//   horizontal  H = S[x0] * a0 + S[x1] * a1            (a = round(coef * 2048) as int16, coef in float32)
+//   vertical    D = (((b0 * (H0 >> 4)) >> 16) + ((b1 * (H1 >> 4)) >> 16) + 2) >> 2
+// with OpenCV's special cases: equal sizes copy, an exact 2x shrink in both axes is INTER_AREA ((s00+s01+s10+s11+2)>>2).
+// The per-axis tables (source index, two fixed-point weights) depend only on (source size, destination size) and
+// come from the host (ocrfa_b200/crops.py restates OpenCV's float32 coefficient arithmetic).
+// Memory bound: <= 4 source bytes read (L1/L2 hits) and 1 byte written per output pixel.
+#pragma once
+#include <stdint.h>
+#include "../../include/ocrfa_b200.h"
+
+namespace ocrfa {
+
+enum : int { kCropLinear = 0, kCropCopy = 1, kCropArea2 = 2 };
+
+// one thread = 4 consecutive output pixels of one row (one 32-bit store when the line start is 4-byte aligned)
+__global__ void __launch_bounds__(256) crop_resize_u8_kernel(const uint8_t* __restrict__ page, int page_stride,
+                                                             const ocrfa_crop_desc* __restrict__ desc,
+                                                             const int32_t* __restrict__ tables, int n,
+                                                             uint8_t* __restrict__ out) {
+  const int b = blockIdx.y;
+  if (b >= n) return;
+  const ocrfa_crop_desc d = desc[b];
+  const int quads = (d.dst_w + 3) >> 2;
+  const long long total = (long long)quads * d.dst_h;
+  const uint8_t* src = page + (size_t)d.y0 * page_stride + d.x0;
+  uint8_t* dst = out + d.out_off;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
+    const int dy = (int)(g / quads);
+    const int dx0 = (int)(g - (long long)dy * quads) * 4;
+    uint32_t v[4];
+    if (d.mode == kCropCopy) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = dx0 + i < d.dst_w ? src[(size_t)dy * page_stride + dx0 + i] : 0u;
+    } else if (d.mode == kCropArea2) {
+      const uint8_t* r0 = src + (size_t)(2 * dy) * page_stride;
+      const uint8_t* r1 = r0 + page_stride;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int x = 2 * (dx0 + i);
+        v[i] = dx0 + i < d.dst_w ? ((uint32_t)r0[x] + r0[x + 1] + r1[x] + r1[x + 1] + 2u) >> 2 : 0u;
+      }
+    } else {
+      // tables: x: [dst_w] {x0, a0 | a1 << 16}, y: [dst_h] {y0 (unclamped), b0 | b1 << 16}
+      const int2 ty = reinterpret_cast<const int2*>(tables + d.ytab_off)[dy];
+      const int ya = min(max(ty.x, 0), d.src_h - 1), yb = min(max(ty.x + 1, 0), d.src_h - 1);
+      const int b0 = (int16_t)(ty.y & 0xffff), b1 = (int16_t)(ty.y >> 16);
+      const uint8_t* r0 = src + (size_t)ya * page_stride;
+      const uint8_t* r1 = src + (size_t)yb * page_stride;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        v[i] = 0u;
+        if (dx0 + i < d.dst_w) {
+          const int2 tx = reinterpret_cast<const int2*>(tables + d.xtab_off)[dx0 + i];
+          const int xa = tx.x, xb = min(tx.x + 1, d.src_w - 1);
+          const int a0 = (int16_t)(tx.y & 0xffff), a1 = (int16_t)(tx.y >> 16);
+          const int h0 = r0[xa] * a0 + r0[xb] * a1;
+          const int h1 = r1[xa] * a0 + r1[xb] * a1;
+          const int val = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+          v[i] = (uint32_t)min(max(val, 0), 255);
+        }
+      }
+    }
+    uint8_t* op = dst + (size_t)dy * d.dst_w + dx0;
+    if (dx0 + 4 <= d.dst_w && ((reinterpret_cast<uintptr_t>(op) & 3) == 0)) {
+      *reinterpret_cast<uint32_t*>(op) = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24);
+    } else {
+      for (int i = 0; i < 4 && dx0 + i < d.dst_w; ++i) op[i] = (uint8_t)v[i];
+    }
+  }
+}
+
+}  // namespace ocrfa

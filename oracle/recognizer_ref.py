@@ -503,3 +503,79 @@ def ignore_idx_ref(character: str, ignore_char: str) -> List[int]:
         if k >= 0:
             out.append(k + 1)
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# get_image_list / compute_ratio_and_resize for axis-aligned boxes (utils.py:1351-1418). The reference's
+# cv2.resize(..., interpolation=Image.Resampling.LANCZOS) is OpenCV INTER_LINEAR (the enum's value is 1); OpenCV
+# 4.x is a third-party dependency (requirements.txt: opencv-python~=4.9.0.80), so its published 8-bit arithmetic
+# (imgproc/resize.cpp: HResizeLinear / VResizeLinear with INTER_RESIZE_COEF_BITS = 11) is restated here and pinned
+# by tests/golden/crops.npz, which oracle/gen_golden_crops.py produced with the reference's own get_image_list.
+# ------------------------------------------------------------------------------------------------------------------
+def _cv_linear_axis(src: int, dst: int, clamp: bool):
+    scale = 1.0 / (float(dst) / src)
+    idx = np.zeros(dst, np.int64)
+    w = np.zeros((dst, 2), np.int64)
+    for d in range(dst):
+        f = np.float32((d + 0.5) * scale - 0.5)
+        s = int(math.floor(f))
+        f = np.float32(f - np.float32(s))
+        if clamp:
+            if s < 0:
+                f, s = np.float32(0), 0
+            if s >= src - 1:
+                f, s = np.float32(0), src - 1
+        idx[d] = s
+        w[d, 0] = int(np.rint(np.float32((np.float32(1.0) - f) * np.float32(2048))))
+        w[d, 1] = int(np.rint(np.float32(f * np.float32(2048))))
+    return idx, w
+
+
+def cv_resize_linear_u8_ref(img: np.ndarray, dw: int, dh: int) -> np.ndarray:
+    sh, sw = img.shape
+    if (dw, dh) == (sw, sh):
+        return img.copy()
+    if sw == 2 * dw and sh == 2 * dh:  # exact 2x shrink: resize() switches INTER_LINEAR to INTER_AREA
+        s = img.astype(np.int64)
+        return ((s[0::2, 0::2] + s[0::2, 1::2] + s[1::2, 0::2] + s[1::2, 1::2] + 2) >> 2).astype(np.uint8)
+    xo, xa = _cv_linear_axis(sw, dw, True)
+    yo, yb = _cv_linear_axis(sh, dh, False)
+    S = img.astype(np.int64)
+    x1 = np.minimum(xo + 1, sw - 1)
+    H = S[:, xo] * xa[:, 0] + S[:, x1] * xa[:, 1]
+    out = np.zeros((dh, dw), np.uint8)
+    for d in range(dh):
+        r0 = min(max(int(yo[d]), 0), sh - 1)
+        r1 = min(max(int(yo[d]) + 1, 0), sh - 1)
+        v = ((yb[d, 0] * (H[r0] >> 4)) >> 16) + ((yb[d, 1] * (H[r1] >> 4)) >> 16) + 2
+        out[d] = np.clip(v >> 2, 0, 255).astype(np.uint8)
+    return out
+
+
+def get_image_list_ref(horizontal_list, img: np.ndarray, model_height: int = 64, sort_output: bool = True):
+    """utils.py:1375-1418 with free_list = []."""
+    maximum_y, maximum_x = img.shape
+    image_list = []
+    max_ratio_hori = 1
+    for box in horizontal_list:
+        x_min, x_max = max(0, box[0]), min(box[1], maximum_x)
+        y_min, y_max = max(0, box[2]), min(box[3], maximum_y)
+        crop = img[y_min:y_max, x_min:x_max]
+        width, height = x_max - x_min, y_max - y_min
+        ratio = width / height
+        if ratio < 1.0:
+            ratio = 1.0 / ratio
+        if int(model_height * ratio) == 0:
+            continue
+        ratio = width / height
+        if ratio < 1.0:
+            ratio = 1.0 / ratio
+            crop = cv_resize_linear_u8_ref(crop, model_height, int(model_height * ratio))
+        else:
+            crop = cv_resize_linear_u8_ref(crop, int(model_height * ratio), model_height)
+        image_list.append(([[x_min, y_min], [x_max, y_min], [x_max, y_max], [x_min, y_max]], crop))
+        max_ratio_hori = max(ratio, max_ratio_hori)
+    max_width = math.ceil(max(math.ceil(max_ratio_hori), 1)) * model_height
+    if sort_output:
+        image_list = sorted(image_list, key=lambda item: item[0][0][1])
+    return image_list, max_width

@@ -1,0 +1,100 @@
+"""get_image_list (crop + OpenCV-exact INTER_LINEAR resize; reference utils.py:1375-1418): the oracle and the host
+coefficient tables against the reference-generated fixture on CPU, the CUDA kernel against both on the GPU."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+
+def _golden_lists(g, mh):
+    n = int(g[f"mh{mh}_n"])
+    return [(g[f"mh{mh}_box{i}"].tolist(), g[f"mh{mh}_crop{i}"]) for i in range(n)], int(g[f"mh{mh}_max_width"])
+
+
+@pytest.mark.parametrize("mh", [32, 64])
+def test_oracle_get_image_list_matches_reference_fixture(mh):
+    from oracle import recognizer_ref as R
+
+    g = load_golden("crops")
+    want, want_mw = _golden_lists(g, mh)
+    got, mw = R.get_image_list_ref(g["boxes"].tolist(), g["page"], model_height=mh)
+    assert mw == want_mw and len(got) == len(want)
+    for (gb, gc), (wb, wc) in zip(got, want):
+        assert gb == wb
+        assert gc.shape == wc.shape and np.array_equal(gc, wc)
+
+
+def test_host_tables_match_oracle_axis_coefficients():
+    """ocrfa_b200.crops.linear_table (vectorised) == the oracle's scalar restatement of OpenCV's set-up loop."""
+    from oracle import recognizer_ref as R
+    from ocrfa_b200.crops import linear_table
+
+    rng = np.random.default_rng(3)
+    for _ in range(60):
+        src, dst = int(rng.integers(2, 700)), int(rng.integers(1, 900))
+        for clamp in (True, False):
+            idx, w = R._cv_linear_axis(src, dst, clamp)
+            t = linear_table(src, dst, clamp)
+            assert np.array_equal(t[:, 0], idx)
+            a0 = (t[:, 1] & 0xffff).astype(np.int16).astype(np.int64)
+            a1 = ((t[:, 1] >> 16) & 0xffff).astype(np.int16).astype(np.int64)
+            assert np.array_equal(a0, w[:, 0]) and np.array_equal(a1, w[:, 1])
+
+
+def test_oracle_resize_matches_installed_opencv():
+    """Extra pin where cv2 is installed (it is in this image): random sizes against cv2.resize(interpolation=1)."""
+    cv2 = pytest.importorskip("cv2")
+    from oracle import recognizer_ref as R
+
+    rng = np.random.default_rng(0)
+    for it in range(60):
+        sh, sw = int(rng.integers(2, 90)), int(rng.integers(2, 300))
+        dh, dw = int(rng.choice([32, 64, int(rng.integers(2, 100))])), int(rng.integers(2, 400))
+        if it % 10 == 0:
+            dh, dw = max(1, sh // 2), max(1, sw // 2)
+            sh, sw = 2 * dh, 2 * dw
+        img = rng.integers(0, 256, (sh, sw), dtype=np.uint8)
+        assert np.array_equal(R.cv_resize_linear_u8_ref(img, dw, dh), cv2.resize(img, (dw, dh), interpolation=1))
+
+
+def test_free_list_is_rejected_without_a_gpu_call():
+    import ocrfa_b200 as ob
+
+    with pytest.raises(NotImplementedError):
+        ob.get_image_list([], [[[0, 0], [10, 0], [10, 10], [0, 10]]], np.zeros((20, 20), np.uint8))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mh", [32, 64])
+def test_gpu_get_image_list_bit_exact_with_reference_fixture(mh):
+    import ocrfa_b200 as ob
+
+    g = load_golden("crops")
+    want, want_mw = _golden_lists(g, mh)
+    got, mw = ob.get_image_list(g["boxes"].tolist(), [], g["page"], model_height=mh)
+    assert mw == want_mw and len(got) == len(want)
+    for (gb, gc), (wb, wc) in zip(got, want):
+        assert gb == wb
+        assert gc.dtype == np.uint8 and gc.shape == wc.shape and np.array_equal(gc, wc)
+
+
+@pytest.mark.gpu
+def test_gpu_crops_vs_oracle_random_boxes():
+    """Seeded random page and boxes (ragged, clipped, tall) at sizes the oracle finishes in seconds."""
+    import ocrfa_b200 as ob
+    from oracle import recognizer_ref as R
+
+    rng = np.random.default_rng(5)
+    page = rng.integers(0, 256, (500, 900), dtype=np.uint8)
+    boxes = []
+    for _ in range(120):
+        w, h = int(rng.integers(4, 880)), int(rng.integers(4, 200))
+        x0, y0 = int(rng.integers(-30, 890)), int(rng.integers(-30, 490))
+        boxes.append([x0, x0 + w, y0, y0 + h])
+    boxes = [b for b in boxes if min(b[1], 900) - max(b[0], 0) > 0 and min(b[3], 500) - max(b[2], 0) > 0]
+    for mh in (32, 64):
+        want, want_mw = R.get_image_list_ref(boxes, page, model_height=mh)
+        got, mw = ob.get_image_list(boxes, [], page, model_height=mh)
+        assert mw == want_mw and len(got) == len(want)
+        for (gb, gc), (wb, wc) in zip(got, want):
+            assert gb == wb and np.array_equal(gc, wc)
