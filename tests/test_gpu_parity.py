@@ -308,6 +308,26 @@ def test_f16_strings_vs_fp32_at_config2_size(env):
     assert same >= 150  # near-ties (top-2 margin < 0.03) flip under any 16-bit evaluation of this random-weight network
 
 
+@pytest.mark.parametrize("prec", ["bf16", "f16"])
+@pytest.mark.parametrize("hw", [(32, 4), (32, 36), (32, 100), (32, 260), (48, 72), (64, 136)])
+def test_16bit_paths_on_awkward_geometries_vs_fp32(env, prec, hw):
+    """Widths that do not tile into the halo-staged kernel's boxes mix kernels (32-channel stem + halo conv0_2 +
+    per-tap igemm for the later layers, or the per-tap path throughout): every combination must stay within the
+    16-bit tolerance of the fp32 parity path on the same device."""
+    from oracle.synth import synth_lines
+
+    H, W = hw
+    imgs = synth_lines(3, H, W, seed=H * 1000 + W)
+    x = torch.from_numpy(((imgs.astype(np.float32) / 255.0) - 0.5) / 0.5).unsqueeze(1).cuda()
+    ref = env["models"]["fp32"](x, None).cpu().numpy()
+    got = env["models"][prec](x, None).cpu().numpy()
+    assert got.shape == ref.shape and np.isfinite(got).all()
+    d = np.abs(got - ref).max()
+    bound = (2e-2 if prec == "bf16" else 4e-3) * np.abs(ref).max()
+    print(f"{prec} {H}x{W}: max abs {d:.3g} (bound {bound:.3g})")
+    assert d <= bound
+
+
 def test_bf16_strings_vs_fp32_at_config2_size(env):
     """BASELINE config 2 shape (256 lines of 32x512): bf16 tensor-core path against the fp32 parity path on the
     same device - string agreement is reported and must be high; per-timestep argmax flips only where the fp32
