@@ -104,20 +104,35 @@ int ocrfa_align_collate_u8(const uint8_t* d_src, const ocrfa_line_desc* d_desc, 
 /* get_image_list / compute_ratio_and_resize for axis-aligned boxes (src/ocrfa/utils.py:1361-1418): crops n boxes out
  * of one uint8 page image and resizes each with OpenCV's 8-bit INTER_LINEAR arithmetic (what the reference's
  * cv2.resize(..., interpolation=Image.Resampling.LANCZOS) executes: the enum's value is 1), bit-exact with cv2.
- * The per-axis index/weight tables are produced on the host (ocrfa_b200/crops.py). Outputs are packed back to back
- * in d_out: uint8 [dst_h][dst_w] at out_off - the layout ocrfa_align_collate_u8 takes as d_src. */
+ * Sources are boxes of a page image or the warped boxes ocrfa_warp_perspective_u8 produced (each desc carries its own
+ * offset and row stride). The per-axis index/weight tables are produced on the host (ocrfa_b200/crops.py). Outputs
+ * are packed back to back in d_out: uint8 [dst_h][dst_w] at out_off - the layout ocrfa_align_collate_u8 takes as d_src. */
 typedef struct ocrfa_crop_desc {
   int64_t out_off;            /* byte offset of the resized crop in d_out */
-  int32_t x0, y0;             /* top-left corner of the (already clipped) box in the page */
-  int32_t src_w, src_h;       /* box size */
+  int64_t src_off;            /* byte offset of the box's top-left pixel in d_src */
+  int32_t src_stride;         /* bytes between rows of the source */
+  int32_t src_w, src_h;       /* box size (already clipped to the source) */
   int32_t dst_w, dst_h;       /* resized size */
   int32_t xtab_off, ytab_off; /* int32 offsets into d_tables: per output column {x0, a0 | a1 << 16}, per row {y0, b0 | b1 << 16} */
   int32_t mode;               /* 0 = bilinear, 1 = copy (equal sizes), 2 = exact 2x shrink (OpenCV switches to INTER_AREA) */
-  int32_t reserved;
 } ocrfa_crop_desc;
-int ocrfa_crop_resize_u8(const uint8_t* d_page, int32_t page_h, int32_t page_w, int32_t page_stride,
-                         const ocrfa_crop_desc* d_desc, const int32_t* d_tables, int32_t n, uint8_t* d_out,
-                         void* stream);
+int ocrfa_crop_resize_u8(const uint8_t* d_src, const ocrfa_crop_desc* d_desc, const int32_t* d_tables, int32_t n,
+                         uint8_t* d_out, void* stream);
+
+/* four_point_transform for rotated boxes (src/ocrfa/utils.py:1218-1231): cv2.warpPerspective(page, M, (dst_w, dst_h))
+ * with INTER_LINEAR / BORDER_CONSTANT 0, bit-exact with OpenCV's fixed-point remap. minv is the INVERSE of the
+ * reference's getPerspectiveTransform matrix (float64, row-major; ocrfa_b200/crops.py restates OpenCV's LU solve
+ * and 3x3 inverse); block_w is the column-block width OpenCV evaluates row starts at. Warped boxes are packed back
+ * to back in d_out (uint8 [dst_h][dst_w] at out_off), ready for ocrfa_crop_resize_u8. */
+typedef struct ocrfa_warp_desc {
+  int64_t out_off;
+  int32_t dst_w, dst_h;
+  int32_t block_w;
+  int32_t reserved;
+  double m[9];
+} ocrfa_warp_desc;
+int ocrfa_warp_perspective_u8(const uint8_t* d_page, int32_t page_h, int32_t page_w, int32_t page_stride,
+                              const ocrfa_warp_desc* d_desc, int32_t n, uint8_t* d_out, void* stream);
 
 /* d_x: float32 [B,1,H,W]; d_logits: float32 [B,T,num_class]. */
 int ocrfa_forward(ocrfa_handle* h, const float* d_x, int32_t B, int32_t H, int32_t W, float* d_logits, void* d_ws,

@@ -1,15 +1,16 @@
 """Host side of the GPU crop + resize that feeds the recognizer (include/ocrfa_b200.h: ocrfa_crop_resize_u8).
 
 Mirrors the reference's `get_image_list` / `compute_ratio_and_resize` / `calculate_ratio`
-(/root/reference/src/ocrfa/utils.py:1351-1418) for axis-aligned boxes (`horizontal_list`): same arguments, same
+(/root/reference/src/ocrfa/utils.py:1218-1231, 1351-1418): same arguments, same
 return value `(image_list, max_width)`, crops bit-identical to the reference's
 `cv2.resize(..., interpolation=Image.Resampling.LANCZOS)` - the PIL enum's value is 1, i.e. OpenCV INTER_LINEAR.
 The pixel arithmetic runs on the GPU; this module restates OpenCV's per-axis coefficient set-up (imgproc
 resize.cpp: float32 `fx = (dx + 0.5) * scale - 0.5`, border clamps, `saturate_cast<short>(coef * 2048)`), which
 depends only on (source size, destination size) and is cached.
 
-Rotated boxes (`free_list`, `four_point_transform` = cv2.warpPerspective) are not ported: a non-empty `free_list`
-raises NotImplementedError rather than silently taking another code path.
+Rotated boxes (`free_list`, `four_point_transform` = cv2.getPerspectiveTransform + cv2.warpPerspective) take the
+perspective-warp kernel: the 3x3 matrices are parameters, computed here with OpenCV's operation order (float32
+cross terms, float64 LU solve, closed-form 3x3 inverse); the per-pixel fixed-point remap runs on the GPU.
 """
 from __future__ import annotations
 
@@ -23,10 +24,12 @@ import torch
 
 from . import _lib
 
-CROP_DESC = np.dtype([("out_off", "<i8"), ("x0", "<i4"), ("y0", "<i4"), ("src_w", "<i4"), ("src_h", "<i4"),
-                      ("dst_w", "<i4"), ("dst_h", "<i4"), ("xtab_off", "<i4"), ("ytab_off", "<i4"), ("mode", "<i4"),
-                      ("reserved", "<i4")])
+CROP_DESC = np.dtype([("out_off", "<i8"), ("src_off", "<i8"), ("src_stride", "<i4"), ("src_w", "<i4"), ("src_h", "<i4"),
+                      ("dst_w", "<i4"), ("dst_h", "<i4"), ("xtab_off", "<i4"), ("ytab_off", "<i4"), ("mode", "<i4")])
 assert CROP_DESC.itemsize == 48
+WARP_DESC = np.dtype([("out_off", "<i8"), ("dst_w", "<i4"), ("dst_h", "<i4"), ("block_w", "<i4"), ("reserved", "<i4"),
+                      ("m", "<f8", (9,))])
+assert WARP_DESC.itemsize == 96
 MODE_LINEAR, MODE_COPY, MODE_AREA2 = 0, 1, 2
 _COEF_SCALE = np.float32(2048.0)  # INTER_RESIZE_COEF_SCALE = 1 << 11
 
@@ -73,61 +76,189 @@ def linear_table(src: int, dst: int, clamp: bool) -> np.ndarray:
     return np.stack([s, packed], axis=1).astype(np.int32)
 
 
-def crop_resize_device(page: torch.Tensor, boxes: Sequence[Tuple[int, int, int, int]], model_height: int):
-    """boxes: clipped (x_min, x_max, y_min, y_max) with non-empty area. Returns (uint8 CUDA buffer with the resized
-    crops packed back to back, list of (offset, dst_h, dst_w))."""
+# ------------------------------------------------------------------------------------------------------------------
+# rotated boxes: four_point_transform (utils.py:1218-1231). The 3x3 matrices are parameters (9 doubles per box), so
+# they are computed here exactly as OpenCV computes them; the per-pixel warp runs on the GPU.
+# ------------------------------------------------------------------------------------------------------------------
+def _lu_solve8(a: np.ndarray, b: np.ndarray):
+    """OpenCV's LUImpl<double> (core/matrix_decomp.cpp) on an 8x8 system: partial pivoting, `d = -1/a[i][i]`,
+    row updates `a[j][k] += alpha * a[i][k]`, then back substitution - same operation order, float64."""
+    a = a.copy()
+    b = b.copy()
+    m = 8
+    eps = np.finfo(np.float64).eps * 100
+    for i in range(m):
+        k = i
+        for j in range(i + 1, m):
+            if abs(a[j, i]) > abs(a[k, i]):
+                k = j
+        if abs(a[k, i]) < eps:
+            return None
+        if k != i:
+            a[[i, k], i:] = a[[k, i], i:]
+            b[[i, k]] = b[[k, i]]
+        d = -1.0 / a[i, i]
+        for j in range(i + 1, m):
+            alpha = a[j, i] * d
+            for kk in range(i + 1, m):
+                a[j, kk] += alpha * a[i, kk]
+            b[j] += alpha * b[i]
+    for i in range(m - 1, -1, -1):
+        sacc = b[i]
+        for kk in range(i + 1, m):
+            sacc -= a[i, kk] * b[kk]
+        b[i] = sacc / a[i, i]
+    return b
+
+
+def get_perspective_transform(src: np.ndarray, dst: np.ndarray) -> np.ndarray:
+    """cv2.getPerspectiveTransform(src, dst) for float32 [4, 2] points (imgproc/imgwarp.cpp: the cross terms are
+    float32 products, the 8x8 system is solved in float64 by LU)."""
+    src = np.asarray(src, dtype=np.float32)
+    dst = np.asarray(dst, dtype=np.float32)
+    a = np.zeros((8, 8), np.float64)
+    b = np.zeros(8, np.float64)
+    for i in range(4):
+        a[i, 0] = a[i + 4, 3] = src[i, 0]
+        a[i, 1] = a[i + 4, 4] = src[i, 1]
+        a[i, 2] = a[i + 4, 5] = 1
+        a[i, 6] = np.float32(-src[i, 0] * dst[i, 0])
+        a[i, 7] = np.float32(-src[i, 1] * dst[i, 0])
+        a[i + 4, 6] = np.float32(-src[i, 0] * dst[i, 1])
+        a[i + 4, 7] = np.float32(-src[i, 1] * dst[i, 1])
+        b[i] = dst[i, 0]
+        b[i + 4] = dst[i, 1]
+    x = _lu_solve8(a, b)
+    if x is None:
+        x = np.zeros(8)  # cv::solve leaves zeros for a singular system
+    return np.append(x, 1.0).reshape(3, 3)
+
+
+def invert3(S: np.ndarray) -> np.ndarray:
+    """cv::invert of a 3x3 float64 matrix (closed form, core/lapack.cpp), as warpPerspective applies it."""
+    det = (S[0, 0] * (S[1, 1] * S[2, 2] - S[1, 2] * S[2, 1]) - S[0, 1] * (S[1, 0] * S[2, 2] - S[1, 2] * S[2, 0]) +
+           S[0, 2] * (S[1, 0] * S[2, 1] - S[1, 1] * S[2, 0]))
+    if det == 0.0:
+        return np.zeros((3, 3))
+    d = 1.0 / det
+    t = np.empty(9)
+    t[0] = (S[1, 1] * S[2, 2] - S[1, 2] * S[2, 1]) * d
+    t[1] = (S[0, 2] * S[2, 1] - S[0, 1] * S[2, 2]) * d
+    t[2] = (S[0, 1] * S[1, 2] - S[0, 2] * S[1, 1]) * d
+    t[3] = (S[1, 2] * S[2, 0] - S[1, 0] * S[2, 2]) * d
+    t[4] = (S[0, 0] * S[2, 2] - S[0, 2] * S[2, 0]) * d
+    t[5] = (S[0, 2] * S[1, 0] - S[0, 0] * S[1, 2]) * d
+    t[6] = (S[1, 0] * S[2, 1] - S[1, 1] * S[2, 0]) * d
+    t[7] = (S[0, 1] * S[2, 0] - S[0, 0] * S[2, 1]) * d
+    t[8] = (S[0, 0] * S[1, 1] - S[0, 1] * S[1, 0]) * d
+    return t.reshape(3, 3)
+
+
+def four_point_geometry(rect: np.ndarray):
+    """(mw, mh, inverse matrix) of four_point_transform (utils.py:1218-1231) for rect = float32 [4, 2] (tl, tr, br, bl)."""
+    (tl, tr, br, bl) = rect
+    width_a = np.sqrt(((br[0] - bl[0]) ** 2) + ((br[1] - bl[1]) ** 2))
+    width_bs = np.sqrt(((tr[0] - tl[0]) ** 2) + ((tr[1] - tl[1]) ** 2))
+    mw = max(int(width_a), int(width_bs))
+    height_a = np.sqrt(((tr[0] - br[0]) ** 2) + ((tr[1] - br[1]) ** 2))
+    height_bs = np.sqrt(((tl[0] - bl[0]) ** 2) + ((tl[1] - bl[1]) ** 2))
+    mh = max(int(height_a), int(height_bs))
+    dst = np.array([[0, 0], [mw - 1, 0], [mw - 1, mh - 1], [0, mh - 1]], dtype="float32")
+    return mw, mh, invert3(get_perspective_transform(rect, dst))
+
+
+def warp_block_width(dst_w: int, dst_h: int) -> int:
+    """Column-block width of OpenCV's WarpPerspectiveInvoker (BLOCK_SZ = 32)."""
+    bh0 = min(16, dst_h)
+    return min(1024 // bh0, dst_w)
+
+
+def _resize_desc(d, src_off, src_stride, w, h, model_height, cache, tables, t_off):
+    dw, dh, _ = resized_shape(w, h, model_height)
+    d["src_off"], d["src_stride"], d["src_w"], d["src_h"], d["dst_w"], d["dst_h"] = src_off, src_stride, w, h, dw, dh
+    if (dw, dh) == (w, h):
+        d["mode"] = MODE_COPY
+    elif w == 2 * dw and h == 2 * dh:
+        d["mode"] = MODE_AREA2  # resize(): INTER_LINEAR with an exact 2x shrink in both axes is run as INTER_AREA
+    else:
+        d["mode"] = MODE_LINEAR
+        for key, src, dst, clamp, field in (("x", w, dw, True, "xtab_off"), ("y", h, dh, False, "ytab_off")):
+            k = (key, src, dst)
+            if k not in cache:
+                t = linear_table(src, dst, clamp)
+                cache[k] = t_off[0]
+                tables.append(t.reshape(-1))
+                t_off[0] += t.size
+            d[field] = cache[k]
+    return dw, dh
+
+
+def crop_resize_device(page: torch.Tensor, boxes: Sequence[Tuple[int, int, int, int]], model_height: int,
+                       quads: Sequence[Tuple[int, int, np.ndarray]] = ()):
+    """boxes: clipped (x_min, x_max, y_min, y_max) with non-empty area; quads: (mw, mh, inverse matrix) of rotated
+    boxes. Returns (uint8 CUDA buffer with the resized crops packed back to back - quads first, then boxes - and the
+    list of (offset, dst_h, dst_w))."""
     lib = _lib.load()
-    if page.dim() != 2 or page.dtype != torch.uint8 or not page.is_cuda:
-        raise ValueError("page must be a 2-D uint8 CUDA tensor")
-    n = len(boxes)
-    desc = np.zeros(n, dtype=CROP_DESC)
+    if page.dim() != 2 or page.dtype != torch.uint8 or not page.is_cuda or page.stride(1) != 1:
+        raise ValueError("page must be a 2-D uint8 CUDA tensor with contiguous rows")
+    dev = page.device
+    nq, nb = len(quads), len(boxes)
     tables: List[np.ndarray] = []
-    t_off = 0
+    t_off = [0]
     cache = {}
     layout = []
     off = 0
-    for i, (x0, x1, y0, y1) in enumerate(boxes):
-        w, h = x1 - x0, y1 - y0
-        dw, dh, _ = resized_shape(w, h, model_height)
-        d = desc[i]
-        d["out_off"] = off
-        d["x0"], d["y0"], d["src_w"], d["src_h"], d["dst_w"], d["dst_h"] = x0, y0, w, h, dw, dh
-        if (dw, dh) == (w, h):
-            d["mode"] = MODE_COPY
-        elif w == 2 * dw and h == 2 * dh:
-            d["mode"] = MODE_AREA2  # resize(): INTER_LINEAR with an exact 2x shrink in both axes is run as INTER_AREA
-        else:
-            d["mode"] = MODE_LINEAR
-            for key, src, dst, clamp, field in (("x", w, dw, True, "xtab_off"), ("y", h, dh, False, "ytab_off")):
-                k = (key, src, dst)
-                if k not in cache:
-                    t = linear_table(src, dst, clamp)
-                    cache[k] = t_off
-                    tables.append(t.reshape(-1))
-                    t_off += t.size
-                d[field] = cache[k]
-        layout.append((off, dh, dw))
-        off += dw * dh
-        off = (off + 3) & ~3  # keep every crop 4-byte aligned (32-bit stores)
-    tab = np.concatenate(tables) if tables else np.zeros(2, dtype=np.int32)
-    dev = page.device
+    stream = torch.cuda.current_stream(dev).cuda_stream
+
+    def finish(desc, n_off):
+        return (n_off + 3) & ~3  # keep every crop 4-byte aligned (32-bit stores)
+
     with torch.cuda.device(dev):
-        d_desc = torch.from_numpy(desc.view(np.uint8).reshape(-1)).to(dev)
+        warped = None
+        qdesc = np.zeros(nq, dtype=CROP_DESC)
+        if nq:
+            wdesc = np.zeros(nq, dtype=WARP_DESC)
+            woff = 0
+            for i, (mw, mh, minv) in enumerate(quads):
+                wd = wdesc[i]
+                wd["out_off"], wd["dst_w"], wd["dst_h"], wd["block_w"] = woff, mw, mh, warp_block_width(mw, mh)
+                wd["m"] = np.asarray(minv, dtype=np.float64).reshape(9)
+                d = qdesc[i]
+                d["out_off"] = off
+                dw, dh = _resize_desc(d, woff, mw, mw, mh, model_height, cache, tables, t_off)
+                layout.append((off, dh, dw))
+                off = finish(d, off + dw * dh)
+                woff += mw * mh
+            warped = torch.empty(max(4, woff), dtype=torch.uint8, device=dev)
+            d_wdesc = torch.from_numpy(wdesc.view(np.uint8).reshape(-1)).to(dev)
+            _lib.check(lib.ocrfa_warp_perspective_u8(C.c_void_p(page.data_ptr()), page.shape[0], page.shape[1],
+                                                     page.stride(0), C.c_void_p(d_wdesc.data_ptr()), nq,
+                                                     C.c_void_p(warped.data_ptr()), C.c_void_p(stream)))
+        bdesc = np.zeros(nb, dtype=CROP_DESC)
+        for i, (x0, x1, y0, y1) in enumerate(boxes):
+            d = bdesc[i]
+            d["out_off"] = off
+            dw, dh = _resize_desc(d, y0 * page.stride(0) + x0, page.stride(0), x1 - x0, y1 - y0, model_height, cache,
+                                  tables, t_off)
+            layout.append((off, dh, dw))
+            off = finish(d, off + dw * dh)
+        tab = np.concatenate(tables) if tables else np.zeros(2, dtype=np.int32)
         d_tab = torch.from_numpy(tab).to(dev)
         out = torch.empty(max(4, off), dtype=torch.uint8, device=dev)
-        stream = torch.cuda.current_stream(dev).cuda_stream
-        if n:
-            _lib.check(lib.ocrfa_crop_resize_u8(C.c_void_p(page.data_ptr()), page.shape[0], page.shape[1], page.stride(0),
-                                                C.c_void_p(d_desc.data_ptr()), C.c_void_p(d_tab.data_ptr()), n,
-                                                C.c_void_p(out.data_ptr()), C.c_void_p(stream)))
+        for src, desc, n in ((warped, qdesc, nq), (page, bdesc, nb)):
+            if n:
+                d_desc = torch.from_numpy(desc.view(np.uint8).reshape(-1)).to(dev)
+                _lib.check(lib.ocrfa_crop_resize_u8(C.c_void_p(src.data_ptr()), C.c_void_p(d_desc.data_ptr()),
+                                                    C.c_void_p(d_tab.data_ptr()), n, C.c_void_p(out.data_ptr()),
+                                                    C.c_void_p(stream)))
+        torch.cuda.current_stream(dev).synchronize()  # the descriptor / table tensors are released on return
     return out, layout
 
 
 def get_image_list(horizontal_list, free_list, img, model_height=64, sort_output=True, device="cuda"):
     """Drop-in for the reference's get_image_list (utils.py:1375-1418): `img` is the uint8 grayscale page (numpy
-    [H, W] or a CUDA tensor); returns ([(box, crop uint8 ndarray)], max_width). Crops are computed on the GPU."""
-    if len(free_list) > 0:
-        raise NotImplementedError("rotated boxes (free_list / four_point_transform) are not ported to the GPU path")
+    [H, W] or a CUDA tensor); returns ([(box, crop uint8 ndarray)], max_width). Rotated boxes (free_list) go through
+    the perspective-warp kernel, axis-aligned ones are cropped in place; both are resized on the GPU."""
     if isinstance(img, np.ndarray):
         if img.ndim != 2 or img.dtype != np.uint8:
             raise ValueError("img must be a uint8 grayscale page [H, W]")
@@ -139,8 +270,19 @@ def get_image_list(horizontal_list, free_list, img, model_height=64, sort_output
         page = img
     maximum_y, maximum_x = page.shape
     max_ratio_hori, max_ratio_free = 1, 1
+    kept, quads, boxes = [], [], []
+    for box in free_list:
+        rect = np.array(box, dtype="float32")
+        mw, mh, minv = four_point_geometry(rect)
+        ratio = calculate_ratio(mw, mh)
+        new_width = int(model_height * ratio)
+        if new_width == 0:
+            continue
+        _, _, ratio = resized_shape(mw, mh, model_height)
+        kept.append(box)  # box = [[x1,y1],[x2,y2],[x3,y3],[x4,y4]]
+        quads.append((mw, mh, minv))
+        max_ratio_free = max(ratio, max_ratio_free)
     max_ratio_free = math.ceil(max_ratio_free)
-    kept, boxes = [], []
     for box in horizontal_list:
         x_min = max(0, box[0])
         x_max = min(box[1], maximum_x)
@@ -157,8 +299,8 @@ def get_image_list(horizontal_list, free_list, img, model_height=64, sort_output
         boxes.append((int(x_min), int(x_max), int(y_min), int(y_max)))
         max_ratio_hori = max(ratio, max_ratio_hori)
     image_list = []
-    if boxes:
-        out, layout = crop_resize_device(page, boxes, model_height)
+    if kept:
+        out, layout = crop_resize_device(page, boxes, model_height, quads)
         host = out.cpu().numpy()
         for coords, (off, dh, dw) in zip(kept, layout):
             image_list.append((coords, host[off:off + dh * dw].reshape(dh, dw).copy()))

@@ -17,7 +17,7 @@ namespace ocrfa {
 enum : int { kCropLinear = 0, kCropCopy = 1, kCropArea2 = 2 };
 
 // one thread = 4 consecutive output pixels of one row (one 32-bit store when the line start is 4-byte aligned)
-__global__ void __launch_bounds__(256) crop_resize_u8_kernel(const uint8_t* __restrict__ page, int page_stride,
+__global__ void __launch_bounds__(256) crop_resize_u8_kernel(const uint8_t* __restrict__ page,
                                                              const ocrfa_crop_desc* __restrict__ desc,
                                                              const int32_t* __restrict__ tables, int n,
                                                              uint8_t* __restrict__ out) {
@@ -26,7 +26,8 @@ __global__ void __launch_bounds__(256) crop_resize_u8_kernel(const uint8_t* __re
   const ocrfa_crop_desc d = desc[b];
   const int quads = (d.dst_w + 3) >> 2;
   const long long total = (long long)quads * d.dst_h;
-  const uint8_t* src = page + (size_t)d.y0 * page_stride + d.x0;
+  const uint8_t* src = page + d.src_off;
+  const int page_stride = d.src_stride;
   uint8_t* dst = out + d.out_off;
   for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
     const int dy = (int)(g / quads);
@@ -70,6 +71,47 @@ __global__ void __launch_bounds__(256) crop_resize_u8_kernel(const uint8_t* __re
     } else {
       for (int i = 0; i < 4 && dx0 + i < d.dst_w; ++i) op[i] = (uint8_t)v[i];
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// four_point_transform (utils.py:1218-1231) = cv2.warpPerspective(image, M, (mw, mh)): INTER_LINEAR, BORDER_CONSTANT 0.
+// OpenCV's arithmetic, restated: the inverse map is evaluated in float64 per 64-column block (X0 = M0*x + M1*y + M2 at
+// the block's first column, then (X0 + M0*x1) * (32 / (W0 + M6*x1)) per pixel, no fused multiply-adds), rounded to
+// nearest-even into 1/32-pixel fixed point; the four neighbours are blended with the integer weights
+// (32-fy)(32-fx)*32 ... (sum 32768) and (acc + 16384) >> 15. Pixels outside the page read 0.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) warp_perspective_u8_kernel(const uint8_t* __restrict__ page, int page_h, int page_w,
+                                                                  int page_stride, const ocrfa_warp_desc* __restrict__ desc,
+                                                                  int n, uint8_t* __restrict__ out) {
+  const int b = blockIdx.y;
+  if (b >= n) return;
+  const ocrfa_warp_desc d = desc[b];
+  const long long total = (long long)d.dst_w * d.dst_h;
+  uint8_t* dst = out + d.out_off;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
+    const int y = (int)(g / d.dst_w);
+    const int x = (int)(g - (long long)y * d.dst_w);
+    const int xb = (x / d.block_w) * d.block_w;  // OpenCV evaluates the row start at the block's first column
+    const double x1 = (double)(x - xb), xs = (double)xb, ys = (double)y;
+    const double X0 = __dadd_rn(__dadd_rn(__dmul_rn(d.m[0], xs), __dmul_rn(d.m[1], ys)), d.m[2]);
+    const double Y0 = __dadd_rn(__dadd_rn(__dmul_rn(d.m[3], xs), __dmul_rn(d.m[4], ys)), d.m[5]);
+    const double W0 = __dadd_rn(__dadd_rn(__dmul_rn(d.m[6], xs), __dmul_rn(d.m[7], ys)), d.m[8]);
+    double W = __dadd_rn(W0, __dmul_rn(d.m[6], x1));
+    W = W != 0.0 ? __ddiv_rn(32.0, W) : 0.0;
+    double fX = __dmul_rn(__dadd_rn(X0, __dmul_rn(d.m[0], x1)), W);
+    double fY = __dmul_rn(__dadd_rn(Y0, __dmul_rn(d.m[3], x1)), W);
+    fX = fmax(-2147483648.0, fmin(2147483647.0, fX));
+    fY = fmax(-2147483648.0, fmin(2147483647.0, fY));
+    const int X = __double2int_rn(fX), Y = __double2int_rn(fY);
+    const int sx = min(max(X >> 5, -32768), 32767), sy = min(max(Y >> 5, -32768), 32767);
+    const int ax = X & 31, ay = Y & 31;
+    const int w00 = (32 - ay) * (32 - ax) * 32, w01 = (32 - ay) * ax * 32, w10 = ay * (32 - ax) * 32, w11 = ay * ax * 32;
+    auto px = [&](int yy, int xx) -> int {
+      return (yy >= 0 && yy < page_h && xx >= 0 && xx < page_w) ? (int)page[(size_t)yy * page_stride + xx] : 0;
+    };
+    const int acc = px(sy, sx) * w00 + px(sy, sx + 1) * w01 + px(sy + 1, sx) * w10 + px(sy + 1, sx + 1) * w11;
+    dst[g] = (uint8_t)min(max((acc + (1 << 14)) >> 15, 0), 255);
   }
 }
 

@@ -1002,14 +1002,23 @@ int ocrfa_align_collate_u8(const uint8_t* d_src, const ocrfa_line_desc* d_desc, 
   return 0;
 }
 
-int ocrfa_crop_resize_u8(const uint8_t* d_page, int32_t page_h, int32_t page_w, int32_t page_stride,
-                         const ocrfa_crop_desc* d_desc, const int32_t* d_tables, int32_t n, uint8_t* d_out,
-                         void* stream) {
-  if (!d_page || !d_desc || !d_tables || !d_out || n <= 0 || page_h <= 0 || page_w <= 0 || page_stride < page_w)
-    return fail(OCRFA_ERR_ARG, "bad argument");
+int ocrfa_crop_resize_u8(const uint8_t* d_src, const ocrfa_crop_desc* d_desc, const int32_t* d_tables, int32_t n,
+                         uint8_t* d_out, void* stream) {
+  if (!d_src || !d_desc || !d_tables || !d_out || n <= 0) return fail(OCRFA_ERR_ARG, "bad argument");
   if (n > 65535) return fail(OCRFA_ERR_ARG, "at most 65535 boxes per call");
   dim3 grid(64, (unsigned)n);
-  crop_resize_u8_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_page, page_stride, d_desc, d_tables, n, d_out);
+  crop_resize_u8_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_src, d_desc, d_tables, n, d_out);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int ocrfa_warp_perspective_u8(const uint8_t* d_page, int32_t page_h, int32_t page_w, int32_t page_stride,
+                              const ocrfa_warp_desc* d_desc, int32_t n, uint8_t* d_out, void* stream) {
+  if (!d_page || !d_desc || !d_out || n <= 0 || page_h <= 0 || page_w <= 0 || page_stride < page_w)
+    return fail(OCRFA_ERR_ARG, "bad argument");
+  if (n > 65535) return fail(OCRFA_ERR_ARG, "at most 65535 boxes per call");
+  dim3 grid(32, (unsigned)n);
+  warp_perspective_u8_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_page, page_h, page_w, page_stride, d_desc, n, d_out);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

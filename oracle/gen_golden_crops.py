@@ -1,6 +1,6 @@
 """Generates tests/golden/crops.npz by running the UNMODIFIED reference's get_image_list
-(/root/reference/src/ocrfa/utils.py:1375-1418, which calls cv2.resize with interpolation value 1) on a synthetic
-page. TEST INFRASTRUCTURE, dev container only (needs /root/reference):
+(/root/reference/src/ocrfa/utils.py:1375-1418: cv2.resize with interpolation value 1 for every box, and
+four_point_transform = cv2.warpPerspective for the rotated ones) on a synthetic page. TEST INFRASTRUCTURE, dev container only (needs /root/reference):
 
     python oracle/gen_golden_crops.py
 """
@@ -42,9 +42,19 @@ def main():
               [300, 364, 100, 132], [5, 69, 5, 37],           # equal to the model size: copy
               [400, 410, 20, 200], [500, 519, 0, 299],        # tall boxes (ratio < 1 branch)
               [0, 520, 0, 32], [0, 520, 268, 300]]            # full-width lines
-    out = {"page": page, "boxes": np.array(boxes, dtype=np.int64)}
+    # rotated quads (tl, tr, br, bl), some sticking out of the page: the four_point_transform / warpPerspective path
+    import math
+    free = []
+    for _ in range(10):
+        cx, cy = rng.uniform(20, 500), rng.uniform(10, 290)
+        bw, bh, ang = rng.uniform(20, 260), rng.uniform(8, 60), rng.uniform(-0.9, 0.9)
+        c, s_ = math.cos(ang), math.sin(ang)
+        pts = np.array([[-bw / 2, -bh / 2], [bw / 2, -bh / 2], [bw / 2, bh / 2], [-bw / 2, bh / 2]])
+        quad = pts @ np.array([[c, s_], [-s_, c]]) + [cx, cy] + rng.uniform(-2, 2, (4, 2))
+        free.append(np.rint(quad).astype(int).tolist())  # the reference's boxes are integer pixel coordinates
+    out = {"page": page, "boxes": np.array(boxes, dtype=np.int64), "free": np.array(free, dtype=np.int64)}
     for mh in (32, 64):
-        image_list, max_width = utils.get_image_list(boxes, [], page, model_height=mh, sort_output=True)
+        image_list, max_width = utils.get_image_list(boxes, free, page, model_height=mh, sort_output=True)
         out[f"mh{mh}_max_width"] = np.int64(max_width)
         out[f"mh{mh}_n"] = np.int64(len(image_list))
         for i, (coords, crop) in enumerate(image_list):

@@ -552,11 +552,134 @@ def cv_resize_linear_u8_ref(img: np.ndarray, dw: int, dh: int) -> np.ndarray:
     return out
 
 
-def get_image_list_ref(horizontal_list, img: np.ndarray, model_height: int = 64, sort_output: bool = True):
-    """utils.py:1375-1418 with free_list = []."""
+def _cv_get_perspective_transform_ref(src: np.ndarray, dst: np.ndarray) -> np.ndarray:
+    """cv2.getPerspectiveTransform (OpenCV imgproc/imgwarp.cpp): 8x8 system with float32 cross terms, solved in
+    float64 by OpenCV's own LU (core/matrix_decomp.cpp LUImpl: partial pivoting, d = -1/pivot, row updates, back
+    substitution)."""
+    src = src.astype(np.float32)
+    dst = dst.astype(np.float32)
+    A = np.zeros((8, 8))
+    b = np.zeros(8)
+    for i in range(4):
+        A[i, 0:3] = (src[i, 0], src[i, 1], 1.0)
+        A[i + 4, 3:6] = (src[i, 0], src[i, 1], 1.0)
+        A[i, 6], A[i, 7] = np.float32(-src[i, 0] * dst[i, 0]), np.float32(-src[i, 1] * dst[i, 0])
+        A[i + 4, 6], A[i + 4, 7] = np.float32(-src[i, 0] * dst[i, 1]), np.float32(-src[i, 1] * dst[i, 1])
+        b[i], b[i + 4] = dst[i, 0], dst[i, 1]
+    eps = np.finfo(np.float64).eps * 100
+    for i in range(8):
+        k = i + int(np.argmax(np.abs(A[i:, i])))  # first maximum, like the strict '>' scan
+        if abs(A[k, i]) < eps:
+            return np.append(np.zeros(8), 1.0).reshape(3, 3)
+        if k != i:
+            A[[i, k]] = A[[k, i]]
+            b[[i, k]] = b[[k, i]]
+        d = -1.0 / A[i, i]
+        for j in range(i + 1, 8):
+            alpha = A[j, i] * d
+            for c in range(i + 1, 8):
+                A[j, c] += alpha * A[i, c]
+            b[j] += alpha * b[i]
+    for i in range(7, -1, -1):
+        acc = b[i]
+        for c in range(i + 1, 8):
+            acc -= A[i, c] * b[c]
+        b[i] = acc / A[i, i]
+    return np.append(b, 1.0).reshape(3, 3)
+
+
+def _cv_invert3_ref(S: np.ndarray) -> np.ndarray:
+    """cv::invert, 3x3 float64 closed form (core/lapack.cpp)."""
+    c00 = S[1, 1] * S[2, 2] - S[1, 2] * S[2, 1]
+    c01 = S[1, 0] * S[2, 2] - S[1, 2] * S[2, 0]
+    c02 = S[1, 0] * S[2, 1] - S[1, 1] * S[2, 0]
+    det = S[0, 0] * c00 - S[0, 1] * c01 + S[0, 2] * c02
+    if det == 0.0:
+        return np.zeros((3, 3))
+    d = 1.0 / det
+    return np.array([[c00 * d, (S[0, 2] * S[2, 1] - S[0, 1] * S[2, 2]) * d, (S[0, 1] * S[1, 2] - S[0, 2] * S[1, 1]) * d],
+                     [(S[1, 2] * S[2, 0] - S[1, 0] * S[2, 2]) * d, (S[0, 0] * S[2, 2] - S[0, 2] * S[2, 0]) * d,
+                      (S[0, 2] * S[1, 0] - S[0, 0] * S[1, 2]) * d],
+                     [c02 * d, (S[0, 1] * S[2, 0] - S[0, 0] * S[2, 1]) * d, (S[0, 0] * S[1, 1] - S[0, 1] * S[1, 0]) * d]])
+
+
+def cv_warp_perspective_u8_ref(src: np.ndarray, M: np.ndarray, dw: int, dh: int) -> np.ndarray:
+    """cv2.warpPerspective(src, M, (dw, dh)) - INTER_LINEAR, BORDER_CONSTANT 0 (imgproc/imgwarp.cpp
+    WarpPerspectiveInvoker + remapBilinear): float64 inverse map per 32x32-area block, 1/32-pixel fixed point,
+    integer bilinear weights summing to 32768."""
+    Mi = _cv_invert3_ref(np.asarray(M, dtype=np.float64))
+    sh, sw = src.shape
+    bh0 = min(16, dh)
+    bw0 = min(1024 // bh0, dw)
+    ys, xs = np.meshgrid(np.arange(dh), np.arange(dw), indexing="ij")
+    xb = (xs // bw0) * bw0
+    x1 = (xs - xb).astype(np.float64)
+    xbf, yf = xb.astype(np.float64), ys.astype(np.float64)
+    X0 = (Mi[0, 0] * xbf + Mi[0, 1] * yf) + Mi[0, 2]
+    Y0 = (Mi[1, 0] * xbf + Mi[1, 1] * yf) + Mi[1, 2]
+    W0 = (Mi[2, 0] * xbf + Mi[2, 1] * yf) + Mi[2, 2]
+    W = W0 + Mi[2, 0] * x1
+    with np.errstate(divide="ignore"):
+        W = np.where(W != 0.0, 32.0 / W, 0.0)
+    fX = np.clip((X0 + Mi[0, 0] * x1) * W, -2147483648.0, 2147483647.0)
+    fY = np.clip((Y0 + Mi[1, 0] * x1) * W, -2147483648.0, 2147483647.0)
+    X = np.rint(fX).astype(np.int64)
+    Y = np.rint(fY).astype(np.int64)
+    sx, sy = np.clip(X >> 5, -32768, 32767), np.clip(Y >> 5, -32768, 32767)
+    ax, ay = X & 31, Y & 31
+    S = np.zeros((sh + 2, sw + 2), np.int64)  # zero border
+    S[1:-1, 1:-1] = src
+
+    def px(yy, xx):
+        ok = (yy >= 0) & (yy < sh) & (xx >= 0) & (xx < sw)
+        return np.where(ok, S[np.clip(yy, -1, sh) + 1, np.clip(xx, -1, sw) + 1], 0)
+
+    acc = (px(sy, sx) * ((32 - ay) * (32 - ax) * 32) + px(sy, sx + 1) * ((32 - ay) * ax * 32) +
+           px(sy + 1, sx) * (ay * (32 - ax) * 32) + px(sy + 1, sx + 1) * (ay * ax * 32))
+    return np.clip((acc + (1 << 14)) >> 15, 0, 255).astype(np.uint8)
+
+
+def four_point_transform_ref(image: np.ndarray, rect: np.ndarray) -> np.ndarray:
+    """utils.py:1218-1231."""
+    (tl, tr, br, bl) = rect
+    width_a = np.sqrt(((br[0] - bl[0]) ** 2) + ((br[1] - bl[1]) ** 2))
+    width_bs = np.sqrt(((tr[0] - tl[0]) ** 2) + ((tr[1] - tl[1]) ** 2))
+    mw = max(int(width_a), int(width_bs))
+    height_a = np.sqrt(((tr[0] - br[0]) ** 2) + ((tr[1] - br[1]) ** 2))
+    height_bs = np.sqrt(((tl[0] - bl[0]) ** 2) + ((tl[1] - bl[1]) ** 2))
+    mh = max(int(height_a), int(height_bs))
+    dst = np.array([[0, 0], [mw - 1, 0], [mw - 1, mh - 1], [0, mh - 1]], dtype="float32")
+    return cv_warp_perspective_u8_ref(image, _cv_get_perspective_transform_ref(rect, dst), mw, mh)
+
+
+def _resize_to_model_height_ref(crop: np.ndarray, model_height: int):
+    """compute_ratio_and_resize, utils.py:1361-1372."""
+    height, width = crop.shape
+    ratio = width / height
+    if ratio < 1.0:
+        ratio = 1.0 / ratio
+        return cv_resize_linear_u8_ref(crop, model_height, int(model_height * ratio)), ratio
+    return cv_resize_linear_u8_ref(crop, int(model_height * ratio), model_height), ratio
+
+
+def get_image_list_ref(horizontal_list, img: np.ndarray, model_height: int = 64, sort_output: bool = True, free_list=()):
+    """utils.py:1375-1418."""
     maximum_y, maximum_x = img.shape
     image_list = []
-    max_ratio_hori = 1
+    max_ratio_hori, max_ratio_free = 1, 1
+    for box in free_list:
+        rect = np.array(box, dtype="float32")
+        warped = four_point_transform_ref(img, rect)
+        h, w = warped.shape
+        ratio = w / h
+        if ratio < 1.0:
+            ratio = 1.0 / ratio
+        if int(model_height * ratio) == 0:
+            continue
+        crop, ratio = _resize_to_model_height_ref(warped, model_height)
+        image_list.append((box, crop))
+        max_ratio_free = max(ratio, max_ratio_free)
+    max_ratio_free = math.ceil(max_ratio_free)
     for box in horizontal_list:
         x_min, x_max = max(0, box[0]), min(box[1], maximum_x)
         y_min, y_max = max(0, box[2]), min(box[3], maximum_y)
@@ -567,15 +690,10 @@ def get_image_list_ref(horizontal_list, img: np.ndarray, model_height: int = 64,
             ratio = 1.0 / ratio
         if int(model_height * ratio) == 0:
             continue
-        ratio = width / height
-        if ratio < 1.0:
-            ratio = 1.0 / ratio
-            crop = cv_resize_linear_u8_ref(crop, model_height, int(model_height * ratio))
-        else:
-            crop = cv_resize_linear_u8_ref(crop, int(model_height * ratio), model_height)
+        crop, ratio = _resize_to_model_height_ref(crop, model_height)
         image_list.append(([[x_min, y_min], [x_max, y_min], [x_max, y_max], [x_min, y_max]], crop))
         max_ratio_hori = max(ratio, max_ratio_hori)
-    max_width = math.ceil(max(math.ceil(max_ratio_hori), 1)) * model_height
+    max_width = math.ceil(max(math.ceil(max_ratio_hori), max_ratio_free)) * model_height
     if sort_output:
         image_list = sorted(image_list, key=lambda item: item[0][0][1])
     return image_list, max_width

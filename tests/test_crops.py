@@ -17,7 +17,7 @@ def test_oracle_get_image_list_matches_reference_fixture(mh):
 
     g = load_golden("crops")
     want, want_mw = _golden_lists(g, mh)
-    got, mw = R.get_image_list_ref(g["boxes"].tolist(), g["page"], model_height=mh)
+    got, mw = R.get_image_list_ref(g["boxes"].tolist(), g["page"], model_height=mh, free_list=g["free"].tolist())
     assert mw == want_mw and len(got) == len(want)
     for (gb, gc), (wb, wc) in zip(got, want):
         assert gb == wb
@@ -57,11 +57,43 @@ def test_oracle_resize_matches_installed_opencv():
         assert np.array_equal(R.cv_resize_linear_u8_ref(img, dw, dh), cv2.resize(img, (dw, dh), interpolation=1))
 
 
-def test_free_list_is_rejected_without_a_gpu_call():
-    import ocrfa_b200 as ob
+def test_host_perspective_matrices_match_oracle_and_opencv():
+    """ocrfa_b200.crops restates getPerspectiveTransform (LU) + the 3x3 inverse: bit-equal to the oracle's restatement
+    and, where cv2 is installed, to cv2 itself."""
+    from oracle import recognizer_ref as R
+    from ocrfa_b200.crops import get_perspective_transform, invert3
 
-    with pytest.raises(NotImplementedError):
-        ob.get_image_list([], [[[0, 0], [10, 0], [10, 10], [0, 10]]], np.zeros((20, 20), np.uint8))
+    rng = np.random.default_rng(9)
+    try:
+        import cv2
+    except ImportError:
+        cv2 = None
+    for _ in range(200):
+        quad = (rng.uniform(0, 600, (4, 2))).astype(np.float32)
+        mw, mh = int(rng.integers(2, 400)), int(rng.integers(2, 90))
+        dst = np.array([[0, 0], [mw - 1, 0], [mw - 1, mh - 1], [0, mh - 1]], dtype="float32")
+        M = get_perspective_transform(quad, dst)
+        assert np.array_equal(M, R._cv_get_perspective_transform_ref(quad, dst))
+        assert np.array_equal(invert3(M), R._cv_invert3_ref(M))
+        if cv2 is not None:
+            assert np.array_equal(M, cv2.getPerspectiveTransform(quad, dst))
+            assert np.array_equal(invert3(M), cv2.invert(M)[1])
+
+
+def test_oracle_warp_matches_installed_opencv():
+    cv2 = pytest.importorskip("cv2")
+    from oracle import recognizer_ref as R
+
+    rng = np.random.default_rng(4)
+    for _ in range(25):
+        img = rng.integers(0, 256, (int(rng.integers(40, 160)), int(rng.integers(60, 300))), dtype=np.uint8)
+        quad = np.rint(rng.uniform(-10, 1, (4, 2)) + np.array([[20, 10], [img.shape[1] - 30, 14], [img.shape[1] - 25, img.shape[0] - 5],
+                                                                [15, img.shape[0] - 12]])).astype(np.float32)
+        got = R.four_point_transform_ref(img, quad)
+        mh, mw = got.shape
+        dst = np.array([[0, 0], [mw - 1, 0], [mw - 1, mh - 1], [0, mh - 1]], dtype="float32")
+        want = cv2.warpPerspective(img, cv2.getPerspectiveTransform(quad, dst), (mw, mh))
+        assert np.array_equal(got, want)
 
 
 @pytest.mark.gpu
@@ -71,7 +103,7 @@ def test_gpu_get_image_list_bit_exact_with_reference_fixture(mh):
 
     g = load_golden("crops")
     want, want_mw = _golden_lists(g, mh)
-    got, mw = ob.get_image_list(g["boxes"].tolist(), [], g["page"], model_height=mh)
+    got, mw = ob.get_image_list(g["boxes"].tolist(), g["free"].tolist(), g["page"], model_height=mh)
     assert mw == want_mw and len(got) == len(want)
     for (gb, gc), (wb, wc) in zip(got, want):
         assert gb == wb
@@ -92,9 +124,15 @@ def test_gpu_crops_vs_oracle_random_boxes():
         x0, y0 = int(rng.integers(-30, 890)), int(rng.integers(-30, 490))
         boxes.append([x0, x0 + w, y0, y0 + h])
     boxes = [b for b in boxes if min(b[1], 900) - max(b[0], 0) > 0 and min(b[3], 500) - max(b[2], 0) > 0]
+    free = []
+    for _ in range(40):
+        quad = rng.uniform(-20, 20, (4, 2))
+        cx, cy, bw, bh = rng.uniform(0, 900), rng.uniform(0, 500), rng.uniform(10, 500), rng.uniform(5, 90)
+        quad += np.array([[cx, cy], [cx + bw, cy + rng.uniform(-40, 40)], [cx + bw, cy + bh], [cx, cy + bh]])
+        free.append(np.rint(quad).astype(int).tolist())
     for mh in (32, 64):
-        want, want_mw = R.get_image_list_ref(boxes, page, model_height=mh)
-        got, mw = ob.get_image_list(boxes, [], page, model_height=mh)
+        want, want_mw = R.get_image_list_ref(boxes, page, model_height=mh, free_list=free)
+        got, mw = ob.get_image_list(boxes, free, page, model_height=mh)
         assert mw == want_mw and len(got) == len(want)
         for (gb, gc), (wb, wc) in zip(got, want):
             assert gb == wb and np.array_equal(gc, wc)
