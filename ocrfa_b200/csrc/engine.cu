@@ -438,7 +438,11 @@ bool halo_wanted(const ocrfa_handle* h, const ConvW& cw, const Act& in, bool poo
   int tw = 0, th = 0;
   halo_choose_tile(in.w, in.h, pool, &tw, &th);
   const double cover = double(ceil_div(in.w, tw) * tw) * double(ceil_div(in.h, th) * th) / (double(in.w) * in.h);
-  return cover <= 1.06;  // e.g. 4 x 129 feature maps tile better as {4, 4, 8} boxes across images (igemm_tc)
+  if (cover > 1.06) return false;  // e.g. 4 x 129 feature maps tile better as {4, 4, 8} boxes across images (igemm_tc)
+  // latency shapes: a wide layer with only a few M tiles spreads over more SMs as narrow N tiles of the per-tap kernel
+  const int pair_items = ceil_div(ceil_div(in.w, tw) * ceil_div(in.h, th) * in.n, 2);
+  if (cw.cout > 128 && pair_items < kPlanSmCount / 8) return false;
+  return true;
 }
 
 int run_conv_halo(ocrfa_handle* h, const ConvW& cw, const Act& in, const Act* ds_src, const void* residual, void* out,

@@ -24,6 +24,7 @@ struct TileShape {
 };
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+constexpr int kPlanSmCount = 148;  // B200
 
 // 128 output pixels per M tile, arranged as a {tw, th, tn} box (powers of two) that wastes the fewest
 // MMA rows on the ragged edges of (W, H, N).
@@ -75,6 +76,14 @@ inline int plan_conv(IgemmTcParams* p, const ConvGeom& g, const void* in, int ci
   p->n_img = g.n; p->h_out = ho; p->w_out = wo;
   p->block_n = choose_block_n(g.cout);
   if (split) p->block_n = ceil_div(p->block_n, 64) * 64;  // the split epilogue halves a tile in 32-column groups
+  // latency shapes (a handful of M tiles, e.g. one 32x128 line): narrower N tiles spread the layer over more SMs -
+  // the K loop of a single 128 x 256 tile at K = 4608 is ~20 us on one SM while the other SMs idle
+  {
+    const int m_items = ceil_div(p->tiles_w * p->tiles_h * p->tiles_n, 2);  // CTA pairs take two M tiles
+    while (p->block_n > 64 && p->block_n % 128 == 0 && g.cout % (p->block_n / 2) == 0 &&
+           m_items * ceil_div(g.cout, p->block_n) * 2 <= kPlanSmCount / 2)
+      p->block_n /= 2;
+  }
   p->n_tiles = ceil_div(g.cout, p->block_n);
   p->n_valid = g.cout;
   p->kchunks = cin_pad / 64;
@@ -96,6 +105,7 @@ inline int plan_conv(IgemmTcParams* p, const ConvGeom& g, const void* in, int ci
       else { d.dr = static_cast<int16_t>(r); d.dh = 0; }  // h_in = 2*h_out + r
     }
   p->num_taps = nt;
+  p->korder = (!split && g.kh == 3 && g.kw == 3 && g.sh == 1) ? 1 : 0;
   const int R = g.sh;
   const int km = split ? 2 : 1;
   int rc = make_act_tmap(&p->tmA, in, km * cin_buf, g.w_in, R, g.h_in / R, g.n, t.tw, t.th, t.tn);

@@ -68,6 +68,8 @@ struct alignas(64) IgemmTcParams {
   int pair;      // 1: CTA-pair kernel (kModePair): M = 256 across two SMs, each CTA holds half of the weight tile
   int split;     // 1: fp16 hi/lo operands, three products per K chunk (see the header comment)
   int f16;       // 1 (non-split): operands and 16-bit outputs are fp16 instead of bf16
+  int korder;    // 1 (3x3 stride-1 taps, non-split): K blocks run (dx, chunk, dy) like igemm_halo, so that a layer gives
+                 // bit-identical sums whichever of the two kernels the planner picks for a batch size
   int a_lo;      // split: channel offset of the lo half inside source 0's pixel (= its channel count)
   int a_lo2;     // ... inside source 1's pixel
   int out_lo;    // split, !out_f32: channel offset of the lo half inside the output pixel (ldo = 2 * out_lo)
@@ -277,6 +279,16 @@ __global__ void __launch_bounds__(MODE == kModeSplit ? kTcThreadsSplit : kTcThre
       if (rem < chunks) break;
       rem -= chunks;
       kb_base += npass == 1 ? chunks : 2 * chunks;
+    }
+    if (p.korder && npass == 1 && kb < 9 * p.kchunks) {
+      // (dx, chunk, dy) order over the nine taps of source 0 (taps[] is dy-major: tap = dy * 3 + dx)
+      const int dxi = kb / (3 * p.kchunks);
+      const int r2 = kb - dxi * 3 * p.kchunks;
+      const int c = r2 / 3, dyi = r2 - 3 * c;
+      t = dyi * 3 + dxi;
+      rem = c;
+      chunks = p.kchunks;
+      kb_base = t * p.kchunks;
     }
     const TapDesc tap = p.taps[t];
     const int a_c = (pass == 1 ? (tap.src ? p.a_lo2 : p.a_lo) : 0) + rem * kTcBlockK;
