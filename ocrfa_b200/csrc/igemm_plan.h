@@ -106,6 +106,7 @@ inline int plan_conv(IgemmTcParams* p, const ConvGeom& g, const void* in, int ci
     }
   p->num_taps = nt;
   p->korder = (!split && g.kh == 3 && g.kw == 3 && g.sh == 1) ? 1 : 0;
+  if (const char* e = std::getenv("OCRFA_KORDER")) { if (e[0] == '0') p->korder = 0; }  // experiment switch
   const int R = g.sh;
   const int km = split ? 2 : 1;
   int rc = make_act_tmap(&p->tmA, in, km * cin_buf, g.w_in, R, g.h_in / R, g.n, t.tw, t.th, t.tn);
