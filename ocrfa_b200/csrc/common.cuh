@@ -292,6 +292,16 @@ __host__ __device__ __forceinline__ uint32_t make_idesc_f16(uint32_t m, uint32_t
 }
 
 // ---------------------------------------------------------------------------------------------
+// host: function attributes (opt-in shared memory) are per DEVICE: remember them per (kernel slot, device)
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxDevices = 64;
+inline int current_device_slot() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= kMaxDevices) return 0;
+  return d;
+}
+
+// ---------------------------------------------------------------------------------------------
 // numeric helpers
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {

@@ -1119,7 +1119,8 @@ static int beam_launch(const float* d_probs, const int32_t* d_span_row0, const i
   p.hs = hs;
   const size_t smem = beam_smem_bytes(C, beam_width, p.emax, hs, T);
   if (smem > 227 * 1024) return fail(OCRFA_ERR_ARG, "beam_width * num_class too large for shared memory (%zu B)", smem);
-  static size_t attr_smem = 0;
+  static size_t attr_smem_dev[kMaxDevices] = {};
+  size_t& attr_smem = attr_smem_dev[current_device_slot()];
   if (smem > attr_smem) {
     CUDA_TRY(cudaFuncSetAttribute(ctc_beam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_smem = smem;

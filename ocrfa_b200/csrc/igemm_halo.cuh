@@ -402,7 +402,8 @@ inline size_t igemm_halo_smem_bytes(int block_n, int tw, int th, int total_kb, i
 }
 
 inline cudaError_t igemm_halo_launch(const IgemmHaloParams& p, int num_sms, cudaStream_t stream) {
-  static bool attr_set = false;
+  static bool attr_set_dev[kMaxDevices] = {};
+  bool& attr_set = attr_set_dev[current_device_slot()];
   const int total_kb = 9 * p.kchunks + p.kchunks2;
   const size_t b_bytes = static_cast<size_t>(p.block_n / 2) * kTcBlockK * 2;
   const size_t a_halo = static_cast<size_t>(p.th + 2) * p.tw * 128;

@@ -599,7 +599,8 @@ inline int make_rows64_tmap(CUtensorMap* tm, const void* base, long long rows, i
 }
 
 inline cudaError_t igemm_tc_launch(const IgemmTcParams& p, int /*mode*/, int num_sms, cudaStream_t stream) {
-  static bool attr_set[3] = {false, false, false};
+  static bool attr_set_dev[kMaxDevices][3] = {};
+  bool* attr_set = attr_set_dev[current_device_slot()];
   const int mode = p.split ? kModeSplit : (p.pair ? kModePair : kModeStd);
   int stages = 0;
   const size_t smem = igemm_tc_smem_bytes(p.block_n, &stages, p.pair);

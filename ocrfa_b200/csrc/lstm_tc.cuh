@@ -384,7 +384,8 @@ inline size_t lstm_tc_smem_bytes() { return 2048 + kLstmWSlabs * 8192 + static_c
 
 // Cooperative launch (all CTAs co-resident). `sync` must hold 2*m_tiles zeroed counters.
 inline cudaError_t lstm_tc_launch(const LstmTcParams& p, int mode, cudaStream_t stream) {
-  static bool attr_set[3] = {false, false, false};
+  static bool attr_set_dev[kMaxDevices][3] = {};
+  bool* attr_set = attr_set_dev[current_device_slot()];
   const size_t smem = lstm_tc_smem_bytes();
   void* fn = mode == kLstmF16Split    ? reinterpret_cast<void*>(lstm_tc_persistent_kernel<kLstmF16Split>)
              : mode == kLstmF16FusedX ? reinterpret_cast<void*>(lstm_tc_persistent_kernel<kLstmF16FusedX>)
