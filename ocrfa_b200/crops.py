@@ -34,6 +34,27 @@ MODE_LINEAR, MODE_COPY, MODE_AREA2 = 0, 1, 2
 _COEF_SCALE = np.float32(2048.0)  # INTER_RESIZE_COEF_SCALE = 1 << 11
 
 
+class DeviceLine:
+    """A resized crop that stays on the GPU: a [h, w] uint8 window at byte offset `off` of a packed CUDA buffer
+    (the layout ocrfa_align_collate_u8 reads). `get_image_list(..., as_device=True)` returns these instead of numpy
+    arrays so that crop -> AlignCollate -> recognition never round-trips through the host."""
+
+    __slots__ = ("buffer", "off", "shape")
+    ndim = 2
+    dtype = np.dtype(np.uint8)
+
+    def __init__(self, buffer: torch.Tensor, off: int, h: int, w: int):
+        self.buffer, self.off, self.shape = buffer, int(off), (int(h), int(w))
+
+    def numpy(self) -> np.ndarray:
+        h, w = self.shape
+        return self.buffer[self.off:self.off + h * w].cpu().numpy().reshape(h, w)
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.numpy()
+        return a if dtype is None else a.astype(dtype)
+
+
 def calculate_ratio(width, height):
     """utils.py:1351-1358."""
     ratio = width / height
@@ -255,10 +276,11 @@ def crop_resize_device(page: torch.Tensor, boxes: Sequence[Tuple[int, int, int, 
     return out, layout
 
 
-def get_image_list(horizontal_list, free_list, img, model_height=64, sort_output=True, device="cuda"):
+def get_image_list(horizontal_list, free_list, img, model_height=64, sort_output=True, device="cuda", as_device=False):
     """Drop-in for the reference's get_image_list (utils.py:1375-1418): `img` is the uint8 grayscale page (numpy
     [H, W] or a CUDA tensor); returns ([(box, crop uint8 ndarray)], max_width). Rotated boxes (free_list) go through
-    the perspective-warp kernel, axis-aligned ones are cropped in place; both are resized on the GPU."""
+    the perspective-warp kernel, axis-aligned ones are cropped in place; both are resized on the GPU.
+    as_device=True keeps the crops on the GPU (DeviceLine items, accepted by this package's AlignCollate / get_text)."""
     if isinstance(img, np.ndarray):
         if img.ndim != 2 or img.dtype != np.uint8:
             raise ValueError("img must be a uint8 grayscale page [H, W]")
@@ -301,9 +323,13 @@ def get_image_list(horizontal_list, free_list, img, model_height=64, sort_output
     image_list = []
     if kept:
         out, layout = crop_resize_device(page, boxes, model_height, quads)
-        host = out.cpu().numpy()
-        for coords, (off, dh, dw) in zip(kept, layout):
-            image_list.append((coords, host[off:off + dh * dw].reshape(dh, dw).copy()))
+        if as_device:
+            for coords, (off, dh, dw) in zip(kept, layout):
+                image_list.append((coords, DeviceLine(out, off, dh, dw)))
+        else:
+            host = out.cpu().numpy()
+            for coords, (off, dh, dw) in zip(kept, layout):
+                image_list.append((coords, host[off:off + dh * dw].reshape(dh, dw).copy()))
     max_ratio_hori = math.ceil(max_ratio_hori)
     max_ratio = max(max_ratio_hori, max_ratio_free)
     max_width = math.ceil(max_ratio) * model_height

@@ -82,18 +82,20 @@ class AlignCollate:
         self.adjust_contrast = adjust_contrast
 
     def __call__(self, batch) -> LineBatch:
-        images = [np.asarray(b) for b in batch if b is not None]
+        dev_lines = len(batch) > 0 and all(hasattr(b, "buffer") and hasattr(b, "off") for b in batch)  # crops.DeviceLine
+        images = list(batch) if dev_lines else [np.asarray(b) for b in batch if b is not None]
         for img in images:
             if img.ndim != 2 or img.dtype != np.uint8:
                 raise ValueError("lines must be uint8 grayscale arrays [h, w]")
         rws = [resized_width(img.shape[1], img.shape[0], self.imgH, self.imgW) for img in images]
-        identity = self.adjust_contrast <= 0 and all(img.shape == (self.imgH, rw) for img, rw in zip(images, rws))
+        identity = (not dev_lines and self.adjust_contrast <= 0 and
+                    all(img.shape == (self.imgH, rw) for img, rw in zip(images, rws)))
         if not identity:
             # contrast stretch and/or Pillow-exact BICUBIC resize: GPU kernels (ocrfa_align_collate_u8)
             if not torch.cuda.is_available():
                 raise _lib.OcrfaError("AlignCollate needs a CUDA device for lines that are not at model height "
                                       "(no CPU fallback)")
-            dev = torch.device("cuda", torch.cuda.current_device())
+            dev = images[0].buffer.device if dev_lines else torch.device("cuda", torch.cuda.current_device())
             out, widths = align_collate_device(images, self.imgH, self.imgW, self.adjust_contrast, dev)
             return LineBatch(out, widths)
         out = torch.empty((len(images), self.imgH, self.imgW), dtype=torch.uint8)

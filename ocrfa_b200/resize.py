@@ -91,11 +91,17 @@ def align_collate_device(images: Sequence[np.ndarray], img_h: int, img_w: int, a
         t_off += arr.size
         return off
 
+    # lines that already live on the GPU (crops.DeviceLine windows of ONE packed buffer) are read in place
+    on_device = len(images) > 0 and all(hasattr(img, "buffer") and hasattr(img, "off") for img in images)
+    if on_device and any(img.buffer is not images[0].buffer for img in images):
+        raise ValueError("device lines of one batch must share one packed buffer")
     cache = {}
     for i, img in enumerate(images):
         if img.ndim != 2 or img.dtype != np.uint8:
             raise ValueError("lines must be uint8 grayscale arrays [h, w]")
         h, w = img.shape
+        if on_device:
+            src_off = img.off
         rw = resized_width(w, h, img_h, img_w)
         d = desc[i]
         d["src_off"], d["tmp_off"] = src_off, tmp_off
@@ -116,15 +122,16 @@ def align_collate_device(images: Sequence[np.ndarray], img_h: int, img_w: int, a
         widths[i] = rw
         src_off += h * w
         tmp_off += h * rw
-    src = torch.empty(max(1, src_off), dtype=torch.uint8).pin_memory()
-    src_np = src.numpy()
-    o = 0
-    for img in images:
-        src_np[o:o + img.size] = img.reshape(-1)
-        o += img.size
+    if not on_device:
+        src = torch.empty(max(1, src_off), dtype=torch.uint8).pin_memory()
+        src_np = src.numpy()
+        o = 0
+        for img in images:
+            src_np[o:o + img.size] = img.reshape(-1)
+            o += img.size
     tab = np.concatenate(tables) if tables else np.zeros(1, dtype=np.int32)
     with torch.cuda.device(device):
-        d_src = src.to(device, non_blocking=True)
+        d_src = images[0].buffer if on_device else src.to(device, non_blocking=True)
         d_desc = torch.from_numpy(desc.view(np.uint8).reshape(-1)).to(device)
         d_tab = torch.from_numpy(tab).to(device)
         d_tmp = torch.empty(max(1, tmp_off), dtype=torch.uint8, device=device)

@@ -136,3 +136,30 @@ def test_gpu_crops_vs_oracle_random_boxes():
         assert mw == want_mw and len(got) == len(want)
         for (gb, gc), (wb, wc) in zip(got, want):
             assert gb == wb and np.array_equal(gc, wc)
+
+
+@pytest.mark.gpu
+def test_device_resident_crops_feed_get_text_identically(synth_sd, charset):
+    """page -> get_image_list -> get_text with the crops kept on the GPU (DeviceLine) must give exactly the strings
+    and confidences of the host-array route (same kernels, no host round trip in between)."""
+    import torch
+
+    import ocrfa_b200 as ob
+
+    g = load_golden("crops")
+    chars = str(charset["character"])
+    conv = ob.CTCLabelConverter(chars)
+    model = ob.Model(1, 512, 512, len(conv.character), precision="f16")
+    model.load_state_dict({"module." + k: torch.from_numpy(v) for k, v in synth_sd.items()})
+    boxes, free = g["boxes"].tolist(), g["free"].tolist()
+    host_list, mw = ob.get_image_list(boxes, free, g["page"], model_height=32)
+    dev_list, mw2 = ob.get_image_list(boxes, free, g["page"], model_height=32, as_device=True)
+    assert mw == mw2 and len(host_list) == len(dev_list)
+    for (hb, hc), (db, dc) in zip(host_list, dev_list):
+        assert hb == db and np.array_equal(hc, dc.numpy())
+    # tall crops (vertical text) are wider than imgW allows after AlignCollate's resize: both routes clip alike
+    kw = dict(ignore_char=ob.default_ignore_char(), decoder="greedy", batch_size=16, device="cuda")
+    r_host = ob.get_text(chars, 32, int(mw), model, conv, host_list, **kw)
+    r_dev = ob.get_text(chars, 32, int(mw), model, conv, dev_list, **kw)
+    assert [(b, s) for b, s, _ in r_host] == [(b, s) for b, s, _ in r_dev]
+    np.testing.assert_array_equal(np.array([c for _, _, c in r_host]), np.array([c for _, _, c in r_dev]))
