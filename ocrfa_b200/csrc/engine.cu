@@ -753,10 +753,11 @@ int forward_impl(ocrfa_handle* h, const float* d_x, const uint8_t* d_u8, const i
         memset(&lp, 0, sizeof(lp));
         lp.m_tiles = ceil_div(nb, 128);
         lp.hx = ws + L.hx;
-        int r2 = make_rows64_tmap(&lp.tmX, lp.hx, lstm_hx_rows(mode, lp.m_tiles), 128);
+        lp.box_rows = lp.m_tiles > 1 ? 128 : std::max(8, (nb + 7) & ~7);
+        int r2 = make_rows64_tmap(&lp.tmX, lp.hx, lstm_hx_rows(mode, lp.m_tiles), lp.box_rows);
         if (r2 == 0) r2 = make_wgt_tmap(&lp.tmW, lw.d_whh, 1024, 4096, 64);
         if (r2 == 0 && !sp)
-          r2 = make_act_tmap(&lp.tmS, (const __nv_bfloat16*)seq_in + (size_t)b0 * T * 512, 512, T, 1, nb, 1, 1, 128, 1);
+          r2 = make_act_tmap(&lp.tmS, (const __nv_bfloat16*)seq_in + (size_t)b0 * T * 512, 512, T, 1, nb, 1, 1, lp.box_rows, 1);
         if (r2) return fail(OCRFA_ERR_CUDA, "LSTM tensor map failed: %d", r2);
         lp.xproj = sp ? xproj + (size_t)b0 * T * 4096 : nullptr;
         lp.bias = lw.d_bih;

@@ -57,6 +57,8 @@ struct alignas(64) LstmTcParams {
   long long* dbg;            // optional [64 steps][16] SM-clock timestamps of CTA 0 (bring-up profiling), or null
   float acc_scale;           // split mode: 2^-k undoing the power-of-two pre-scale of W_hh
   int B, T, m_tiles;
+  int box_rows;              // batch rows per TMA slab: 128, or B rounded up to 8 when one M tile holds the whole batch
+                             // (a step is paced by the bytes each SM ingests: 64 lines load half of them)
 };
 
 __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
@@ -159,6 +161,7 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_tc_persistent_kernel(con
       for (int i = 0; i < kLstmWSlabs; ++i) tma_load_2d(w_smem + i * 8192, &p.tmW, w_full, i * 64, n_tile * 64);
       int stage = 0;
       uint32_t phase = 0;
+      const uint32_t slab_bytes = static_cast<uint32_t>(p.box_rows) * 128u;  // rows >= box_rows of a ring slot are never read back
       const int oob_row = static_cast<int>(lstm_hx_rows(MODE, p.m_tiles));
       for (int s = 0; s < T; ++s) {
         LSTM_TS(s, 0);
@@ -167,7 +170,7 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_tc_persistent_kernel(con
           const int t_cur = dir == 0 ? s : T - 1 - s;
           for (int kb = 0; kb < 8; ++kb) {
             mbar_wait(&a_empty[stage], phase ^ 1u, 10);
-            mbar_expect_tx(&a_full[stage], 16384);
+            mbar_expect_tx(&a_full[stage], slab_bytes);
             tma_load_5d(ring + stage * 16384, &p.tmS, &a_full[stage], kb * 64, t_cur, 0, m_tile * 128, 0);
             if (++stage == kLstmRing) { stage = 0; phase ^= 1u; }
           }
@@ -195,7 +198,7 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_tc_persistent_kernel(con
         const int xrow0 = s == 0 ? oob_row : (((dir * p.m_tiles + m_tile) * 2 + ((s - 1) & 1)) * kHxSlabs) * 128;
         for (int i = 0; i < kHxSlabs; ++i) {
           mbar_wait(&a_empty[stage], phase ^ 1u, 11);
-          mbar_expect_tx(&a_full[stage], 16384);
+          mbar_expect_tx(&a_full[stage], slab_bytes);
           tma_load_2d(ring + stage * 16384, &p.tmX, &a_full[stage], 0, xrow0 + i * 128);
           if (++stage == kLstmRing) { stage = 0; phase ^= 1u; }
         }
@@ -278,6 +281,12 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_tc_persistent_kernel(con
       mbar_arrive(&tempty[as]);
       if (et == 0) LSTM_TS(s, 9);
       float hout[16];
+      // a warp whose 32 rows are all beyond the batch skips the gate math: the activations are MUFU bound and shared
+      // by the four epilogue warps (64 lines: half of the SM's transcendental work would be on padding rows)
+      const bool warp_live = (m_tile * 128 + q * 32) < p.B;
+#pragma unroll
+      for (int u = 0; u < 16; ++u) hout[u] = 0.f;
+      if (warp_live)
 #pragma unroll
       for (int g4 = 0; g4 < 4; ++g4) {
         float4 ai, af, ag, ao;
