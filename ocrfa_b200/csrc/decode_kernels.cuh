@@ -156,6 +156,7 @@ struct BeamParams {
   int B, T, C, bw;
   int emax;              // bw * (C + 1)
   int hs;                // hash slots (power of two >= 2 * emax)
+  int ht32;              // 1: 32-bit hash slots
 };
 
 enum : int { kOpSame = 0, kOpAppend = 1, kOpReplace = 2 };
@@ -178,23 +179,24 @@ struct BeamSmem {
   float *xp_b, *xp_2;                  // [bw] per parent: the copy-beam's prBlank contribution / its "extend by blank" one
   int32_t* e_first;                    // creation order of the labeling (min member entry index)
   int16_t *e_len, *e_rep;              // labeling length; representative entry of this entry's labeling
-  int16_t* e_c; uint8_t *e_parent, *e_op, *e_flags;
-  uint16_t* ht;      // [hs], 0xffff = empty
+  uint32_t* e_meta;                    // class | parent << 16 | op << 24 | flags << 26
+  uint16_t* ht16;    // [hs] hash slots, 0xffff = empty (wide beams: the table must fit beside the entries)
+  int32_t* ht32;     // [hs] ... or 32-bit slots (-1 = empty) when shared memory allows: native atomicCAS
   uint32_t* chain;   // [T] back-pointers of the winning path
   int16_t* raw;      // [T] its raw labeling
 };
 enum : int { kEfActive = 1, kEfSecond = 2 };
-constexpr int kBeamEntryBytes = 8 + 4 * 3 + 4 + 4 + 2 * 3 + 3;  // 37
+constexpr int kBeamEntryBytes = 8 + 4 * 3 + 4 + 4 + 2 * 2 + 4;  // 36
 constexpr int kBeamRegChunks = 8;  // register-resident top-bw selection up to 32 * 8 candidate entries
 
-__host__ __device__ inline size_t beam_smem_bytes(int C, int bw, int emax, int hs, int T) {
+__host__ __device__ inline size_t beam_smem_bytes(int C, int bw, int emax, int hs, int T, int ht32 = 0) {
   size_t n = 0;
   n += (size_t)C * 4 + (size_t)((C * 2 + 7) & ~7);
   n += (size_t)2 * bw * (4 * 3 + 4 + 2 * 2 + 8 * 2) + (size_t)bw * 8;
   n = (n + 7) & ~(size_t)7;
   n += (size_t)emax * kBeamEntryBytes;
   n = (n + 7) & ~(size_t)7;
-  n += (size_t)hs * 2;
+  n += (size_t)hs * (ht32 ? 4 : 2);
   n += (size_t)T * 4 + (size_t)((T * 2 + 7) & ~7);
   return n + 64;
 }
@@ -233,17 +235,15 @@ __global__ void __launch_bounds__(32) ctc_beam_kernel(const BeamParams p) {
   s.xp_b = reinterpret_cast<float*>(q); q += (size_t)bw * 4;
   s.xp_2 = reinterpret_cast<float*>(q); q += (size_t)bw * 4;
   s.chain = reinterpret_cast<uint32_t*>(q); q += (size_t)T * 4;
-  s.ht = reinterpret_cast<uint16_t*>(q); q += (size_t)p.hs * 2;
+  s.e_meta = reinterpret_cast<uint32_t*>(q); q += (size_t)emax * 4;
+  s.ht32 = reinterpret_cast<int32_t*>(q);
+  s.ht16 = reinterpret_cast<uint16_t*>(q); q += (size_t)p.hs * (p.ht32 ? 4 : 2);
   s.e_len = reinterpret_cast<int16_t*>(q); q += (size_t)emax * 2;
   s.e_rep = reinterpret_cast<int16_t*>(q); q += (size_t)emax * 2;
   s.b_last = reinterpret_cast<int16_t*>(q); q += (size_t)2 * bw * 2;
   s.b_last2 = reinterpret_cast<int16_t*>(q); q += (size_t)2 * bw * 2;
-  s.e_c = reinterpret_cast<int16_t*>(q); q += (size_t)emax * 2;
   s.cand = reinterpret_cast<int16_t*>(q); q += (size_t)C * 2;
   s.raw = reinterpret_cast<int16_t*>(q); q += (size_t)T * 2;
-  s.e_parent = q; q += emax;
-  s.e_op = q; q += emax;
-  s.e_flags = q; q += emax;
 
   const float thr = static_cast<float>(0.5 / static_cast<double>(C));  // np.float32(0.5 / maxC)
   const float* mat = p.probs + (p.span_row0 ? (size_t)p.span_row0[b] * C : (size_t)b * T * C);
@@ -267,6 +267,13 @@ __global__ void __launch_bounds__(32) ctc_beam_kernel(const BeamParams p) {
   }
   __syncwarp();
 
+#ifdef OCRFA_BEAM_PROF
+  long long prof[6] = {0, 0, 0, 0, 0, 0};
+  long long pt0 = clock64();
+#define BEAM_PROF(i) do { const long long n_ = clock64(); prof[i] += n_ - pt0; pt0 = n_; } while (0)
+#else
+#define BEAM_PROF(i) do { } while (0)
+#endif
   for (int t = 0; t < Tb; ++t) {
     // ---- a. stage the probability row, list the classes above threshold in ascending order
     int ncand = 0;
@@ -307,9 +314,11 @@ __global__ void __launch_bounds__(32) ctc_beam_kernel(const BeamParams p) {
     const int E = nb * per_parent;
     int hs = 64;
     while (hs < 2 * E) hs <<= 1;
-    for (int i = lane; i < hs; i += 32) s.ht[i] = 0xffffu;
+    if (p.ht32) { for (int i = lane; i < hs; i += 32) s.ht32[i] = -1; }
+    else { for (int i = lane; i < hs; i += 32) s.ht16[i] = 0xffffu; }
     __syncwarp();
     const bool blank_cand = ncand > 0 && s.cand[0] == 0;  // blank passes the threshold
+    BEAM_PROF(0);
 
     const float* pt = s.b_tot + cur * bw; const float* pn = s.b_nb + cur * bw; const float* pb = s.b_b + cur * bw;
     const int32_t* pl = s.b_len + cur * bw; const int16_t* pla = s.b_last + cur * bw; const int16_t* pl2 = s.b_last2 + cur * bw;
@@ -355,35 +364,48 @@ __global__ void __launch_bounds__(32) ctc_beam_kernel(const BeamParams p) {
         }
       }
       if (self < E) {
-        s.e_hash[self] = nhash; s.e_len[self] = static_cast<int16_t>(nlen); s.e_c[self] = static_cast<int16_t>(c);
-        s.e_parent[self] = static_cast<uint8_t>(i); s.e_op[self] = static_cast<uint8_t>(op);
-        s.e_flags[self] = static_cast<uint8_t>((active ? kEfActive : 0) | (second ? kEfSecond : 0));
+        s.e_hash[self] = nhash; s.e_len[self] = static_cast<int16_t>(nlen);
+        s.e_meta[self] = static_cast<uint32_t>(c) | (static_cast<uint32_t>(i) << 16) | (static_cast<uint32_t>(op) << 24) |
+                         (static_cast<uint32_t>((active ? kEfActive : 0) | (second ? kEfSecond : 0)) << 26);
         s.x_nb[self] = add_nb;
         if (k == 0) { s.xp_b[i] = add_b; s.xp_2[i] = add_2; }
         s.a_tot[self] = 0.f; s.a_nb[self] = 0.f; s.a_b[self] = 0.f;
         s.e_first[self] = 0x7fffffff; s.e_rep[self] = -1;
       }
-      __syncwarp();
-      if (active) {
+    }
+    __syncwarp();
+    // second pass: find or create the representative of every active entry's labeling
+    for (int e0 = 0; e0 < E; e0 += 32) {
+      const int self = e0 + lane;
+      if (self < E && ((s.e_meta[self] >> 26) & kEfActive)) {
+        const uint64_t nhash = s.e_hash[self];
+        const int nlen = s.e_len[self];
         uint32_t slot = static_cast<uint32_t>(nhash ^ (nhash >> 32)) & (hs - 1);
         int rep;
         while (true) {
-          const int seen = atomicCAS(&s.ht[slot], static_cast<unsigned short>(0xffffu), static_cast<unsigned short>(self));
-          if (seen == 0xffff) { rep = self; break; }
+          int seen;
+          if (p.ht32) {
+            seen = atomicCAS(&s.ht32[slot], -1, self);
+          } else {
+            const unsigned short got = atomicCAS(&s.ht16[slot], static_cast<unsigned short>(0xffffu), static_cast<unsigned short>(self));
+            seen = got == 0xffffu ? -1 : static_cast<int>(got);
+          }
+          if (seen == -1) { rep = self; break; }
           if (s.e_hash[seen] == nhash && s.e_len[seen] == nlen) { rep = seen; break; }
           slot = (slot + 1) & (hs - 1);
         }
         s.e_rep[self] = static_cast<int16_t>(rep);
         atomicMin(&s.e_first[rep], self);
       }
-      __syncwarp();
     }
+    __syncwarp();
 
+    BEAM_PROF(1);
     // ---- b2. ordered accumulation: parent by parent (no two entries of one parent share a labeling)
     for (int i = 0; i < nb; ++i) {
       for (int k = lane; k < per_parent; k += 32) {
         const int self = i * per_parent + k;
-        const int fl = s.e_flags[self];
+        const int fl = static_cast<int>(s.e_meta[self] >> 26);
         if (fl & kEfActive) {
           const int r = s.e_rep[self];
           const float xnb = s.x_nb[self];
@@ -398,13 +420,15 @@ __global__ void __launch_bounds__(32) ctc_beam_kernel(const BeamParams p) {
       __syncwarp();
     }
 
+    BEAM_PROF(2);
     // ---- c. keep the best `bw` labelings: prTotal descending, creation order ascending on ties (stable sort)
     const int nxt = cur ^ 1;
     uint32_t* trow = trel + (size_t)t * bw;
     int n_new = 0;
     auto emit = [&](int j, int r) {
       // labeling represented by entry j becomes beam r of the next step
-      const int par = s.e_parent[j], op = s.e_op[j], c = s.e_c[j];
+      const uint32_t meta = s.e_meta[j];
+      const int par = (meta >> 16) & 0xff, op = (meta >> 24) & 3, c = meta & 0xffff;
       const int o = nxt * bw + r;
       s.b_tot[o] = s.a_tot[j]; s.b_nb[o] = s.a_nb[j]; s.b_b[o] = s.a_b[j]; s.b_len[o] = s.e_len[j];
       s.b_hash[o] = s.e_hash[j];
@@ -423,6 +447,9 @@ __global__ void __launch_bounds__(32) ctc_beam_kernel(const BeamParams p) {
         key[m] = 0u; first[m] = 0x7fffffff;
         if (j < E && s.e_rep[j] == j) { key[m] = __float_as_uint(s.a_tot[j]) + 1u; first[m] = s.e_first[j]; }
       }
+      // the rounds only pick the winners (two warp reductions each); the state of the surviving beams is written
+      // afterwards by bw lanes in parallel instead of one lane per round
+      int my_j0 = -1, my_j1 = -1;  // winners of rounds lane and lane + 32 (bw <= 64)
       for (int r = 0; r < bw; ++r) {
         uint32_t lmax = 0u;
 #pragma unroll
@@ -433,11 +460,16 @@ __global__ void __launch_bounds__(32) ctc_beam_kernel(const BeamParams p) {
 #pragma unroll
         for (int m = 0; m < kBeamRegChunks; ++m) lfirst = (key[m] == wmax && first[m] < lfirst) ? first[m] : lfirst;
         const int wfirst = __reduce_min_sync(0xffffffffu, lfirst);
+        int lj = -1;
 #pragma unroll
         for (int m = 0; m < kBeamRegChunks; ++m)
-          if (key[m] == wmax && first[m] == wfirst) { emit(lane + 32 * m, r); key[m] = 0u; }
+          if (key[m] == wmax && first[m] == wfirst) { lj = lane + 32 * m; key[m] = 0u; }
+        const int wj = __reduce_max_sync(0xffffffffu, lj);  // exactly one lane holds the winner (creation order is unique)
+        if ((r & 31) == lane) { if (r < 32) my_j0 = wj; else my_j1 = wj; }
         ++n_new;
       }
+      if (my_j0 >= 0) emit(my_j0, lane);
+      if (my_j1 >= 0) emit(my_j1, lane + 32);
     } else {
       // many candidates (flat distributions): scan shared memory each round
       for (int r = 0; r < bw; ++r) {
@@ -458,7 +490,13 @@ __global__ void __launch_bounds__(32) ctc_beam_kernel(const BeamParams p) {
     nb = n_new;
     cur = nxt;
     __syncwarp();
+    BEAM_PROF(3);
   }
+#ifdef OCRFA_BEAM_PROF
+  if (b == 0 && lane == 0)
+    printf("[beam prof] T=%d cycles/step: stage+clear %lld, build %lld, accumulate %lld, select %lld\n", Tb,
+           prof[0] / Tb, prof[1] / Tb, prof[2] / Tb, prof[3] / Tb);
+#endif
 
   // ---- rebuild the best labeling from the trellis, then drop ignored indices and adjacent duplicates of the RAW
   // labeling (utils.py:1031-1035). The trellis of this line is staged in the (now dead) entry arrays when it fits.

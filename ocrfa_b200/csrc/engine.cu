@@ -1118,7 +1118,8 @@ static int beam_launch(const float* d_probs, const int32_t* d_span_row0, const i
   int hs = 64;
   while (hs < 2 * p.emax) hs <<= 1;
   p.hs = hs;
-  const size_t smem = beam_smem_bytes(C, beam_width, p.emax, hs, T);
+  p.ht32 = beam_smem_bytes(C, beam_width, p.emax, hs, T, 1) <= 227 * 1024 ? 1 : 0;
+  const size_t smem = beam_smem_bytes(C, beam_width, p.emax, hs, T, p.ht32);
   if (smem > 227 * 1024) return fail(OCRFA_ERR_ARG, "beam_width * num_class too large for shared memory (%zu B)", smem);
   static size_t attr_smem_dev[kMaxDevices] = {};
   size_t& attr_smem = attr_smem_dev[current_device_slot()];
