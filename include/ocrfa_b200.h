@@ -67,6 +67,16 @@ const char* ocrfa_last_error(void);
 int ocrfa_create(const ocrfa_config* cfg, ocrfa_handle** out);
 void ocrfa_destroy(ocrfa_handle* h);
 
+/* CRAFT text detector (src/ocrfa/utils.py:31-98 class OCRFA over modules/blocks.py:27-82 Vgg16BN; called at
+ * detectors.py:43-47): a second kind of handle. Load the detector's state dict with ocrfa_load_weight, call
+ * ocrfa_finalize_weights, then ocrfa_craft_forward = OCRFA.forward: d_x float32 [N,3,H,W] (mean/variance normalised,
+ * H and W multiples of 32 as resize_aspect_ratio produces) -> d_y float32 [N,H/2,W/2,2] (text, link score maps, the
+ * reference's y.permute(0,2,3,1)) and, when not NULL, d_feature float32 [N,32,H/2,W/2]. precision: BF16 or F16. */
+int ocrfa_craft_create(int32_t precision, int32_t device, ocrfa_handle** out);
+size_t ocrfa_craft_workspace_bytes(const ocrfa_handle* h, int32_t N, int32_t H, int32_t W);
+int ocrfa_craft_forward(ocrfa_handle* h, const float* d_x, int32_t N, int32_t H, int32_t W, float* d_y, float* d_feature,
+                        void* d_ws, size_t ws_bytes, void* stream);
+
 /* One state-dict entry (float32, host memory, PyTorch layout); an optional "module." prefix is stripped.
  * Integer entries (num_batches_tracked) may be skipped by the caller. */
 int ocrfa_load_weight(ocrfa_handle* h, const char* name, const float* h_data, const int64_t* shape, int32_t ndim);

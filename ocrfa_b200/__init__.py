@@ -11,6 +11,7 @@ from ._lib import OcrfaError
 from .charset import (ARABIC_G1_CHARACTERS, ARABIC_G1_SYMBOLS, default_character, default_ignore_char,
                       default_lang_char)
 from .converter import CTCLabelConverter
+from .craft import CraftNet, get_detector, synth_craft_state_dict
 from .crops import calculate_ratio, get_image_list
 from .model import Model
 from .recognition import (AlignCollate, LineBatch, ListDataset, adjust_contrast_grey, contrast_grey, custom_mean,
@@ -20,5 +21,5 @@ __all__ = [
     "Model", "CTCLabelConverter", "get_recognizer", "get_text", "recognizer_predict", "recognize_host",
     "AlignCollate", "ListDataset", "LineBatch", "custom_mean", "contrast_grey", "adjust_contrast_grey",
     "default_character", "default_lang_char", "default_ignore_char", "ARABIC_G1_CHARACTERS", "ARABIC_G1_SYMBOLS",
-    "OcrfaError", "get_image_list", "calculate_ratio",
+    "OcrfaError", "get_image_list", "calculate_ratio", "CraftNet", "get_detector",
 ]

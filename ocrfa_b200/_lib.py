@@ -21,6 +21,7 @@ PRECISIONS = {"fp32": PRECISION_FP32, "bf16": PRECISION_BF16, "f16x3": PRECISION
 SYMBOLS = (
     "ocrfa_abi_version", "ocrfa_last_error", "ocrfa_create", "ocrfa_destroy", "ocrfa_load_weight",
     "ocrfa_finalize_weights", "ocrfa_out_timesteps", "ocrfa_workspace_bytes", "ocrfa_preprocess_u8", "ocrfa_align_collate_u8", "ocrfa_crop_resize_u8", "ocrfa_warp_perspective_u8",
+    "ocrfa_craft_create", "ocrfa_craft_workspace_bytes", "ocrfa_craft_forward",
     "ocrfa_forward", "ocrfa_forward_features", "ocrfa_forward_sequence", "ocrfa_forward_u8", "ocrfa_ctc_greedy", "ocrfa_ctc_collapse", "ocrfa_argmax_rows",
     "ocrfa_beam_workspace_bytes", "ocrfa_ctc_beam", "ocrfa_ctc_beam_spans", "ocrfa_recognize_host",
     "ocrfa_recognize_device", "ocrfa_recognize_workspace_bytes", "ocrfa_profile_begin", "ocrfa_profile_end",
@@ -80,6 +81,10 @@ def load():
     lib.ocrfa_profile_end.argtypes = [vp, vp, vp, vp]
     lib.ocrfa_recognize_workspace_bytes.argtypes = [vp, i32, i32, i32, i32]
     lib.ocrfa_recognize_workspace_bytes.restype = sz
+    lib.ocrfa_craft_create.argtypes = [i32, i32, C.POINTER(vp)]
+    lib.ocrfa_craft_workspace_bytes.argtypes = [vp, i32, i32, i32]
+    lib.ocrfa_craft_workspace_bytes.restype = sz
+    lib.ocrfa_craft_forward.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, sz, vp]
     lib.ocrfa_launch_count.argtypes = [vp]
     lib.ocrfa_launch_count.restype = i64
     for name in SYMBOLS:

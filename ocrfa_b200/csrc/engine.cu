@@ -52,7 +52,7 @@ struct HostTensor {
 // extra K columns). Geometry per /root/reference/src/ocrfa/modules/blocks.py:239-322.
 struct ConvW {
   std::string name;
-  int cin = 0, cout = 0, kh = 0, kw = 0, sh = 1, ph = 0, pw = 0;
+  int cin = 0, cout = 0, kh = 0, kw = 0, sh = 1, ph = 0, pw = 0, dil = 1;
   int cin_pad = 0;     // channels of the input buffer the tensor-core path reads (multiple of 64)
   int ds_cin = 0;      // > 0: fused downsample source channels (bf16 path)
   int ktotal = 0;      // K of the packed weight matrix
@@ -120,6 +120,7 @@ struct ocrfa_handle {
   Profiler prof;
   ocrfa_config cfg;
   int num_sms = 148;
+  int network = 0;     // 0 = recognizer (ocrfa_create), 1 = CRAFT detector (ocrfa_craft_create)
   int halo_level = 2;  // OCRFA_HALO: 0 = igemm_tc only, 1 = halo-staged kernel for Cout <= 128, 2 = wherever it tiles well
   bool finalized = false;
   std::map<std::string, HostTensor> host;
@@ -432,7 +433,7 @@ struct LaunchScope {
 // max pool fused. Returns 1 when the layer is not a candidate (the caller falls back to igemm_tc [+ pool kernel]).
 bool halo_wanted(const ocrfa_handle* h, const ConvW& cw, const Act& in, bool pool) {
   if (!h->bf16() || h->halo_level <= 0) return false;
-  const ConvGeom g{in.n, in.h, in.w, cw.cin, cw.cout, cw.kh, cw.kw, cw.sh, cw.ph, cw.pw};
+  const ConvGeom g{in.n, in.h, in.w, cw.cin, cw.cout, cw.kh, cw.kw, cw.sh, cw.ph, cw.pw, cw.dil};
   if (!halo_eligible(g, pool) || (long long)in.n * in.h * in.w >= (1ll << 31)) return false;
   if (cw.cout > 128 && h->halo_level < 2) return false;
   int tw = 0, th = 0;
@@ -446,15 +447,15 @@ bool halo_wanted(const ocrfa_handle* h, const ConvW& cw, const Act& in, bool poo
 }
 
 int run_conv_halo(ocrfa_handle* h, const ConvW& cw, const Act& in, const Act* ds_src, const void* residual, void* out,
-                  bool relu, bool pool, cudaStream_t st) {
+                  bool relu, bool pool, cudaStream_t st, int ldo = 0) {
   IgemmHaloParams p;
-  const ConvGeom g{in.n, in.h, in.w, cw.cin, cw.cout, cw.kh, cw.kw, cw.sh, cw.ph, cw.pw};
+  const ConvGeom g{in.n, in.h, in.w, cw.cin, cw.cout, cw.kh, cw.kw, cw.sh, cw.ph, cw.pw, cw.dil};
   if (cw.ds_cin && !ds_src) return fail(OCRFA_ERR_STATE, "%s expects a fused downsample source", cw.name.c_str());
   int rc = plan_halo(&p, g, in.p, in.c, cw.d_wgt, pool, cw.ds_cin ? ds_src->p : nullptr, cw.ds_cin, cw.ds_cin ? ds_src->c : 0);
   if (rc) return fail(OCRFA_ERR_CUDA, "plan_halo(%s) failed: %d", cw.name.c_str(), rc);
   p.bias = cw.d_bias;
   p.residual = residual; p.ldr = cw.cout;
-  p.out = out; p.ldo = cw.cout; p.relu = relu ? 1 : 0;
+  p.out = out; p.ldo = ldo > 0 ? ldo : cw.cout; p.relu = relu ? 1 : 0;
   p.f16 = h->f16() ? 1 : 0;
   const double flops = 2.0 * (double)in.n * in.h * in.w * cw.cout * (9.0 * cw.cin + cw.ds_cin);
   LaunchScope ls(h, kClsIgemmTc, flops, st);
@@ -465,10 +466,10 @@ int run_conv_halo(ocrfa_handle* h, const ConvW& cw, const Act& in, const Act* ds
 int run_conv_tc(ocrfa_handle* h, const ConvW& cw, const Act& in, const Act* ds_src, const void* residual, void* out,
                 bool relu, bool out_f32, int ldo, cudaStream_t st) {
   IgemmTcParams p;
-  ConvGeom g{in.n, in.h, in.w, cw.cin, cw.cout, cw.kh, cw.kw, cw.sh, cw.ph, cw.pw};
+  ConvGeom g{in.n, in.h, in.w, cw.cin, cw.cout, cw.kh, cw.kw, cw.sh, cw.ph, cw.pw, cw.dil};
   const bool split = h->split();
-  if (!out_f32 && ldo == cw.cout && halo_wanted(h, cw, in, false))
-    return run_conv_halo(h, cw, in, ds_src, residual, out, relu, false, st);
+  if (!out_f32 && (ldo % 8) == 0 && halo_wanted(h, cw, in, false))
+    return run_conv_halo(h, cw, in, ds_src, residual, out, relu, false, st, ldo);
   int rc = plan_conv(&p, g, in.p, in.c, cw.d_wgt, nullptr, split);
   if (rc) return fail(OCRFA_ERR_CUDA, "plan_conv(%s) failed: %d", cw.name.c_str(), rc);
   if (cw.ds_cin) {
@@ -811,6 +812,8 @@ int forward_impl(ocrfa_handle* h, const float* d_x, const uint8_t* d_u8, const i
   return 0;
 }
 
+#include "craft_engine.inc"
+
 size_t beam_ws_bytes(int B, int T, int C, int bw) {
   (void)C;
   return align_up((size_t)B * 2 * bw * T * sizeof(int16_t), 256);
@@ -880,6 +883,29 @@ int ocrfa_create(const ocrfa_config* cfg, ocrfa_handle** out) {
   return 0;
 }
 
+int ocrfa_craft_create(int32_t precision, int32_t device, ocrfa_handle** out) {
+  if (!out) return fail(OCRFA_ERR_ARG, "null argument");
+  if (precision != OCRFA_PRECISION_BF16 && precision != OCRFA_PRECISION_F16)
+    return fail(OCRFA_ERR_ARG, "the CRAFT forward runs in the 16-bit tensor-core modes only (bf16 / f16)");
+  ocrfa_config cfg;
+  cfg.input_channel = 1; cfg.output_channel = 512; cfg.hidden_size = 512; cfg.num_class = 2;
+  cfg.precision = precision; cfg.device = device;
+  const int rc = ocrfa_create(&cfg, out);
+  if (rc) return rc;
+  (*out)->network = 1;
+  return 0;
+}
+
+size_t ocrfa_craft_workspace_bytes(const ocrfa_handle* h, int32_t N, int32_t H, int32_t W) {
+  if (!h || N <= 0 || H <= 0 || W <= 0) return 0;
+  return craft_layout(N, H, W).total;
+}
+
+int ocrfa_craft_forward(ocrfa_handle* h, const float* d_x, int32_t N, int32_t H, int32_t W, float* d_y, float* d_feature,
+                        void* d_ws, size_t ws_bytes, void* stream) {
+  return craft_forward_impl(h, d_x, N, H, W, d_y, d_feature, d_ws, ws_bytes, (cudaStream_t)stream);
+}
+
 void ocrfa_destroy(ocrfa_handle* h) {
   if (!h) return;
   for (GraphEntry& e : h->graphs) cudaGraphExecDestroy(e.exec);
@@ -909,6 +935,12 @@ int ocrfa_finalize_weights(ocrfa_handle* h, void* stream) {
   if (h->finalized) return fail(OCRFA_ERR_STATE, "weights already finalized");
   CUDA_TRY(cudaSetDevice(h->cfg.device));
   int rc;
+  if (h->network == 1) {
+    if ((rc = prep_craft(h))) return rc;
+    h->host.clear();
+    h->finalized = true;
+    return 0;
+  }
   // stem: conv0_1 [32][1][3][3] -> [9][32] fp32 with bn0_1 folded
   {
     std::vector<double> sc, sf;

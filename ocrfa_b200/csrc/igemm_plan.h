@@ -15,9 +15,18 @@ struct ConvGeom {
   int kh, kw;  // filter
   int sh;      // stride in H (1 or 2); stride in W is always 1 on this path
   int ph, pw;  // zero padding
-  int h_out() const { return (h_in + 2 * ph - kh) / sh + 1; }
-  int w_out() const { return w_in + 2 * pw - kw + 1; }
+  int dil = 1; // dilation (CRAFT's fc6: 3x3, dilation 6, padding 6; stride 1 only)
+  int h_out() const { return (h_in + 2 * ph - dil * (kh - 1) - 1) / sh + 1; }
+  int w_out() const { return w_in + 2 * pw - dil * (kw - 1); }
 };
+
+// Channel count of an activation buffer the TMA box (64 channels) can read: a multiple of 64, or 8/16/32 channels
+// (pixel rows of 16/32/64 bytes) when the layer has at most 64 input channels - the box then reaches past the
+// tensor's channel extent and TMA zero-fills the rest (the weights carry zeros there).
+inline bool act_channels_ok(int cin_buf, int cin_pad) {
+  if (cin_buf % 64 == 0) return cin_buf >= cin_pad;
+  return cin_pad == 64 && (cin_buf == 8 || cin_buf == 16 || cin_buf == 32);
+}
 
 struct TileShape {
   int tw, th, tn;
@@ -64,8 +73,9 @@ inline int plan_conv(IgemmTcParams* p, const ConvGeom& g, const void* in, int ci
   std::memset(p, 0, sizeof(*p));
   const int ho = g.h_out(), wo = g.w_out();
   const int cin_pad = ceil_div(g.cin, 64) * 64;
-  if (cin_buf % 64 != 0 || cin_buf < cin_pad) return -2;
+  if (!act_channels_ok(cin_buf, cin_pad)) return -2;
   if (g.sh != 1 && g.sh != 2) return -3;
+  if (g.dil != 1 && g.sh != 1) return -7;
   if (g.sh == 2 && (g.h_in % 2 != 0 || g.ph != 0 || g.kh != 2)) return -4;
   if (g.kh * g.kw > kTcMaxTaps - 1) return -5;
   const TileShape t = forced_tile ? *forced_tile : choose_tile(wo, ho, g.n);
@@ -100,12 +110,12 @@ inline int plan_conv(IgemmTcParams* p, const ConvGeom& g, const void* in, int ci
     for (int s = 0; s < g.kw; ++s) {
       TapDesc& d = p->taps[nt++];
       d.src = 0;
-      d.dw = static_cast<int16_t>(s - g.pw);
-      if (g.sh == 1) { d.dr = 0; d.dh = static_cast<int16_t>(r - g.ph); }
+      d.dw = static_cast<int16_t>(s * g.dil - g.pw);
+      if (g.sh == 1) { d.dr = 0; d.dh = static_cast<int16_t>(r * g.dil - g.ph); }
       else { d.dr = static_cast<int16_t>(r); d.dh = 0; }  // h_in = 2*h_out + r
     }
   p->num_taps = nt;
-  p->korder = (!split && g.kh == 3 && g.kw == 3 && g.sh == 1) ? 1 : 0;
+  p->korder = (!split && g.kh == 3 && g.kw == 3 && g.sh == 1 && g.dil == 1 && g.ph == 1 && g.pw == 1) ? 1 : 0;
   if (const char* e = std::getenv("OCRFA_KORDER")) { if (e[0] == '0') p->korder = 0; }  // experiment switch
   const int R = g.sh;
   const int km = split ? 2 : 1;
@@ -136,7 +146,7 @@ inline int plan_add_source(IgemmTcParams* p, const void* in2, int cin2, int cin2
 // halo-staged kernel (igemm_halo.cuh): 3x3 / stride 1 / pad 1, Cout a multiple of 32
 // ---------------------------------------------------------------------------------------------
 inline bool halo_eligible(const ConvGeom& g, bool pool) {
-  if (g.kh != 3 || g.kw != 3 || g.sh != 1 || g.ph != 1 || g.pw != 1) return false;
+  if (g.kh != 3 || g.kw != 3 || g.sh != 1 || g.ph != 1 || g.pw != 1 || g.dil != 1) return false;
   if (g.cout % 32 != 0) return false;
   if (pool && ((g.h_in & 1) || (g.w_in & 1))) return false;
   return true;
@@ -162,7 +172,7 @@ inline int plan_halo(IgemmHaloParams* p, const ConvGeom& g, const void* in, int 
   std::memset(p, 0, sizeof(*p));
   if (!halo_eligible(g, pool)) return -20;
   const int cin_pad = ceil_div(g.cin, 64) * 64;
-  if (!(cin_buf == 32 && cin_pad == 64) && (cin_buf % 64 != 0 || cin_buf < cin_pad)) return -21;
+  if (!act_channels_ok(cin_buf, cin_pad)) return -21;
   const int cin2_pad = in2 ? ceil_div(cin2, 64) * 64 : 0;
   if (in2 && (cin2_buf % 64 != 0 || cin2_buf < cin2_pad)) return -22;
   halo_choose_tile(g.w_in, g.h_in, pool, &p->tw, &p->th);

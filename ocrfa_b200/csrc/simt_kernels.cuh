@@ -540,4 +540,108 @@ __global__ void lstm_cell_f32_kernel(const float* __restrict__ hh /*[2][B][2048]
   hseq[((long long)b * T + t) * 1024 + dir * 512 + j] = go * tanhf(cn);
 }
 
+// ---------------------------------------------------------------------------------------------
+// CRAFT detector glue kernels (reference: OCRFA / Vgg16BN, /root/reference/src/ocrfa/utils.py:48-98 and
+// /root/reference/src/ocrfa/modules/blocks.py:27-82). 16-bit NHWC activations (bf16 or fp16, `f16` flag), 8 channels
+// per thread; inputs / outputs may be channel slices of wider buffers (ld_in / ld_out = channels of the buffer), which
+// is how the U-net's torch.cat never costs a copy.
+// ---------------------------------------------------------------------------------------------
+// x [N,3,H,W] float32 (already mean/variance normalised, detectors.py:38-40) -> NHWC with 8 channels (3 real + 5 zero)
+__global__ void nchw3_to_nhwc8_kernel(const float* __restrict__ x, uint4* __restrict__ out, int n, int h, int w, int f16) {
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long hw = (long long)h * w;
+  if (pix >= (long long)n * hw) return;
+  const long long b = pix / hw, r = pix - b * hw;
+  const float* xp = x + b * 3 * hw + r;
+  const float c0 = __ldg(xp), c1 = __ldg(xp + hw), c2 = __ldg(xp + 2 * hw);
+  uint4 o;
+  o.x = pack16x2(c0, c1, f16 != 0); o.y = pack16x2(c2, 0.f, f16 != 0); o.z = 0u; o.w = 0u;
+  out[pix] = o;
+}
+
+// max pool k x k (k = 1: plain copy), stride s, -inf padding p, optional ReLU on the result (max and ReLU commute, so
+// "ReLU then pool" of the reference is computed as pool then ReLU). Covers VGG's 2x2/2 pools, slice5's 3x3/1 pad 1
+// pool and the "ReLU of a tensor that is also needed before its ReLU" copies.
+__global__ void pool16_kernel(const uint16_t* __restrict__ in, int ld_in, uint16_t* __restrict__ out, int ld_out, int n,
+                              int h_in, int w_in, int c, int k, int stride, int pad, int relu, int f16) {
+  const int cv = c / 8;
+  const int h_out = (h_in + 2 * pad - k) / stride + 1, w_out = (w_in + 2 * pad - k) / stride + 1;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (long long)n * h_out * w_out * cv) return;
+  const int cg = gid % cv;
+  const long long pix = gid / cv;
+  const int wo = pix % w_out, ho = (pix / w_out) % h_out;
+  const int b = pix / ((long long)w_out * h_out);
+  const bool hf = f16 != 0;
+  float m[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) m[i] = -INFINITY;
+  for (int r = 0; r < k; ++r)
+    for (int s2 = 0; s2 < k; ++s2) {
+      const int hi = ho * stride + r - pad, wi = wo * stride + s2 - pad;
+      if (hi < 0 || hi >= h_in || wi < 0 || wi >= w_in) continue;
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + (((long long)b * h_in + hi) * w_in + wi) * ld_in + cg * 8));
+      m[0] = fmaxf(m[0], lo16_to_f32(v.x, hf)); m[1] = fmaxf(m[1], hi16_to_f32(v.x, hf));
+      m[2] = fmaxf(m[2], lo16_to_f32(v.y, hf)); m[3] = fmaxf(m[3], hi16_to_f32(v.y, hf));
+      m[4] = fmaxf(m[4], lo16_to_f32(v.z, hf)); m[5] = fmaxf(m[5], hi16_to_f32(v.z, hf));
+      m[6] = fmaxf(m[6], lo16_to_f32(v.w, hf)); m[7] = fmaxf(m[7], hi16_to_f32(v.w, hf));
+    }
+  if (relu) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], 0.f);
+  }
+  uint4 o;
+  o.x = pack16x2(m[0], m[1], hf); o.y = pack16x2(m[2], m[3], hf); o.z = pack16x2(m[4], m[5], hf); o.w = pack16x2(m[6], m[7], hf);
+  *reinterpret_cast<uint4*>(out + pix * ld_out + cg * 8) = o;
+}
+
+// F.interpolate(y, size = 2x, mode="bilinear", align_corners=False) (utils.py:84, 88, 92): source index
+// max(0, (dst + 0.5) / 2 - 0.5), neighbours clamped at the border, fp32 blend in PyTorch's order
+// h0 * (w0 * v00 + w1 * v01) + h1 * (w0 * v10 + w1 * v11).
+__global__ void upsample2x_bilinear16_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, int ld_out, int n,
+                                             int h_in, int w_in, int c, int f16) {
+  const int cv = c / 8;
+  const int h_out = 2 * h_in, w_out = 2 * w_in;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (long long)n * h_out * w_out * cv) return;
+  const int cg = gid % cv;
+  const long long pix = gid / cv;
+  const int wo = pix % w_out, ho = (pix / w_out) % h_out;
+  const int b = pix / ((long long)w_out * h_out);
+  const bool hf = f16 != 0;
+  const float fy = fmaxf(0.f, (ho + 0.5f) * 0.5f - 0.5f), fx = fmaxf(0.f, (wo + 0.5f) * 0.5f - 0.5f);
+  const int y0 = (int)fy, x0 = (int)fx;
+  const int y1 = min(y0 + 1, h_in - 1), x1 = min(x0 + 1, w_in - 1);
+  const float ly1 = fy - y0, lx1 = fx - x0, ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+  auto ld = [&](int yy, int xx) {
+    return __ldg(reinterpret_cast<const uint4*>(in + (((long long)b * h_in + yy) * w_in + xx) * c + cg * 8));
+  };
+  const uint4 v00 = ld(y0, x0), v01 = ld(y0, x1), v10 = ld(y1, x0), v11 = ld(y1, x1);
+  const uint32_t a[4] = {v00.x, v00.y, v00.z, v00.w}, bq[4] = {v01.x, v01.y, v01.z, v01.w};
+  const uint32_t cq[4] = {v10.x, v10.y, v10.z, v10.w}, dq[4] = {v11.x, v11.y, v11.z, v11.w};
+  uint32_t o[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float lo = ly0 * (lx0 * lo16_to_f32(a[i], hf) + lx1 * lo16_to_f32(bq[i], hf)) +
+                     ly1 * (lx0 * lo16_to_f32(cq[i], hf) + lx1 * lo16_to_f32(dq[i], hf));
+    const float hi = ly0 * (lx0 * hi16_to_f32(a[i], hf) + lx1 * hi16_to_f32(bq[i], hf)) +
+                     ly1 * (lx0 * hi16_to_f32(cq[i], hf) + lx1 * hi16_to_f32(dq[i], hf));
+    o[i] = pack16x2(lo, hi, hf);
+  }
+  *reinterpret_cast<uint4*>(out + pix * ld_out + cg * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+// NHWC 16-bit [N,H,W,ld] (first c channels) -> NCHW float32 [N,c,H,W] (the `feature` output of OCRFA.forward)
+__global__ void nhwc16_to_nchw_f32_kernel(const uint16_t* __restrict__ in, int ld_in, float* __restrict__ out, int n, int h,
+                                          int w, int c, int f16) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long hw = (long long)h * w;
+  if (gid >= (long long)n * c * hw) return;
+  const long long r = gid % hw;
+  const int ch = (gid / hw) % c;
+  const long long b = gid / (hw * c);
+  const uint32_t v = in[(b * hw + r) * ld_in + ch];
+  out[gid] = f16 ? f16bits_to_f32(v) : __uint_as_float(v << 16);
+}
+
 }  // namespace ocrfa
