@@ -77,6 +77,48 @@ size_t ocrfa_craft_workspace_bytes(const ocrfa_handle* h, int32_t N, int32_t H, 
 int ocrfa_craft_forward(ocrfa_handle* h, const float* d_x, int32_t N, int32_t H, int32_t W, float* d_y, float* d_feature,
                         void* d_ws, size_t ws_bytes, void* stream);
 
+/* Detector preprocessing (detectors.py:33-43): resize_aspect_ratio (src/ocrfa/utils.py:497-524: cv2.resize with
+ * INTER_LINEAR to dst_w x dst_h, pasted into a zero canvas of H32 x W32) + normalize_mean_variance (utils.py:479-484:
+ * (v - mean*255) / (variance*255) in float32, applied to the canvas INCLUDING its zero padding) + HWC -> CHW, in one
+ * kernel: d_img uint8 [src_h][src_w][3] (src_stride bytes per row) -> d_out float32 [3][H32][W32], bit-exact with
+ * the reference's x. d_xtab / d_ytab are the per-axis tables of ocrfa_crop_resize_u8 (int32 [dst][2]); mode as in
+ * ocrfa_crop_desc. mean255 / var255: 3 host floats each (float32(mean*255), float32(variance*255)). */
+int ocrfa_det_preprocess_u8(const uint8_t* d_img, int32_t src_h, int32_t src_w, int32_t src_stride, int32_t dst_h,
+                            int32_t dst_w, int32_t H32, int32_t W32, const int32_t* d_xtab, const int32_t* d_ytab,
+                            int32_t mode, const float* mean255, const float* var255, float* d_out, void* stream);
+
+/* reformat_input's grey page for a colour ndarray (src/ocrfa/utils.py:1545-1547): cv2.cvtColor(image, COLOR_BGR2GRAY)
+ * on uint8 [H][W][3] (img_stride bytes per row) -> uint8 [H][W] (gray_stride bytes per row), bit-exact with OpenCV's
+ * 15-bit fixed point (first channel x 3735 + second x 19235 + third x 9798, + 16384, >> 15). */
+int ocrfa_bgr2gray_u8(const uint8_t* d_img, int32_t img_stride, int32_t H, int32_t W, uint8_t* d_gray,
+                      int32_t gray_stride, void* stream);
+
+/* The pixel work of get_det_boxes_core (src/ocrfa/utils.py:106-153): thresholds, 4-connected labeling with
+ * cv2.connectedComponentsWithStats' label numbers and stats, the per-label maximum of the text map, the size (< 10)
+ * and score (< text_threshold) filters, niter and the dilation ROI, and the rectangle dilation of each surviving
+ * component (minus its link-only pixels) expressed as ROW EXTENTS: for ROI row sy + r the dilated mask's smallest and
+ * largest x (min > max = empty row). cv2.minAreaRect depends on a pixel set only through its convex hull, hence only
+ * through these extents, so the host finishes each box from (ey - sy) pairs (ocrfa_b200/detection.py).
+ * d_text / d_link: float32 maps, element (y, x) at [(y*W + x) * pix_stride] (2 for the CRAFT output's interleaved
+ * [H,W,2] layout with d_link = d_text + 1; 1 for planar maps). Thresholds are float32 as cv2.threshold / NumPy compare
+ * them. d_labels: int32 [H][W] out (cv2's labels; may be NULL). d_comps: the surviving components in label order.
+ * d_extents: int32 [max_rows][2]. d_counts int32 [4]: nLabels (cv2's, background included), components written,
+ * extent rows written, overflow flag (1 when max_comps / max_rows were too small: results are then incomplete). */
+typedef struct ocrfa_det_comp {
+  int32_t label;                    /* k */
+  int32_t area;                     /* stats[k, CC_STAT_AREA] */
+  int32_t left, top, width, height; /* stats[k, CC_STAT_LEFT / TOP / WIDTH / HEIGHT] */
+  int32_t niter;
+  int32_t sx, sy, ex, ey;           /* dilation ROI */
+  int32_t row_off;                  /* first row of this component in d_extents; it owns ey - sy rows */
+  float max_text;                   /* np.max(textmap[labels == k]) */
+} ocrfa_det_comp;
+size_t ocrfa_det_workspace_bytes(int32_t H, int32_t W, int32_t max_rows);
+int ocrfa_det_components(const float* d_text, const float* d_link, int32_t pix_stride, int32_t H, int32_t W,
+                         float low_text, float link_threshold, float text_threshold, int32_t* d_labels,
+                         ocrfa_det_comp* d_comps, int32_t max_comps, int32_t* d_extents, int32_t max_rows,
+                         int32_t* d_counts, void* d_ws, size_t ws_bytes, void* stream);
+
 /* One state-dict entry (float32, host memory, PyTorch layout); an optional "module." prefix is stripped.
  * Integer entries (num_batches_tracked) may be skipped by the caller. */
 int ocrfa_load_weight(ocrfa_handle* h, const char* name, const float* h_data, const int64_t* shape, int32_t ndim);

@@ -22,6 +22,7 @@ SYMBOLS = (
     "ocrfa_abi_version", "ocrfa_last_error", "ocrfa_create", "ocrfa_destroy", "ocrfa_load_weight",
     "ocrfa_finalize_weights", "ocrfa_out_timesteps", "ocrfa_workspace_bytes", "ocrfa_preprocess_u8", "ocrfa_align_collate_u8", "ocrfa_crop_resize_u8", "ocrfa_warp_perspective_u8",
     "ocrfa_craft_create", "ocrfa_craft_workspace_bytes", "ocrfa_craft_forward",
+    "ocrfa_det_preprocess_u8", "ocrfa_bgr2gray_u8", "ocrfa_det_workspace_bytes", "ocrfa_det_components",
     "ocrfa_forward", "ocrfa_forward_features", "ocrfa_forward_sequence", "ocrfa_forward_u8", "ocrfa_ctc_greedy", "ocrfa_ctc_collapse", "ocrfa_argmax_rows",
     "ocrfa_beam_workspace_bytes", "ocrfa_ctc_beam", "ocrfa_ctc_beam_spans", "ocrfa_recognize_host",
     "ocrfa_recognize_device", "ocrfa_recognize_workspace_bytes", "ocrfa_profile_begin", "ocrfa_profile_end",
@@ -85,6 +86,13 @@ def load():
     lib.ocrfa_craft_workspace_bytes.argtypes = [vp, i32, i32, i32]
     lib.ocrfa_craft_workspace_bytes.restype = sz
     lib.ocrfa_craft_forward.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, sz, vp]
+    lib.ocrfa_det_preprocess_u8.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, i32, C.POINTER(C.c_float),
+                                            C.POINTER(C.c_float), vp, vp]
+    lib.ocrfa_bgr2gray_u8.argtypes = [vp, i32, i32, i32, vp, i32, vp]
+    lib.ocrfa_det_workspace_bytes.argtypes = [i32, i32, i32]
+    lib.ocrfa_det_workspace_bytes.restype = sz
+    lib.ocrfa_det_components.argtypes = [vp, vp, i32, i32, i32, C.c_float, C.c_float, C.c_float, vp, vp, i32, vp, i32, vp,
+                                         vp, sz, vp]
     lib.ocrfa_launch_count.argtypes = [vp]
     lib.ocrfa_launch_count.restype = i64
     for name in SYMBOLS:

@@ -18,6 +18,7 @@
 #include "../../include/ocrfa_b200.h"
 #include "decode_kernels.cuh"
 #include "crop_kernels.cuh"
+#include "det_kernels.cuh"
 #include "igemm_plan.h"
 #include "lstm_tc.cuh"
 #include "resize_kernels.cuh"
@@ -1056,6 +1057,101 @@ int ocrfa_warp_perspective_u8(const uint8_t* d_page, int32_t page_h, int32_t pag
   if (n > 65535) return fail(OCRFA_ERR_ARG, "at most 65535 boxes per call");
   dim3 grid(32, (unsigned)n);
   warp_perspective_u8_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_page, page_h, page_w, page_stride, d_desc, n, d_out);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int ocrfa_det_preprocess_u8(const uint8_t* d_img, int32_t src_h, int32_t src_w, int32_t src_stride, int32_t dst_h,
+                            int32_t dst_w, int32_t H32, int32_t W32, const int32_t* d_xtab, const int32_t* d_ytab,
+                            int32_t mode, const float* mean255, const float* var255, float* d_out, void* stream) {
+  if (!d_img || !d_out || !mean255 || !var255 || src_h <= 0 || src_w <= 0 || src_stride < 3 * src_w || dst_h <= 0 ||
+      dst_w <= 0 || H32 < dst_h || W32 < dst_w || mode < 0 || mode > 2 || (mode == 0 && (!d_xtab || !d_ytab)))
+    return fail(OCRFA_ERR_ARG, "bad argument");
+  if ((mode == 1 && (dst_h != src_h || dst_w != src_w)) || (mode == 2 && (2 * dst_h != src_h || 2 * dst_w != src_w)))
+    return fail(OCRFA_ERR_ARG, "resize mode does not match the sizes");
+  const long long total = (long long)H32 * W32;
+  const unsigned blocks = (unsigned)std::min<long long>((total + 255) / 256, 148 * 16);
+  det_preprocess_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_img, src_h, src_w, src_stride, dst_h, dst_w, H32, W32,
+                                                                 d_xtab, d_ytab, mode, mean255[0], mean255[1], mean255[2],
+                                                                 var255[0], var255[1], var255[2], d_out);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int ocrfa_bgr2gray_u8(const uint8_t* d_img, int32_t img_stride, int32_t H, int32_t W, uint8_t* d_gray,
+                      int32_t gray_stride, void* stream) {
+  if (!d_img || !d_gray || H <= 0 || W <= 0 || img_stride < 3 * W || gray_stride < W) return fail(OCRFA_ERR_ARG, "bad argument");
+  const long long total = (long long)((W + 3) / 4) * H;
+  const unsigned blocks = (unsigned)std::min<long long>((total + 255) / 256, 148 * 16);
+  bgr2gray_u8_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_img, img_stride, H, W, d_gray, gray_stride);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+namespace {
+struct DetLayout {
+  size_t parent, rank, flags, block_roots, stats, slot, src_ext, total;
+  int n, nb, cap;
+};
+DetLayout det_layout(int H, int W, int max_rows) {
+  DetLayout L;
+  L.n = H * W;
+  L.nb = (L.n + 1023) / 1024;
+  L.cap = L.n / 2 + 2;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+  L.parent = take((size_t)L.n * 4);
+  L.rank = take((size_t)L.n * 4);
+  L.flags = take((size_t)L.n);
+  L.block_roots = take((size_t)L.nb * 4);
+  L.stats = take((size_t)L.cap * 4 * 6);
+  L.slot = take((size_t)L.cap * 4);
+  L.src_ext = take((size_t)std::max(max_rows, 1) * 8);
+  L.total = off;
+  return L;
+}
+}  // namespace
+
+size_t ocrfa_det_workspace_bytes(int32_t H, int32_t W, int32_t max_rows) {
+  if (H <= 0 || W <= 0 || max_rows < 0 || (long long)H * W > (1 << 28)) return 0;
+  return det_layout(H, W, max_rows).total;
+}
+
+int ocrfa_det_components(const float* d_text, const float* d_link, int32_t pix_stride, int32_t H, int32_t W,
+                         float low_text, float link_threshold, float text_threshold, int32_t* d_labels,
+                         ocrfa_det_comp* d_comps, int32_t max_comps, int32_t* d_extents, int32_t max_rows,
+                         int32_t* d_counts, void* d_ws, size_t ws_bytes, void* stream) {
+  if (!d_text || !d_link || !d_comps || !d_extents || !d_counts || !d_ws || pix_stride <= 0 || H <= 0 || W <= 0 ||
+      max_comps <= 0 || max_rows <= 0 || (long long)H * W > (1 << 28))
+    return fail(OCRFA_ERR_ARG, "bad argument");
+  const DetLayout L = det_layout(H, W, max_rows);
+  if (ws_bytes < L.total) return fail(OCRFA_ERR_WORKSPACE, "workspace too small: %zu < %zu", ws_bytes, L.total);
+  if (((uintptr_t)d_ws & 255) != 0) return fail(OCRFA_ERR_WORKSPACE, "workspace must be 256-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = (char*)d_ws;
+  int* parent = (int*)(ws + L.parent);
+  int* rank = (int*)(ws + L.rank);
+  uint8_t* flags = (uint8_t*)(ws + L.flags);
+  int* block_roots = (int*)(ws + L.block_roots);
+  DetStats s;
+  int* sb = (int*)(ws + L.stats);
+  s.area = sb; s.minx = sb + L.cap; s.maxx = sb + 2 * (size_t)L.cap; s.miny = sb + 3 * (size_t)L.cap;
+  s.maxy = sb + 4 * (size_t)L.cap; s.maxtext = (uint32_t*)(sb + 5 * (size_t)L.cap);
+  int* slot = (int*)(ws + L.slot);
+  int2* src_ext = (int2*)(ws + L.src_ext);
+  const unsigned g256 = (unsigned)((L.n + 255) / 256);
+  CUDA_TRY(cudaMemsetAsync(d_counts, 0, 4 * sizeof(int32_t), st));
+  det_init_kernel<<<g256, 256, 0, st>>>(d_text, d_link, pix_stride, L.n, low_text, link_threshold, parent, flags);
+  det_stats_init_kernel<<<(unsigned)((L.cap + 255) / 256), 256, 0, st>>>(s, L.cap);
+  det_merge_kernel<<<g256, 256, 0, st>>>(parent, flags, H, W);
+  det_flatten_kernel<<<(unsigned)L.nb, 1024, 0, st>>>(parent, L.n, block_roots);
+  det_scan_blocks_kernel<<<1, 1024, 0, st>>>(block_roots, L.nb, d_counts);
+  det_rank_kernel<<<(unsigned)L.nb, 1024, 0, st>>>(parent, L.n, block_roots, rank);
+  det_label_stats_kernel<<<g256, 256, 0, st>>>(parent, rank, d_text, pix_stride, H, W, d_labels, s);
+  det_select_kernel<<<1, 1024, 0, st>>>(s, H, W, text_threshold, d_comps, max_comps, max_rows, slot, d_counts);
+  det_rows_init_kernel<<<148, 256, 0, st>>>(src_ext, d_counts);
+  det_row_extents_kernel<<<g256, 256, 0, st>>>(parent, rank, flags, H, W, slot, d_comps, src_ext);
+  det_dilate_rows_kernel<<<296, 128, 0, st>>>(d_comps, d_counts, src_ext, (int2*)d_extents);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
