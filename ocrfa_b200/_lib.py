@@ -95,10 +95,8 @@ def load():
                                          vp, sz, vp]
     lib.ocrfa_launch_count.argtypes = [vp]
     lib.ocrfa_launch_count.restype = i64
-    for name in SYMBOLS:
-        fn = getattr(lib, name)
-        if fn.restype is C.c_int and name not in ("ocrfa_abi_version",):
-            pass
+    for name in SYMBOLS:  # a missing export is a build error, not something to discover at call time
+        getattr(lib, name)
     _lib = lib
     return lib
 

@@ -160,34 +160,4 @@ def components_ref(textmap, linkmap, text_threshold, link_threshold, low_text):
     return n_labels, labels.astype(np.int32), comps, np.array(ext, dtype=np.int32).reshape(-1, 2)
 
 
-def synth_score_maps(h: int, w: int, seed: int, n_words: int = 14) -> Tuple[np.ndarray, np.ndarray]:
-    """CRAFT-like region / affinity maps: words are rows of Gaussian character blobs (some rotated, some touching the
-    border, some tiny, some weak), affinity blobs sit between neighbouring characters."""
-    rng = np.random.default_rng(seed)
-    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
-    text = np.zeros((h, w), np.float32)
-    link = np.zeros((h, w), np.float32)
-
-    def blob(cx, cy, sx_, sy_, ang, amp):
-        c, s = math.cos(ang), math.sin(ang)
-        u = (xx - cx) * c + (yy - cy) * s
-        v = -(xx - cx) * s + (yy - cy) * c
-        return amp * np.exp(-0.5 * ((u / sx_) ** 2 + (v / sy_) ** 2)).astype(np.float32)
-
-    for _ in range(n_words):
-        n_ch = int(rng.integers(1, 9))
-        cx, cy = rng.uniform(-4, w + 4), rng.uniform(-2, h + 2)
-        ang = rng.choice([0.0, 0.0, rng.uniform(-0.6, 0.6), math.pi / 2])
-        size = rng.uniform(1.2, 5.0)
-        amp = rng.choice([1.0, 0.95, 0.8, 0.62])
-        step = size * rng.uniform(1.8, 2.6)
-        prev = None
-        for i in range(n_ch):
-            px, py = cx + i * step * math.cos(ang), cy + i * step * math.sin(ang)
-            text = np.maximum(text, blob(px, py, size, size * rng.uniform(0.8, 1.4), ang, amp))
-            if prev is not None:
-                link = np.maximum(link, blob((px + prev[0]) / 2, (py + prev[1]) / 2, size * 0.7, size * 0.6, ang,
-                                             rng.choice([0.9, 0.6, 0.3])))
-            prev = (px, py)
-    noise = rng.normal(0, 0.01, (h, w)).astype(np.float32)
-    return np.clip(text + noise, 0, 1).astype(np.float32), np.clip(link - noise, 0, 1).astype(np.float32)
+from ocrfa_b200.synth import synth_score_maps  # noqa: E402,F401  (plain data generation, shared with tools/)

@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from ocrfa_b200.detection import detector_input, get_det_boxes  # noqa: E402
 from ocrfa_b200.reader import bgr2gray_device  # noqa: E402
-from oracle.det_ref import synth_score_maps  # noqa: E402  (synthetic inputs only)
+from ocrfa_b200.synth import synth_score_maps  # noqa: E402
 
 rng = np.random.default_rng(0)
 page = torch.from_numpy(rng.integers(0, 256, (2200, 3400, 3), dtype=np.uint8)).cuda()
