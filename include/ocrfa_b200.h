@@ -186,6 +186,11 @@ typedef struct ocrfa_warp_desc {
 int ocrfa_warp_perspective_u8(const uint8_t* d_page, int32_t page_h, int32_t page_w, int32_t page_stride,
                               const ocrfa_warp_desc* d_desc, int32_t n, uint8_t* d_out, void* stream);
 
+/* make_rotated_img_list for right angles (src/ocrfa/utils.py:1599-1612): scipy.ndimage.rotate(img, 90*k, reshape=True)
+ * of a uint8 image = np.rot90(img, k), k in {1, 2, 3}: d_src uint8 [h][w] contiguous -> d_dst uint8 [w][h] (k odd) or
+ * [h][w] (k = 2). */
+int ocrfa_rot90_u8(const uint8_t* d_src, int32_t h, int32_t w, int32_t k, uint8_t* d_dst, void* stream);
+
 /* d_x: float32 [B,1,H,W]; d_logits: float32 [B,T,num_class]. */
 int ocrfa_forward(ocrfa_handle* h, const float* d_x, int32_t B, int32_t H, int32_t W, float* d_logits, void* d_ws,
                   size_t ws_bytes, void* stream);

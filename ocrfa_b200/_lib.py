@@ -20,7 +20,7 @@ PRECISIONS = {"fp32": PRECISION_FP32, "bf16": PRECISION_BF16, "f16x3": PRECISION
 # every symbol include/ocrfa_b200.h declares (tests/test_cabi_symbols.py checks the header against this list)
 SYMBOLS = (
     "ocrfa_abi_version", "ocrfa_last_error", "ocrfa_create", "ocrfa_destroy", "ocrfa_load_weight",
-    "ocrfa_finalize_weights", "ocrfa_out_timesteps", "ocrfa_workspace_bytes", "ocrfa_preprocess_u8", "ocrfa_align_collate_u8", "ocrfa_crop_resize_u8", "ocrfa_warp_perspective_u8",
+    "ocrfa_finalize_weights", "ocrfa_out_timesteps", "ocrfa_workspace_bytes", "ocrfa_preprocess_u8", "ocrfa_align_collate_u8", "ocrfa_crop_resize_u8", "ocrfa_warp_perspective_u8", "ocrfa_rot90_u8",
     "ocrfa_craft_create", "ocrfa_craft_workspace_bytes", "ocrfa_craft_forward",
     "ocrfa_det_preprocess_u8", "ocrfa_bgr2gray_u8", "ocrfa_det_workspace_bytes", "ocrfa_det_components",
     "ocrfa_forward", "ocrfa_forward_features", "ocrfa_forward_sequence", "ocrfa_forward_u8", "ocrfa_ctc_greedy", "ocrfa_ctc_collapse", "ocrfa_argmax_rows",
@@ -93,6 +93,7 @@ def load():
     lib.ocrfa_det_workspace_bytes.restype = sz
     lib.ocrfa_det_components.argtypes = [vp, vp, i32, i32, i32, C.c_float, C.c_float, C.c_float, vp, vp, i32, vp, i32, vp,
                                          vp, sz, vp]
+    lib.ocrfa_rot90_u8.argtypes = [vp, i32, i32, i32, vp, vp]
     lib.ocrfa_launch_count.argtypes = [vp]
     lib.ocrfa_launch_count.restype = i64
     for name in SYMBOLS:  # a missing export is a build error, not something to discover at call time

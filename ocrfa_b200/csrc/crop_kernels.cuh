@@ -115,4 +115,36 @@ __global__ void __launch_bounds__(256) warp_perspective_u8_kernel(const uint8_t*
   }
 }
 
+// make_rotated_img_list (utils.py:1599-1612) for right angles: scipy.ndimage.rotate(img, 90 k, reshape=True) on a uint8
+// image equals np.rot90(img, k) bit for bit (checked against scipy in tests/test_reader.py), i.e. a pure permutation:
+//   k = 1: out[i][j] = in[j][w-1-i]   (h x w -> w x h)      k = 2: out[i][j] = in[h-1-i][w-1-j]
+//   k = 3: out[i][j] = in[h-1-j][i]   (h x w -> w x h)
+// 32 x 32 tiles through shared memory so that both the reads and the writes are row-contiguous.
+__global__ void __launch_bounds__(256) rot90_u8_kernel(const uint8_t* __restrict__ src, int h, int w, int k,
+                                                       uint8_t* __restrict__ dst) {
+  __shared__ uint8_t tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8 threads
+  const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
+  for (int r = ty; r < 32; r += 8) {
+    const int y = y0 + r, x = x0 + tx;
+    tile[r][tx] = (y < h && x < w) ? src[(size_t)y * w + x] : (uint8_t)0;
+  }
+  __syncthreads();
+  if (k == 2) {
+    for (int r = ty; r < 32; r += 8) {
+      const int y = y0 + r, x = x0 + tx;
+      if (y < h && x < w) dst[(size_t)(h - 1 - y) * w + (w - 1 - x)] = tile[r][tx];
+    }
+    return;
+  }
+  // transposed tile: thread (tx, r) writes the element read as tile[tx][r] = in[y0 + tx][x0 + r]
+  for (int r = ty; r < 32; r += 8) {
+    const int y = y0 + tx, x = x0 + r;
+    if (y < h && x < w) {
+      const size_t o = k == 1 ? (size_t)(w - 1 - x) * h + y : (size_t)x * h + (h - 1 - y);
+      dst[o] = tile[tx][r];
+    }
+  }
+}
+
 }  // namespace ocrfa

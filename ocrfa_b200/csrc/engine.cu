@@ -1156,6 +1156,15 @@ int ocrfa_det_components(const float* d_text, const float* d_link, int32_t pix_s
   return 0;
 }
 
+int ocrfa_rot90_u8(const uint8_t* d_src, int32_t h, int32_t w, int32_t k, uint8_t* d_dst, void* stream) {
+  if (!d_src || !d_dst || h <= 0 || w <= 0 || k < 1 || k > 3) return fail(OCRFA_ERR_ARG, "bad argument");
+  dim3 grid((unsigned)((w + 31) / 32), (unsigned)((h + 31) / 32));
+  if (grid.y > 65535) return fail(OCRFA_ERR_ARG, "image too tall");
+  rot90_u8_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_src, h, w, k, d_dst);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 int ocrfa_forward(ocrfa_handle* h, const float* d_x, int32_t B, int32_t H, int32_t W, float* d_logits, void* d_ws,
                   size_t ws_bytes, void* stream) {
   return forward_impl(h, d_x, nullptr, nullptr, B, H, W, d_logits, d_ws, ws_bytes, (cudaStream_t)stream);

@@ -11,8 +11,8 @@ list / string logic between them. There is no CPU path: `gpu=False` raises.
 Differences from the reference, all explicit:
   * no downloads (this package never touches the network): a missing model file raises FileNotFoundError, as the
     reference does with download_enabled=False; `verify_md5=False` accepts weights other than the released files;
-  * DBNet (`detect_network="dbnet18"`), `rotation_info` (scipy.ndimage.rotate test-time augmentation) and
-    `optimal_num_chars` are not offered (NotImplementedError);
+  * DBNet (`detect_network="dbnet18"`), `optimal_num_chars` and `rotation_info` angles that are not multiples of 90
+    degrees (scipy's spline resampling) are not offered (NotImplementedError);
   * right-to-left display order uses python-bidi's `get_display` when that package is importable; without it the
     logical-order string is returned and `OCR.bidi_available` is False.
 """
@@ -31,7 +31,7 @@ import torch
 from . import _lib
 from .charset import ARABIC_G1_CHARACTERS, ARABIC_G1_SYMBOLS, FA_LANG_LETTERS
 from .craft import get_detector
-from .crops import get_image_list
+from .crops import DeviceLine, get_image_list
 from .detection import get_textbox, group_text_box
 from .recognition import get_recognizer, get_text
 
@@ -138,6 +138,42 @@ def reformat_input_batched(image, n_width=None, n_height=None, device="cuda"):
         return [p[0] for p in pairs], [p[1] for p in pairs]
     img, grey = reformat_input(image, device)
     return [img], [grey]
+
+
+def make_rotated_img_list(rotationInfo, img_list):
+    """utils.py:1599-1612 for right angles: appends, per angle, every crop rotated by it. The reference calls
+    scipy.ndimage.rotate(img, angle, reshape=True), which for multiples of 90 degrees is the exact permutation
+    np.rot90(img, angle / 90); those run on the GPU (ocrfa_rot90_u8) on the device-resident crops. Other angles need
+    scipy's cubic-spline resampling, which this package does not restate."""
+    turns = []
+    for angle in rotationInfo:
+        if angle % 90 != 0:
+            raise NotImplementedError("rotation_info supports multiples of 90 degrees only")
+        turns.append(int(angle // 90) % 4)
+    if not img_list:
+        return img_list[:]
+    lib = _lib.load()
+    sizes = [((line.shape[0] * line.shape[1] + 3) & ~3) for _, line in img_list]
+    dev = img_list[0][1].buffer.device
+    result = []
+    with torch.cuda.device(dev):
+        # originals and rotations share ONE packed buffer (a batch handed to AlignCollate reads from a single buffer)
+        out = torch.empty(max(4, sum(sizes) * (1 + len(turns))), dtype=torch.uint8, device=dev)
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        off = 0
+        for k in [0] + turns:
+            for (box, line), nbytes in zip(img_list, sizes):
+                h, w = line.shape
+                if k == 0:
+                    out[off:off + h * w].copy_(line.buffer[line.off:line.off + h * w])
+                    rotated = DeviceLine(out, off, h, w)
+                else:
+                    _lib.check(lib.ocrfa_rot90_u8(C.c_void_p(line.buffer.data_ptr() + line.off), h, w, k,
+                                                  C.c_void_p(out.data_ptr() + off), stream))
+                    rotated = DeviceLine(out, off, *((w, h) if k & 1 else (h, w)))
+                result.append((box, rotated))
+                off += nbytes
+    return result
 
 
 def set_result_with_confidence(results):
@@ -348,8 +384,6 @@ class OCR:
                   output_format="standard", img_height=64):
         """ocr.py:357-502. `img_cv_grey`: the grey page (uint8 [H, W], numpy or CUDA tensor) or, with reformat=True,
         anything `reformat_input` accepts."""
-        if rotation_info:
-            raise NotImplementedError("rotation_info (rotated test-time augmentation) is not part of ocrfa_b200")
         if reformat:
             _, img_cv_grey = reformat_input(img_cv_grey, self.device)
         elif isinstance(img_cv_grey, np.ndarray):
@@ -366,7 +400,7 @@ class OCR:
             horizontal_list = [[0, x_max, 0, y_max]]
             free_list = []
         args = (img_height, ignore_char, decoder, beamWidth, batch_size, contrast_ths, adjust_contrast, filter_ths, workers)
-        if batch_size == 1:
+        if batch_size == 1 and not rotation_info:
             # the reference reads box by box here, each line padded to ITS OWN width (ocr.py:398-444); batching
             # (batch_size > 1) pads every line to the widest one, which changes the logits - so the split is kept
             result = []
@@ -374,8 +408,22 @@ class OCR:
                 result += self._read_boxes(img_cv_grey, [bbox], [], *args)
             for bbox in free_list:
                 result += self._read_boxes(img_cv_grey, [], [bbox], *args)
-        else:
+        elif not rotation_info:
             result = self._read_boxes(img_cv_grey, horizontal_list, free_list, *args)
+        else:
+            # test-time augmentation (ocr.py:446-473): every crop is also read rotated, the most confident reading wins
+            image_list, max_width = get_image_list(horizontal_list, free_list, img_cv_grey, model_height=img_height,
+                                                   as_device=True)
+            image_len = len(image_list)
+            if image_list:
+                image_list = make_rotated_img_list(rotation_info, image_list)
+                max_width = max(max_width, img_height)
+            result = get_text(self.character, img_height, int(max_width), self.recognizer, self.converter, image_list,
+                              ignore_char, decoder, beamWidth, batch_size, contrast_ths, adjust_contrast, filter_ths,
+                              workers, self.device)
+            if horizontal_list + free_list:
+                result = set_result_with_confidence(
+                    [result[image_len * i:image_len * (i + 1)] for i in range(len(rotation_info) + 1)])
         if self.model_lang == "arabic":
             direction_mode = "rtl"
             result = [list(item) for item in result]

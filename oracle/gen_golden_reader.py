@@ -36,6 +36,16 @@ def pack_result(out, key, result):
     out[key + "_box"] = np.array([np.array(r[0], dtype=np.float64) for r in result], dtype=np.float64).reshape(-1, 4, 2)
 
 
+def rotation_cases(reader, page, h_list, f_list, out):
+    """E. rotation_info test-time augmentation (ocr.py:446-473, utils.py:1599-1631): scipy.ndimage.rotate by right angles."""
+    reader.device = torch.device("cpu")
+    res = reader.recognize(page, h_list[:4], f_list[:1], rotation_info=[90, 180, 270], batch_size=4, reformat=False)
+    pack_result(out, "rec_rot", res)
+    res = reader.recognize(page, h_list[4:6], [], rotation_info=[180], batch_size=1, reformat=False, img_height=32)
+    pack_result(out, "rec_rot180", res)
+    reader.device = "cpu"
+
+
 def main():
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     utils, _ = import_reference()
@@ -55,6 +65,14 @@ def main():
     page = crops["page"]  # 300 x 520 grey
     h_list = [b for b in crops["boxes"].tolist()][:10]
     f_list = crops["free"].tolist()[:3]
+    path = os.path.join(GOLDEN, "reader.npz")
+    if "--add-rotation" in sys.argv:  # extend the existing fixture without re-running the other cases
+        out = dict(np.load(path))
+        rotation_cases(reader, page, h_list, f_list, out)
+        np.savez_compressed(path, **out)
+        print("added rotation cases:", out["rec_rot_text"], out["rec_rot_conf"], out["rec_rot180_text"])
+        return
+    rotation_cases(reader, page, h_list, f_list, out)
     out["rec_h_list"] = np.array(h_list, dtype=np.int64)
     out["rec_f_list"] = np.array(f_list, dtype=np.int64)
     # A. per-box path (batch_size=1): every line padded to its own width

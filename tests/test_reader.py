@@ -139,6 +139,51 @@ def test_gpu_recognize_matches_reference(reader):
 
 
 @pytest.mark.gpu
+def test_gpu_rotation_info_matches_reference(reader):
+    """rotation_info test-time augmentation: crops rotated on the GPU (= scipy.ndimage.rotate for right angles), every
+    variant recognized, the most confident reading kept (ocr.py:446-473)."""
+    g = load_golden("reader")
+    page = load_golden("crops")["page"]
+    h_list, f_list = g["rec_h_list"].tolist(), g["rec_f_list"].tolist()
+    got = reader.recognize(page, h_list[:4], f_list[:1], rotation_info=[90, 180, 270], batch_size=4, reformat=False)
+    _assert_results(got, _result(g, "rec_rot"))
+    got = reader.recognize(page, h_list[4:6], [], rotation_info=[180], batch_size=1, reformat=False, img_height=32)
+    _assert_results(got, _result(g, "rec_rot180"))
+    with pytest.raises(NotImplementedError):
+        reader.recognize(page, h_list[:1], [], rotation_info=[45], reformat=False)
+
+
+@pytest.mark.gpu
+def test_gpu_rot90_equals_scipy_rotate():
+    ndimage = pytest.importorskip("scipy.ndimage")
+    import torch
+    from ocrfa_b200.crops import DeviceLine
+    from ocrfa_b200.reader import make_rotated_img_list
+
+    rng = np.random.default_rng(6)
+    shapes = [(64, 200), (32, 77), (1, 1), (64, 64), (33, 101), (5, 300)]
+    imgs = [rng.integers(0, 256, s, dtype=np.uint8) for s in shapes]
+    offs, off = [], 0
+    for im in imgs:
+        offs.append(off)
+        off += (im.size + 3) & ~3
+    buf = torch.zeros(off, dtype=torch.uint8, device="cuda")
+    for im, o in zip(imgs, offs):
+        buf[o:o + im.size] = torch.from_numpy(im.reshape(-1)).cuda()
+    lines = [([[0, 0]] * 4, DeviceLine(buf, o, *im.shape)) for im, o in zip(imgs, offs)]
+    angles = [90, 180, 270, -90, 360]
+    out = make_rotated_img_list(angles, lines)
+    assert len(out) == len(imgs) * (1 + len(angles))
+    for i, im in enumerate(imgs):
+        assert np.array_equal(out[i][1].numpy(), im)
+    for a, angle in enumerate(angles):
+        for i, im in enumerate(imgs):
+            got = out[(a + 1) * len(imgs) + i][1].numpy()
+            want = ndimage.rotate(im, angle, reshape=True)
+            assert got.shape == want.shape and np.array_equal(got, want), (angle, im.shape)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("case", [0, 1])
 def test_gpu_readtext_matches_reference_behind_fixture_detector(reader, case):
     """readtext end to end - grey conversion, detector input, labeling, boxes, grouping, crops, recognition - with the
