@@ -121,8 +121,7 @@ def _lu_solve8(a: np.ndarray, b: np.ndarray):
         d = -1.0 / a[i, i]
         for j in range(i + 1, m):
             alpha = a[j, i] * d
-            for kk in range(i + 1, m):
-                a[j, kk] += alpha * a[i, kk]
+            a[j, i + 1:] += alpha * a[i, i + 1:]  # element-wise, the same products and sums as the scalar loop
             b[j] += alpha * b[i]
     for i in range(m - 1, -1, -1):
         sacc = b[i]

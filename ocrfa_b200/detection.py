@@ -152,20 +152,35 @@ def boxes_from_components(comps: np.ndarray, extents: np.ndarray) -> Tuple[List[
     import cv2
 
     det, mapper = [], []
-    for c in comps:
-        rows = int(c["ey"] - c["sy"])
-        e = extents[int(c["row_off"]):int(c["row_off"]) + rows]
-        ys = np.nonzero(e[:, 1] >= 0)[0]
-        lo, hi = e[ys, 0].astype(np.int64), e[ys, 1].astype(np.int64)
-        yy = ys.astype(np.int64) + int(c["sy"])
-        # row-major order like np.where on the mask: (min x, y) then (max x, y) of every non-empty row
-        pts = np.stack([np.stack([lo, yy], axis=1), np.stack([hi, yy], axis=1)], axis=1).reshape(-1, 2)
-        if len(pts):
-            pts = pts[np.concatenate([[True], np.any(pts[1:] != pts[:-1], axis=1)])]  # single-pixel rows: one point
+    if len(comps) == 0:
+        return det, mapper
+    # all components at once: the point list of a mask is, row by row, (min x, y) then (max x, y) - the order np.where
+    # gives on the full mask - with empty rows dropped and single-pixel rows contributing one point
+    extents = np.asarray(extents).reshape(-1, 2)
+    rows = (comps["ey"] - comps["sy"]).astype(np.int64)
+    row_off = comps["row_off"].astype(np.int64)
+    comp_of_row = np.repeat(np.arange(len(comps)), rows)
+    first_row = np.repeat(row_off, rows)
+    idx = first_row + (np.arange(rows.sum()) - np.repeat(np.cumsum(rows) - rows, rows))
+    lo, hi = extents[idx, 0].astype(np.int64), extents[idx, 1].astype(np.int64)
+    yy = (idx - first_row) + np.repeat(comps["sy"].astype(np.int64), rows)
+    live = hi >= 0
+    pts_all = np.stack([np.stack([lo, yy], axis=1), np.stack([hi, yy], axis=1)], axis=1)  # [rows, 2 points, (x, y)]
+    keep = np.stack([live, live & (hi != lo)], axis=1)
+    per_comp = np.bincount(comp_of_row, weights=keep.sum(axis=1), minlength=len(comps)).astype(np.int64)
+    flat = pts_all[keep]
+    ends = np.cumsum(per_comp)
+    big = np.iinfo(np.int64).max
+    x_lo = np.minimum.reduceat(np.where(live, lo, big), np.cumsum(rows) - rows)
+    x_hi = np.maximum.reduceat(np.where(live, hi, -1), np.cumsum(rows) - rows)
+    y_lo = np.minimum.reduceat(np.where(live, yy, big), np.cumsum(rows) - rows)
+    y_hi = np.maximum.reduceat(np.where(live, yy, -1), np.cumsum(rows) - rows)
+    for n, c in enumerate(comps):
+        pts = flat[ends[n] - per_comp[n]:ends[n]]
         box = cv2.boxPoints(cv2.minAreaRect(pts))
         side_a, side_b = np.linalg.norm(box[0] - box[1]), np.linalg.norm(box[1] - box[2])
         if abs(1 - max(side_a, side_b) / (min(side_a, side_b) + 1e-5)) <= 0.1:
-            l, r, t, b = lo.min(), hi.max(), yy.min(), yy.max()
+            l, r, t, b = x_lo[n], x_hi[n], y_lo[n], y_hi[n]
             box = np.array([[l, t], [r, t], [r, b], [l, b]], dtype=np.float32)
         first = box.sum(axis=1).argmin()
         det.append(np.array(np.roll(box, 4 - first, 0)))
@@ -272,14 +287,16 @@ def group_text_box(polys, slope_ths=0.1, ycenter_ths=0.5, height_ths=0.5, width_
         level = sorted(level, key=lambda item: item[4])
 
     # 1. text lines: consecutive boxes whose centre stays within ycenter_ths x (mean height) of the line's mean centre
-    lines, line, heights, centres = [], [], [], []
+    # (the reference takes np.mean of the growing lists; heights are integers and centres multiples of 0.5, so the sums
+    # are exact in float64 and sum / count is the same correctly rounded quotient)
+    lines, line, height_sum, centre_sum = [], [], 0.0, 0.0
     for box in level:
-        if line and not abs(np.mean(centres) - box[4]) < ycenter_ths * np.mean(heights):
+        if line and not abs(centre_sum / len(line) - box[4]) < ycenter_ths * (height_sum / len(line)):
             lines.append(line)
-            line, heights, centres = [], [], []
+            line, height_sum, centre_sum = [], 0.0, 0.0
         line.append(box)
-        heights.append(box[5])
-        centres.append(box[4])
+        height_sum += float(box[5])
+        centre_sum += float(box[4])
     lines.append(line)
 
     # 2. inside a line, left to right: chain boxes of comparable height that sit closer than width_ths x (box height)
@@ -289,14 +306,16 @@ def group_text_box(polys, slope_ths=0.1, ycenter_ths=0.5, height_ths=0.5, width_
             box = line[0]
             merged_list.append(_merge_margin(add_margin, box[0], box[1], box[2], box[3], min(box[1] - box[0], box[5])))
             continue
-        chains, chain, heights, x_right = [], [], [], None
+        chains, chain, height_sum, x_right = [], [], 0.0, None
         for box in sorted(line, key=lambda item: item[0]):
-            if chain and not ((abs(np.mean(heights) - box[5]) < height_ths * np.mean(heights))
-                              and ((box[0] - x_right) < width_ths * (box[3] - box[2]))):
-                chains.append(chain)
-                chain, heights = [], []
+            if chain:
+                mean_height = height_sum / len(chain)
+                if not ((abs(mean_height - box[5]) < height_ths * mean_height)
+                        and ((box[0] - x_right) < width_ths * (box[3] - box[2]))):
+                    chains.append(chain)
+                    chain, height_sum = [], 0.0
             chain.append(box)
-            heights.append(box[5])
+            height_sum += float(box[5])
             x_right = box[1]
         if chain:
             chains.append(chain)
