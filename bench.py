@@ -133,7 +133,7 @@ def dist_env():
 # ------------------------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference's CPU path (recognizer_predict on torch CPU fp32)
 # ------------------------------------------------------------------------------------------------------------------
-def cpu_lines_per_s(cfg_name: str, sample_lines: int, repeats: int, warmup: int):
+def cpu_lines_per_s(cfg_name: str, sample_lines: int, repeats: int, warmup: int, quantize: bool = False):
     from oracle import recognizer_ref as R
     from ocrfa_b200.synth import synth_lines, synth_state_dict
     import ocrfa_b200.charset as cs
@@ -149,7 +149,7 @@ def cpu_lines_per_s(cfg_name: str, sample_lines: int, repeats: int, warmup: int)
 
     def one_pass():
         x = R.align_collate_ref(list(imgs), H, W)
-        return R.recognizer_predict_ref(sd, x, chars, ign, decoder, beam if decoder != "greedy" else 5)
+        return R.recognizer_predict_ref(sd, x, chars, ign, decoder, beam if decoder != "greedy" else 5, quantize=quantize)
 
     for _ in range(warmup):
         one_pass()
@@ -357,6 +357,10 @@ def run_gpu_arm(args):
             line["cpu_baseline"] = {"value": lps, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": f"{n} lines of {H}x{W}, best-effort mean of 2 passes after 1 warm-up, torch CPU fp32 "
                                               f"{threads} threads (oracle port of recognizer_predict, {decoder})"}
+            # the reference's literal CPU default, OCR(gpu=False, quantize=True): dynamic int8 LSTM / Linear layers
+            q_lps, _, _, _ = cpu_lines_per_s(args.config, sample, 2, 1, quantize=True)
+            line["cpu_baseline"]["quantize_true"] = {"value": q_lps, "unit": UNIT,
+                                                     "note": "same sample with torch dynamic int8 LSTM/Linear (utils.py:686-690)"}
         print(json.dumps(line), flush=True)
     if world > 1:
         import torch.distributed as dist

@@ -242,6 +242,53 @@ def model_forward_ref(sd: Dict[str, np.ndarray], x, return_features: bool = Fals
     return logits
 
 
+class _QuantizedHead(torch.nn.Module):
+    """The recognizer's nn.LSTM / nn.Linear modules (blocks.py:85-102, 438), the ones get_recognizer's
+    torch.quantization.quantize_dynamic(model, dtype=torch.qint8) rewrites when quantize=True (utils.py:686-690)."""
+
+    def __init__(self, sd):
+        super().__init__()
+        num_class = _t(sd, "Prediction.weight").shape[0]
+        self.rnn0 = torch.nn.LSTM(512, 512, bidirectional=True, batch_first=True)
+        self.lin0 = torch.nn.Linear(1024, 512)
+        self.rnn1 = torch.nn.LSTM(512, 512, bidirectional=True, batch_first=True)
+        self.lin1 = torch.nn.Linear(1024, 512)
+        self.pred = torch.nn.Linear(512, num_class)
+        with torch.no_grad():
+            for li, (rnn, lin) in enumerate(((self.rnn0, self.lin0), (self.rnn1, self.lin1))):
+                pre = f"SequenceModeling.{li}."
+                for name, param in rnn.named_parameters():
+                    param.copy_(_t(sd, pre + "rnn." + name))
+                lin.weight.copy_(_t(sd, pre + "linear.weight"))
+                lin.bias.copy_(_t(sd, pre + "linear.bias"))
+            self.pred.weight.copy_(_t(sd, "Prediction.weight"))
+            self.pred.bias.copy_(_t(sd, "Prediction.bias"))
+
+    def forward(self, v):
+        s = self.lin0(self.rnn0(v)[0])
+        s = self.lin1(self.rnn1(s)[0])
+        return self.pred(s)
+
+
+_QUANT_HEADS: Dict[int, torch.nn.Module] = {}
+
+
+def model_forward_int8_ref(sd: Dict[str, np.ndarray], x):
+    """Model.forward as the reference's CPU default runs it (quantize=True): fp32 ResNet, dynamically quantized int8
+    LSTM / Linear layers. A recorded baseline column, not a parity target."""
+    head = _QUANT_HEADS.get(id(sd))
+    if head is None:
+        head = _QuantizedHead(sd).eval()
+        torch.quantization.quantize_dynamic(head, dtype=torch.qint8, inplace=True)
+        _QUANT_HEADS.clear()
+        _QUANT_HEADS[id(sd)] = head
+    with torch.no_grad():
+        x = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x))
+        f = resnet_ref(sd, x.float())
+        v = f.permute(0, 3, 1, 2).mean(dim=3)
+        return head(v)
+
+
 # --------------------------------------------------------------------------------------------------------------
 # bf16 emulation of the same forward: identical math, with the tensor-core path's rounding points
 # (weights with BN folded -> bf16; every stored activation -> bf16; fp32 accumulate, bias, gate math, cell state).
@@ -480,9 +527,10 @@ def wordbeam_decode_ref(probs: np.ndarray, character: Sequence[str], beam_width:
 # recognizer_predict restated end to end  (src/ocrfa/utils.py:605-662)
 # --------------------------------------------------------------------------------------------------------------
 def recognizer_predict_ref(sd, x: np.ndarray, character: Sequence[str], ignore_idx: Sequence[int],
-                           decoder: str = "greedy", beam_width: int = 5):
-    """x: float32 [B,1,H,W] (already collated). Returns [[str, conf], ...] like the reference."""
-    logits = model_forward_ref(sd, x)
+                           decoder: str = "greedy", beam_width: int = 5, quantize: bool = False):
+    """x: float32 [B,1,H,W] (already collated). Returns [[str, conf], ...] like the reference. quantize=True runs the
+    LSTM / Linear layers dynamically quantized to int8, as get_recognizer(device="cpu", quantize=True) does."""
+    logits = model_forward_int8_ref(sd, x) if quantize else model_forward_ref(sd, x)
     probs = probs_ref(logits, ignore_idx)
     if decoder == "greedy":
         strs = greedy_decode_ref(probs, character)

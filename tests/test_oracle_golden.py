@@ -77,3 +77,29 @@ def test_ignore_idx_matches_reference(charset):
     ign = R.ignore_idx_ref(str(charset["character"]), str(charset["ignore_char"]))
     assert sorted(ign) == charset["ignore_idx"].tolist()
     assert len(ign) == 69 and 0 not in ign
+
+
+def test_oracle_strings_match_reference_fp32_column_int8_column_recorded(synth_sd, charset):
+    """tests/golden/quantized_int8.npz (oracle/gen_golden_quant.py): the reference's get_text strings with
+    quantize=False - the oracle must reproduce them - and with quantize=True (dynamic int8, the OCR(gpu=False)
+    default), kept as a recorded second column."""
+    from oracle import recognizer_ref as R
+    from oracle.synth import synth_lines
+
+    g = load_golden("quantized_int8")
+    imgs = synth_lines(64, 32, 128, seed=int(g["seed"]))
+    chars = str(charset["character"])
+    res = R.recognizer_predict_ref(synth_sd, R.align_collate_ref(list(imgs), 32, 128), ["[blank]"] + list(chars),
+                                   charset["ignore_idx"].tolist(), "greedy", 5)
+    want32, want8 = g["fp32_text"][:-1].tolist(), g["int8_text"][:-1].tolist()
+    assert [r[0] for r in res] == want32
+    np.testing.assert_allclose([r[1] for r in res], g["fp32_conf"], rtol=1e-4, atol=1e-12)
+    assert len(want8) == 64 and 0 < sum(a == b for a, b in zip(want8, want32)) < 64  # int8 is a different arithmetic
+    # the oracle's int8 leg (bench.py's quantize_true baseline row) reproduces that column; the reference ran batches of
+    # 32 and dynamic quantization picks its activation scales per batch
+    got8 = []
+    for i in (0, 32):
+        x = R.align_collate_ref(list(imgs[i:i + 32]), 32, 128)
+        got8 += [r[0] for r in R.recognizer_predict_ref(synth_sd, x, ["[blank]"] + list(chars),
+                                                        charset["ignore_idx"].tolist(), "greedy", 5, quantize=True)]
+    assert got8 == want8
