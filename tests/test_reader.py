@@ -236,6 +236,29 @@ def test_gpu_readtext_with_the_craft_forward(reader):
 
 
 @pytest.mark.gpu
+def test_gpu_default_precision_reader_reads_the_same_boxes(reader, tmp_path, synth_sd):
+    """The constructor's defaults (bf16 recognizer, f16 detector): same boxes as the fp32 reader (the detector is the
+    same), strings that agree with it on most lines (bf16 tolerance)."""
+    import torch
+    import ocrfa_b200 as ob
+
+    torch.save({k: torch.from_numpy(v) for k, v in synth_sd.items()}, os.path.join(tmp_path, "arabic.pth"))
+    torch.save({k: torch.from_numpy(v) for k, v in ob.synth_craft_state_dict(0).items()},
+               os.path.join(tmp_path, "craft_mlt_25k.pth"))
+    fast = ob.OCR(model_storage_directory=str(tmp_path), verify_md5=False)
+    assert fast.precision == "bf16" and fast.detector_precision == "f16" and fast.model_lang == "arabic"
+    g = load_golden("reader")
+    page = load_golden("crops")["page"]
+    h_list, f_list = g["rec_h_list"].tolist(), g["rec_f_list"].tolist()
+    got = fast.recognize(page, h_list, f_list, batch_size=16, reformat=False)
+    want = reader.recognize(page, h_list, f_list, batch_size=16, reformat=False)
+    assert [r[0] for r in got] == [r[0] for r in want]
+    same = sum(a[1] == b[1] for a, b in zip(got, want))
+    print(f"bf16 reader vs fp32 reader: {same}/{len(want)} identical strings")
+    assert same >= len(want) // 2
+
+
+@pytest.mark.gpu
 def test_gpu_bgr2gray_bit_exact_with_opencv():
     cv2 = pytest.importorskip("cv2")
     import torch
