@@ -55,9 +55,106 @@ def wall_ms(fn, reps):
     return (time.perf_counter() - t) * 1e3 / reps
 
 
+def cpu_readtext_legs(reader, rgb, tt, lt, low):
+    """The reference's CPU path for the same page, leg by leg, with the oracle's restatements (torch CPU fp32 with all
+    host threads for the two networks, OpenCV / NumPy for the rest): one pass, the timed thing is the oracle."""
+    import cv2
+    from oracle import craft_ref, det_ref as D, recognizer_ref as R
+    from ocrfa_b200.detection import group_text_box
+    from ocrfa_b200.synth import synth_state_dict
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    legs = {}
+
+    def leg(name, fn):
+        t0 = time.perf_counter()
+        out = fn()
+        legs[name + "_ms"] = round((time.perf_counter() - t0) * 1e3, 1)
+        return out
+
+    grey = leg("grey", lambda: cv2.cvtColor(rgb, cv2.COLOR_BGR2GRAY))
+    x, ratio = leg("detector_input", lambda: D.detector_input_ref(rgb, 2560, 1.0))
+    sd_craft = ob.synth_craft_state_dict(0)
+    y, _ = leg("craft_forward", lambda: craft_ref.craft_forward_ref(sd_craft, x[None]))
+    y = y[0].numpy()
+    polys = leg("boxes", lambda: D.textbox_from_maps_ref(np.ascontiguousarray(y[:, :, 0]), np.ascontiguousarray(y[:, :, 1]),
+                                                        ratio, tt, lt, low))
+    h_list, f_list = leg("grouping", lambda: group_text_box(polys, 0.1, 0.5, 0.5, 0.5, 0.1, True))
+    h_list = [b for b in h_list if max(b[1] - b[0], b[3] - b[2]) > 10]
+    f_list = [b for b in f_list if max(max(c[0] for c in b) - min(c[0] for c in b),
+                                       max(c[1] for c in b) - min(c[1] for c in b)) > 10]
+    def crops_cv2():  # get_image_list with the library calls the reference makes (utils.py:1218-1231, 1361-1418)
+        out, max_ratio = [], 1.0
+        for quad in f_list:
+            rect = np.array(quad, dtype="float32")
+            (tl, tr, br, bl) = rect
+            mw = max(int(np.linalg.norm(br - bl)), int(np.linalg.norm(tr - tl)))
+            mh = max(int(np.linalg.norm(tr - br)), int(np.linalg.norm(tl - bl)))
+            if mw <= 0 or mh <= 0:
+                continue
+            dst = np.array([[0, 0], [mw - 1, 0], [mw - 1, mh - 1], [0, mh - 1]], dtype="float32")
+            out.append((quad[0][1], cv2.warpPerspective(grey, cv2.getPerspectiveTransform(rect, dst), (mw, mh))))
+        for b in h_list:
+            x0, x1, y0, y1 = max(0, int(b[0])), min(int(b[1]), grey.shape[1]), max(0, int(b[2])), min(int(b[3]), grey.shape[0])
+            if x1 > x0 and y1 > y0:
+                out.append((y0, grey[y0:y1, x0:x1]))
+        resized = []
+        for key, crop in out:
+            h, w = crop.shape
+            ratio = w / h
+            if ratio < 1.0:
+                ratio = 1.0 / ratio
+                size = (64, int(64 * ratio))
+            else:
+                size = (int(64 * ratio), 64)
+            if min(size) == 0:
+                continue
+            max_ratio = max(max_ratio, ratio)
+            resized.append((key, cv2.resize(crop, size, interpolation=1)))
+        resized.sort(key=lambda kc: kc[0])
+        return [(None, c) for _, c in resized], int(np.ceil(max_ratio)) * 64
+
+    image_list, max_width = leg("crops", crops_cv2)
+
+    def collate_pil(lines, img_h, img_w, contrast):  # AlignCollate / NormalizePAD with Pillow, as the reference (utils.py:533-602)
+        import math
+        from PIL import Image
+
+        out = np.zeros((len(lines), 1, img_h, img_w), np.float32)
+        for i, im in enumerate(lines):
+            if contrast > 0:
+                im = R.adjust_contrast_grey_ref(im, contrast)
+            h, w = im.shape
+            rw = min(img_w, math.ceil(img_h * (w / float(h))))
+            a = (np.asarray(Image.fromarray(im, "L").resize((rw, img_h), Image.BICUBIC), np.float32) / 255.0 - 0.5) / 0.5
+            out[i, 0, :, :rw] = a
+            out[i, 0, :, rw:] = a[:, rw - 1:rw]
+        return out
+
+    sd = synth_state_dict(0)
+    chars = ["[blank]"] + list(reader.character)
+    ign = R.ignore_idx_ref(reader.character, "".join(set(reader.character) - set(reader.lang_char)))
+    crops = [c for _, c in image_list]
+
+    def recognize():
+        n = 0
+        for contrast in (0.0, 0.5):  # with untrained weights every line takes the low-confidence second pass
+            for i in range(0, len(crops), 64):
+                xb = collate_pil(crops[i:i + 64], 64, int(max_width), contrast)
+                n += len(R.recognizer_predict_ref(sd, xb, chars, ign, "greedy", 5))
+        return n
+
+    leg("recognition", recognize)
+    legs["lines"] = len(crops)
+    legs["threads"] = os.cpu_count() or 1
+    legs["total_ms"] = round(sum(v for k, v in legs.items() if k.endswith("_ms")), 1)
+    return legs
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU leg of the readtext line (about a minute)")
     args = ap.parse_args()
     from oracle import det_ref as D  # CPU baseline + synthetic score maps
 
@@ -129,10 +226,13 @@ def main():
     ms = wall_ms(lambda: reader.readtext(rgb, **kw), 5)
     det_ms = wall_ms(lambda: reader.transform_ua(rgb, reformat=False, text_threshold=tt, low_text=low, link_threshold=lt,
                                                  min_size=10), 5)
-    print(json.dumps({"what": "readtext", "page": [736, 1280], "lines": len(res), "batch_size": 64,
-                      "readtext_wall_ms": round(ms, 2), "detect_wall_ms": round(det_ms, 2),
-                      "note": "synthetic weights; thresholds taken from the score-map quantiles so that boxes exist"}),
-          flush=True)
+    line = {"what": "readtext", "page": [736, 1280], "lines": len(res), "batch_size": 64,
+            "readtext_wall_ms": round(ms, 2), "detect_wall_ms": round(det_ms, 2),
+            "note": "synthetic weights; thresholds taken from the score-map quantiles so that boxes exist"}
+    if not args.no_cpu:
+        line["reference_cpu"] = cpu_readtext_legs(reader, rgb.cpu().numpy(), tt, lt, low)
+        line["speedup_vs_cpu"] = round(line["reference_cpu"]["total_ms"] / ms, 1)
+    print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":
