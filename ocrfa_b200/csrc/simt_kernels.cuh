@@ -233,6 +233,94 @@ __global__ void __launch_bounds__(256) stem_conv32_kernel(const float* __restric
   }
 }
 
+// Same arithmetic, four horizontally adjacent pixels per thread (W is a multiple of 4 on every path that reaches the
+// stem). The one-pixel kernel above is issue bound on everything AROUND its 288 FFMAs (about 1000 instructions per
+// pixel: uniform-register weight loads, index math, the 16-bit format select); here the 3 x 6 input window, the weight
+// loads and the index math are shared by four pixels (about 430 instructions per pixel), the output format is a
+// template parameter, and each warp stages its 128 pixels x 64 B (8 KB, contiguous in NHWC) through shared memory with a
+// conflict-free swizzle so that every store instruction writes 512 contiguous bytes. Bit-identical results: per pixel
+// the same fmaf chain in the same order.
+template <bool F16>
+__global__ void __launch_bounds__(128) stem_conv32x4_kernel(const float* __restrict__ x, const uint8_t* __restrict__ x_u8,
+                                                            const int32_t* __restrict__ widths,
+                                                            const __grid_constant__ StemWeights sw,
+                                                            __nv_bfloat16* __restrict__ out, int B, int H, int W) {
+  __shared__ float lut[256];
+  __shared__ uint4 stg[4][128 * 4];  // per warp: slot (pixel) x 4 pieces of 16 B
+  lut[threadIdx.x] = normalize_u8(threadIdx.x);
+  lut[threadIdx.x + 128] = normalize_u8(threadIdx.x + 128);
+  __syncthreads();
+  const unsigned qpr = static_cast<unsigned>(W) >> 2;             // quads per row
+  const unsigned total_q = static_cast<unsigned>(B) * H * qpr;    // < 2^29 (checked by the caller)
+  const unsigned q = blockIdx.x * 128u + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint4* my = &stg[warp][0];
+  const int slot_flip = (lane >> 2) & 1, piece_flip = lane & 3;
+  if (q < total_q) {
+    const unsigned rowi = q / qpr;  // b * H + y
+    const int xq = static_cast<int>(q - rowi * qpr) * 4;
+    const int b = static_cast<int>(rowi / static_cast<unsigned>(H));
+    const int y = static_cast<int>(rowi - static_cast<unsigned>(b) * H);
+    const int wv = (x_u8 && widths) ? min(max(__ldg(widths + b), 1), W) : W;
+    // column offsets and validity are the same for the three rows: columns xq-1 .. xq+4, the uint8 path reads the last
+    // valid column for x >= widths[b] (NormalizePAD's replicate pad), outside the line the conv's zero padding applies
+    int coff[6];
+    bool cok[6];
+#pragma unroll
+    for (int s2 = 0; s2 < 6; ++s2) {
+      const int xx = xq + s2 - 1;
+      cok[s2] = xx >= 0 && xx < W;
+      coff[s2] = x_u8 ? min(max(xx, 0), wv - 1) : min(max(xx, 0), W - 1);
+    }
+    float v[3][6];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int yy = y + r - 1;
+      const bool row_ok = yy >= 0 && yy < H;
+      const size_t roff = (static_cast<size_t>(b) * H + (row_ok ? yy : y)) * W;
+#pragma unroll
+      for (int s2 = 0; s2 < 6; ++s2) {
+        float t = x_u8 ? lut[__ldg(x_u8 + roff + coff[s2])] : __ldg(x + roff + coff[s2]);
+        v[r][s2] = (row_ok && cok[s2]) ? t : 0.f;
+      }
+    }
+#pragma unroll
+    for (int cg = 0; cg < 4; ++cg) {
+      float acc[4][8];
+#pragma unroll
+      for (int c8 = 0; c8 < 8; ++c8) {
+        const int c = cg * 8 + c8;
+#pragma unroll
+        for (int px = 0; px < 4; ++px) {
+          float a = 0.f;
+#pragma unroll
+          for (int k = 0; k < 9; ++k) a = fmaf(v[k / 3][px + k % 3], sw.w[k * 32 + c], a);
+          acc[px][c8] = fmaxf(a + sw.b[c], 0.f);
+        }
+      }
+#pragma unroll
+      for (int px = 0; px < 4; ++px) {
+        uint4 o;
+        o.x = pack16x2(acc[px][0], acc[px][1], F16); o.y = pack16x2(acc[px][2], acc[px][3], F16);
+        o.z = pack16x2(acc[px][4], acc[px][5], F16); o.w = pack16x2(acc[px][6], acc[px][7], F16);
+        my[(lane * 4 + (px ^ slot_flip)) * 4 + (cg ^ piece_flip)] = o;
+      }
+    }
+  }
+  __syncwarp();
+  // the warp's 32 quads are 128 consecutive pixels = 8 KB contiguous; instruction k writes pixels 8k .. 8k+7
+  const size_t warp_pix0 = (static_cast<size_t>(blockIdx.x) * 128u + warp * 32u) * 4u;
+  const size_t total_pix = static_cast<size_t>(total_q) * 4u;
+  uint4* op = reinterpret_cast<uint4*>(out + warp_pix0 * 32);
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const int pr = 8 * k + (lane >> 2), piece = lane & 3;  // pixel of the warp, 16-byte piece of its 64 B
+    const int owner = pr >> 2, px = pr & 3;               // the lane that computed it and its position in that lane's quad
+    if (warp_pix0 + pr < total_pix)
+      op[pr * 4 + piece] = my[(owner * 4 + (px ^ ((owner >> 2) & 1))) * 4 + (piece ^ (owner & 3))];
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // generic CUDA-core implicit GEMM (fp32 accumulate): conv kh x kw, stride (sh,1), zero pad (ph,pw), NHWC.
 // 64 pixels x 64 output channels per 256-thread block, 4x4 outputs per thread, K staged 16 at a time.
