@@ -254,14 +254,30 @@ def run_gpu_arm(args):
         sampler.start()
     launches0 = lib.ocrfa_launch_count(handle)
     _lib.check(lib.ocrfa_profile_begin(handle, 1 << 1))
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # A step whose working set (activation workspace + 108 MB of weights) fits the 126 MB L2 would be timed on a warm
+    # cache: such configurations (c1) get an explicit flush - a 256 MB fill - before every timed step, and the step is
+    # bracketed by its own event pair so that the flush is not in the sum. The big configurations stream > 1 GB per step.
+    flush_l2 = int(ws_bytes) + 110 * (1 << 20) < 512 * (1 << 20)
     barrier()
-    e0.record(stream)
-    for _ in range(args.steps):
-        step_device()
-    e1.record(stream)
-    barrier()
-    dev_ms = e0.elapsed_time(e1)
+    if flush_l2:
+        flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        with torch.cuda.stream(stream):
+            for i, (a, b) in enumerate(pairs):
+                flush_buf.fill_(i & 0xff)
+                a.record(stream)
+                step_device()
+                b.record(stream)
+        barrier()
+        dev_ms = sum(a.elapsed_time(b) for a, b in pairs)
+    else:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            step_device()
+        e1.record(stream)
+        barrier()
+        dev_ms = e0.elapsed_time(e1)
     ms_cls = (C.c_double * 8)()
     fl_cls = (C.c_double * 8)()
     n_cls = (C.c_int64 * 8)()
@@ -281,11 +297,21 @@ def run_gpu_arm(args):
 
     step_host()
     barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_host()
-    torch.cuda.synchronize(dev)
-    host_s = time.perf_counter() - t0
+    if flush_l2:
+        host_s = 0.0
+        for i in range(args.steps):
+            flush_buf.fill_(i & 0xff)
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            step_host()
+            torch.cuda.synchronize(dev)
+            host_s += time.perf_counter() - t0
+    else:
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_host()
+        torch.cuda.synchronize(dev)
+        host_s = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- extra pass (not timed): per-class kernel time shares for the record
@@ -329,7 +355,10 @@ def run_gpu_arm(args):
                       "fp32": "f32"}[args.precision], "data": "synthetic",
             "config": {"workload": f"{args.config}: {B} lines of {H}x{W} per rank per step, {decoder}"
                                    + (f" beam={beam}" if decoder != "greedy" else "") + ", reference default model (ResNet-29 + 2xBiLSTM + Linear185), random-init weights",
-                       "l2": "per-step working set (>2 GB of activations at c2) exceeds the 126 MB L2; no explicit flush",
+                       "l2": ("explicit flush: a 256 MB fill before every timed step (the working set of this configuration "
+                              "would fit the 126 MB L2), each step bracketed by its own CUDA event pair") if flush_l2 else
+                             (f"per-step working set ({int(ws_bytes) / 2**30:.1f} GB activation workspace streamed every step + "
+                              "108 MB of weights) exceeds the 126 MB L2; no explicit flush"),
                        "parallelism": f"dp{world} (independent ranks, no collective on the path)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * H * W + Cn),
                     "d2h_bytes_per_step": int(B * T * 4 + B * 4 + B * 8), "ms_per_step": host_ms_max / args.steps},

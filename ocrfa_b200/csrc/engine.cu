@@ -668,7 +668,9 @@ int forward_impl(ocrfa_handle* h, const float* d_x, const uint8_t* d_u8, const i
     const long long pix = (long long)B * H * W;
     const unsigned grid = (unsigned)((pix + 255) / 256);
     LaunchScope ls(h, kClsStem, 2.0 * (double)pix * 32 * 9, st);
-    if (stem32 && (W & 3) == 0 && !getenv("OCRFA_STEM_1PX")) {
+    // four pixels per thread once there are enough pixels to fill the machine; small batches keep one pixel per thread
+    // (a latency shape: 4096 pixels at config 1)
+    if (stem32 && (W & 3) == 0 && pix >= (1ll << 20) && !getenv("OCRFA_STEM_1PX")) {
       const unsigned g4 = (unsigned)((pix / 4 + 127) / 128);
       if (h->f16()) stem_conv32x4_kernel<true><<<g4, 128, 0, st>>>(d_x, d_u8, d_widths, h->stem_host, (__nv_bfloat16*)a.p, B, H, W);
       else stem_conv32x4_kernel<false><<<g4, 128, 0, st>>>(d_x, d_u8, d_widths, h->stem_host, (__nv_bfloat16*)a.p, B, H, W);
