@@ -598,6 +598,21 @@ inline int make_rows64_tmap(CUtensorMap* tm, const void* base, long long rows, i
   return rc == CUDA_SUCCESS ? 0 : -static_cast<int>(rc) - 1000;
 }
 
+// The same [rows][64] matrix as the DESTINATION of the LSTM's TMA publish: un-swizzled {16 units, box_rows} boxes
+// (32 bytes per row), stored from a dense [box_rows][16] shared-memory tile.
+inline int make_rows64_store_tmap(CUtensorMap* tm, const void* base, long long rows, int box_rows) {
+  PFN_tmapEncodeTiled enc = get_tmap_encode();
+  if (!enc) return -1;
+  cuuint64_t dims[2] = {64, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {128};
+  cuuint32_t box[2] = {16, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult rc = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return rc == CUDA_SUCCESS ? 0 : -static_cast<int>(rc) - 1000;
+}
+
 inline cudaError_t igemm_tc_launch(const IgemmTcParams& p, int /*mode*/, int num_sms, cudaStream_t stream) {
   static bool attr_set_dev[kMaxDevices][3] = {};
   bool* attr_set = attr_set_dev[current_device_slot()];

@@ -32,7 +32,24 @@
 namespace ocrfa {
 
 constexpr int kLstmThreads = 192;
+// How a CTA publishes its slice of h_t to the group (fused-x modes):
+//   generic  per-thread 16-byte stores + CTA barrier + red.release.gpu. The release is MEMBAR.ALL.GPU + ERRBAR in SASS and
+//            waits for the 256 scattered stores: measured 1.4 k cycles per step (4.68 -> 3.94 us/step with the fence
+//            removed, which is not a correct program).
+//   TMA      the slice is staged in shared memory (4 KB), one elected thread issues a TMA tensor store, waits for the
+//            bulk group to COMPLETE (cp.async.bulk.wait_group 0: the writes are performed at L2, which is where the
+//            peers' TMA loads read them) and then bumps the counter with a relaxed red - no gpu-scope fence on the path.
+//            The staging buffer takes the room of one ring stage.
+#ifndef OCRFA_LSTM_GENERIC_PUBLISH
+#define OCRFA_LSTM_TMA_PUBLISH 1
+#endif
+#ifdef OCRFA_LSTM_TMA_PUBLISH
+constexpr int kLstmRing = 5;          // A-ring stages of 16 KB
+constexpr int kLstmStageBytes = 4096; // h slice staging: 128 rows x 16 units x 2 B
+#else
 constexpr int kLstmRing = 6;          // A-ring stages of 16 KB
+constexpr int kLstmStageBytes = 0;
+#endif
 constexpr int kLstmTmemCols = 128;    // 2 accumulators x 64 columns
 constexpr int kLstmGroupCtas = 32;    // CTAs per (direction, m_tile) group = 512 hidden units / 16
 constexpr int kLstmWSlabs = 16;       // resident weight slabs (8 KB each) = 128 KB
@@ -49,6 +66,7 @@ struct alignas(64) LstmTcParams {
   CUtensorMap tmX;  // exchange buffer [2 dirs][m_tiles][2 parities][slabs][128 rows][64] as 2-D (64, rows), box {64,128}
   CUtensorMap tmW;  // resident weights [4096][1024] (bf16: [W_ih | W_hh]; split: [W_hi | W_lo]), box {64, 64}
   CUtensorMap tmS;  // bf16 mode: layer input [B][T][512] bf16 as the 5-D activation map, box {64,1,1,128,1}
+  CUtensorMap tmP;  // fused-x modes, TMA publish: the exchange buffer again, un-swizzled, box {16 units, box_rows}
   const float* xproj;        // split mode: [B*T][4096] fp32 gate pre-activations (bias included)
   const float* bias;         // bf16 mode: [4096] b_ih + b_hh in the permuted order
   void* hseq;                // layer output: bf16 [B][T][1024] (fwd | bwd), or fp16 [B][T][hi 1024 | lo 1024]
@@ -67,12 +85,30 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
   return v;
 }
 __device__ __forceinline__ void red_release_gpu_add(unsigned int* p, unsigned int v) {
+#ifdef OCRFA_LSTM_RELAXED_PUBLISH
+  // MEASUREMENT ONLY (tools/test_igemm.cu, never the product library): drops the gpu-scope fence of the release
+  // (MEMBAR.ALL.GPU + ERRBAR in SASS) to see what it costs per step; without it the exchange stores are not ordered
+  // before the counter update.
+  asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+#else
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+#endif
 }
 // The h slabs are GLOBAL memory written through the generic proxy by the peer CTAs and read back by TMA (async proxy):
 // the fence is restricted to the global state space - measured 36 cycles against 770 for the all-spaces form, which
 // sat on the critical path of every step.
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+__device__ __forceinline__ void red_relaxed_gpu_add(unsigned int* p, unsigned int v) {
+  asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const void* tmap, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit_and_wait_all() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
 
 // ex2.approx-based gate activations (abs error ~1e-6, far below the bf16 rounding of h); saturate cleanly at +-inf.
 #ifdef OCRFA_LSTM_TANH_APPROX
@@ -124,6 +160,8 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_tc_persistent_kernel(con
   float* sbias = reinterpret_cast<float*>(smem + 512);    // [64] (bf16 mode)
   uint8_t* w_smem = smem + 1024;                          // kLstmWSlabs x (64 rows x 128 B) = 128 KB
   uint8_t* ring = w_smem + kLstmWSlabs * 8192;            // kLstmRing x 16 KB
+  uint8_t* hstage = ring + kLstmRing * 16384;             // kLstmStageBytes (TMA publish)
+  (void)hstage;
 
   constexpr int kHxSlabs = lstm_hx_slabs(MODE);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -145,6 +183,9 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_tc_persistent_kernel(con
     tma_prefetch_desc(&p.tmX);
     tma_prefetch_desc(&p.tmW);
     if (MODE == kLstmBf16FusedX) tma_prefetch_desc(&p.tmS);
+#ifdef OCRFA_LSTM_TMA_PUBLISH
+    if (MODE == kLstmBf16FusedX) tma_prefetch_desc(&p.tmP);
+#endif
   }
   if (warp == 1) { tmem_alloc(tmem_slot, kLstmTmemCols); tmem_relinquish(); }
   if (MODE == kLstmBf16FusedX && threadIdx.x >= 64 && threadIdx.x < 128)
@@ -334,6 +375,30 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_tc_persistent_kernel(con
         o1.z = pack16x2(hout[12], hout[13], kHalf16); o1.w = pack16x2(hout[14], hout[15], kHalf16);
         l0 = o0; l1 = o1;
       }
+#ifdef OCRFA_LSTM_TMA_PUBLISH
+      constexpr bool kTmaPublish = MODE != kLstmF16Split;
+#else
+      constexpr bool kTmaPublish = false;
+#endif
+      if (kTmaPublish) {
+        // stage the CTA's [rows][16 units] slice (rows beyond the batch carry whatever the padding lanes computed: they
+        // land in exchange rows that never reach a valid result), hand it to the async proxy, one TMA store, wait for
+        // the bulk group to complete, relaxed counter update
+        uint4* sp4 = reinterpret_cast<uint4*>(hstage) + row * 2;
+        sp4[0] = o0;
+        sp4[1] = o1;
+        fence_proxy_async_smem();
+        if (et == 0) LSTM_TS(s, 11);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (et == 0) {
+          LSTM_TS(s, 13);
+          const int slab_row0 = static_cast<int>(((hx_region + (s & 1)) * kHxSlabs + (j0 >> 6)) * 128);
+          tma_store_2d(&p.tmP, hstage, j0 & 63, slab_row0);
+          tma_store_commit_and_wait_all();
+          red_relaxed_gpu_add(group_ctr, 1u);
+          LSTM_TS(s, 14);
+        }
+      } else {
       if (valid) {
         // rows >= B of the exchange buffer are never read back into valid results
         uint16_t* hx = reinterpret_cast<uint16_t*>(p.hx);
@@ -355,6 +420,7 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_tc_persistent_kernel(con
         LSTM_TS(s, 13);
         red_release_gpu_add(group_ctr, 1u);
         LSTM_TS(s, 14);
+      }
       }
       if (valid) {
         uint16_t* hs = reinterpret_cast<uint16_t*>(p.hseq);
@@ -392,7 +458,9 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_tc_persistent_kernel(con
   }
 }
 
-inline size_t lstm_tc_smem_bytes() { return 2048 + kLstmWSlabs * 8192 + static_cast<size_t>(kLstmRing) * 16384; }
+inline size_t lstm_tc_smem_bytes() {
+  return 2048 + kLstmWSlabs * 8192 + static_cast<size_t>(kLstmRing) * 16384 + kLstmStageBytes;
+}
 
 // Cooperative launch (all CTAs co-resident). `sync` must hold 2*m_tiles zeroed counters.
 inline cudaError_t lstm_tc_launch(const LstmTcParams& p, int mode, cudaStream_t stream) {
