@@ -21,7 +21,7 @@
 //                    igemm; accurate expf/tanhf gate math.
 //
 // The only cross-CTA dependency is "all 32 CTAs of my (direction, m_tile) group wrote h_t": a monotonic global
-// counter per group (release add / acquire poll), no kernel relaunch, no grid-wide barrier. All CTAs must be
+// counter per group (counter add after the slice is at L2 / acquire poll), no kernel relaunch, no grid-wide barrier. All CTAs must be
 // co-resident (<= 128 CTAs, 1 per SM): the host uses a cooperative launch, and every spin is bounded (trap on
 // timeout) so a scheduling surprise surfaces as an error, not a hung GPU.
 #pragma once
@@ -399,28 +399,28 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_tc_persistent_kernel(con
           LSTM_TS(s, 14);
         }
       } else {
-      if (valid) {
-        // rows >= B of the exchange buffer are never read back into valid results
-        uint16_t* hx = reinterpret_cast<uint16_t*>(p.hx);
-        const size_t slab = (hx_region + (s & 1)) * kHxSlabs + (j0 >> 6);
-        uint16_t* xp2 = hx + (slab * 128 + row) * 64 + (j0 & 63);
-        *reinterpret_cast<uint4*>(xp2) = o0;
-        *reinterpret_cast<uint4*>(xp2 + 8) = o1;
-        if (MODE == kLstmF16Split) {
-          uint16_t* xp3 = xp2 + static_cast<size_t>(8) * 128 * 64;  // lo slabs follow the 8 hi slabs
-          *reinterpret_cast<uint4*>(xp3) = l0;
-          *reinterpret_cast<uint4*>(xp3 + 8) = l1;
+        if (valid) {
+          // rows >= B of the exchange buffer are never read back into valid results
+          uint16_t* hx = reinterpret_cast<uint16_t*>(p.hx);
+          const size_t slab = (hx_region + (s & 1)) * kHxSlabs + (j0 >> 6);
+          uint16_t* xp2 = hx + (slab * 128 + row) * 64 + (j0 & 63);
+          *reinterpret_cast<uint4*>(xp2) = o0;
+          *reinterpret_cast<uint4*>(xp2 + 8) = o1;
+          if (MODE == kLstmF16Split) {
+            uint16_t* xp3 = xp2 + static_cast<size_t>(8) * 128 * 64;  // lo slabs follow the 8 hi slabs
+            *reinterpret_cast<uint4*>(xp3) = l0;
+            *reinterpret_cast<uint4*>(xp3 + 8) = l1;
+          }
         }
-      }
-      // publish: the CTA barrier orders every epilogue thread's exchange stores before thread 0's gpu-scope release
-      // (cumulative), which the peers' acquire polls + proxy fence pair with
-      if (et == 0) LSTM_TS(s, 11);
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (et == 0) {
-        LSTM_TS(s, 13);
-        red_release_gpu_add(group_ctr, 1u);
-        LSTM_TS(s, 14);
-      }
+        // publish: the CTA barrier orders every epilogue thread's exchange stores before thread 0's gpu-scope release
+        // (cumulative), which the peers' acquire polls + proxy fence pair with
+        if (et == 0) LSTM_TS(s, 11);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (et == 0) {
+          LSTM_TS(s, 13);
+          red_release_gpu_add(group_ctr, 1u);
+          LSTM_TS(s, 14);
+        }
       }
       if (valid) {
         uint16_t* hs = reinterpret_cast<uint16_t*>(p.hseq);
