@@ -45,10 +45,17 @@ constexpr int kLstmThreads = 192;
 #endif
 #ifdef OCRFA_LSTM_TMA_PUBLISH
 constexpr int kLstmRing = 5;          // A-ring stages of 16 KB
+#ifdef OCRFA_LSTM_TMA_PUBLISH_SPLIT      // also for the split-precision mode (hi and lo tiles): compiled in only on request
+constexpr int kLstmStageBytes = 8192; // until it has been through the GPU suite
+constexpr bool kLstmTmaPublishSplit = true;
+#else
 constexpr int kLstmStageBytes = 4096; // h slice staging: 128 rows x 16 units x 2 B
+constexpr bool kLstmTmaPublishSplit = false;
+#endif
 #else
 constexpr int kLstmRing = 6;          // A-ring stages of 16 KB
 constexpr int kLstmStageBytes = 0;
+constexpr bool kLstmTmaPublishSplit = false;
 #endif
 constexpr int kLstmTmemCols = 128;    // 2 accumulators x 64 columns
 constexpr int kLstmGroupCtas = 32;    // CTAs per (direction, m_tile) group = 512 hidden units / 16
@@ -66,7 +73,7 @@ struct alignas(64) LstmTcParams {
   CUtensorMap tmX;  // exchange buffer [2 dirs][m_tiles][2 parities][slabs][128 rows][64] as 2-D (64, rows), box {64,128}
   CUtensorMap tmW;  // resident weights [4096][1024] (bf16: [W_ih | W_hh]; split: [W_hi | W_lo]), box {64, 64}
   CUtensorMap tmS;  // bf16 mode: layer input [B][T][512] bf16 as the 5-D activation map, box {64,1,1,128,1}
-  CUtensorMap tmP;  // fused-x modes, TMA publish: the exchange buffer again, un-swizzled, box {16 units, box_rows}
+  CUtensorMap tmP;  // TMA publish: the exchange buffer again, un-swizzled, box {16 units, box_rows}
   const float* xproj;        // split mode: [B*T][4096] fp32 gate pre-activations (bias included)
   const float* bias;         // bf16 mode: [4096] b_ih + b_hh in the permuted order
   void* hseq;                // layer output: bf16 [B][T][1024] (fwd | bwd), or fp16 [B][T][hi 1024 | lo 1024]
@@ -184,7 +191,7 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_tc_persistent_kernel(con
     tma_prefetch_desc(&p.tmW);
     if (MODE == kLstmBf16FusedX) tma_prefetch_desc(&p.tmS);
 #ifdef OCRFA_LSTM_TMA_PUBLISH
-    if (MODE == kLstmBf16FusedX) tma_prefetch_desc(&p.tmP);
+    tma_prefetch_desc(&p.tmP);
 #endif
   }
   if (warp == 1) { tmem_alloc(tmem_slot, kLstmTmemCols); tmem_relinquish(); }
@@ -376,7 +383,7 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_tc_persistent_kernel(con
         l0 = o0; l1 = o1;
       }
 #ifdef OCRFA_LSTM_TMA_PUBLISH
-      constexpr bool kTmaPublish = MODE != kLstmF16Split;
+      constexpr bool kTmaPublish = MODE != kLstmF16Split || kLstmTmaPublishSplit;
 #else
       constexpr bool kTmaPublish = false;
 #endif
@@ -387,6 +394,10 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_tc_persistent_kernel(con
         uint4* sp4 = reinterpret_cast<uint4*>(hstage) + row * 2;
         sp4[0] = o0;
         sp4[1] = o1;
+        if (MODE == kLstmF16Split) {  // the lo halves: second staging tile, stored 8 slabs further
+          sp4[256] = l0;
+          sp4[257] = l1;
+        }
         fence_proxy_async_smem();
         if (et == 0) LSTM_TS(s, 11);
         asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -394,6 +405,7 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_tc_persistent_kernel(con
           LSTM_TS(s, 13);
           const int slab_row0 = static_cast<int>(((hx_region + (s & 1)) * kHxSlabs + (j0 >> 6)) * 128);
           tma_store_2d(&p.tmP, hstage, j0 & 63, slab_row0);
+          if (MODE == kLstmF16Split) tma_store_2d(&p.tmP, hstage + 4096, j0 & 63, slab_row0 + 8 * 128);
           tma_store_commit_and_wait_all();
           red_relaxed_gpu_add(group_ctr, 1u);
           LSTM_TS(s, 14);
