@@ -9,7 +9,7 @@ no dict/ directory in the repo: ocr.py:102, 172-174) and are rejected here inste
 from __future__ import annotations
 
 import ctypes as C
-from typing import List, Sequence
+from typing import List
 
 import numpy as np
 import torch

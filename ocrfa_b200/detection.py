@@ -18,8 +18,7 @@ a few hundred boxes). There is no CPU path for the pixel work: without the CUDA 
 from __future__ import annotations
 
 import ctypes as C
-import math
-from typing import List, Optional, Sequence, Tuple
+from typing import List, Tuple
 
 import numpy as np
 import torch

@@ -23,7 +23,6 @@ import hashlib
 import json
 import os
 from logging import getLogger
-from typing import List, Optional
 
 import numpy as np
 import torch

@@ -10,8 +10,7 @@ Pillow-exact BICUBIC resize (utils.py:598) and the percentile contrast stretch o
 from __future__ import annotations
 
 import ctypes as C
-import math
-from typing import Iterable, List, Optional, Sequence
+from typing import Iterable, Optional, Sequence
 
 import numpy as np
 import torch
