@@ -69,6 +69,32 @@ def test_host_boxes_from_row_extents_match_reference_boxes():
         assert mapper == g[f"map{i}_thr{j}_mapper"].tolist()
 
 
+def test_host_boxes_from_row_extents_equal_full_mask_boxes_on_random_maps():
+    """The claim the GPU post-processing rests on, beyond the fixture: for 30 random CRAFT-like map pairs (rotated words,
+    border contact, tiny and weak blobs) the boxes rebuilt from dilated row extents equal, bit for bit, the oracle's
+    get_det_boxes_core (minAreaRect over the full dilated mask)."""
+    from oracle import det_ref as D
+    from ocrfa_b200.detection import DET_COMP, boxes_from_components
+
+    rng = np.random.default_rng(17)
+    n_boxes = 0
+    for it in range(30):
+        h, w = int(rng.integers(24, 140)), int(rng.integers(24, 220))
+        text, link = D.synth_score_maps(h, w, 1000 + it, int(rng.integers(2, 30)))
+        tt, lt, low = ((0.7, 0.4, 0.4), (0.5, 0.3, 0.25), (0.9, 0.6, 0.2))[it % 3]
+        want, _, want_mapper = D.get_det_boxes_core_ref(text, link, tt, lt, low)
+        _, _, comps, ext = D.components_ref(text, link, tt, lt, low)
+        arr = np.zeros(len(comps), dtype=DET_COMP)
+        for n, c in enumerate(comps):
+            for k, v in c.items():
+                arr[n][k] = v
+        got, mapper = boxes_from_components(arr, ext)
+        _assert_boxes_equal(got, want)
+        assert mapper == want_mapper
+        n_boxes += len(got)
+    assert n_boxes > 80
+
+
 def test_host_resize_geometry_and_coordinates():
     from ocrfa_b200.detection import adjust_result_coordinates, resize_geometry
 
