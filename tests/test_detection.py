@@ -247,3 +247,47 @@ def test_gpu_components_edge_cases():
     l2[12:14, 30:50] = 0.9
     t2[10:16, 50:70] = 0.8
     assert _check_components(t2, l2, 0.7, 0.4, 0.4) == 1
+
+
+def test_labeling_rule_reproduces_opencv_label_numbers():
+    """The numbering rule the CUDA labeling implements (det_kernels.cuh): union-find over left / upper neighbours with
+    the smaller index as root, so that a component's root is its first pixel in raster order; labels are the ranks of
+    the roots. Emulated here in NumPy on random masks (sparse, dense, stripes, checkerboards) and compared with
+    cv2.connectedComponentsWithStats(connectivity=4), whose numbers the reference's `mapper` / `labels` carry."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(23)
+
+    def label_by_rule(mask):
+        h, w = mask.shape
+        parent = np.where(mask.reshape(-1) != 0, np.arange(h * w), -1)
+
+        def find(a):
+            while parent[a] != a:
+                a = parent[a]
+            return a
+
+        for p in np.flatnonzero(mask.reshape(-1)):
+            y, x = divmod(int(p), w)
+            for q in ((p - 1) if x > 0 and mask[y, x - 1] else -1, (p - w) if y > 0 and mask[y - 1, x] else -1):
+                if q >= 0:
+                    a, b = find(int(p)), find(int(q))
+                    if a != b:
+                        parent[max(a, b)] = min(a, b)
+        roots = np.array([find(int(p)) if parent[p] >= 0 else -1 for p in range(h * w)])
+        is_root = roots == np.arange(h * w)
+        rank = np.cumsum(is_root)  # 1-based rank of every root in raster order
+        return np.where(roots >= 0, rank[np.maximum(roots, 0)], 0).reshape(h, w), int(is_root.sum()) + 1
+
+    masks = [(rng.random((int(rng.integers(3, 40)), int(rng.integers(3, 60)))) < p).astype(np.uint8)
+             for p in (0.05, 0.3, 0.5, 0.5, 0.7, 0.95) for _ in range(4)]
+    masks.append((np.add.outer(np.arange(9), np.arange(14)) % 2).astype(np.uint8))
+    masks.append(np.tile(np.array([[1], [0]], np.uint8), (6, 17)))
+    masks.append(np.zeros((5, 7), np.uint8))
+    masks.append(np.ones((5, 7), np.uint8))
+    u_shape = np.zeros((8, 9), np.uint8)  # two arms that meet only at the bottom: provisional labels merge late
+    u_shape[:, 1] = u_shape[:, 7] = u_shape[7, 1:8] = 1
+    masks.append(u_shape)
+    for m in masks:
+        n_ref, lab_ref = cv2.connectedComponents(m, connectivity=4)
+        lab, n = label_by_rule(m)
+        assert n == n_ref and np.array_equal(lab, lab_ref)

@@ -275,3 +275,18 @@ def test_gpu_bgr2gray_bit_exact_with_opencv():
     g2 = rng.integers(0, 256, (40, 60), dtype=np.uint8)
     colour, grey = reformat_input(g2)
     assert np.array_equal(grey.cpu().numpy(), g2) and np.array_equal(colour.cpu().numpy(), cv2.cvtColor(g2, cv2.COLOR_GRAY2BGR))
+
+
+def test_reformat_input_rejects_what_the_reference_rejects():
+    """Argument errors surface before any device work (utils.py:1564-1565; URL fetching is not offered)."""
+    from ocrfa_b200.reader import make_rotated_img_list, reformat_input
+
+    with pytest.raises(ValueError):
+        reformat_input("https://example.org/page.png")
+    with pytest.raises(ValueError):
+        reformat_input(12345)
+    with pytest.raises(ValueError):
+        reformat_input("/nonexistent/page.png")
+    with pytest.raises(NotImplementedError):
+        make_rotated_img_list([30], [])
+    assert make_rotated_img_list([90, 180], []) == []
