@@ -102,6 +102,22 @@ def load():
     return lib
 
 
+def resolve_device(device="cuda"):
+    """The one place a `device` argument becomes a torch.device: a bare "cuda" means the CURRENT CUDA device
+    (what `tensor.to("cuda")` means in torch and hence in the reference, utils.py:621), never a hard-coded cuda:0,
+    so the page, crops, detector and recognizer of one call always live on the same GPU."""
+    import torch
+
+    dev = device if isinstance(device, torch.device) else torch.device(str(device))
+    if dev.type != "cuda":
+        raise OcrfaError(f"ocrfa_b200 has no CPU path; got device={device!r}")
+    if dev.index is None:
+        if not torch.cuda.is_available():
+            raise OcrfaError("ocrfa_b200 needs a CUDA device (there is no CPU fallback)")
+        dev = torch.device("cuda", torch.cuda.current_device())
+    return dev
+
+
 def check(rc: int) -> None:
     if rc != 0:
         msg = load().ocrfa_last_error()

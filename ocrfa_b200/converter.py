@@ -18,9 +18,7 @@ from . import _lib
 
 
 def _dev() -> torch.device:
-    if not torch.cuda.is_available():
-        raise _lib.OcrfaError("ocrfa_b200 decode kernels need a CUDA device (no CPU fallback)")
-    return torch.device("cuda", torch.cuda.current_device())
+    return _lib.resolve_device("cuda")
 
 
 def _ptr(t):

@@ -283,9 +283,7 @@ def get_image_list(horizontal_list, free_list, img, model_height=64, sort_output
     if isinstance(img, np.ndarray):
         if img.ndim != 2 or img.dtype != np.uint8:
             raise ValueError("img must be a uint8 grayscale page [H, W]")
-        dev = torch.device(device if device != "cuda" else "cuda:0")
-        if dev.type != "cuda":
-            raise _lib.OcrfaError("ocrfa_b200 has no CPU path: device must be a CUDA device")
+        dev = _lib.resolve_device(device)
         page = torch.from_numpy(np.ascontiguousarray(img)).to(dev)
     else:
         page = img
@@ -295,6 +293,9 @@ def get_image_list(horizontal_list, free_list, img, model_height=64, sort_output
     for box in free_list:
         rect = np.array(box, dtype="float32")
         mw, mh, minv = four_point_geometry(rect)
+        if mw <= 0 or mh <= 0:
+            # the reference fails inside cv2.warpPerspective / cv2.resize on an empty crop (utils.py:1218-1231, 1361)
+            raise ValueError(f"degenerate free-form box {box!r}: warped size {mw} x {mh}")
         ratio = calculate_ratio(mw, mh)
         new_width = int(model_height * ratio)
         if new_width == 0:
@@ -311,6 +312,9 @@ def get_image_list(horizontal_list, free_list, img, model_height=64, sort_output
         y_max = min(box[3], maximum_y)
         width = x_max - x_min
         height = y_max - y_min
+        if width <= 0 or height <= 0:
+            # a box that is empty after clipping to the page: the reference raises from cv2.resize (utils.py:1398-1405)
+            raise ValueError(f"box {list(box)!r} is empty after clipping to the {maximum_x} x {maximum_y} page")
         ratio = calculate_ratio(width, height)
         new_width = int(model_height * ratio)
         if new_width == 0:

@@ -116,7 +116,9 @@ struct GraphEntry {
 
 struct ocrfa_handle {
   std::vector<GraphEntry> graphs;
-  int graphs_enabled = 1;  // OCRFA_GRAPHS=0 disables; also cleared if a capture ever fails
+  int graphs_enabled = 1;  // OCRFA_GRAPHS=0 disables; also cleared after kMaxGraphFailures failed captures
+  int graph_failures = 0;
+  bool stem_1px = false;   // OCRFA_STEM_1PX (experiment switch), read once in ocrfa_create
   uint64_t graph_tick = 0;
   Profiler prof;
   ocrfa_config cfg;
@@ -670,7 +672,7 @@ int forward_impl(ocrfa_handle* h, const float* d_x, const uint8_t* d_u8, const i
     LaunchScope ls(h, kClsStem, 2.0 * (double)pix * 32 * 9, st);
     // four pixels per thread once there are enough pixels to fill the machine; small batches keep one pixel per thread
     // (a latency shape: 4096 pixels at config 1)
-    if (stem32 && (W & 3) == 0 && pix >= (1ll << 20) && !getenv("OCRFA_STEM_1PX")) {
+    if (stem32 && (W & 3) == 0 && pix >= (1ll << 20) && !h->stem_1px) {
       const unsigned g4 = (unsigned)((pix / 4 + 127) / 128);
       if (h->f16()) stem_conv32x4_kernel<true><<<g4, 128, 0, st>>>(d_x, d_u8, d_widths, h->stem_host, (__nv_bfloat16*)a.p, B, H, W);
       else stem_conv32x4_kernel<false><<<g4, 128, 0, st>>>(d_x, d_u8, d_widths, h->stem_host, (__nv_bfloat16*)a.p, B, H, W);
@@ -885,6 +887,7 @@ int ocrfa_create(const ocrfa_config* cfg, ocrfa_handle** out) {
   h->cfg = *cfg;
   h->num_sms = prop.multiProcessorCount;
   if (const char* hl = getenv("OCRFA_HALO")) h->halo_level = atoi(hl);
+  h->stem_1px = getenv("OCRFA_STEM_1PX") != nullptr;
   const char* g = getenv("OCRFA_GRAPHS");
   if (g && g[0] == '0') h->graphs_enabled = 0;
   *out = h;
@@ -1279,6 +1282,7 @@ static int beam_launch(const float* d_probs, const int32_t* d_span_row0, const i
 }  // extern "C"
 
 namespace {
+constexpr int kMaxGraphFailures = 3;  // a transient capture / instantiate failure does not switch graphs off for good
 int recognize_device_body(ocrfa_handle* h, const uint8_t* d_img, const int32_t* d_widths, int B, int H, int W,
                           const uint8_t* d_ignore_mask, int decoder, int beam_width, int32_t* d_labels, int32_t* d_len,
                           double* d_conf, void* d_ws, size_t ws_bytes, cudaStream_t st) {
@@ -1314,7 +1318,11 @@ int recognize_device_impl(ocrfa_handle* h, const uint8_t* d_img, const int32_t* 
                           const uint8_t* d_ignore_mask, int decoder, int beam_width, int32_t* d_labels, int32_t* d_len,
                           double* d_conf, void* d_ws, size_t ws_bytes, cudaStream_t st) {
   if (!h) return fail(OCRFA_ERR_ARG, "null handle");
-  if (!h->graphs_enabled || h->prof.mask != 0 || !h->tc())
+  // Stream capture is illegal on the legacy default stream (and on cudaStreamPerThread's implicit siblings): such callers
+  // run eagerly, WITHOUT switching graphs off for later calls on a capturable stream. Callers that want graph replay
+  // pass a stream created with cudaStreamCreate / torch.cuda.Stream ("Streams").
+  const bool capturable = st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread;
+  if (!h->graphs_enabled || !capturable || h->prof.mask != 0 || !h->tc())
     return recognize_device_body(h, d_img, d_widths, B, H, W, d_ignore_mask, decoder, beam_width, d_labels, d_len, d_conf,
                                  d_ws, ws_bytes, st);
   const GraphKey key{d_img, d_widths, d_ignore_mask, d_labels, d_len, d_conf, d_ws, ws_bytes, B, H, W, decoder, beam_width};
@@ -1338,9 +1346,8 @@ int recognize_device_impl(ocrfa_handle* h, const uint8_t* d_img, const int32_t* 
   for (int i = 0; i < kNumClasses; ++i) c0[i] = h->prof.launches[i];
   if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
     cudaGetLastError();
-    h->graphs_enabled = 0;
-    return recognize_device_body(h, d_img, d_widths, B, H, W, d_ignore_mask, decoder, beam_width, d_labels, d_len, d_conf,
-                                 d_ws, ws_bytes, st);
+    if (++h->graph_failures >= kMaxGraphFailures) h->graphs_enabled = 0;
+    return 0;  // the eager run above already produced this call's outputs
   }
   const int rc = recognize_device_body(h, d_img, d_widths, B, H, W, d_ignore_mask, decoder, beam_width, d_labels, d_len,
                                        d_conf, d_ws, ws_bytes, st);
@@ -1350,7 +1357,7 @@ int recognize_device_impl(ocrfa_handle* h, const uint8_t* d_img, const int32_t* 
   if (rc != 0 || ce != cudaSuccess || graph == nullptr || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
     cudaGetLastError();
     if (graph) cudaGraphDestroy(graph);
-    h->graphs_enabled = 0;  // fall back to eager launches for the rest of this handle's life
+    if (++h->graph_failures >= kMaxGraphFailures) h->graphs_enabled = 0;  // then eager for the rest of the handle's life
     h->launches = l0;
     for (int i = 0; i < kNumClasses; ++i) h->prof.launches[i] = c0[i];
     if (rc != 0) return rc;
@@ -1361,7 +1368,7 @@ int recognize_device_impl(ocrfa_handle* h, const uint8_t* d_img, const int32_t* 
   GraphEntry e;
   e.key = key; e.exec = exec; e.launches = h->launches - l0; e.last_use = ++h->graph_tick;
   for (int i = 0; i < kNumClasses; ++i) e.by_class[i] = h->prof.launches[i] - c0[i];
-  if (h->graphs.size() >= 8) {  // evict the least recently used
+  if (h->graphs.size() >= 16) {  // evict the least recently used
     size_t victim = 0;
     for (size_t i = 1; i < h->graphs.size(); ++i)
       if (h->graphs[i].last_use < h->graphs[victim].last_use) victim = i;

@@ -105,6 +105,13 @@ inline int plan_conv(IgemmTcParams* p, const ConvGeom& g, const void* in, int ci
   p->pair = (!split && p->tiles_w * p->tiles_h * p->tiles_n >= 2 && (p->block_n & 15) == 0) ? 1 : 0;
   if (const char* e = std::getenv("OCRFA_IGEMM_PAIR")) { if (e[0] == '0') p->pair = 0; }
   igemm_tc_smem_bytes(p->block_n, &p->num_stages, p->pair);
+  if (split) {
+    // fp32-grade mode: always the fused-stage CTA-pair kernel (igemm_x3.cuh); a lone M tile leaves the peer CTA with
+    // an out-of-range tile (TMA zero-fills, nothing is stored). OCRFA_X3=0 selects the older single-CTA kernel (A/B runs).
+    p->pair = 1;
+    if (const char* e = std::getenv("OCRFA_X3")) { if (e[0] == '0') p->pair = 0; }
+    if (p->pair) igemm_x3_smem_bytes(p->block_n, &p->num_stages);
+  }
   int nt = 0;
   for (int r = 0; r < g.kh; ++r)
     for (int s = 0; s < g.kw; ++s) {

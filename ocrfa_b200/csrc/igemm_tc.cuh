@@ -613,7 +613,10 @@ inline int make_rows64_store_tmap(CUtensorMap* tm, const void* base, long long r
   return rc == CUDA_SUCCESS ? 0 : -static_cast<int>(rc) - 1000;
 }
 
+inline cudaError_t igemm_x3_launch(const IgemmTcParams& p, int num_sms, cudaStream_t stream);  // igemm_x3.cuh
+
 inline cudaError_t igemm_tc_launch(const IgemmTcParams& p, int /*mode*/, int num_sms, cudaStream_t stream) {
+  if (p.split && p.pair) return igemm_x3_launch(p, num_sms, stream);  // fp32-grade mode: the fused-stage CTA-pair kernel
   static bool attr_set_dev[kMaxDevices][3] = {};
   bool* attr_set = attr_set_dev[current_device_slot()];
   const int mode = p.split ? kModeSplit : (p.pair ? kModePair : kModeStd);
@@ -660,3 +663,5 @@ inline cudaError_t igemm_tc_launch(const IgemmTcParams& p, int /*mode*/, int num
 }
 
 }  // namespace ocrfa
+
+#include "igemm_x3.cuh"

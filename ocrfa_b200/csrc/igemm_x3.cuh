@@ -1,0 +1,301 @@
+// Split-precision (fp32-grade) tcgen05 implicit GEMM: the "f16x3" mode of every convolution / linear layer.
+//
+//   reference arithmetic being matched: fp32 convs and GEMMs of
+//     /root/reference/src/ocrfa/modules/blocks.py:200-223, 239-322 (ResNet), :89-101 (BiLSTM GEMMs), :438 (Prediction)
+//
+// Every operand is an fp16 pair x = hi + lo (22 significant bits; activations NHWC [hi(C) | lo(C)] per pixel, weights
+// [Cout][tap][hi(C) | lo(C)] pre-scaled by a power of two) and every algorithmic MAC costs three tensor-core
+// products: hi.hi + lo.hi + hi.lo (the dropped lo.lo term is ~2^-22 relative).
+//
+// Design (what differs from igemm_tc_kernel<kModeSplit>, which this kernel replaces):
+//   * CTA pair (cta_group::2, M = 256 over the two SMs of a TPC): each CTA stages its own 128 pixel rows and HALF of
+//     the weight tile, so the weight bytes per SM halve.
+//   * ONE shared-memory stage per K chunk holds all four operand tiles {A_hi, A_lo, W_hi, W_lo} and feeds twelve
+//     MMAs (three products x K = 64): 64 KB per 12 MMAs instead of 48 KB per 4 - the operands are fetched once,
+//     not once per product (L2 -> SM bytes per MMA fall 2.25x).
+//   * The tensor core's fp32 accumulate truncates (error linear in the number of chained MMAs), so
+//       - the hi.hi products of ONE K chunk (four MMAs, K = 64) go to a fresh TMEM accumulator ("main") that the
+//         eight epilogue warps drain into fp32 REGISTER accumulators with round-to-nearest adds, chunk after chunk;
+//       - the lo.hi / hi.lo products (2^-11 of the result) chain in a second TMEM accumulator ("corr") for the
+//         whole tile - their truncation error is 2^-11 of an already negligible term - and are added once at the end.
+//     The MMA issuer orders a stage as corr, corr, main: while the epilogue drains chunk k from "main", the tensor
+//     pipe is busy with the eight corr MMAs of chunk k+1, so the drain (4 TMEM loads + 128 FADDs per thread) is
+//     hidden and a single "main" buffer suffices (TMEM: 256 + 256 columns).
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (leader CTA) + TMEM alloc, warps 2..9 = epilogue.
+#pragma once
+#include <cstdlib>
+#include "igemm_tc.cuh"
+
+namespace ocrfa {
+
+constexpr int kX3Threads = 320;
+constexpr int kX3CorrCol = 256;  // TMEM column of the corr accumulator (main starts at column 0)
+constexpr int kX3DefaultSub = 1;
+
+inline size_t igemm_x3_smem_bytes(int block_n, int* stages_out) {
+  const size_t stage = 2 * static_cast<size_t>(kTcBlockM) * kTcBlockK * 2 + 2 * static_cast<size_t>(block_n / 2) * kTcBlockK * 2;
+  const size_t header = 1024 + kTcSmemHeader;
+  const size_t budget = 227 * 1024 - header;
+  int stages = static_cast<int>(budget / stage);
+  if (stages > kTcMaxStages) stages = kTcMaxStages;
+  if (stages_out) *stages_out = stages;
+  return header + stages * stage;
+}
+
+// SUB = "main" chunks per K chunk of 64 (1, 2 or 4): the hi.hi products of one stage are split into SUB fresh
+// accumulations of 4 / SUB chained MMAs each, interleaved with 8 / SUB corr MMAs that cover the drain.
+template <int SUB>
+__global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_constant__ IgemmTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);  // [kTcMaxStages]
+  uint64_t* empty_bar = full_bar + kTcMaxStages;           // [kTcMaxStages]
+  uint64_t* main_full = empty_bar + kTcMaxStages;          // hi.hi chunk complete (both CTAs, multicast commit)
+  uint64_t* main_empty = main_full + 1;                    // chunk drained by the 16 epilogue warps of the pair (leader's copy)
+  uint64_t* corr_full = main_empty + 1;                    // every MMA of the tile complete
+  uint64_t* corr_empty = corr_full + 1;                    // corr read back by the 16 epilogue warps (leader's copy)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(corr_empty + 1);
+  int4* kb_table = reinterpret_cast<int4*>(smem + 256);    // [total_kb][2]: {a_c, dw, dr, dh}, {src, b_k, a_lo, b_lo}
+  uint8_t* stage_base = smem + kTcSmemHeader;
+
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool leader = cta_rank == 0;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int stages = p.num_stages;
+  const int block_n = p.block_n;
+  const int b_rows = block_n >> 1;
+  const uint32_t a_bytes = kTcBlockM * kTcBlockK * 2;
+  const uint32_t b_bytes = static_cast<uint32_t>(b_rows) * kTcBlockK * 2;
+  const uint32_t stage_bytes = 2u * a_bytes + 2u * b_bytes;
+
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int total_tiles = ((m_tiles + 1) >> 1) * p.n_tiles;
+  const int worker = static_cast<int>(blockIdx.x >> 1);
+  const int num_workers = static_cast<int>(gridDim.x >> 1);
+  int total_kb = 0;
+  for (int t = 0; t < p.num_taps; ++t) total_kb += p.taps[t].src ? p.kchunks2 : p.kchunks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full_bar[s], 2);  // the leader's expect_tx arrive + the peer's remote arrive
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(main_full, 1);
+    mbar_init(main_empty, 16);
+    mbar_init(corr_full, 1);
+    mbar_init(corr_empty, 16);
+    fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmB);
+    tma_prefetch_desc(&p.tmA2);
+  }
+  // K-chunk schedule (tap-major, 64-channel chunk minor). Weight K blocks of a tap are [hi chunks | lo chunks].
+  for (int kb = threadIdx.x; kb < total_kb; kb += blockDim.x) {
+    int rem = kb, kb_base = 0, t = 0, chunks = 0;
+    for (; t < p.num_taps; ++t) {
+      chunks = p.taps[t].src ? p.kchunks2 : p.kchunks;
+      if (rem < chunks) break;
+      rem -= chunks;
+      kb_base += 2 * chunks;
+    }
+    const TapDesc tap = p.taps[t];
+    kb_table[2 * kb] = make_int4(rem * kTcBlockK, tap.dw, tap.dr, tap.dh);
+    kb_table[2 * kb + 1] = make_int4(tap.src, (kb_base + rem) * kTcBlockK, tap.src ? p.a_lo2 : p.a_lo, chunks * kTcBlockK);
+  }
+  if (warp == 1) { tmem_alloc_pair(tmem_slot, kTcTmemCols); tmem_relinquish_pair(); }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================== TMA producer (both CTAs) =========================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = worker; tile < total_tiles; tile += num_workers) {
+        const int n_tile = tile % p.n_tiles;
+        // an odd tail leaves the peer with m_tile == m_tiles: its image coordinate is out of range, TMA zero-fills
+        const int m_tile = ((tile / p.n_tiles) << 1) + static_cast<int>(cta_rank);
+        const int iw = m_tile % p.tiles_w;
+        const int ih = (m_tile / p.tiles_w) % p.tiles_h;
+        const int in = m_tile / (p.tiles_w * p.tiles_h);
+        const int w0 = iw * p.tw, h0 = ih * p.th, n0 = in * p.tn;
+        const int b_col = n_tile * block_n + static_cast<int>(cta_rank) * b_rows;
+        for (int kb = 0; kb < total_kb; ++kb) {
+          const int4 e0 = kb_table[2 * kb];
+          const int4 e1 = kb_table[2 * kb + 1];
+          mbar_wait(&empty_bar[stage], phase ^ 1u, 1);
+          uint8_t* sa = stage_base + static_cast<size_t>(stage) * stage_bytes;
+          const void* tm = e1.x ? static_cast<const void*>(&p.tmA2) : static_cast<const void*>(&p.tmA);
+          if (leader) mbar_expect_tx(&full_bar[stage], 2u * stage_bytes);
+          tma_load_5d_pair(sa, tm, &full_bar[stage], e0.x, w0 + e0.y, e0.z, h0 + e0.w, n0);
+          tma_load_5d_pair(sa + a_bytes, tm, &full_bar[stage], e0.x + e1.z, w0 + e0.y, e0.z, h0 + e0.w, n0);
+          tma_load_2d_pair(sa + 2u * a_bytes, &p.tmB, &full_bar[stage], e1.y, b_col);
+          tma_load_2d_pair(sa + 2u * a_bytes + b_bytes, &p.tmB, &full_bar[stage], e1.y + e1.w, b_col);
+          if (!leader) mbar_arrive_remote(&full_bar[stage], 0u);
+          if (++stage == stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer (leader CTA only) =====================
+    if (leader && elect_one()) {
+      const uint32_t idesc = make_idesc_f16(2 * kTcBlockM, static_cast<uint32_t>(block_n));
+      const uint32_t d_main = tmem_base;
+      const uint32_t d_corr = tmem_base + static_cast<uint32_t>(kX3CorrCol);
+      int stage = 0;
+      uint32_t phase = 0, mph = 0, cph = 0;
+      for (int tile = worker; tile < total_tiles; tile += num_workers) {
+        mbar_wait(corr_empty, cph ^ 1u, 2);  // the previous tile's corr has been read back
+        cph ^= 1u;
+        for (int kb = 0; kb < total_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase, 3);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(stage_base + static_cast<size_t>(stage) * stage_bytes);
+          const uint64_t a_hi = make_sw128_kmajor_desc(sa);
+          const uint64_t a_lo = make_sw128_kmajor_desc(sa + a_bytes);
+          const uint64_t b_hi = make_sw128_kmajor_desc(sa + 2u * a_bytes);
+          const uint64_t b_lo = make_sw128_kmajor_desc(sa + 2u * a_bytes + b_bytes);
+#pragma unroll
+          for (int sc = 0; sc < SUB; ++sc) {
+            // corr MMAs j = 0..7 of this stage are lo.hi (k = j) for j < 4 and hi.lo (k = j - 4) after
+#pragma unroll
+            for (int j = sc * (8 / SUB); j < (sc + 1) * (8 / SUB); ++j) {
+              const int k = j & 3;
+              umma_bf16_pair(d_corr, (j < 4 ? a_lo : a_hi) + static_cast<uint64_t>(2 * k),
+                             (j < 4 ? b_hi : b_lo) + static_cast<uint64_t>(2 * k), idesc, (kb > 0 || j > 0) ? 1u : 0u);
+            }
+            // "main" is free again once the epilogue warps have drained the previous chunk - they do that while the
+            // corr MMAs above keep the tensor pipe busy
+            mbar_wait(main_empty, mph ^ 1u, 4);
+            mph ^= 1u;
+            tc_fence_after();
+#pragma unroll
+            for (int k = sc * (4 / SUB); k < (sc + 1) * (4 / SUB); ++k)
+              umma_bf16_pair(d_main, a_hi + static_cast<uint64_t>(2 * k), b_hi + static_cast<uint64_t>(2 * k), idesc,
+                             k > sc * (4 / SUB) ? 1u : 0u);
+            if (sc == SUB - 1) umma_commit_pair(&empty_bar[stage]);  // frees the slot in both CTAs once these MMAs have read it
+            umma_commit_pair(main_full);                             // this hi.hi chunk is complete -> epilogue (both CTAs)
+          }
+          if (++stage == stages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit_pair(corr_full);
+      }
+    }
+  } else {
+    // ===================================== epilogue (8 warps per CTA) =======================
+    // warp (q, half): TMEM lane quarter q (rows q*32..), column half `half` of the tile
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    const int half_cols = block_n >> 1;  // multiple of 32
+    uint32_t mph = 0, cph = 0;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(half * half_cols);
+    for (int tile = worker; tile < total_tiles; tile += num_workers) {
+      const int n_tile = tile % p.n_tiles;
+      const int m_tile = ((tile / p.n_tiles) << 1) + static_cast<int>(cta_rank);
+      const int iw = m_tile % p.tiles_w;
+      const int ih = (m_tile / p.tiles_w) % p.tiles_h;
+      const int in = m_tile / (p.tiles_w * p.tiles_h);
+      const int ww = row % p.tw;
+      const int hh = (row / p.tw) % p.th;
+      const int nn = row / (p.tw * p.th);
+      const int w = iw * p.tw + ww, h = ih * p.th + hh, n = in * p.tn + nn;
+      const bool valid = (w < p.w_out) && (h < p.h_out) && (n < p.n_img);
+      const size_t pix = (static_cast<size_t>(n) * p.h_out + h) * p.w_out + w;
+      const int n_off = n_tile * block_n + half * half_cols;
+      float racc[128];
+#pragma unroll
+      for (int i = 0; i < 128; ++i) racc[i] = 0.f;
+      const int nchunks = total_kb * SUB;
+      for (int ch = 0; ch <= nchunks; ++ch) {
+        // ch < nchunks: hi.hi chunk from "main"; ch == nchunks: the tile's lo.hi + hi.lo sum from "corr"
+        const bool last = ch == nchunks;
+        if (last) { mbar_wait(corr_full, cph, 5); cph ^= 1u; }
+        else { mbar_wait(main_full, mph, 6); mph ^= 1u; }
+        tc_fence_after();
+        const uint32_t taddr = t_lane + (last ? static_cast<uint32_t>(kX3CorrCol) : 0u);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (g * 32 < half_cols) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(g * 32), v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) racc[g * 32 + i] += __uint_as_float(v[i]);
+          }
+        }
+        // hand the buffer back: one arrive per warp (to the leader's barrier) after every lane's reads have landed
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          uint64_t* bar = last ? corr_empty : main_empty;
+          if (leader) mbar_arrive(bar); else mbar_arrive_remote(bar, 0u);
+        }
+      }
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int col0 = n_off + g * 32;
+        if (g * 32 < half_cols && valid && col0 < p.n_valid) {
+          float f[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = racc[g * 32 + i];
+          igemm_finish32(p, f, pix, col0);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // the peer's smem/TMEM stay live until the leader's MMAs are done
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, kTcTmemCols);
+  }
+}
+
+inline cudaError_t igemm_x3_launch(const IgemmTcParams& p, int num_sms, cudaStream_t stream) {
+  static bool attr_set_dev[kMaxDevices] = {};
+  bool& attr_set = attr_set_dev[current_device_slot()];
+  int stages = 0;
+  const size_t smem = igemm_x3_smem_bytes(p.block_n, &stages);
+  if (!p.split || !p.pair || stages != p.num_stages || stages < 2) return cudaErrorInvalidValue;
+  if ((p.block_n & 63) != 0 || p.block_n > 256) return cudaErrorInvalidValue;  // the epilogue halves the tile in 32-column groups
+  int total_kb = 0;
+  for (int t = 0; t < p.num_taps; ++t) total_kb += p.taps[t].src ? p.kchunks2 : p.kchunks;
+  if (total_kb > kTcMaxKb) return cudaErrorInvalidValue;
+  // OCRFA_X3_SUB = 1 | 2 | 4 (bring-up / measurement switch, read once): hi.hi accumulation chunks per K chunk
+  static const int sub = [] { const char* e = std::getenv("OCRFA_X3_SUB"); const int v = e ? std::atoi(e) : kX3DefaultSub;
+                              return (v == 1 || v == 2 || v == 4) ? v : kX3DefaultSub; }();
+  void (*fn)(IgemmTcParams) = sub == 1 ? igemm_x3_kernel<1> : (sub == 2 ? igemm_x3_kernel<2> : igemm_x3_kernel<4>);
+  if (!attr_set) {
+    for (auto f : {igemm_x3_kernel<1>, igemm_x3_kernel<2>, igemm_x3_kernel<4>}) {
+      cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e != cudaSuccess) return e;
+    }
+    attr_set = true;
+  }
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int pair_tiles = ((m_tiles + 1) / 2) * p.n_tiles;
+  const int pairs = pair_tiles < num_sms / 2 ? pair_tiles : num_sms / 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(kX3Threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, fn, p);
+}
+
+}  // namespace ocrfa

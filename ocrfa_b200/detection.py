@@ -35,10 +35,7 @@ _VARIANCE = (0.229, 0.224, 0.225)
 
 
 def _cuda_device(device) -> torch.device:
-    dev = torch.device("cuda:0" if str(device) == "cuda" else device)
-    if dev.type != "cuda":
-        raise _lib.OcrfaError("ocrfa_b200 has no CPU path: device must be a CUDA device")
-    return dev
+    return _lib.resolve_device(device)
 
 
 # ------------------------------------------------------------------------------------------------------------------

@@ -130,7 +130,7 @@ class Model(nn.Module):
 
     def workspace(self, nbytes: int, device: torch.device) -> torch.Tensor:
         """Grow-only device scratch owned by the model (the library never allocates per call)."""
-        if self._ws is None or self._ws.numel() < nbytes or self._ws.device != device:
+        if self._ws is None or self._ws.numel() < nbytes + 1024 or self._ws.device != device:
             self._ws = torch.empty(int(nbytes) + 1024, dtype=torch.uint8, device=device)
         off = (-self._ws.data_ptr()) % 1024
         return self._ws[off:off + nbytes]

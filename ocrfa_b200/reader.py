@@ -81,7 +81,7 @@ def bgr2gray_device(img: torch.Tensor) -> torch.Tensor:
 def reformat_input(image, device="cuda"):
     """utils.py:1525-1565: (img [H, W, 3], img_cv_grey [H, W]), both uint8 CUDA tensors. Files and byte strings are
     decoded on the host by OpenCV (I/O); array inputs are uploaded once and converted on the GPU."""
-    dev = torch.device("cuda:0" if str(device) == "cuda" else device)
+    dev = _lib.resolve_device(device)
     if isinstance(image, (str, bytes)):
         import cv2
 
@@ -386,8 +386,7 @@ class OCR:
         if reformat:
             _, img_cv_grey = reformat_input(img_cv_grey, self.device)
         elif isinstance(img_cv_grey, np.ndarray):
-            img_cv_grey = torch.from_numpy(np.ascontiguousarray(img_cv_grey)).to(
-                "cuda:0" if str(self.device) == "cuda" else self.device)
+            img_cv_grey = torch.from_numpy(np.ascontiguousarray(img_cv_grey)).to(_lib.resolve_device(self.device))
         if allowlist:
             ignore_char = "".join(set(self.character) - set(allowlist))
         elif blocklist:

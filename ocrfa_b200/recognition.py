@@ -154,7 +154,7 @@ def recognizer_predict(model: Model, converter: CTCLabelConverter, test_loader, 
     reference, float tensors [B,1,H,W] already normalised. Returns [[text, confidence], ...]."""
     if str(device) == "cpu":
         raise _lib.OcrfaError("ocrfa_b200 has no CPU path; use device='cuda'")
-    dev = torch.device(device if str(device) != "cuda" else f"cuda:{torch.cuda.current_device()}")
+    dev = _lib.resolve_device(device)
     mask_np = _ignore_mask(len(converter.character), ignore_idx)
     result = []
     lib = _lib.load()

@@ -248,8 +248,9 @@ static float split_pair(float v, __half* hi, __half* lo) {
 }
 
 // activations: [pix][hi(c) | lo(c)]; eff gets hi + lo
+static bool g_split_positive = false;  // --positive: activations in [0, 1) like post-ReLU maps (exposes accumulate bias)
 static void make_split_act(size_t npix, int c, int c_real, float scale, std::vector<__half>& packed, std::vector<float>& eff) {
-  std::uniform_real_distribution<float> d(-1.f, 1.f);
+  std::uniform_real_distribution<float> d(g_split_positive ? 0.f : -1.f, 1.f);
   packed.assign(npix * 2 * c, __float2half(0.f));
   eff.assign(npix * c, 0.f);
   for (size_t px = 0; px < npix; ++px)
@@ -337,10 +338,11 @@ static void run_split_case(const Case& c) {
       for (int co = 0; co < g.cout; ++co)
         got[px * g.cout + co] = __half2float(tmp[px * 2 * g.cout + co]) + __half2float(tmp[px * 2 * g.cout + g.cout + co]);
   }
-  double max_abs = 0, max_ref = 0;
+  double max_abs = 0, max_ref = 0, sum_d = 0, sum_d2 = 0, sum_r2 = 0;
   size_t bad = 0;
   for (size_t i = 0; i < out_elems; ++i) {
     const float d = std::fabs(got[i] - ref[i]);
+    sum_d += (double)got[i] - ref[i]; sum_d2 += ((double)got[i] - ref[i]) * ((double)got[i] - ref[i]); sum_r2 += (double)ref[i] * ref[i];
     if (!(d <= 2e-5f + 2e-5f * std::fabs(ref[i]))) {
       if (bad < 4) printf("    bad pix=%zu co=%zu got=%.8f ref=%.8f\n", i / g.cout, i % g.cout, got[i], ref[i]);
       bad++;
@@ -351,6 +353,13 @@ static void run_split_case(const Case& c) {
   printf("[split %s] n=%d in=%dx%d cin=%d cout=%d k=%dx%d sh=%d bn=%d : max_abs_err=%.3g (max|ref|=%.3g) bad=%zu/%zu %s\n",
          c.name, g.n, g.h_in, g.w_in, g.cin, g.cout, g.kh, g.kw, g.sh, p.block_n, max_abs, max_ref, bad, out_elems,
          bad ? "FAIL" : "ok");
+  {
+    // error against the float64 sum of the SAME operand values, relative to rms(ref): an fp32 round-to-nearest
+    // accumulation of K terms would sit near 2^-24 * sqrt(K) / sqrt(3) rms with zero mean
+    const double rr = std::sqrt(sum_r2 / out_elems);
+    printf("    rel. error vs f64: rms %.3g  mean %+.3g  (pair=%d stages=%d)\n", std::sqrt(sum_d2 / out_elems) / rr,
+           sum_d / out_elems / rr, p.pair, p.num_stages);
+  }
   if (bad) g_fail++;
   if (c.perf_iters > 0 && !bad) {
     cudaEvent_t e0, e1;
@@ -714,11 +723,14 @@ static void run_halo_suite(bool perf) {
 int main(int argc, char** argv) {
   bool perf = false;
   bool halo_only = false;
+  bool split_only = false;  // --split: only the fp32-grade (f16x3) conv / GEMM cases (+ --perf: the c2 layer shapes)
   const char* only = nullptr;  // --only NAME: run one perf case (or "lstm") alone, e.g. under ncu
   for (int i = 1; i < argc; ++i) {
     if (!strcmp(argv[i], "--perf")) perf = true;
     if (!strcmp(argv[i], "--only") && i + 1 < argc) only = argv[++i];
     if (!strcmp(argv[i], "--halo")) halo_only = true;
+    if (!strcmp(argv[i], "--split")) split_only = true;
+    if (!strcmp(argv[i], "--positive")) g_split_positive = true;
   }
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, 0));
@@ -762,6 +774,28 @@ int main(int argc, char** argv) {
       {"c2x2_s2_h8",   {3, 8, 513, 512, 512, 2, 2, 2, 0, 1},  1, 1, 0, 0, 0, 0, 0, 0, 0},
       {"c1x1_ds",      {3, 8, 128, 128, 256, 1, 1, 1, 0, 0},  0, 1, 0, 0, 0, 0, 0, 0, 0},
   };
+  if (split_only) {
+    for (const Case& c : cases) run_split_case(c);
+    if (perf && g_fail == 0) {
+      std::vector<Case> pc = {
+          {"perf_c0_2",    {256, 32, 512, 64, 64, 3, 3, 1, 1, 1},    1, 1, 0, 0, 0, 0, 0, 0, 5},
+          {"perf_l1_c1",   {256, 16, 256, 64, 128, 3, 3, 1, 1, 1},   1, 1, 0, 0, 0, 0, 0, 0, 10},
+          {"perf_l1_c128", {256, 16, 256, 128, 128, 3, 3, 1, 1, 1},  1, 1, 1, 0, 0, 0, 0, 0, 10},
+          {"perf_l2_c1",   {256, 8, 128, 128, 256, 3, 3, 1, 1, 1},   1, 1, 0, 0, 0, 0, 0, 0, 10},
+          {"perf_l2_c256", {256, 8, 128, 256, 256, 3, 3, 1, 1, 1},   1, 1, 1, 0, 0, 0, 0, 0, 10},
+          {"perf_l3_c1",   {256, 4, 129, 256, 512, 3, 3, 1, 1, 1},   1, 1, 0, 0, 0, 0, 0, 0, 10},
+          {"perf_l3_c2_ds",{256, 4, 129, 512, 512, 3, 3, 1, 1, 1},   1, 1, 0, 0, 256, 0, 0, 0, 10},
+          {"perf_l3_c512", {256, 4, 129, 512, 512, 3, 3, 1, 1, 1},   1, 1, 1, 0, 0, 0, 0, 0, 10},
+          {"perf_c4_1",    {256, 4, 129, 512, 512, 2, 2, 2, 0, 1},   1, 1, 0, 0, 0, 0, 0, 0, 10},
+          {"perf_xproj",   {1, 1, 33024, 512, 4096, 1, 1, 1, 0, 0},  0, 1, 0, 1, 0, 0, 0, 0, 10},
+          {"perf_linear",  {1, 1, 33024, 1024, 512, 1, 1, 1, 0, 0},  0, 1, 0, 0, 0, 0, 0, 0, 10},
+          {"perf_pred",    {1, 1, 33024, 512, 185, 1, 1, 1, 0, 0},   0, 1, 0, 1, 0, 0, 0, 0, 10},
+      };
+      for (const Case& c : pc) run_split_case(c);
+    }
+    printf("%s (%d failing cases)\n", g_fail ? "FAILED" : "ALL OK", g_fail);
+    return g_fail ? 1 : 0;
+  }
   for (const Case& c : cases) run_case(c);
   run_halo_suite(false);
   for (const Case& c : cases) run_split_case(c);
