@@ -253,6 +253,32 @@ int ocrfa_recognize_device(ocrfa_handle* h, const uint8_t* d_img, const int32_t*
                            int32_t* d_labels, int32_t* d_len, double* d_conf, void* d_ws, size_t ws_bytes,
                            void* stream);
 
+/* Extended forms. d_margin / h_margin [B] float32 (may be NULL) receive the DECISION MARGIN of every line's greedy
+ * decode (see ocrfa_ctc_margin). flags: OCRFA_FLAG_ASYNC = return without synchronising `stream` - the D2H copies are
+ * still in flight; the caller waits on the stream (or an event) before reading the host buffers, which should be pinned,
+ * and leaves them and the workspace untouched until then. Two calls on two streams with two workspaces overlap the
+ * H2D / D2H copies of one batch with the kernels of the other (what DataLoader(pin_memory=True) + .to(device) is for in
+ * the reference, utils.py:728-730, :621). */
+#define OCRFA_FLAG_ASYNC 1u
+int ocrfa_recognize_host_ex(ocrfa_handle* h, const uint8_t* h_img, const int32_t* h_widths, int32_t B, int32_t H,
+                            int32_t W, const uint8_t* h_ignore_mask, int32_t decoder, int32_t beam_width,
+                            int32_t* h_labels, int32_t* h_len, double* h_conf, float* h_margin, uint32_t flags,
+                            void* d_ws, size_t ws_bytes, void* stream);
+int ocrfa_recognize_device_ex(ocrfa_handle* h, const uint8_t* d_img, const int32_t* d_widths, int32_t B, int32_t H,
+                              int32_t W, const uint8_t* d_ignore_mask, int32_t decoder, int32_t beam_width,
+                              int32_t* d_labels, int32_t* d_len, double* d_conf, float* d_margin, void* d_ws,
+                              size_t ws_bytes, void* stream);
+
+/* Decision margin of the greedy decode (recognizer_predict's preds_prob.max(2), src/ocrfa/utils.py:628-638):
+ *   d_margin[b] = min over timesteps of (largest - second largest logit among the classes with d_ignore_mask[c] == 0)
+ *                 / rms of those logits in the row.
+ * softmax and the renormalisation are monotone, so this is the argmax the reference takes on probabilities. A line
+ * whose margin exceeds twice the relative arithmetic error of the logits decodes to the same greedy string under any
+ * evaluation within that error, the reference's own fp32 run included; smaller margins are near-ties that the
+ * reference itself resolves differently when its batch size changes (profiles/r02_ref_self_consistency.json). */
+int ocrfa_ctc_margin(const float* d_logits, int32_t B, int32_t T, int32_t C, const uint8_t* d_ignore_mask,
+                     float* d_margin, void* stream);
+
 /* Scratch bytes ocrfa_recognize_host needs (forward workspace + staging + decode scratch). */
 size_t ocrfa_recognize_workspace_bytes(const ocrfa_handle* h, int32_t B, int32_t H, int32_t W, int32_t beam_width);
 

@@ -15,6 +15,7 @@ PRECISION_FP32 = 0
 PRECISION_BF16 = 1
 PRECISION_F16X3 = 2
 PRECISION_F16 = 3
+FLAG_ASYNC = 1
 PRECISIONS = {"fp32": PRECISION_FP32, "bf16": PRECISION_BF16, "f16x3": PRECISION_F16X3, "f16": PRECISION_F16}
 
 # every symbol include/ocrfa_b200.h declares (tests/test_cabi_symbols.py checks the header against this list)
@@ -25,7 +26,7 @@ SYMBOLS = (
     "ocrfa_det_preprocess_u8", "ocrfa_bgr2gray_u8", "ocrfa_det_workspace_bytes", "ocrfa_det_components",
     "ocrfa_forward", "ocrfa_forward_features", "ocrfa_forward_sequence", "ocrfa_forward_u8", "ocrfa_ctc_greedy", "ocrfa_ctc_collapse", "ocrfa_argmax_rows",
     "ocrfa_beam_workspace_bytes", "ocrfa_ctc_beam", "ocrfa_ctc_beam_spans", "ocrfa_recognize_host",
-    "ocrfa_recognize_device", "ocrfa_recognize_workspace_bytes", "ocrfa_profile_begin", "ocrfa_profile_end",
+    "ocrfa_recognize_device", "ocrfa_recognize_host_ex", "ocrfa_recognize_device_ex", "ocrfa_ctc_margin", "ocrfa_recognize_workspace_bytes", "ocrfa_profile_begin", "ocrfa_profile_end",
     "ocrfa_launch_count",
 )
 
@@ -78,6 +79,9 @@ def load():
     lib.ocrfa_ctc_beam_spans.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, sz, vp]
     lib.ocrfa_recognize_host.argtypes = [vp, vp, vp, i32, i32, i32, vp, i32, i32, vp, vp, vp, vp, sz, vp]
     lib.ocrfa_recognize_device.argtypes = [vp, vp, vp, i32, i32, i32, vp, i32, i32, vp, vp, vp, vp, sz, vp]
+    lib.ocrfa_recognize_host_ex.argtypes = [vp, vp, vp, i32, i32, i32, vp, i32, i32, vp, vp, vp, vp, C.c_uint32, vp, sz, vp]
+    lib.ocrfa_recognize_device_ex.argtypes = [vp, vp, vp, i32, i32, i32, vp, i32, i32, vp, vp, vp, vp, vp, sz, vp]
+    lib.ocrfa_ctc_margin.argtypes = [vp, i32, i32, i32, vp, vp, vp]
     lib.ocrfa_profile_begin.argtypes = [vp, C.c_uint32]
     lib.ocrfa_profile_end.argtypes = [vp, vp, vp, vp]
     lib.ocrfa_recognize_workspace_bytes.argtypes = [vp, i32, i32, i32, i32]

@@ -141,6 +141,56 @@ __global__ void __launch_bounds__(kGreedyThreads) ctc_greedy_kernel(const Greedy
 }
 
 // ---------------------------------------------------------------------------------------------
+// decision margin of the greedy decode: for every line, the smallest distance between the winning class and the
+// runner-up over all timesteps, measured on the LOGITS of the classes that are not masked (utils.py:630: masked
+// classes get probability 0 and can never win) and normalised by the rms of those logits in the row:
+//     margin[b] = min_t (l_(1) - l_(2)) / rms_c(l)
+// softmax / renormalisation are monotone, so argmax_c p = argmax_c l over the unmasked classes; a line whose margin
+// exceeds twice the arithmetic error of the logits (relative to their rms) decodes to the same greedy string under
+// ANY evaluation within that error - the reference's own fp32 result included. One warp per timestep, 8 per CTA.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ctc_margin_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ ignore,
+                                                         float* __restrict__ margin_out, int T, int C) {
+  __shared__ float s_min[8];
+  const int b = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* lg = logits + (size_t)b * T * C;
+  float line_min = INFINITY;
+  for (int t = warp; t < T; t += 8) {
+    const float* row = lg + (size_t)t * C;
+    float m1 = -INFINITY, m2 = -INFINITY, sq = 0.f;
+    int cnt = 0;
+    for (int c = lane; c < C; c += 32) {
+      if (ignore && ignore[c]) continue;
+      const float v = __ldg(row + c);
+      if (v > m1) { m2 = m1; m1 = v; } else if (v > m2) m2 = v;
+      sq = fmaf(v, v, sq);
+      ++cnt;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float o1 = __shfl_xor_sync(0xffffffffu, m1, o), o2 = __shfl_xor_sync(0xffffffffu, m2, o);
+      // merge two (max, second) pairs: equal maxima in different lanes are two classes at the same logit -> margin 0
+      const float hi = fmaxf(m1, o1), lo = fminf(m1, o1);
+      m2 = fmaxf(lo, fmaxf(m2, o2));
+      m1 = hi;
+      sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    const float rms = sqrtf(sq / (float)(cnt > 0 ? cnt : 1));
+    const float m = cnt >= 2 ? (m1 - m2) / fmaxf(rms, 1e-30f) : INFINITY;
+    line_min = fminf(line_min, m);
+  }
+  if (lane == 0) s_min[warp] = line_min;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = s_min[0];
+    for (int i = 1; i < 8; ++i) m = fminf(m, s_min[i]);
+    margin_out[b] = m;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // prefix beam search (ctcBeamSearch, /root/reference/src/ocrfa/utils.py:949-1038): one warp per line, sequential
 // over T. Labelings are never materialised inside the time loop: every step records, per surviving beam, a
 // back-pointer (parent rank, edit op, class) in a trellis; the best labeling is rebuilt once at the end.

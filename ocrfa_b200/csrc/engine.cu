@@ -103,10 +103,10 @@ struct Profiler {
 
 // One captured recognize step (all kernels of forward + decode) keyed by every pointer and size it bakes in.
 struct GraphKey {
-  const void *img, *widths, *mask; void *labels, *len, *conf, *ws;
+  const void *img, *widths, *mask; void *labels, *len, *conf, *margin, *ws;
   size_t ws_bytes; int B, H, W, decoder, bw;
   bool operator==(const GraphKey& o) const {
-    return img == o.img && widths == o.widths && mask == o.mask && labels == o.labels && len == o.len && conf == o.conf &&
+    return img == o.img && widths == o.widths && mask == o.mask && labels == o.labels && len == o.len && conf == o.conf && margin == o.margin &&
            ws == o.ws && ws_bytes == o.ws_bytes && B == o.B && H == o.H && W == o.W && decoder == o.decoder && bw == o.bw;
   }
 };
@@ -830,7 +830,7 @@ size_t beam_ws_bytes(int B, int T, int C, int bw) {
 }
 
 struct RecLayout {
-  size_t fwd, img, widths, mask, logits, probs, labels, len, conf, beam, total;
+  size_t fwd, img, widths, mask, logits, probs, labels, len, conf, margin, beam, total;
 };
 
 RecLayout rec_layout(const ocrfa_handle* h, int B, int H, int W, int bw) {
@@ -846,6 +846,7 @@ RecLayout rec_layout(const ocrfa_handle* h, int B, int H, int W, int bw) {
   R.labels = off; off += align_up((size_t)B * T * 4, 1024);
   R.len = off; off += align_up((size_t)B * 4, 1024);
   R.conf = off; off += align_up((size_t)B * 8, 1024);
+  R.margin = off; off += align_up((size_t)B * 4, 1024);
   R.beam = off; off += align_up(beam_ws_bytes(B, T, C, bw > 0 ? bw : 1), 1024);
   R.total = off;
   return R;
@@ -857,7 +858,7 @@ namespace {
 // forward + decode on device buffers, asynchronous on `st` (labels/len/conf stay on the device)
 int recognize_device_impl(ocrfa_handle* h, const uint8_t* d_img, const int32_t* d_widths, int B, int H, int W,
                           const uint8_t* d_ignore_mask, int decoder, int beam_width, int32_t* d_labels, int32_t* d_len,
-                          double* d_conf, void* d_ws, size_t ws_bytes, cudaStream_t st);
+                          double* d_conf, float* d_margin, void* d_ws, size_t ws_bytes, cudaStream_t st);
 }  // namespace
 
 // ==============================================================================================================
@@ -1210,6 +1211,14 @@ int ocrfa_ctc_greedy(const float* d_logits, int32_t B, int32_t T, int32_t C, con
   return 0;
 }
 
+int ocrfa_ctc_margin(const float* d_logits, int32_t B, int32_t T, int32_t C, const uint8_t* d_ignore_mask, float* d_margin,
+                     void* stream) {
+  if (!d_logits || !d_margin || B <= 0 || T <= 0 || C < 2) return fail(OCRFA_ERR_ARG, "bad argument");
+  ctc_margin_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(d_logits, d_ignore_mask, d_margin, T, C);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 size_t ocrfa_beam_workspace_bytes(int32_t B, int32_t T, int32_t C, int32_t beam_width) {
   if (B <= 0 || T <= 0 || C <= 0 || beam_width <= 0) return 0;
   return beam_ws_bytes(B, T, C, beam_width);
@@ -1285,7 +1294,7 @@ namespace {
 constexpr int kMaxGraphFailures = 3;  // a transient capture / instantiate failure does not switch graphs off for good
 int recognize_device_body(ocrfa_handle* h, const uint8_t* d_img, const int32_t* d_widths, int B, int H, int W,
                           const uint8_t* d_ignore_mask, int decoder, int beam_width, int32_t* d_labels, int32_t* d_len,
-                          double* d_conf, void* d_ws, size_t ws_bytes, cudaStream_t st) {
+                          double* d_conf, float* d_margin, void* d_ws, size_t ws_bytes, cudaStream_t st) {
   if (!h || !d_img || !d_labels || !d_len || !d_conf || !d_ws) return fail(OCRFA_ERR_ARG, "null pointer");
   if (decoder != 0 && decoder != 1) return fail(OCRFA_ERR_ARG, "decoder must be 0 (greedy) or 1 (beamsearch)");
   const int T = ocrfa_out_timesteps(H, W);
@@ -1304,6 +1313,11 @@ int recognize_device_body(ocrfa_handle* h, const uint8_t* d_img, const int32_t* 
                           d_labels, d_len, d_conf, st);
     if (rc) return rc;
   }
+  if (d_margin) {
+    LaunchScope ls(h, kClsDecode, 0.0, st);
+    rc = ocrfa_ctc_margin(d_logits, B, T, C, d_ignore_mask, d_margin, st);
+    if (rc) return rc;
+  }
   if (decoder == 1) {
     LaunchScope ls(h, kClsBeam, 0.0, st);
     rc = ocrfa_ctc_beam(d_probs, B, T, C, beam_width, nullptr, d_labels, d_len, ws + R.beam, R.total - R.beam, st);
@@ -1316,7 +1330,7 @@ int recognize_device_body(ocrfa_handle* h, const uint8_t* d_img, const int32_t* 
 // encodes, parameter marshalling) and most inter-kernel launch gaps. Captured lazily per (shape, pointers) key.
 int recognize_device_impl(ocrfa_handle* h, const uint8_t* d_img, const int32_t* d_widths, int B, int H, int W,
                           const uint8_t* d_ignore_mask, int decoder, int beam_width, int32_t* d_labels, int32_t* d_len,
-                          double* d_conf, void* d_ws, size_t ws_bytes, cudaStream_t st) {
+                          double* d_conf, float* d_margin, void* d_ws, size_t ws_bytes, cudaStream_t st) {
   if (!h) return fail(OCRFA_ERR_ARG, "null handle");
   // Stream capture is illegal on the legacy default stream (and on cudaStreamPerThread's implicit siblings): such callers
   // run eagerly, WITHOUT switching graphs off for later calls on a capturable stream. Callers that want graph replay
@@ -1324,8 +1338,8 @@ int recognize_device_impl(ocrfa_handle* h, const uint8_t* d_img, const int32_t* 
   const bool capturable = st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread;
   if (!h->graphs_enabled || !capturable || h->prof.mask != 0 || !h->tc())
     return recognize_device_body(h, d_img, d_widths, B, H, W, d_ignore_mask, decoder, beam_width, d_labels, d_len, d_conf,
-                                 d_ws, ws_bytes, st);
-  const GraphKey key{d_img, d_widths, d_ignore_mask, d_labels, d_len, d_conf, d_ws, ws_bytes, B, H, W, decoder, beam_width};
+                                 d_margin, d_ws, ws_bytes, st);
+  const GraphKey key{d_img, d_widths, d_ignore_mask, d_labels, d_len, d_conf, d_margin, d_ws, ws_bytes, B, H, W, decoder, beam_width};
   for (GraphEntry& e : h->graphs)
     if (e.key == key) {
       e.last_use = ++h->graph_tick;
@@ -1338,7 +1352,7 @@ int recognize_device_impl(ocrfa_handle* h, const uint8_t* d_img, const int32_t* 
   // entry points) happens outside the capture; the captured replay below then recomputes the same outputs
   {
     int rc0 = recognize_device_body(h, d_img, d_widths, B, H, W, d_ignore_mask, decoder, beam_width, d_labels, d_len, d_conf,
-                                    d_ws, ws_bytes, st);
+                                    d_margin, d_ws, ws_bytes, st);
     if (rc0) return rc0;
   }
   const int64_t l0 = h->launches;
@@ -1350,7 +1364,7 @@ int recognize_device_impl(ocrfa_handle* h, const uint8_t* d_img, const int32_t* 
     return 0;  // the eager run above already produced this call's outputs
   }
   const int rc = recognize_device_body(h, d_img, d_widths, B, H, W, d_ignore_mask, decoder, beam_width, d_labels, d_len,
-                                       d_conf, d_ws, ws_bytes, st);
+                                       d_conf, d_margin, d_ws, ws_bytes, st);
   cudaGraph_t graph = nullptr;
   const cudaError_t ce = cudaStreamEndCapture(st, &graph);
   cudaGraphExec_t exec = nullptr;
@@ -1362,7 +1376,7 @@ int recognize_device_impl(ocrfa_handle* h, const uint8_t* d_img, const int32_t* 
     for (int i = 0; i < kNumClasses; ++i) h->prof.launches[i] = c0[i];
     if (rc != 0) return rc;
     return recognize_device_body(h, d_img, d_widths, B, H, W, d_ignore_mask, decoder, beam_width, d_labels, d_len, d_conf,
-                                 d_ws, ws_bytes, st);
+                                 d_margin, d_ws, ws_bytes, st);
   }
   cudaGraphDestroy(graph);
   GraphEntry e;
@@ -1388,7 +1402,14 @@ int ocrfa_recognize_device(ocrfa_handle* h, const uint8_t* d_img, const int32_t*
                            const uint8_t* d_ignore_mask, int32_t decoder, int32_t beam_width, int32_t* d_labels,
                            int32_t* d_len, double* d_conf, void* d_ws, size_t ws_bytes, void* stream) {
   return recognize_device_impl(h, d_img, d_widths, B, H, W, d_ignore_mask, decoder, beam_width, d_labels, d_len, d_conf,
-                               d_ws, ws_bytes, (cudaStream_t)stream);
+                               nullptr, d_ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int ocrfa_recognize_device_ex(ocrfa_handle* h, const uint8_t* d_img, const int32_t* d_widths, int32_t B, int32_t H, int32_t W,
+                              const uint8_t* d_ignore_mask, int32_t decoder, int32_t beam_width, int32_t* d_labels,
+                              int32_t* d_len, double* d_conf, float* d_margin, void* d_ws, size_t ws_bytes, void* stream) {
+  return recognize_device_impl(h, d_img, d_widths, B, H, W, d_ignore_mask, decoder, beam_width, d_labels, d_len, d_conf,
+                               d_margin, d_ws, ws_bytes, (cudaStream_t)stream);
 }
 
 // ---- CUDA-event profile of selected kernel classes (bench.py) -----------------------------------------------
@@ -1425,6 +1446,14 @@ size_t ocrfa_recognize_workspace_bytes(const ocrfa_handle* h, int32_t B, int32_t
 int ocrfa_recognize_host(ocrfa_handle* h, const uint8_t* h_img, const int32_t* h_widths, int32_t B, int32_t H, int32_t W,
                          const uint8_t* h_ignore_mask, int32_t decoder, int32_t beam_width, int32_t* h_labels,
                          int32_t* h_len, double* h_conf, void* d_ws, size_t ws_bytes, void* stream) {
+  return ocrfa_recognize_host_ex(h, h_img, h_widths, B, H, W, h_ignore_mask, decoder, beam_width, h_labels, h_len, h_conf,
+                                 nullptr, 0u, d_ws, ws_bytes, stream);
+}
+
+int ocrfa_recognize_host_ex(ocrfa_handle* h, const uint8_t* h_img, const int32_t* h_widths, int32_t B, int32_t H, int32_t W,
+                            const uint8_t* h_ignore_mask, int32_t decoder, int32_t beam_width, int32_t* h_labels,
+                            int32_t* h_len, double* h_conf, float* h_margin, uint32_t flags, void* d_ws, size_t ws_bytes,
+                            void* stream) {
   if (!h || !h_img || !h_labels || !h_len || !h_conf || !d_ws) return fail(OCRFA_ERR_ARG, "null pointer");
   if (decoder != 0 && decoder != 1) return fail(OCRFA_ERR_ARG, "decoder must be 0 (greedy) or 1 (beamsearch)");
   const int T = ocrfa_out_timesteps(H, W);
@@ -1442,16 +1471,20 @@ int ocrfa_recognize_host(ocrfa_handle* h, const uint8_t* h_img, const int32_t* h
   int32_t* d_labels = (int32_t*)(ws + R.labels);
   int32_t* d_len = (int32_t*)(ws + R.len);
   double* d_conf = (double*)(ws + R.conf);
+  float* d_margin = h_margin ? (float*)(ws + R.margin) : nullptr;
   CUDA_TRY(cudaMemcpyAsync(d_img, h_img, (size_t)B * H * W, cudaMemcpyHostToDevice, st));
   if (h_widths) CUDA_TRY(cudaMemcpyAsync(d_w, h_widths, (size_t)B * 4, cudaMemcpyHostToDevice, st));
   if (h_ignore_mask) CUDA_TRY(cudaMemcpyAsync(d_mask, h_ignore_mask, (size_t)C, cudaMemcpyHostToDevice, st));
   int rc = recognize_device_impl(h, d_img, h_widths ? d_w : nullptr, B, H, W, h_ignore_mask ? d_mask : nullptr, decoder,
-                                 beam_width, d_labels, d_len, d_conf, d_ws, ws_bytes, st);
+                                 beam_width, d_labels, d_len, d_conf, d_margin, d_ws, ws_bytes, st);
   if (rc) return rc;
   CUDA_TRY(cudaMemcpyAsync(h_labels, d_labels, (size_t)B * T * 4, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaMemcpyAsync(h_len, d_len, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaMemcpyAsync(h_conf, d_conf, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaStreamSynchronize(st));
+  if (h_margin) CUDA_TRY(cudaMemcpyAsync(h_margin, d_margin, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+  // OCRFA_FLAG_ASYNC: return with the copies still in flight on `stream`; the caller owns the wait (and keeps the
+  // host buffers - which should be pinned - and the workspace untouched until then)
+  if (!(flags & OCRFA_FLAG_ASYNC)) CUDA_TRY(cudaStreamSynchronize(st));
   return 0;
 }
 

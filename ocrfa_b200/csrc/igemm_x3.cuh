@@ -3,34 +3,45 @@
 //   reference arithmetic being matched: fp32 convs and GEMMs of
 //     /root/reference/src/ocrfa/modules/blocks.py:200-223, 239-322 (ResNet), :89-101 (BiLSTM GEMMs), :438 (Prediction)
 //
-// Every operand is an fp16 pair x = hi + lo (22 significant bits; activations NHWC [hi(C) | lo(C)] per pixel, weights
-// [Cout][tap][hi(C) | lo(C)] pre-scaled by a power of two) and every algorithmic MAC costs three tensor-core
-// products: hi.hi + lo.hi + hi.lo (the dropped lo.lo term is ~2^-22 relative).
+// Every operand is an fp16 pair x = hi + lo (22 significant bits + the sign of lo; activations NHWC [hi(C) | lo(C)]
+// per pixel, weights [Cout][tap][hi(C) | lo(C)] pre-scaled by a power of two) and every algorithmic MAC costs three
+// tensor-core products: hi.hi + lo.hi + hi.lo (the dropped lo.lo term is ~2^-22 relative).
 //
-// Design (what differs from igemm_tc_kernel<kModeSplit>, which this kernel replaces):
+// Design:
 //   * CTA pair (cta_group::2, M = 256 over the two SMs of a TPC): each CTA stages its own 128 pixel rows and HALF of
 //     the weight tile, so the weight bytes per SM halve.
-//   * ONE shared-memory stage per K chunk holds all four operand tiles {A_hi, A_lo, W_hi, W_lo} and feeds twelve
-//     MMAs (three products x K = 64): 64 KB per 12 MMAs instead of 48 KB per 4 - the operands are fetched once,
-//     not once per product (L2 -> SM bytes per MMA fall 2.25x).
-//   * The tensor core's fp32 accumulate truncates (error linear in the number of chained MMAs), so
-//       - the hi.hi products of ONE K chunk (four MMAs, K = 64) go to a fresh TMEM accumulator ("main") that the
-//         eight epilogue warps drain into fp32 REGISTER accumulators with round-to-nearest adds, chunk after chunk;
+//   * ONE shared-memory stage per K chunk of 64 holds all four operand tiles {A_hi, A_lo, W_hi, W_lo} and feeds the
+//     three products: 64 KB per 12 K=16 steps instead of 48 KB per 4 - the operands are fetched once, not once per
+//     product (L2 -> SM bytes per MMA fall 2.25x against a kernel that streams one product at a time).
+//   * The tensor core's fp32 accumulate truncates; measured on B200 (tools/test_igemm.cu --split --positive, relu'd
+//     outputs, error against the float64 sum of the same operands, relative to rms): mean -0.8e-8 - 0.56e-8 per chained
+//     MMA, i.e. -5.2e-8 for chains of 8, -3.1e-8 for 4, -1.9e-8 for 2 - a BIAS, which adds up linearly over the 29
+//     layers. So
+//       - the hi.hi products of ONE K chunk (four chained MMAs, K = 64) go to a fresh TMEM accumulator ("main") that
+//         the eight epilogue warps drain into fp32 REGISTER accumulators with round-to-nearest adds, chunk after chunk;
 //       - the lo.hi / hi.lo products (2^-11 of the result) chain in a second TMEM accumulator ("corr") for the
-//         whole tile - their truncation error is 2^-11 of an already negligible term - and are added once at the end.
-//     The MMA issuer orders a stage as corr, corr, main: while the epilogue drains chunk k from "main", the tensor
-//     pipe is busy with the eight corr MMAs of chunk k+1, so the drain (4 TMEM loads + 128 FADDs per thread) is
-//     hidden and a single "main" buffer suffices (TMEM: 256 + 256 columns).
-// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (leader CTA) + TMEM alloc, warps 2..9 = epilogue.
+//         whole tile - their truncation error is 2^-11 of an already small term - and are added once at the end.
+//     The MMA issuer orders a stage as corr (8 MMAs), then main: while the epilogue drains chunk k from "main", the
+//     tensor pipe is busy with the corr MMAs of chunk k+1, so the drain is hidden behind tensor work:
+//       - 256-column tiles (TMEM: main 256 + corr 256 columns): the hi.hi product is issued as two N = 128 halves
+//         with their own barriers; the warps of column half h drain half h. A half is needed again only after the
+//         other half's MMAs and the next corr MMAs (1280 tensor-pipe cycles).
+//       - tiles of <= 128 columns: TWO main buffers (columns 0 and 128) used alternately by successive chunks (the
+//         small-Cout layers have short stages; the drain of chunk k also overlaps the hi.hi MMAs of chunk k+1).
+// Warp roles (12 warps, three warpgroups): warpgroup 0 = TMA producer (warp 0), MMA issuer + TMEM alloc (warp 1, leader
+// CTA) and two idle warps, trimmed to 56 registers with setmaxnreg; warpgroups 1-2 = eight epilogue warps raised to 224
+// registers, so the 128 fp32 accumulators + 64 values in flight from TMEM live in registers (at the 168 registers a
+// flat 320-thread launch gets, ptxas kept 16 accumulators in local memory and re-read / re-wrote them every chunk).
+// The register adds are packed (add.rn.f32x2: two fp32 lanes per instruction).
 #pragma once
 #include <cstdlib>
 #include "igemm_tc.cuh"
 
 namespace ocrfa {
 
-constexpr int kX3Threads = 320;
+constexpr int kX3Threads = 384;
+constexpr int kX3FirstEpiWarp = 4;
 constexpr int kX3CorrCol = 256;  // TMEM column of the corr accumulator (main starts at column 0)
-constexpr int kX3DefaultSub = 1;
 
 inline size_t igemm_x3_smem_bytes(int block_n, int* stages_out) {
   const size_t stage = 2 * static_cast<size_t>(kTcBlockM) * kTcBlockK * 2 + 2 * static_cast<size_t>(block_n / 2) * kTcBlockK * 2;
@@ -42,9 +53,6 @@ inline size_t igemm_x3_smem_bytes(int block_n, int* stages_out) {
   return header + stages * stage;
 }
 
-// SUB = "main" chunks per K chunk of 64 (1, 2 or 4): the hi.hi products of one stage are split into SUB fresh
-// accumulations of 4 / SUB chained MMAs each, interleaved with 8 / SUB corr MMAs that cover the drain.
-template <int SUB>
 __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_constant__ IgemmTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -52,9 +60,9 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
 
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);  // [kTcMaxStages]
   uint64_t* empty_bar = full_bar + kTcMaxStages;           // [kTcMaxStages]
-  uint64_t* main_full = empty_bar + kTcMaxStages;          // hi.hi chunk complete (both CTAs, multicast commit)
-  uint64_t* main_empty = main_full + 1;                    // chunk drained by the 16 epilogue warps of the pair (leader's copy)
-  uint64_t* corr_full = main_empty + 1;                    // every MMA of the tile complete
+  uint64_t* main_full = empty_bar + kTcMaxStages;          // [2] hi.hi chunk (or chunk half) complete (both CTAs, multicast commit)
+  uint64_t* main_empty = main_full + 2;                    // [2] drained by the epilogue warps of the pair (leader's copy)
+  uint64_t* corr_full = main_empty + 2;                    // every MMA of the tile complete
   uint64_t* corr_empty = corr_full + 1;                    // corr read back by the 16 epilogue warps (leader's copy)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(corr_empty + 1);
   int4* kb_table = reinterpret_cast<int4*>(smem + 256);    // [total_kb][2]: {a_c, dw, dr, dh}, {src, b_k, a_lo, b_lo}
@@ -70,6 +78,11 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
   const uint32_t a_bytes = kTcBlockM * kTcBlockK * 2;
   const uint32_t b_bytes = static_cast<uint32_t>(b_rows) * kTcBlockK * 2;
   const uint32_t stage_bytes = 2u * a_bytes + 2u * b_bytes;
+  // wide: a 256-column tile whose hi.hi product is issued as two N = 128 halves (buffer h = columns {h*64 + 0..63,
+  // 128 + h*64 + 0..63} of the tile: an N = 128 pair MMA takes 64 weight rows from each CTA); otherwise two whole-tile
+  // buffers used alternately
+  const bool wide = block_n == 256;
+  const bool alt = block_n <= 128;  // two alternating whole-tile buffers (a 192-column tile has room for one)
 
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
   const int total_tiles = ((m_tiles + 1) >> 1) * p.n_tiles;
@@ -83,8 +96,8 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
       mbar_init(&full_bar[s], 2);  // the leader's expect_tx arrive + the peer's remote arrive
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(main_full, 1);
-    mbar_init(main_empty, 16);
+    // wide: a buffer half is drained by the 4 warps of that column half in each CTA; else by all 8 warps of each CTA
+    for (int b = 0; b < 2; ++b) { mbar_init(&main_full[b], 1); mbar_init(&main_empty[b], wide ? 8 : 16); }
     mbar_init(corr_full, 1);
     mbar_init(corr_empty, 16);
     fence_mbar_init();
@@ -113,6 +126,8 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  if (warp < kX3FirstEpiWarp) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 0) {
     // ===================================== TMA producer (both CTAs) =========================
     if (elect_one()) {
@@ -147,10 +162,12 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
     // ===================================== MMA issuer (leader CTA only) =====================
     if (leader && elect_one()) {
       const uint32_t idesc = make_idesc_f16(2 * kTcBlockM, static_cast<uint32_t>(block_n));
+      const uint32_t idesc_half = make_idesc_f16(2 * kTcBlockM, 128u);
       const uint32_t d_main = tmem_base;
       const uint32_t d_corr = tmem_base + static_cast<uint32_t>(kX3CorrCol);
       int stage = 0;
-      uint32_t phase = 0, mph = 0, cph = 0;
+      uint32_t phase = 0, cph = 0, mph[2] = {0u, 0u};
+      int mb = 0;
       for (int tile = worker; tile < total_tiles; tile += num_workers) {
         mbar_wait(corr_empty, cph ^ 1u, 2);  // the previous tile's corr has been read back
         cph ^= 1u;
@@ -163,40 +180,61 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
           const uint64_t b_hi = make_sw128_kmajor_desc(sa + 2u * a_bytes);
           const uint64_t b_lo = make_sw128_kmajor_desc(sa + 2u * a_bytes + b_bytes);
 #pragma unroll
-          for (int sc = 0; sc < SUB; ++sc) {
-            // corr MMAs j = 0..7 of this stage are lo.hi (k = j) for j < 4 and hi.lo (k = j - 4) after
+          for (int k = 0; k < kTcBlockK / 16; ++k)
+            umma_bf16_pair(d_corr, a_lo + static_cast<uint64_t>(2 * k), b_hi + static_cast<uint64_t>(2 * k), idesc,
+                           (kb > 0 || k > 0) ? 1u : 0u);
 #pragma unroll
-            for (int j = sc * (8 / SUB); j < (sc + 1) * (8 / SUB); ++j) {
-              const int k = j & 3;
-              umma_bf16_pair(d_corr, (j < 4 ? a_lo : a_hi) + static_cast<uint64_t>(2 * k),
-                             (j < 4 ? b_hi : b_lo) + static_cast<uint64_t>(2 * k), idesc, (kb > 0 || j > 0) ? 1u : 0u);
+          for (int k = 0; k < kTcBlockK / 16; ++k)
+            umma_bf16_pair(d_corr, a_hi + static_cast<uint64_t>(2 * k), b_lo + static_cast<uint64_t>(2 * k), idesc, 1u);
+          // a "main" buffer is free again once the epilogue warps have drained its previous contents - they do that
+          // while the corr MMAs above keep the tensor pipe busy
+          if (wide) {
+#pragma unroll
+            for (int hb = 0; hb < 2; ++hb) {
+              mbar_wait(&main_empty[hb], mph[hb] ^ 1u, 4);
+              mph[hb] ^= 1u;
+              tc_fence_after();
+              // rows hb*64 .. hb*64+63 of each CTA's 128-row weight tile: 8 swizzle atoms = 8192 B further
+              const uint64_t b_half = b_hi + static_cast<uint64_t>(hb * (8192 >> 4));
+#pragma unroll
+              for (int k = 0; k < kTcBlockK / 16; ++k)
+                umma_bf16_pair(d_main + static_cast<uint32_t>(hb) * 128u, a_hi + static_cast<uint64_t>(2 * k),
+                               b_half + static_cast<uint64_t>(2 * k), idesc_half, k > 0 ? 1u : 0u);
+              if (hb == 1) umma_commit_pair(&empty_bar[stage]);  // frees the slot in both CTAs once these MMAs have read it
+              umma_commit_pair(&main_full[hb]);                  // this half of the hi.hi chunk is complete (both CTAs)
             }
-            // "main" is free again once the epilogue warps have drained the previous chunk - they do that while the
-            // corr MMAs above keep the tensor pipe busy
-            mbar_wait(main_empty, mph ^ 1u, 4);
-            mph ^= 1u;
+          } else {
+            mbar_wait(&main_empty[mb], mph[mb] ^ 1u, 4);
+            mph[mb] ^= 1u;
             tc_fence_after();
 #pragma unroll
-            for (int k = sc * (4 / SUB); k < (sc + 1) * (4 / SUB); ++k)
-              umma_bf16_pair(d_main, a_hi + static_cast<uint64_t>(2 * k), b_hi + static_cast<uint64_t>(2 * k), idesc,
-                             k > sc * (4 / SUB) ? 1u : 0u);
-            if (sc == SUB - 1) umma_commit_pair(&empty_bar[stage]);  // frees the slot in both CTAs once these MMAs have read it
-            umma_commit_pair(main_full);                             // this hi.hi chunk is complete -> epilogue (both CTAs)
+            for (int k = 0; k < kTcBlockK / 16; ++k)
+              umma_bf16_pair(d_main + static_cast<uint32_t>(mb) * 128u, a_hi + static_cast<uint64_t>(2 * k),
+                             b_hi + static_cast<uint64_t>(2 * k), idesc, k > 0 ? 1u : 0u);
+            umma_commit_pair(&empty_bar[stage]);
+            umma_commit_pair(&main_full[mb]);
+            if (alt) mb ^= 1;
           }
           if (++stage == stages) { stage = 0; phase ^= 1u; }
         }
         umma_commit_pair(corr_full);
       }
     }
+  }
   } else {
     // ===================================== epilogue (8 warps per CTA) =======================
-    // warp (q, half): TMEM lane quarter q (rows q*32..), column half `half` of the tile
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    // warp (q, half): TMEM lane quarter q (rows q*32..), column half `half`
+    //   wide tiles: this warp owns "main" buffer `half` (128 TMEM columns = tile columns {half*64.., 128 + half*64..})
+    //   else:       columns [half * half_cols, (half + 1) * half_cols) of both buffers
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int half = (warp - kX3FirstEpiWarp) >> 2;
     const int row = q * 32 + lane;
     const int half_cols = block_n >> 1;  // multiple of 32
-    uint32_t mph = 0, cph = 0;
-    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(half * half_cols);
+    uint32_t cph = 0, mph[2] = {0u, 0u};
+    int mb = wide ? half : 0;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const uint32_t t_main = t_lane + (wide ? static_cast<uint32_t>(half) * 128u : static_cast<uint32_t>(half * half_cols));
     for (int tile = worker; tile < total_tiles; tile += num_workers) {
       const int n_tile = tile % p.n_tiles;
       const int m_tile = ((tile / p.n_tiles) << 1) + static_cast<int>(cta_rank);
@@ -209,43 +247,59 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
       const int w = iw * p.tw + ww, h = ih * p.th + hh, n = in * p.tn + nn;
       const bool valid = (w < p.w_out) && (h < p.h_out) && (n < p.n_img);
       const size_t pix = (static_cast<size_t>(n) * p.h_out + h) * p.w_out + w;
-      const int n_off = n_tile * block_n + half * half_cols;
-      float racc[128];
+      float2 racc[64];  // register accumulator group g (32 columns) = racc[16 g .. 16 g + 15]
 #pragma unroll
-      for (int i = 0; i < 128; ++i) racc[i] = 0.f;
-      const int nchunks = total_kb * SUB;
-      for (int ch = 0; ch <= nchunks; ++ch) {
-        // ch < nchunks: hi.hi chunk from "main"; ch == nchunks: the tile's lo.hi + hi.lo sum from "corr"
-        const bool last = ch == nchunks;
+      for (int i = 0; i < 64; ++i) racc[i] = make_float2(0.f, 0.f);
+      for (int ch = 0; ch <= total_kb; ++ch) {
+        // ch < total_kb: hi.hi chunk from "main"; ch == total_kb: the tile's lo.hi + hi.lo sum from "corr"
+        const bool last = ch == total_kb;
         if (last) { mbar_wait(corr_full, cph, 5); cph ^= 1u; }
-        else { mbar_wait(main_full, mph, 6); mph ^= 1u; }
+        else { mbar_wait(&main_full[mb], mph[mb], 6); mph[mb] ^= 1u; }
         tc_fence_after();
-        const uint32_t taddr = t_lane + (last ? static_cast<uint32_t>(kX3CorrCol) : 0u);
+        // two TMEM loads (64 columns) in flight per wait
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        for (int g = 0; g < 4; g += 2) {
           if (g * 32 < half_cols) {
-            uint32_t v[32];
-            tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(g * 32), v);
+            uint32_t v0[32], v1[32];
+            const bool two = (g + 1) * 32 < half_cols;
+            // tile column of register group g: wide = {half*64 + 0, +32, 128 + half*64 + 0, +32}, else half*half_cols + 32 g
+            uint32_t a0;
+            if (last) {
+              const uint32_t c0 = wide ? static_cast<uint32_t>((g >> 1) * 128 + half * 64) : static_cast<uint32_t>(half * half_cols + g * 32);
+              a0 = t_lane + static_cast<uint32_t>(kX3CorrCol) + c0;
+            } else {
+              a0 = t_main + (wide ? 0u : static_cast<uint32_t>(mb) * 128u) + static_cast<uint32_t>(g * 32);
+            }
+            tmem_ld_32x32b_x32(a0, v0);
+            if (two) tmem_ld_32x32b_x32(a0 + 32u, v1);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) racc[g * 32 + i] += __uint_as_float(v[i]);
+            for (int i = 0; i < 16; ++i)
+              racc[g * 16 + i] = __fadd2_rn(racc[g * 16 + i], make_float2(__uint_as_float(v0[2 * i]), __uint_as_float(v0[2 * i + 1])));
+            if (two) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                racc[g * 16 + 16 + i] = __fadd2_rn(racc[g * 16 + 16 + i], make_float2(__uint_as_float(v1[2 * i]), __uint_as_float(v1[2 * i + 1])));
+            }
           }
         }
         // hand the buffer back: one arrive per warp (to the leader's barrier) after every lane's reads have landed
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          uint64_t* bar = last ? corr_empty : main_empty;
+          uint64_t* bar = last ? corr_empty : &main_empty[mb];
           if (leader) mbar_arrive(bar); else mbar_arrive_remote(bar, 0u);
         }
+        if (!last && alt) mb ^= 1;
       }
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        const int col0 = n_off + g * 32;
+        const int tcol = wide ? (g >> 1) * 128 + half * 64 + (g & 1) * 32 : half * half_cols + g * 32;
+        const int col0 = n_tile * block_n + tcol;
         if (g * 32 < half_cols && valid && col0 < p.n_valid) {
           float f[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = racc[g * 32 + i];
+          for (int i = 0; i < 16; ++i) { f[2 * i] = racc[g * 16 + i].x; f[2 * i + 1] = racc[g * 16 + i].y; }
           igemm_finish32(p, f, pix, col0);
         }
       }
@@ -271,15 +325,9 @@ inline cudaError_t igemm_x3_launch(const IgemmTcParams& p, int num_sms, cudaStre
   int total_kb = 0;
   for (int t = 0; t < p.num_taps; ++t) total_kb += p.taps[t].src ? p.kchunks2 : p.kchunks;
   if (total_kb > kTcMaxKb) return cudaErrorInvalidValue;
-  // OCRFA_X3_SUB = 1 | 2 | 4 (bring-up / measurement switch, read once): hi.hi accumulation chunks per K chunk
-  static const int sub = [] { const char* e = std::getenv("OCRFA_X3_SUB"); const int v = e ? std::atoi(e) : kX3DefaultSub;
-                              return (v == 1 || v == 2 || v == 4) ? v : kX3DefaultSub; }();
-  void (*fn)(IgemmTcParams) = sub == 1 ? igemm_x3_kernel<1> : (sub == 2 ? igemm_x3_kernel<2> : igemm_x3_kernel<4>);
   if (!attr_set) {
-    for (auto f : {igemm_x3_kernel<1>, igemm_x3_kernel<2>, igemm_x3_kernel<4>}) {
-      cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-      if (e != cudaSuccess) return e;
-    }
+    cudaError_t e = cudaFuncSetAttribute(igemm_x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
     attr_set = true;
   }
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
@@ -295,7 +343,7 @@ inline cudaError_t igemm_x3_launch(const IgemmTcParams& p, int num_sms, cudaStre
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, fn, p);
+  return cudaLaunchKernelEx(&cfg, igemm_x3_kernel, p);
 }
 
 }  // namespace ocrfa

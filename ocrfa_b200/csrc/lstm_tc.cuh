@@ -18,7 +18,11 @@
 //   kLstmF16Split    fp16 hi/lo split operands (fp32-grade): h = h_hi + h_lo, W_hh = W_hi + W_lo (pre-scaled by a
 //                    power of two), three products h_hi.W_hi + h_hi.W_lo + h_lo.W_hi per K block; the resident
 //                    weights are [W_hi | W_lo]; the input projection (fp32, bias included) comes from the split
-//                    igemm; accurate expf/tanhf gate math.
+//                    igemm; accurate expf/tanhf gate math. The tensor core's fp32 accumulate truncates (error
+//                    linear in the number of chained MMAs, see igemm_x3.cuh), so the h_hi.W_hi products of each
+//                    64-wide K block go to a fresh TMEM buffer ("main", four in rotation) that the epilogue warps
+//                    sum in registers with round-to-nearest adds while the next slabs arrive; the two small
+//                    products chain in a separate accumulator ("corr") added once per step.
 //
 // The only cross-CTA dependency is "all 32 CTAs of my (direction, m_tile) group wrote h_t": a monotonic global
 // counter per group (counter add after the slice is at L2 / acquire poll), no kernel relaunch, no grid-wide barrier. All CTAs must be
@@ -57,7 +61,9 @@ constexpr int kLstmRing = 6;          // A-ring stages of 16 KB
 constexpr int kLstmStageBytes = 0;
 constexpr bool kLstmTmaPublishSplit = false;
 #endif
-constexpr int kLstmTmemCols = 128;    // 2 accumulators x 64 columns
+constexpr int kLstmTmemCols = 128;    // fused-x modes: 2 accumulators x 64 columns
+constexpr int kLstmTmemColsSplit = 512;  // split mode: 4 "main" chunk buffers (columns 0..255) + "corr" (column 256)
+constexpr int kLstmCorrCol = 256;
 constexpr int kLstmGroupCtas = 32;    // CTAs per (direction, m_tile) group = 512 hidden units / 16
 constexpr int kLstmWSlabs = 16;       // resident weight slabs (8 KB each) = 128 KB
 
@@ -163,7 +169,9 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_tc_persistent_kernel(con
   uint64_t* tfull = a_empty + kLstmRing;                  // [2]
   uint64_t* tempty = tfull + 2;                           // [2]
   uint64_t* w_full = tempty + 2;                          // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
+  uint64_t* main_full = w_full + 1;                       // [4] split mode: hi.hi chunk complete
+  uint64_t* main_empty = main_full + 4;                   // [4] split mode: chunk drained by the four epilogue warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(main_empty + 4);
   float* sbias = reinterpret_cast<float*>(smem + 512);    // [64] (bf16 mode)
   uint8_t* w_smem = smem + 1024;                          // kLstmWSlabs x (64 rows x 128 B) = 128 KB
   uint8_t* ring = w_smem + kLstmWSlabs * 8192;            // kLstmRing x 16 KB
@@ -184,6 +192,7 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_tc_persistent_kernel(con
     for (int s = 0; s < kLstmRing; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 128); }
     mbar_init(w_full, 1);
+    for (int s = 0; s < 4; ++s) { mbar_init(&main_full[s], 1); mbar_init(&main_empty[s], 4); }
     fence_mbar_init();
   }
   if (warp == 0 && lane == 0) {
@@ -194,7 +203,8 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_tc_persistent_kernel(con
     tma_prefetch_desc(&p.tmP);
 #endif
   }
-  if (warp == 1) { tmem_alloc(tmem_slot, kLstmTmemCols); tmem_relinquish(); }
+  constexpr uint32_t kTmemCols = MODE == kLstmF16Split ? kLstmTmemColsSplit : kLstmTmemCols;
+  if (warp == 1) { tmem_alloc(tmem_slot, kTmemCols); tmem_relinquish(); }
   if (MODE == kLstmBf16FusedX && threadIdx.x >= 64 && threadIdx.x < 128)
     sbias[threadIdx.x - 64] = __ldg(p.bias + n_tile * 64 + (threadIdx.x - 64));
   tc_fence_before();
@@ -260,8 +270,47 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_tc_persistent_kernel(con
       mbar_wait(w_full, 0, 12);
       tc_fence_after();
       int stage = 0, as = 0;
-      uint32_t phase = 0, aphase = 0;
+      uint32_t phase = 0, aphase = 0, mphase = 0;  // mphase: one parity bit per "main" buffer (split mode)
       for (int s = 0; s < T; ++s) {
+        if (MODE == kLstmF16Split) {
+          // corr in TMEM column 256 (one buffer: step s+1's slabs exist only after the epilogue of step s has read it)
+          mbar_wait(&tempty[0], aphase ^ 1u, 13);
+          aphase ^= 1u;
+          tc_fence_after();
+          const uint32_t d_corr = tmem_base + static_cast<uint32_t>(kLstmCorrCol);
+          for (int i = 0; i < 16; ++i) {
+            mbar_wait(&a_full[stage], phase, 14);
+            if (i == 8) LSTM_TS(s, 4);
+            if (i == 15) LSTM_TS(s, 5);
+            tc_fence_after();
+            const uint64_t a_desc = make_sw128_kmajor_desc(smem_u32(ring + stage * 16384));
+            // slabs 0..7 = h_hi: corr += h_hi.W_lo, main[i & 3] = h_hi.W_hi; slabs 8..15 = h_lo: corr += h_lo.W_hi
+            const uint64_t bc_desc = make_sw128_kmajor_desc(smem_u32(w_smem + (i < 8 ? i + 8 : i - 8) * 8192));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(d_corr, a_desc + static_cast<uint64_t>(2 * k), bc_desc + static_cast<uint64_t>(2 * k), idesc,
+                        (i > 0 || k > 0) ? 1u : 0u);
+            if (i < 8) {
+              const int mb = i & 3;
+              mbar_wait(&main_empty[mb], ((mphase >> mb) & 1u) ^ 1u, 16);
+              mphase ^= 1u << mb;
+              tc_fence_after();
+              const uint64_t bm_desc = make_sw128_kmajor_desc(smem_u32(w_smem + i * 8192));
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(tmem_base + static_cast<uint32_t>(mb) * 64u, a_desc + static_cast<uint64_t>(2 * k),
+                          bm_desc + static_cast<uint64_t>(2 * k), idesc, k > 0 ? 1u : 0u);
+              umma_commit(&a_empty[stage]);
+              umma_commit(&main_full[mb]);
+            } else {
+              umma_commit(&a_empty[stage]);
+            }
+            if (++stage == kLstmRing) { stage = 0; phase ^= 1u; }
+          }
+          umma_commit(&tfull[0]);
+          LSTM_TS(s, 6);
+          continue;
+        }
         mbar_wait(&tempty[as], aphase ^ 1u, 13);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as) * 64u;
@@ -315,18 +364,48 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_tc_persistent_kernel(con
     const size_t hx_region = static_cast<size_t>(dir * p.m_tiles + m_tile) * 2;
     int as = 0;
     uint32_t aphase = 0;
+    uint32_t mphase = 0;
     for (int s = 0; s < T; ++s) {
       const int t_cur = dir == 0 ? s : T - 1 - s;
+      uint32_t v0[32], v1[32];
+      if (MODE == kLstmF16Split) {
+        // sum the eight hi.hi chunks in registers (round-to-nearest fp32) as they complete, then add corr
+        float racc[64];
+#pragma unroll
+        for (int i = 0; i < 64; ++i) racc[i] = 0.f;
+        const uint32_t tlane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        for (int i = 0; i <= 8; ++i) {
+          const int mb = i & 3;
+          if (i < 8) { mbar_wait(&main_full[mb], (mphase >> mb) & 1u, 17); mphase ^= 1u << mb; }
+          else { mbar_wait(&tfull[0], aphase, 15); if (et == 0) LSTM_TS(s, 8); }
+          tc_fence_after();
+          const uint32_t taddr = tlane + (i < 8 ? static_cast<uint32_t>(mb) * 64u : static_cast<uint32_t>(kLstmCorrCol));
+          tmem_ld_32x32b_x32(taddr, v0);
+          tmem_ld_32x32b_x32(taddr + 32u, v1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { racc[j] += __uint_as_float(v0[j]); racc[32 + j] += __uint_as_float(v1[j]); }
+          tc_fence_before();
+          if (i < 8) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&main_empty[mb]);
+          } else {
+            mbar_arrive(&tempty[0]);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { v0[j] = __float_as_uint(racc[j]); v1[j] = __float_as_uint(racc[32 + j]); }
+      } else {
       mbar_wait(&tfull[as], aphase, 15);
       if (et == 0) LSTM_TS(s, 8);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as) * 64u;
-      uint32_t v0[32], v1[32];
       tmem_ld_32x32b_x32(taddr, v0);
       tmem_ld_32x32b_x32(taddr + 32u, v1);
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&tempty[as]);
+      }
       if (et == 0) LSTM_TS(s, 9);
       float hout[16];
       // a warp whose 32 rows are all beyond the batch skips the gate math: the activations are MUFU bound and shared
@@ -455,8 +534,12 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_tc_persistent_kernel(con
 #pragma unroll
         for (int i = 0; i < 16; ++i) xr[i] = valid ? __ldg(xp + i) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      as ^= 1;
-      if (as == 0) aphase ^= 1u;
+      if (MODE == kLstmF16Split) {
+        aphase ^= 1u;
+      } else {
+        as ^= 1;
+        if (as == 0) aphase ^= 1u;
+      }
     }
   }
 #undef LSTM_TS
@@ -466,7 +549,7 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_tc_persistent_kernel(con
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
-    tmem_dealloc(tmem_base, kLstmTmemCols);
+    tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
