@@ -119,6 +119,7 @@ struct ocrfa_handle {
   int graphs_enabled = 1;  // OCRFA_GRAPHS=0 disables; also cleared after kMaxGraphFailures failed captures
   int graph_failures = 0;
   bool stem_1px = false;   // OCRFA_STEM_1PX (experiment switch), read once in ocrfa_create
+  int x3_halo_max_cout = 128;  // OCRFA_X3_HALO_MAXC: f16x3 layers up to this Cout use the halo-staged form (0 = never)
   uint64_t graph_tick = 0;
   Profiler prof;
   ocrfa_config cfg;
@@ -466,6 +467,44 @@ int run_conv_halo(ocrfa_handle* h, const ConvW& cw, const Act& in, const Act* ds
   return 0;
 }
 
+// fp32-grade mode: the halo-staged form of igemm_x3_kernel for the 3x3/s1/p1 layers with few output channels on large
+// maps (conv0_2, layer1, conv1: per-tap staging would move more L2 -> SM bytes per MMA than the fabric delivers).
+bool x3_halo_wanted(const ocrfa_handle* h, const ConvW& cw, const Act& in, bool pool) {
+  if (!h->split() || h->halo_level <= 0) return false;
+  const ConvGeom g{in.n, in.h, in.w, cw.cin, cw.cout, cw.kh, cw.kw, cw.sh, cw.ph, cw.pw, cw.dil};
+  if (!halo_eligible(g, pool) || (long long)in.n * in.h * in.w >= (1ll << 31)) return false;
+  if (cw.cout != 64 && cw.cout != 128 && cw.cout != 256) return false;
+  if (cw.cout > h->x3_halo_max_cout || in.c % 64 != 0) return false;
+  int tw = 0, th = 0;
+  halo_choose_tile(in.w, in.h, pool, &tw, &th);
+  const double cover = double(ceil_div(in.w, tw) * tw) * double(ceil_div(in.h, th) * th) / (double(in.w) * in.h);
+  if (cover > 1.06) return false;
+  int stages = 0;
+  igemm_x3_halo_smem_bytes(cw.cout, tw, th, &stages);
+  return stages >= 2;
+}
+
+int run_conv_x3_halo(ocrfa_handle* h, const ConvW& cw, const Act& in, const Act* ds_src, const void* residual, void* out,
+                     bool relu, bool pool, cudaStream_t st) {
+  IgemmTcParams p;
+  const ConvGeom g{in.n, in.h, in.w, cw.cin, cw.cout, cw.kh, cw.kw, cw.sh, cw.ph, cw.pw, cw.dil};
+  int rc = plan_x3_halo(&p, g, in.p, in.c, cw.d_wgt, pool);
+  if (rc) return fail(OCRFA_ERR_CUDA, "plan_x3_halo(%s) failed: %d", cw.name.c_str(), rc);
+  if (cw.ds_cin) {
+    if (!ds_src) return fail(OCRFA_ERR_STATE, "%s expects a fused downsample source", cw.name.c_str());
+    rc = plan_add_source(&p, ds_src->p, cw.ds_cin, ds_src->c, cw.d_wgt, cw.ktotal, cw.cout);
+    if (rc) return fail(OCRFA_ERR_CUDA, "plan_add_source(%s) failed: %d", cw.name.c_str(), rc);
+  }
+  p.bias = cw.d_bias;
+  p.residual = residual; p.ldr = 2 * cw.cout; p.res_lo = cw.cout;
+  p.out = out; p.ldo = 2 * cw.cout; p.out_lo = cw.cout; p.out_f32 = 0; p.relu = relu ? 1 : 0;
+  p.out_scale = cw.out_scale;
+  const double flops = 2.0 * (double)in.n * in.h * in.w * cw.cout * (9.0 * cw.cin + cw.ds_cin);
+  LaunchScope ls(h, kClsIgemmTc, flops, st);
+  CUDA_TRY(igemm_tc_launch(p, kModeStd, h->num_sms, st));
+  return 0;
+}
+
 int run_conv_tc(ocrfa_handle* h, const ConvW& cw, const Act& in, const Act* ds_src, const void* residual, void* out,
                 bool relu, bool out_f32, int ldo, cudaStream_t st) {
   IgemmTcParams p;
@@ -473,6 +512,8 @@ int run_conv_tc(ocrfa_handle* h, const ConvW& cw, const Act& in, const Act* ds_s
   const bool split = h->split();
   if (!out_f32 && (ldo % 8) == 0 && halo_wanted(h, cw, in, false))
     return run_conv_halo(h, cw, in, ds_src, residual, out, relu, false, st, ldo);
+  if (split && !out_f32 && ldo == cw.cout && x3_halo_wanted(h, cw, in, false))
+    return run_conv_x3_halo(h, cw, in, ds_src, residual, out, relu, false, st);
   int rc = plan_conv(&p, g, in.p, in.c, cw.d_wgt, nullptr, split);
   if (rc) return fail(OCRFA_ERR_CUDA, "plan_conv(%s) failed: %d", cw.name.c_str(), rc);
   if (cw.ds_cin) {
@@ -639,9 +680,10 @@ int forward_impl(ocrfa_handle* h, const float* d_x, const uint8_t* d_u8, const i
   auto conv_pool_step = [&](const char* name, Act* a) -> int {
     auto it = h->convs.find(name);
     if (it == h->convs.end()) return fail(OCRFA_ERR_STATE, "conv %s not prepared", name);
-    if (halo_wanted(h, it->second, *a, true)) {
+    if (halo_wanted(h, it->second, *a, true) || x3_halo_wanted(h, it->second, *a, true)) {
       void* o = pool.get();
-      int r = run_conv_halo(h, it->second, *a, nullptr, nullptr, o, true, true, st);
+      int r = sp ? run_conv_x3_halo(h, it->second, *a, nullptr, nullptr, o, true, true, st)
+                 : run_conv_halo(h, it->second, *a, nullptr, nullptr, o, true, true, st);
       if (r) return r;
       pool.put(a->p);
       *a = Act{o, a->n, a->h / 2, a->w / 2, it->second.cout};
@@ -889,6 +931,7 @@ int ocrfa_create(const ocrfa_config* cfg, ocrfa_handle** out) {
   h->num_sms = prop.multiProcessorCount;
   if (const char* hl = getenv("OCRFA_HALO")) h->halo_level = atoi(hl);
   h->stem_1px = getenv("OCRFA_STEM_1PX") != nullptr;
+  if (const char* e = getenv("OCRFA_X3_HALO_MAXC")) h->x3_halo_max_cout = atoi(e);
   const char* g = getenv("OCRFA_GRAPHS");
   if (g && g[0] == '0') h->graphs_enabled = 0;
   *out = h;

@@ -171,6 +171,44 @@ inline void halo_choose_tile(int w, int h, bool pool, int* tw_out, int* th_out) 
   }
 }
 
+// fp32-grade (f16x3) halo-staged plan for igemm_x3_kernel: 3x3 / s1 / p1, Cout in {64, 128, 256} as ONE N tile.
+// `in`: NHWC fp16 hi/lo pixels [hi(cin_buf) | lo(cin_buf)]; `wgt`: [cout][tap][hi(cin_pad) | lo(cin_pad)] (+ fused 1x1
+// source appended by plan_add_source). pool: fuse the following 2x2/2 max pool.
+inline int plan_x3_halo(IgemmTcParams* p, const ConvGeom& g, const void* in, int cin_buf, const void* wgt, bool pool) {
+  std::memset(p, 0, sizeof(*p));
+  if (!halo_eligible(g, pool)) return -30;
+  if (g.cout != 64 && g.cout != 128 && g.cout != 256) return -31;
+  const int cin_pad = ceil_div(g.cin, 64) * 64;
+  if (cin_buf % 64 != 0 || cin_buf < cin_pad) return -32;
+  halo_choose_tile(g.w_in, g.h_in, pool, &p->tw, &p->th);
+  p->tn = 1;
+  p->tiles_w = ceil_div(g.w_in, p->tw);
+  p->tiles_h = ceil_div(g.h_in, p->th);
+  p->tiles_n = g.n;
+  p->n_img = g.n; p->h_out = g.h_in; p->w_out = g.w_in;
+  p->block_n = g.cout;
+  p->n_tiles = 1;
+  p->n_valid = g.cout;
+  p->kchunks = cin_pad / 64;
+  p->kchunks2 = 0;
+  p->split = 1; p->pair = 1; p->halo = 1; p->pool = pool ? 1 : 0;
+  p->a_lo = cin_buf;
+  p->out_scale = 1.0f;
+  igemm_x3_halo_smem_bytes(p->block_n, p->tw, p->th, &p->num_stages);
+  if (p->num_stages < 2) return -33;
+  int nt = 0;
+  for (int r = 0; r < 3; ++r)
+    for (int s2 = 0; s2 < 3; ++s2) {
+      TapDesc& d = p->taps[nt++];
+      d.src = 0; d.dw = static_cast<int16_t>(s2 - 1); d.dr = 0; d.dh = static_cast<int16_t>(r - 1);
+    }
+  p->num_taps = nt;
+  int rc = make_act_tmap(&p->tmA, in, 2 * cin_buf, g.w_in, 1, g.h_in, g.n, p->tw, p->th + 2, 1);
+  if (rc) return rc;
+  p->tmA2 = p->tmA;
+  return make_wgt_tmap(&p->tmB, wgt, 2 * 9 * cin_pad, g.cout, p->block_n / 2);
+}
+
 // `in`: NHWC bf16 [n][h][w][cin_buf]; cin_buf is a multiple of 64 or, for the 32-channel stem output, 32 (the box
 // still asks for 64 channels: TMA zero-fills the out-of-range half, the weights carry zeros there).
 // `in2` (optional): fused 1x1 source [n][h][w][cin2_buf]; the weight matrix then has cin2_pad extra K columns.

@@ -28,6 +28,13 @@
 //         other half's MMAs and the next corr MMAs (1280 tensor-pipe cycles).
 //       - tiles of <= 128 columns: TWO main buffers (columns 0 and 128) used alternately by successive chunks (the
 //         small-Cout layers have short stages; the drain of chunk k also overlaps the hi.hi MMAs of chunk k+1).
+//   * halo mode (IgemmTcParams::halo, the 3x3 / stride 1 / pad 1 layers with Cout <= 128 and large maps - conv0_2,
+//     layer1, conv1): like igemm_halo.cuh, ONE box of (th + 2) x tw pixels per (dx, 64-channel chunk) - once for the hi
+//     and once for the lo halves - feeds the three dy taps (tw is a multiple of 8, so the rows of tap dy start
+//     dy * tw * 128 B into the box, a multiple of the 1024-byte swizzle atom); the six weight blocks (three taps x hi, lo)
+//     of the group travel with it. A stage then carries 36 MMAs: L2 -> SM bytes per MMA fall from 104 (Cout = 64) /
+//     62 (Cout = 128) bytes per tensor-pipe cycle - above what L2 delivers to 148 SMs at once - to 57 / 39. The
+//     following 2x2/2 max pool (max_pool1, max_pool2) can be fused into the epilogue.
 // Warp roles (12 warps, three warpgroups): warpgroup 0 = TMA producer (warp 0), MMA issuer + TMEM alloc (warp 1, leader
 // CTA) and two idle warps, trimmed to 56 registers with setmaxnreg; warpgroups 1-2 = eight epilogue warps raised to 224
 // registers, so the 128 fp32 accumulators + 64 values in flight from TMEM live in registers (at the 168 registers a
@@ -53,6 +60,51 @@ inline size_t igemm_x3_smem_bytes(int block_n, int* stages_out) {
   return header + stages * stage;
 }
 
+// halo mode: a stage = two halo boxes ((th + 2) * tw pixels x 128 B) + six weight blocks
+inline size_t igemm_x3_halo_smem_bytes(int block_n, int tw, int th, int* stages_out) {
+  const size_t stage = 2 * static_cast<size_t>(th + 2) * tw * 128 + 6 * static_cast<size_t>(block_n / 2) * kTcBlockK * 2;
+  const size_t header = 1024 + kTcSmemHeader;
+  const size_t budget = 227 * 1024 - header;
+  int stages = static_cast<int>(budget / stage);
+  if (stages > kTcMaxStages) stages = kTcMaxStages;
+  if (stages_out) *stages_out = stages;
+  return header + stages * stage;
+}
+
+// 8 consecutive output channels of one pooled pixel: (+bias) -> ReLU -> fp16 hi | lo store (halo mode, fused max pool)
+__device__ __forceinline__ void x3_store8_split(const IgemmTcParams& p, float (&g)[8], size_t pix, int col) {
+  const float sc = p.out_scale;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) g[i] *= sc;
+  if (p.bias != nullptr) {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
+    g[0] += b0.x; g[1] += b0.y; g[2] += b0.z; g[3] += b0.w;
+    g[4] += b1.x; g[5] += b1.y; g[6] += b1.z; g[7] += b1.w;
+  }
+  float lo[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (p.relu) g[i] = fmaxf(g[i], 0.0f);
+    const float hv = __half2float(__float2half_rn(g[i]));
+    lo[i] = g[i] - hv;
+    g[i] = hv;
+  }
+  uint4 o, l;
+  __half2 t;
+  t = __floats2half2_rn(g[0], g[1]);   o.x = *reinterpret_cast<uint32_t*>(&t);
+  t = __floats2half2_rn(g[2], g[3]);   o.y = *reinterpret_cast<uint32_t*>(&t);
+  t = __floats2half2_rn(g[4], g[5]);   o.z = *reinterpret_cast<uint32_t*>(&t);
+  t = __floats2half2_rn(g[6], g[7]);   o.w = *reinterpret_cast<uint32_t*>(&t);
+  t = __floats2half2_rn(lo[0], lo[1]); l.x = *reinterpret_cast<uint32_t*>(&t);
+  t = __floats2half2_rn(lo[2], lo[3]); l.y = *reinterpret_cast<uint32_t*>(&t);
+  t = __floats2half2_rn(lo[4], lo[5]); l.z = *reinterpret_cast<uint32_t*>(&t);
+  t = __floats2half2_rn(lo[6], lo[7]); l.w = *reinterpret_cast<uint32_t*>(&t);
+  __half* op = reinterpret_cast<__half*>(p.out) + pix * p.ldo + col;
+  *reinterpret_cast<uint4*>(op) = o;
+  *reinterpret_cast<uint4*>(op + p.out_lo) = l;
+}
+
 __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_constant__ IgemmTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -65,7 +117,7 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
   uint64_t* corr_full = main_empty + 2;                    // every MMA of the tile complete
   uint64_t* corr_empty = corr_full + 1;                    // corr read back by the 16 epilogue warps (leader's copy)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(corr_empty + 1);
-  int4* kb_table = reinterpret_cast<int4*>(smem + 256);    // [total_kb][2]: {a_c, dw, dr, dh}, {src, b_k, a_lo, b_lo}
+  int4* kb_table = reinterpret_cast<int4*>(smem + 256);    // [groups][3]: {a_c, dw, dr, dh}, {src, nsub, a_lo, b_lo}, {b_k of sub 0..2, -}
   uint8_t* stage_base = smem + kTcSmemHeader;
 
   const uint32_t cta_rank = cluster_ctarank();
@@ -77,7 +129,10 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
   const int b_rows = block_n >> 1;
   const uint32_t a_bytes = kTcBlockM * kTcBlockK * 2;
   const uint32_t b_bytes = static_cast<uint32_t>(b_rows) * kTcBlockK * 2;
-  const uint32_t stage_bytes = 2u * a_bytes + 2u * b_bytes;
+  const bool halo = p.halo != 0;
+  const uint32_t tap_bytes = static_cast<uint32_t>(p.tw) * 128u;  // halo: one image row of the box
+  const uint32_t a_slot = halo ? static_cast<uint32_t>(p.th + 2) * tap_bytes : a_bytes;  // room of one A box (hi or lo)
+  const uint32_t stage_bytes = 2u * a_slot + (halo ? 6u : 2u) * b_bytes;
   // wide: a 256-column tile whose hi.hi product is issued as two N = 128 halves (buffer h = columns {h*64 + 0..63,
   // 128 + h*64 + 0..63} of the tile: an N = 128 pair MMA takes 64 weight rows from each CTA); otherwise two whole-tile
   // buffers used alternately
@@ -88,8 +143,16 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
   const int total_tiles = ((m_tiles + 1) >> 1) * p.n_tiles;
   const int worker = static_cast<int>(blockIdx.x >> 1);
   const int num_workers = static_cast<int>(gridDim.x >> 1);
-  int total_kb = 0;
-  for (int t = 0; t < p.num_taps; ++t) total_kb += p.taps[t].src ? p.kchunks2 : p.kchunks;
+  // a GROUP is one shared-memory stage: one K chunk of one tap, or (halo) the three dy taps of one (dx, chunk);
+  // a CHUNK is one fresh hi.hi accumulation (K = 64 of one tap)
+  int total_kb = 0, total_chunks = 0;
+  if (halo) {
+    total_kb = 3 * p.kchunks + p.kchunks2;
+    total_chunks = 9 * p.kchunks + p.kchunks2;
+  } else {
+    for (int t = 0; t < p.num_taps; ++t) total_kb += p.taps[t].src ? p.kchunks2 : p.kchunks;
+    total_chunks = total_kb;
+  }
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) {
@@ -107,8 +170,23 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
     tma_prefetch_desc(&p.tmB);
     tma_prefetch_desc(&p.tmA2);
   }
-  // K-chunk schedule (tap-major, 64-channel chunk minor). Weight K blocks of a tap are [hi chunks | lo chunks].
+  // group schedule. Weight K blocks of a tap are [hi chunks | lo chunks]; taps are dy-major (tap = dy * 3 + dx).
   for (int kb = threadIdx.x; kb < total_kb; kb += blockDim.x) {
+    if (halo) {
+      if (kb < 3 * p.kchunks) {  // dx-major, chunk-minor; the three sub-blocks are the dy taps
+        const int dxi = kb / p.kchunks, c = kb - dxi * p.kchunks;
+        kb_table[3 * kb] = make_int4(c * kTcBlockK, dxi - 1, 0, -1);
+        kb_table[3 * kb + 1] = make_int4(0, 3, p.a_lo, p.kchunks * kTcBlockK);
+        kb_table[3 * kb + 2] = make_int4(((0 * 3 + dxi) * 2 * p.kchunks + c) * kTcBlockK, ((1 * 3 + dxi) * 2 * p.kchunks + c) * kTcBlockK,
+                                         ((2 * 3 + dxi) * 2 * p.kchunks + c) * kTcBlockK, 0);
+      } else {  // fused 1x1 source
+        const int c = kb - 3 * p.kchunks;
+        kb_table[3 * kb] = make_int4(c * kTcBlockK, 0, 0, 0);
+        kb_table[3 * kb + 1] = make_int4(1, 1, p.a_lo2, p.kchunks2 * kTcBlockK);
+        kb_table[3 * kb + 2] = make_int4((9 * 2 * p.kchunks + c) * kTcBlockK, 0, 0, 0);
+      }
+      continue;
+    }
     int rem = kb, kb_base = 0, t = 0, chunks = 0;
     for (; t < p.num_taps; ++t) {
       chunks = p.taps[t].src ? p.kchunks2 : p.kchunks;
@@ -117,8 +195,9 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
       kb_base += 2 * chunks;
     }
     const TapDesc tap = p.taps[t];
-    kb_table[2 * kb] = make_int4(rem * kTcBlockK, tap.dw, tap.dr, tap.dh);
-    kb_table[2 * kb + 1] = make_int4(tap.src, (kb_base + rem) * kTcBlockK, tap.src ? p.a_lo2 : p.a_lo, chunks * kTcBlockK);
+    kb_table[3 * kb] = make_int4(rem * kTcBlockK, tap.dw, tap.dr, tap.dh);
+    kb_table[3 * kb + 1] = make_int4(tap.src, 1, tap.src ? p.a_lo2 : p.a_lo, chunks * kTcBlockK);
+    kb_table[3 * kb + 2] = make_int4((kb_base + rem) * kTcBlockK, 0, 0, 0);
   }
   if (warp == 1) { tmem_alloc_pair(tmem_slot, kTcTmemCols); tmem_relinquish_pair(); }
   tc_fence_before();
@@ -143,16 +222,27 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
         const int w0 = iw * p.tw, h0 = ih * p.th, n0 = in * p.tn;
         const int b_col = n_tile * block_n + static_cast<int>(cta_rank) * b_rows;
         for (int kb = 0; kb < total_kb; ++kb) {
-          const int4 e0 = kb_table[2 * kb];
-          const int4 e1 = kb_table[2 * kb + 1];
+          const int4 e0 = kb_table[3 * kb];
+          const int4 e1 = kb_table[3 * kb + 1];
+          const int4 e2 = kb_table[3 * kb + 2];
           mbar_wait(&empty_bar[stage], phase ^ 1u, 1);
           uint8_t* sa = stage_base + static_cast<size_t>(stage) * stage_bytes;
           const void* tm = e1.x ? static_cast<const void*>(&p.tmA2) : static_cast<const void*>(&p.tmA);
-          if (leader) mbar_expect_tx(&full_bar[stage], 2u * stage_bytes);
+          // bytes of this group: two A boxes (halo boxes for the 3x3 source, plain 128-pixel boxes otherwise) + 2 * nsub
+          // weight blocks; both CTAs' loads complete on the leader's barrier
+          const uint32_t a_box = (halo && e1.x == 0) ? a_slot : a_bytes;
+          if (leader) mbar_expect_tx(&full_bar[stage], 2u * (2u * a_box + 2u * static_cast<uint32_t>(e1.y) * b_bytes));
           tma_load_5d_pair(sa, tm, &full_bar[stage], e0.x, w0 + e0.y, e0.z, h0 + e0.w, n0);
-          tma_load_5d_pair(sa + a_bytes, tm, &full_bar[stage], e0.x + e1.z, w0 + e0.y, e0.z, h0 + e0.w, n0);
-          tma_load_2d_pair(sa + 2u * a_bytes, &p.tmB, &full_bar[stage], e1.y, b_col);
-          tma_load_2d_pair(sa + 2u * a_bytes + b_bytes, &p.tmB, &full_bar[stage], e1.y + e1.w, b_col);
+          tma_load_5d_pair(sa + a_slot, tm, &full_bar[stage], e0.x + e1.z, w0 + e0.y, e0.z, h0 + e0.w, n0);
+          uint8_t* sb = sa + 2u * a_slot;
+          tma_load_2d_pair(sb, &p.tmB, &full_bar[stage], e2.x, b_col);
+          tma_load_2d_pair(sb + b_bytes, &p.tmB, &full_bar[stage], e2.x + e1.w, b_col);
+          if (e1.y == 3) {
+            tma_load_2d_pair(sb + 2u * b_bytes, &p.tmB, &full_bar[stage], e2.y, b_col);
+            tma_load_2d_pair(sb + 3u * b_bytes, &p.tmB, &full_bar[stage], e2.y + e1.w, b_col);
+            tma_load_2d_pair(sb + 4u * b_bytes, &p.tmB, &full_bar[stage], e2.z, b_col);
+            tma_load_2d_pair(sb + 5u * b_bytes, &p.tmB, &full_bar[stage], e2.z + e1.w, b_col);
+          }
           if (!leader) mbar_arrive_remote(&full_bar[stage], 0u);
           if (++stage == stages) { stage = 0; phase ^= 1u; }
         }
@@ -174,15 +264,20 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
         for (int kb = 0; kb < total_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase, 3);
           tc_fence_after();
-          const uint32_t sa = smem_u32(stage_base + static_cast<size_t>(stage) * stage_bytes);
+          const uint32_t sa0 = smem_u32(stage_base + static_cast<size_t>(stage) * stage_bytes);
+          const int nsub = kb_table[3 * kb + 1].y;
+          for (int j = 0; j < nsub; ++j) {
+          // sub-block j: the rows of tap dy = j start j * tap_bytes into the halo boxes; its weight blocks are (hi, lo) pair j
+          const uint32_t sa = sa0 + static_cast<uint32_t>(j) * tap_bytes;
+          const uint32_t sb = sa0 + 2u * a_slot + static_cast<uint32_t>(2 * j) * b_bytes;
           const uint64_t a_hi = make_sw128_kmajor_desc(sa);
-          const uint64_t a_lo = make_sw128_kmajor_desc(sa + a_bytes);
-          const uint64_t b_hi = make_sw128_kmajor_desc(sa + 2u * a_bytes);
-          const uint64_t b_lo = make_sw128_kmajor_desc(sa + 2u * a_bytes + b_bytes);
+          const uint64_t a_lo = make_sw128_kmajor_desc(sa + a_slot);
+          const uint64_t b_hi = make_sw128_kmajor_desc(sb);
+          const uint64_t b_lo = make_sw128_kmajor_desc(sb + b_bytes);
 #pragma unroll
           for (int k = 0; k < kTcBlockK / 16; ++k)
             umma_bf16_pair(d_corr, a_lo + static_cast<uint64_t>(2 * k), b_hi + static_cast<uint64_t>(2 * k), idesc,
-                           (kb > 0 || k > 0) ? 1u : 0u);
+                           (kb > 0 || j > 0 || k > 0) ? 1u : 0u);
 #pragma unroll
           for (int k = 0; k < kTcBlockK / 16; ++k)
             umma_bf16_pair(d_corr, a_hi + static_cast<uint64_t>(2 * k), b_lo + static_cast<uint64_t>(2 * k), idesc, 1u);
@@ -200,7 +295,7 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
               for (int k = 0; k < kTcBlockK / 16; ++k)
                 umma_bf16_pair(d_main + static_cast<uint32_t>(hb) * 128u, a_hi + static_cast<uint64_t>(2 * k),
                                b_half + static_cast<uint64_t>(2 * k), idesc_half, k > 0 ? 1u : 0u);
-              if (hb == 1) umma_commit_pair(&empty_bar[stage]);  // frees the slot in both CTAs once these MMAs have read it
+              if (hb == 1 && j == nsub - 1) umma_commit_pair(&empty_bar[stage]);  // frees the slot in both CTAs once these MMAs have read it
               umma_commit_pair(&main_full[hb]);                  // this half of the hi.hi chunk is complete (both CTAs)
             }
           } else {
@@ -211,10 +306,11 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
             for (int k = 0; k < kTcBlockK / 16; ++k)
               umma_bf16_pair(d_main + static_cast<uint32_t>(mb) * 128u, a_hi + static_cast<uint64_t>(2 * k),
                              b_hi + static_cast<uint64_t>(2 * k), idesc, k > 0 ? 1u : 0u);
-            umma_commit_pair(&empty_bar[stage]);
+            if (j == nsub - 1) umma_commit_pair(&empty_bar[stage]);
             umma_commit_pair(&main_full[mb]);
             if (alt) mb ^= 1;
           }
+          }  // sub-blocks
           if (++stage == stages) { stage = 0; phase ^= 1u; }
         }
         umma_commit_pair(corr_full);
@@ -250,9 +346,9 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
       float2 racc[64];  // register accumulator group g (32 columns) = racc[16 g .. 16 g + 15]
 #pragma unroll
       for (int i = 0; i < 64; ++i) racc[i] = make_float2(0.f, 0.f);
-      for (int ch = 0; ch <= total_kb; ++ch) {
-        // ch < total_kb: hi.hi chunk from "main"; ch == total_kb: the tile's lo.hi + hi.lo sum from "corr"
-        const bool last = ch == total_kb;
+      for (int ch = 0; ch <= total_chunks; ++ch) {
+        // ch < total_chunks: hi.hi chunk from "main"; ch == total_chunks: the tile's lo.hi + hi.lo sum from "corr"
+        const bool last = ch == total_chunks;
         if (last) { mbar_wait(corr_full, cph, 5); cph ^= 1u; }
         else { mbar_wait(&main_full[mb], mph[mb], 6); mph[mb] ^= 1u; }
         tc_fence_after();
@@ -292,6 +388,29 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
         }
         if (!last && alt) mb ^= 1;
       }
+      if (p.pool) {
+        // fused 2x2/2 max pool (halo mode): the window of a pixel lives in lanes {l, l^1, l^tw, l^tw^1} of this warp; the
+        // bias add and ReLU commute with the max, so they run once, on the pooled value. Lane (ww & 1, hh & 1) of a window
+        // stores 8 of every 32 channels.
+        const int sub = (ww & 1) | ((hh & 1) << 1);
+        const size_t ppix = (static_cast<size_t>(n) * (p.h_out >> 1) + (h >> 1)) * (p.w_out >> 1) + (w >> 1);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int tcol = wide ? (g >> 1) * 128 + half * 64 + (g & 1) * 32 : half * half_cols + g * 32;
+          const int col0 = n_tile * block_n + tcol;
+          if (g * 32 < half_cols) {
+            float g8[8];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              float x = (i & 1) ? racc[g * 16 + (i >> 1)].y : racc[g * 16 + (i >> 1)].x;
+              x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 1));
+              x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, p.tw));
+              if ((i >> 3) == sub) g8[i & 7] = x;
+            }
+            if (valid && col0 + 8 * sub < p.n_valid) x3_store8_split(p, g8, ppix, col0 + 8 * sub);
+          }
+        }
+      } else
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         const int tcol = wide ? (g >> 1) * 128 + half * 64 + (g & 1) * 32 : half * half_cols + g * 32;
@@ -319,12 +438,16 @@ inline cudaError_t igemm_x3_launch(const IgemmTcParams& p, int num_sms, cudaStre
   static bool attr_set_dev[kMaxDevices] = {};
   bool& attr_set = attr_set_dev[current_device_slot()];
   int stages = 0;
-  const size_t smem = igemm_x3_smem_bytes(p.block_n, &stages);
+  const size_t smem = p.halo ? igemm_x3_halo_smem_bytes(p.block_n, p.tw, p.th, &stages) : igemm_x3_smem_bytes(p.block_n, &stages);
   if (!p.split || !p.pair || stages != p.num_stages || stages < 2) return cudaErrorInvalidValue;
+  if (p.halo && (p.tn != 1 || (p.tw & 7) != 0 || p.tw * p.th != kTcBlockM)) return cudaErrorInvalidValue;
+  if (p.pool && (!p.halo || p.residual != nullptr || p.out_f32 || p.tw > 16 || (p.h_out & 1) || (p.w_out & 1) || (p.n_valid & 31)))
+    return cudaErrorInvalidValue;
   if ((p.block_n & 63) != 0 || p.block_n > 256) return cudaErrorInvalidValue;  // the epilogue halves the tile in 32-column groups
   int total_kb = 0;
   for (int t = 0; t < p.num_taps; ++t) total_kb += p.taps[t].src ? p.kchunks2 : p.kchunks;
-  if (total_kb > kTcMaxKb) return cudaErrorInvalidValue;
+  if (p.halo) total_kb = 3 * p.kchunks + p.kchunks2;
+  if (total_kb > (kTcSmemHeader - 256) / 48) return cudaErrorInvalidValue;  // group schedule: 48 B per group
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(igemm_x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;

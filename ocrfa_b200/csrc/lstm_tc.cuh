@@ -486,7 +486,11 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_tc_persistent_kernel(con
           tma_store_2d(&p.tmP, hstage, j0 & 63, slab_row0);
           if (MODE == kLstmF16Split) tma_store_2d(&p.tmP, hstage + 4096, j0 & 63, slab_row0 + 8 * 128);
           tma_store_commit_and_wait_all();
+#ifdef OCRFA_LSTM_PUBLISH_RELEASE
+          red_release_gpu_add(group_ctr, 1u);  // measurement switch: gpu-scope release after the bulk group has completed
+#else
           red_relaxed_gpu_add(group_ctr, 1u);
+#endif
           LSTM_TS(s, 14);
         }
       } else {

@@ -13,8 +13,9 @@ Differences from the reference, all explicit:
     reference does with download_enabled=False; `verify_md5=False` accepts weights other than the released files;
   * DBNet (`detect_network="dbnet18"`), `optimal_num_chars` and `rotation_info` angles that are not multiples of 90
     degrees (scipy's spline resampling) are not offered (NotImplementedError);
-  * right-to-left display order uses python-bidi's `get_display` when that package is importable; without it the
-    logical-order string is returned and `OCR.bidi_available` is False.
+  * right-to-left display order (ocr.py:474-478) uses python-bidi's `get_display` when that package is importable and
+    `ocrfa_b200.bidi.get_display` - a restatement of the algorithm it implements, UAX #9 - otherwise
+    (`OCR.bidi_backend` names the one in use); `display_order=False` returns logical-order strings.
 """
 from __future__ import annotations
 
@@ -45,8 +46,10 @@ RECOGNITION_MODELS = {"arabic_g1": {"filename": "arabic.pth", "model_script": "a
 
 try:  # ocr.py:30
     from bidi.algorithm import get_display as _bidi_get_display
-except Exception:  # python-bidi is not part of this image
-    _bidi_get_display = None
+    _BIDI_BACKEND = "python-bidi"
+except Exception:  # python-bidi is not part of this image: the restatement of the algorithm it implements (UAX #9)
+    from .bidi import get_display as _bidi_get_display
+    _BIDI_BACKEND = "ocrfa_b200.bidi"
 
 
 def calculate_md5(fname) -> str:
@@ -81,6 +84,14 @@ def bgr2gray_device(img: torch.Tensor) -> torch.Tensor:
 def reformat_input(image, device="cuda"):
     """utils.py:1525-1565: (img [H, W, 3], img_cv_grey [H, W]), both uint8 CUDA tensors. Files and byte strings are
     decoded on the host by OpenCV (I/O); array inputs are uploaded once and converted on the GPU."""
+    if not isinstance(image, (str, bytes, torch.Tensor, np.ndarray)) and not hasattr(image, "__array__"):
+        raise ValueError("Invalid input type. Supporting format = string(file path), bytes, numpy array")
+    if isinstance(image, str) and (image.startswith("http://") or image.startswith("https://")):
+        raise ValueError("ocrfa_b200 does not fetch URLs: pass a file path, bytes or an array")
+    if isinstance(image, (torch.Tensor, np.ndarray)) and image.dtype not in (torch.uint8, np.uint8):
+        raise ValueError("image arrays must be uint8")
+    if isinstance(image, str) and not os.path.exists(os.path.expanduser(image)):
+        raise ValueError(f"cannot read image file {image!r}")
     dev = _lib.resolve_device(device)
     if isinstance(image, (str, bytes)):
         import cv2
@@ -272,7 +283,8 @@ class OCR:
 
     def __init__(self, gpu=True, recog_network="standard", download_enabled=True, detector=True, recognizer=True,
                  model_storage_directory=None, user_network_directory=None, detect_network="craft", verbose=True,
-                 quantize=True, cudnn_benchmark=False, *, precision="bf16", detector_precision="f16", verify_md5=True):
+                 quantize=True, cudnn_benchmark=False, *, precision="f16x3", detector_precision="f16", verify_md5=True,
+                 display_order=True):
         self.verbose = verbose
         self.download_enabled = download_enabled
         self.model_storage_directory = model_storage_directory or (MODULE_PATH + "/model")
@@ -288,7 +300,9 @@ class OCR:
         self.detection_models = DETECTION_MODELS
         self.recognition_models = {"gen1": RECOGNITION_MODELS, "gen2": {}}
         self.support_detection_network = ["craft"]
-        self.bidi_available = _bidi_get_display is not None
+        self.bidi_available = True
+        self.bidi_backend = _BIDI_BACKEND  # which get_display runs: the reference's dependency, or ocrfa_b200.bidi
+        self.display_order = bool(display_order)
         if recog_network not in ("standard", "arabic_g1"):
             raise ValueError("only the reference's default Farsi recognizer ('standard' / 'arabic_g1') is available")
         # language_list is fixed to ["fa"] (ocr.py:57): setModelLanguage("arabic", ...), arabic_g1, generation1
@@ -425,7 +439,7 @@ class OCR:
         if self.model_lang == "arabic":
             direction_mode = "rtl"
             result = [list(item) for item in result]
-            if _bidi_get_display is not None:
+            if self.display_order:  # ocr.py:474-478
                 for item in result:
                     item[1] = _bidi_get_display(item[1])
         else:

@@ -175,10 +175,21 @@ def recognizer_predict(model: Model, converter: CTCLabelConverter, test_loader, 
     return result
 
 
+# A greedy string is CERTIFIED when the line's decision margin (ocrfa_ctc_margin: smallest top-2 logit gap over the
+# timesteps, relative to the rms of the row's logits) exceeds this bound: ~9 standard deviations of the f16x3 mode's
+# measured logit-difference error (2.4e-6 of the rms per logit, tools/error_budget.py), so every evaluation of the network
+# within fp32-grade error - the reference's own - takes the same argmax at every timestep of such a line. Lines below it
+# hold a near-tie that the reference itself resolves differently when only its batch size changes
+# (profiles/r02_ref_self_consistency.json).
+CERTIFY_MARGIN = 3e-5
+
+
 def recognize_host(model: Model, converter: CTCLabelConverter, images_u8: torch.Tensor, widths: Optional[torch.Tensor],
-                   mask_np: Optional[np.ndarray], decoder: str, beamWidth: int, dev: torch.device):
-    """One batch through ocrfa_recognize_host: host uint8 lines in, strings + confidences out (the end-to-end call:
-    H2D, preprocess, forward, decode and D2H all inside)."""
+                   mask_np: Optional[np.ndarray], decoder: str, beamWidth: int, dev: torch.device,
+                   return_margin: bool = False):
+    """One batch through ocrfa_recognize_host_ex: host uint8 lines in, strings + confidences out (the end-to-end call:
+    H2D, preprocess, forward, decode and D2H all inside). return_margin=True also returns the per-line decision margin
+    of the greedy decode (float32 [B]); the last call's margins stay on `model.last_margins` either way."""
     lib = _lib.load()
     if images_u8.is_cuda or images_u8.dtype != torch.uint8 or images_u8.dim() != 3:
         raise ValueError("images_u8 must be a host uint8 tensor [B, H, W]")
@@ -195,21 +206,28 @@ def recognize_host(model: Model, converter: CTCLabelConverter, images_u8: torch.
         labels = torch.empty((B, T), dtype=torch.int32).pin_memory()
         lens = torch.empty(B, dtype=torch.int32).pin_memory()
         conf = torch.empty(B, dtype=torch.float64).pin_memory()
+        margin = torch.empty(B, dtype=torch.float32).pin_memory()
         w32 = widths.to(torch.int32).contiguous() if widths is not None else None
         mask = np.ascontiguousarray(mask_np, dtype=np.uint8) if mask_np is not None else None
         stream = torch.cuda.current_stream(dev).cuda_stream
-        _lib.check(lib.ocrfa_recognize_host(
+        _lib.check(lib.ocrfa_recognize_host_ex(
             handle, C.c_void_p(img.data_ptr()), C.c_void_p(w32.data_ptr()) if w32 is not None else None, B, H, W,
             mask.ctypes.data_as(C.c_void_p) if mask is not None else None, 1 if decoder == "beamsearch" else 0, bw,
             C.c_void_p(labels.data_ptr()), C.c_void_p(lens.data_ptr()), C.c_void_p(conf.data_ptr()),
-            C.c_void_p(ws.data_ptr()), ws_bytes, C.c_void_p(stream)))
-    return converter.labels_to_text(labels.numpy(), lens.numpy()), conf.numpy().copy()
+            C.c_void_p(margin.data_ptr()), 0, C.c_void_p(ws.data_ptr()), ws_bytes, C.c_void_p(stream)))
+    model.last_margins = margin.numpy().copy()
+    strs = converter.labels_to_text(labels.numpy(), lens.numpy())
+    if return_margin:
+        return strs, conf.numpy().copy(), model.last_margins
+    return strs, conf.numpy().copy()
 
 
 def get_recognizer(recog_network, network_params, character, separator_list, dict_list, model_path, device="cuda",
-                   quantize=True, precision="bf16"):
+                   quantize=True, precision="f16x3"):
     """utils.py:665-695. `quantize` (dynamic int8 of the reference's CPU path) has no meaning here and is ignored;
-    `precision` selects bf16 tensor-core or fp32 parity arithmetic."""
+    `precision`: "f16x3" (default: fp32-grade tensor-core arithmetic, the mode whose strings are checked against the
+    reference), "bf16" / "f16" (single-pass tensor-core modes, 3.5x faster, 16-bit rounding noise in the logits) or
+    "fp32" (CUDA-core arithmetic with fp64 accumulation, 25x slower; the reference point of the parity runs)."""
     if str(device) == "cpu":
         raise _lib.OcrfaError("ocrfa_b200 has no CPU path; use device='cuda'")
     converter = CTCLabelConverter(character, separator_list, dict_list)

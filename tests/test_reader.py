@@ -90,7 +90,9 @@ def reader(tmp_path_factory, synth_sd):
         ob.OCR(model_storage_directory=str(d))
     with pytest.raises(FileNotFoundError):
         ob.OCR(model_storage_directory=str(d / "nothing_here"), verify_md5=False)
-    return ob.OCR(model_storage_directory=str(d), verify_md5=False, precision="fp32", detector_precision="f16")
+    # display_order=False: the fixture was generated with python-bidi stubbed to the identity (oracle/_refimport.py)
+    return ob.OCR(model_storage_directory=str(d), verify_md5=False, precision="fp32", detector_precision="f16",
+                  display_order=False)
 
 
 def _assert_results(got, want, conf_rtol=5e-3):
@@ -237,25 +239,30 @@ def test_gpu_readtext_with_the_craft_forward(reader):
 
 @pytest.mark.gpu
 def test_gpu_default_precision_reader_reads_the_same_boxes(reader, tmp_path, synth_sd):
-    """The constructor's defaults (bf16 recognizer, f16 detector): same boxes as the fp32 reader (the detector is the
-    same), strings that agree with it on most lines (bf16 tolerance)."""
+    """The constructor's defaults (f16x3 recognizer - fp32-grade tensor-core arithmetic - and f16 detector): the same
+    boxes AND the same strings as the fp32 (CUDA-core) reader; display_order=True additionally applies the RTL display
+    order (ocr.py:474-478) to every string."""
     import torch
     import ocrfa_b200 as ob
+    from ocrfa_b200.bidi import get_display
 
     torch.save({k: torch.from_numpy(v) for k, v in synth_sd.items()}, os.path.join(tmp_path, "arabic.pth"))
     torch.save({k: torch.from_numpy(v) for k, v in ob.synth_craft_state_dict(0).items()},
                os.path.join(tmp_path, "craft_mlt_25k.pth"))
     fast = ob.OCR(model_storage_directory=str(tmp_path), verify_md5=False)
-    assert fast.precision == "bf16" and fast.detector_precision == "f16" and fast.model_lang == "arabic"
+    assert fast.precision == "f16x3" and fast.detector_precision == "f16" and fast.model_lang == "arabic"
+    assert fast.display_order and fast.bidi_backend in ("python-bidi", "ocrfa_b200.bidi")
     g = load_golden("reader")
     page = load_golden("crops")["page"]
     h_list, f_list = g["rec_h_list"].tolist(), g["rec_f_list"].tolist()
     got = fast.recognize(page, h_list, f_list, batch_size=16, reformat=False)
-    want = reader.recognize(page, h_list, f_list, batch_size=16, reformat=False)
+    want = reader.recognize(page, h_list, f_list, batch_size=16, reformat=False)  # logical order (display_order=False)
     assert [r[0] for r in got] == [r[0] for r in want]
-    same = sum(a[1] == b[1] for a, b in zip(got, want))
-    print(f"bf16 reader vs fp32 reader: {same}/{len(want)} identical strings")
-    assert same >= len(want) // 2
+    if fast.bidi_backend == "ocrfa_b200.bidi":
+        assert [r[1] for r in got] == [get_display(r[1]) for r in want]
+    fast.display_order = False
+    got = fast.recognize(page, h_list, f_list, batch_size=16, reformat=False)
+    assert [r[1] for r in got] == [r[1] for r in want]
 
 
 @pytest.mark.gpu

@@ -258,7 +258,8 @@ static void make_split_act(size_t npix, int c, int c_real, float scale, std::vec
       eff[px * c + ch] = split_pair(d(rng) * scale, &packed[px * 2 * c + ch], &packed[px * 2 * c + c + ch]);
 }
 
-static void run_split_case(const Case& c) {
+// halo = true: the halo-staged form of igemm_x3_kernel (plan_x3_halo), optionally with the 2x2/2 max pool fused
+static void run_split_case(const Case& c, bool halo = false, bool pool = false) {
   const ConvGeom& g = c.g;
   const int ho = g.h_out(), wo = g.w_out();
   const int cin_pad = ceil_div(g.cin, 64) * 64;
@@ -311,8 +312,9 @@ static void run_split_case(const Case& c) {
 
   IgemmTcParams p;
   TileShape forced{c.tw, c.th, c.tn};
-  int rc = plan_conv(&p, g, d_in, cin_pad, d_w, c.tw ? &forced : nullptr, true);
+  int rc = halo ? plan_x3_halo(&p, g, d_in, cin_pad, d_w, pool) : plan_conv(&p, g, d_in, cin_pad, d_w, c.tw ? &forced : nullptr, true);
   if (rc == 0 && c.fuse_cin2) rc = plan_add_source(&p, d_in2, c.fuse_cin2, cin2_pad, d_w, ktotal, g.cout);
+  if (halo && rc == -33) { printf("[split-halo %s] skipped: fewer than two stages fit (Cout = %d)\n", c.name, g.cout); return; }
   if (rc) { printf("[split %s] plan failed rc=%d\n", c.name, rc); g_fail++; return; }
   p.bias = c.use_bias ? d_bias : nullptr;
   p.residual = d_res; p.ldr = 2 * g.cout; p.res_lo = g.cout;
@@ -329,18 +331,38 @@ static void run_split_case(const Case& c) {
   CK(cudaDeviceSynchronize());
   std::vector<float> ref(out_elems), got(out_elems);
   CK(cudaMemcpy(ref.data(), d_ref, out_elems * 4, cudaMemcpyDeviceToHost));
+  size_t cmp_elems = out_elems, cmp_pix = npix_out;
+  if (pool) {
+    // max-pool the full-resolution reference on the host (bias + ReLU already applied: they commute with the max)
+    const int hp = ho / 2, wp = wo / 2;
+    std::vector<float> pr((size_t)g.n * hp * wp * g.cout);
+    for (int n = 0; n < g.n; ++n)
+      for (int y = 0; y < hp; ++y)
+        for (int x = 0; x < wp; ++x)
+          for (int co = 0; co < g.cout; ++co) {
+            float m = -INFINITY;
+            for (int dy = 0; dy < 2; ++dy)
+              for (int dx = 0; dx < 2; ++dx)
+                m = std::max(m, ref[(((size_t)n * ho + 2 * y + dy) * wo + 2 * x + dx) * g.cout + co]);
+            pr[(((size_t)n * hp + y) * wp + x) * g.cout + co] = m;
+          }
+    ref.swap(pr);
+    cmp_pix = (size_t)g.n * hp * wp;
+    cmp_elems = cmp_pix * g.cout;
+    got.resize(cmp_elems);
+  }
   if (c.out_f32) {
-    CK(cudaMemcpy(got.data(), d_out, out_elems * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(got.data(), d_out, cmp_elems * 4, cudaMemcpyDeviceToHost));
   } else {
-    std::vector<__half> tmp(out_elems * 2);
-    CK(cudaMemcpy(tmp.data(), d_out, out_elems * 4, cudaMemcpyDeviceToHost));
-    for (size_t px = 0; px < npix_out; ++px)
+    std::vector<__half> tmp(cmp_elems * 2);
+    CK(cudaMemcpy(tmp.data(), d_out, cmp_elems * 4, cudaMemcpyDeviceToHost));
+    for (size_t px = 0; px < cmp_pix; ++px)
       for (int co = 0; co < g.cout; ++co)
         got[px * g.cout + co] = __half2float(tmp[px * 2 * g.cout + co]) + __half2float(tmp[px * 2 * g.cout + g.cout + co]);
   }
   double max_abs = 0, max_ref = 0, sum_d = 0, sum_d2 = 0, sum_r2 = 0;
   size_t bad = 0;
-  for (size_t i = 0; i < out_elems; ++i) {
+  for (size_t i = 0; i < cmp_elems; ++i) {
     const float d = std::fabs(got[i] - ref[i]);
     sum_d += (double)got[i] - ref[i]; sum_d2 += ((double)got[i] - ref[i]) * ((double)got[i] - ref[i]); sum_r2 += (double)ref[i] * ref[i];
     if (!(d <= 2e-5f + 2e-5f * std::fabs(ref[i]))) {
@@ -350,15 +372,15 @@ static void run_split_case(const Case& c) {
     if (d > max_abs || std::isnan(d)) max_abs = d;
     max_ref = std::max(max_ref, (double)std::fabs(ref[i]));
   }
-  printf("[split %s] n=%d in=%dx%d cin=%d cout=%d k=%dx%d sh=%d bn=%d : max_abs_err=%.3g (max|ref|=%.3g) bad=%zu/%zu %s\n",
-         c.name, g.n, g.h_in, g.w_in, g.cin, g.cout, g.kh, g.kw, g.sh, p.block_n, max_abs, max_ref, bad, out_elems,
-         bad ? "FAIL" : "ok");
+  printf("[split%s%s %s] n=%d in=%dx%d cin=%d cout=%d k=%dx%d sh=%d bn=%d tile=%dx%dx%d : max_abs_err=%.3g (max|ref|=%.3g) bad=%zu/%zu %s\n",
+         halo ? "-halo" : "", pool ? "+pool" : "", c.name, g.n, g.h_in, g.w_in, g.cin, g.cout, g.kh, g.kw, g.sh, p.block_n, p.tw, p.th, p.tn,
+         max_abs, max_ref, bad, cmp_elems, bad ? "FAIL" : "ok");
   {
     // error against the float64 sum of the SAME operand values, relative to rms(ref): an fp32 round-to-nearest
     // accumulation of K terms would sit near 2^-24 * sqrt(K) / sqrt(3) rms with zero mean
-    const double rr = std::sqrt(sum_r2 / out_elems);
-    printf("    rel. error vs f64: rms %.3g  mean %+.3g  (pair=%d stages=%d)\n", std::sqrt(sum_d2 / out_elems) / rr,
-           sum_d / out_elems / rr, p.pair, p.num_stages);
+    const double rr = std::sqrt(sum_r2 / cmp_elems);
+    printf("    rel. error vs f64: rms %.3g  mean %+.3g  (pair=%d stages=%d)\n", std::sqrt(sum_d2 / cmp_elems) / rr,
+           sum_d / cmp_elems / rr, p.pair, p.num_stages);
   }
   if (bad) g_fail++;
   if (c.perf_iters > 0 && !bad) {
@@ -383,7 +405,10 @@ static void run_split_case(const Case& c) {
 // ---------------------------------------------------------------------------------------------
 // persistent LSTM recurrence (both arithmetic modes) against a host reference
 // ---------------------------------------------------------------------------------------------
-static void run_lstm_case(int B, int T, int mode) {
+// repeat > 0: stress run of the cross-CTA publish - `repeat` more launches, each against a re-poisoned (NaN) exchange
+// buffer, every one compared bit for bit with the first launch over ALL batch rows (a stale or torn read of a peer's h
+// slice changes some row of some step; the first launch itself is held to the float64 host recurrence below)
+static void run_lstm_case(int B, int T, int mode, int repeat = 0) {
   const int H = 512;
   const bool sp = mode == kLstmF16Split;
   std::uniform_real_distribution<float> ud(-1.f, 1.f);
@@ -528,6 +553,27 @@ static void run_lstm_case(int B, int T, int mode) {
     memcpy(&lo, &hgot[((size_t)b * T + t) * 2048 + 1024 + col], 2);
     return __half2float(hi) + __half2float(lo);
   };
+  if (repeat > 0) {
+    std::vector<uint16_t> again(hgot.size());
+    int bad_launches = 0;
+    size_t bad_values = 0;
+    for (int it = 0; it < repeat; ++it) {
+      CK(cudaMemsetAsync(d_hx, 0xff, hx_rows * 128));
+      CK(cudaMemsetAsync(d_hseq, 0, (size_t)B * T * hs_row * 2));
+      CK(cudaMemsetAsync(d_sync, 0, 64));
+      CK(lstm_tc_launch(lp, mode, 0));
+      cudaError_t e2 = cudaDeviceSynchronize();
+      if (e2 != cudaSuccess) { printf("[lstm stress] kernel failed: %s\n", cudaGetErrorString(e2)); exit(3); }
+      CK(cudaMemcpy(again.data(), d_hseq, again.size() * 2, cudaMemcpyDeviceToHost));
+      size_t diff = 0;
+      for (size_t i = 0; i < again.size(); ++i) diff += again[i] != hgot[i];
+      if (diff) { bad_launches++; bad_values += diff; }
+    }
+    printf("[lstm stress %s] B=%d T=%d : %d launches x %d steps x %d CTAs, %d launches differ from the first (%zu values) %s\n",
+           sp ? "f16-split" : (mode == kLstmF16FusedX ? "f16-fused-x" : "bf16-fused-x"), B, T, repeat, T, 64 * lp.m_tiles,
+           bad_launches, bad_values, bad_launches ? "FAIL" : "ok");
+    if (bad_launches) g_fail++;
+  }
   const float tol = sp ? 2e-5f : 2e-2f;
   double max_abs = 0; size_t bad = 0, cnt = 0;
   for (int b = 0; b < bcheck; ++b)
@@ -723,6 +769,7 @@ static void run_halo_suite(bool perf) {
 int main(int argc, char** argv) {
   bool perf = false;
   bool halo_only = false;
+  int lstm_stress = 0;      // --lstm-stress N: N extra launches per geometry / mode of the persistent LSTM (publish stress)
   bool split_only = false;  // --split: only the fp32-grade (f16x3) conv / GEMM cases (+ --perf: the c2 layer shapes)
   const char* only = nullptr;  // --only NAME: run one perf case (or "lstm") alone, e.g. under ncu
   for (int i = 1; i < argc; ++i) {
@@ -731,12 +778,23 @@ int main(int argc, char** argv) {
     if (!strcmp(argv[i], "--halo")) halo_only = true;
     if (!strcmp(argv[i], "--split")) split_only = true;
     if (!strcmp(argv[i], "--positive")) g_split_positive = true;
+    if (!strcmp(argv[i], "--lstm-stress") && i + 1 < argc) lstm_stress = atoi(argv[++i]);
   }
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, 0));
   g_sms = prop.multiProcessorCount;
   printf("device: %s, %d SMs, cc %d.%d\n", prop.name, g_sms, prop.major, prop.minor);
 
+  if (lstm_stress > 0) {
+    // c1 / c2 / c3 geometries (B = 1, 256, 64 lines; T = 33, 129, 513), both publish paths (TMA store / generic stores)
+    for (int mode : {kLstmBf16FusedX, kLstmF16Split}) {  // (the fp16 fused-x mode is the bf16 code path with another operand format)
+      run_lstm_case(1, 33, mode, lstm_stress);
+      run_lstm_case(256, 129, mode, lstm_stress);
+      run_lstm_case(64, 513, mode, lstm_stress / 4 > 0 ? lstm_stress / 4 : 1);
+    }
+    printf("%s (%d failing cases)\n", g_fail ? "FAILED" : "ALL OK", g_fail);
+    return g_fail ? 1 : 0;
+  }
   if (halo_only) {
     run_halo_suite(perf);
     printf("%s (%d failing cases)\n", g_fail ? "FAILED" : "ALL OK", g_fail);
@@ -776,6 +834,21 @@ int main(int argc, char** argv) {
   };
   if (split_only) {
     for (const Case& c : cases) run_split_case(c);
+    {
+      // halo-staged form: odd sizes, fused downsample source, residual, fused pool
+      std::vector<Case> hc = {
+          {"h_c64",        {2, 32, 512, 64, 64, 3, 3, 1, 1, 1},   1, 1, 0, 0, 0, 0, 0, 0, 0},
+          {"h_c64_128",    {2, 16, 256, 64, 128, 3, 3, 1, 1, 1},  1, 1, 0, 0, 0, 0, 0, 0, 0},
+          {"h_c128_res",   {3, 16, 256, 128, 128, 3, 3, 1, 1, 1}, 1, 1, 1, 0, 0, 0, 0, 0, 0},
+          {"h_c128_ds",    {3, 16, 256, 128, 128, 3, 3, 1, 1, 1}, 1, 1, 0, 0, 64, 0, 0, 0, 0},
+          {"h_c256",       {3, 8, 128, 256, 256, 3, 3, 1, 1, 1},  1, 1, 1, 0, 0, 0, 0, 0, 0},
+          {"h_c256_ds",    {3, 8, 128, 256, 256, 3, 3, 1, 1, 1},  1, 1, 0, 0, 128, 0, 0, 0, 0},
+          {"h_ragged",     {3, 20, 72, 64, 64, 3, 3, 1, 1, 1},    1, 1, 0, 0, 0, 0, 0, 0, 0},
+          {"h_one_image",  {1, 64, 96, 128, 128, 3, 3, 1, 1, 1},  0, 1, 0, 0, 0, 0, 0, 0, 0},
+      };
+      for (const Case& c : hc) run_split_case(c, true, false);
+      for (const Case& c : hc) if (!c.use_res && !c.fuse_cin2) run_split_case(c, true, true);
+    }
     if (perf && g_fail == 0) {
       std::vector<Case> pc = {
           {"perf_c0_2",    {256, 32, 512, 64, 64, 3, 3, 1, 1, 1},    1, 1, 0, 0, 0, 0, 0, 0, 5},
@@ -792,6 +865,12 @@ int main(int argc, char** argv) {
           {"perf_pred",    {1, 1, 33024, 512, 185, 1, 1, 1, 0, 0},   0, 1, 0, 1, 0, 0, 0, 0, 10},
       };
       for (const Case& c : pc) run_split_case(c);
+      // halo-staged form on the layers it is meant for (and on the 256-channel ones for comparison)
+      for (int i : {0, 1, 2, 3, 4}) run_split_case(pc[i], true, false);
+      run_split_case(pc[0], true, true);
+      run_split_case({"perf_conv1_pool", {256, 16, 256, 128, 128, 3, 3, 1, 1, 1}, 1, 1, 0, 0, 0, 0, 0, 0, 10}, true, true);
+      run_split_case({"perf_l1_c2_ds", {256, 16, 256, 128, 128, 3, 3, 1, 1, 1}, 1, 1, 0, 0, 64, 0, 0, 0, 10}, true, false);
+      run_split_case({"perf_l1_c2_ds", {256, 16, 256, 128, 128, 3, 3, 1, 1, 1}, 1, 1, 0, 0, 64, 0, 0, 0, 10}, false, false);
     }
     printf("%s (%d failing cases)\n", g_fail ? "FAILED" : "ALL OK", g_fail);
     return g_fail ? 1 : 0;
