@@ -1,19 +1,23 @@
 #!/usr/bin/env python
 """bench.py - text lines/sec of the OCR-FA recognition hot path on B200 (BASELINE.json metric).
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--config c2|c1|c3|c4]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--config c2|c1|c3|c4] [--precision f16x3|bf16|f16|fp32]
 
 A step = one pass of the hot path (uint8 lines -> fused normalise+stem -> ResNet-29 -> 2xBiLSTM -> Linear -> softmax/
 mask/renorm/argmax/CTC collapse/confidence) over one batch of synthetic lines per rank. Default workload is BASELINE
-config 2 (256 lines of 32x512, greedy, bf16 tensor-core arithmetic); ranks are independent (weak scaling), NCCL is
-used only to gather timings and decoded labels after the timed region.
+config 2 (256 lines of 32x512, greedy) in the DEFAULT precision of the library, f16x3: fp32-grade tensor-core
+arithmetic, the mode whose decoded strings are held to the reference's (the `parity` object of the line, measured in
+this run against the oracle). The BASELINE config's bf16 arithmetic is timed in the same run and reported under
+`other_precisions` (and is the headline of `--precision bf16`). Ranks are independent (weak scaling): rank r reads lines
+[r*B, (r+1)*B) of a synthetic set in which a line is a function of its global index; NCCL is used only after the timed
+regions, to gather timings and decoded labels (rank 0 then recomputes every rank's lines itself and compares).
 
-JSON line keys: value = whole-job lines/s with inputs resident in HBM (CUDA events, max over ranks);
-e2e = the same through ocrfa_recognize_host with pinned HOST buffers (H2D + D2H inside the timed region);
-roofline = tcgen05 implicit-GEMM kernel, algorithmic FLOPs / CUDA-event kernel time vs MEASURED_PEAKS.json;
-cpu_baseline = the oracle (port of the reference's CPU path) on a bounded sample, rank 0, N=1 only.
-`--impl reference` times that CPU path alone (the reference is Python and cannot travel to the GPU box, so the
-oracle port pinned against it in tests/test_oracle_golden.py is what runs).
+JSON line keys: value = whole-job lines/s with inputs resident in HBM (CUDA events on the launching stream, max over
+ranks); e2e = the same through ocrfa_recognize_host_ex with pinned HOST buffers, H2D + D2H inside the timed region,
+two batches in flight on two streams; roofline = the tcgen05 implicit-GEMM kernels, algorithmic FLOPs / CUDA-event
+kernel time in the timed region vs MEASURED_PEAKS.json; cpu_baseline = the oracle (port of the reference's CPU path)
+on a bounded sample, rank 0, N=1 only. `--impl reference` times that CPU path alone (the reference is Python and cannot
+travel to the GPU box, so the oracle port pinned against it in tests/test_oracle_golden.py is what runs).
 """
 from __future__ import annotations
 
@@ -45,6 +49,17 @@ CONFIGS = {
 }
 # algorithmic FLOPs per line (2*MAC of every conv/LSTM/Linear), SURVEY.md section 8d / BASELINE.md section 3
 FLOPS_PER_LINE = {(32, 128): 13.453e9, (32, 512): 52.788e9, (64, 2048): 411.546e9}
+DTYPE_TEXT = {
+    "f16x3": "f16x3 (fp16 hi/lo split operands on tcgen05, 3 products per MAC, hi.hi summed per K chunk in fp32 registers: fp32-grade)",
+    "bf16": "bf16", "f16": "f16 (fp16 operands/activations, fp32 accumulate: the bf16 kernels, 3 more mantissa bits)", "fp32": "f32",
+}
+LINE_SEED = 1234  # line g of the synthetic set is synth_lines(seed = LINE_SEED + g)
+
+
+def workload_text(cfg_name: str) -> str:
+    B, H, W, decoder, beam = CONFIGS[cfg_name]
+    return (f"{cfg_name}: {B} lines of {H}x{W} per rank per step, {decoder}" + (f" beam={beam}" if decoder != "greedy" else "")
+            + ", reference default model (ResNet-29 + 2xBiLSTM + Linear185), random-init weights")
 
 
 def load_peaks():
@@ -52,17 +67,9 @@ def load_peaks():
     if os.path.exists(path):
         with open(path) as f:
             p = json.load(f)
-        return {"bf16_sustained": float(p.get("bf16_tflops_sustained", 1354.4)), "hbm": float(p.get("hbm_gbs", 6550.4)),
-                "source": "measured (MEASURED_PEAKS.json)"}
-    return {"bf16_sustained": 1400.0, "hbm": 6650.0, "source": "fallback (B200_PROFILING.md)"}
-
-
-def load_burst() -> float:
-    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(path):
-        with open(path) as f:
-            return float(json.load(f).get("bf16_tflops", 1654.9))
-    return 1590.0
+        return {"bf16_sustained": float(p.get("bf16_tflops_sustained", 1354.4)), "bf16_burst": float(p.get("bf16_tflops", 1654.9)),
+                "hbm": float(p.get("hbm_gbs", 6550.4)), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"bf16_sustained": 1400.0, "bf16_burst": 1590.0, "hbm": 6650.0, "source": "fallback (B200_PROFILING.md)"}
 
 
 def load_traffic(config: str, precision: str):
@@ -172,8 +179,7 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": lps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.config}: {B} lines of {H}x{W}, {decoder}" + (f" beam={beam}" if decoder != "greedy" else ""),
-                   "sample": f"{n} lines per step on the host CPU"},
+        "config": {"workload": workload_text(args.config), "sample": f"{n} lines per step on the host CPU"},
         "cpu_baseline": {"value": lps, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{n} lines of {H}x{W} per step, torch CPU fp32, {threads} threads (oracle port of "
                                    "recognizer_predict; the Python reference cannot travel to the GPU box)"},
@@ -186,10 +192,78 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------------------------
+class Slot:
+    """One in-flight batch of the end-to-end path: its own stream, workspace and pinned result buffers."""
+
+    def __init__(self, lib, handle, B, H, W, T, bw, dev):
+        self.stream = torch.cuda.Stream(dev)
+        self.ws_bytes = lib.ocrfa_recognize_workspace_bytes(handle, B, H, W, bw)
+        buf = torch.empty(int(self.ws_bytes) + 1024, dtype=torch.uint8, device=dev)
+        off = (-buf.data_ptr()) % 1024
+        self.ws = buf[off:off + self.ws_bytes]
+        self.labels = torch.empty((B, T), dtype=torch.int32).pin_memory()
+        self.lens = torch.empty(B, dtype=torch.int32).pin_memory()
+        self.conf = torch.empty(B, dtype=torch.float64).pin_memory()
+        self.margin = torch.empty(B, dtype=torch.float32).pin_memory()
+
+
+def measure_device(lib, _lib, handle, geom, d_img, d_mask, dec, bw, ws, ws_bytes, outs, stream, steps, warmup, dev, world,
+                   profile_mask, flush_l2):
+    """K steps on device-resident inputs, CUDA events on the launching stream. Returns (ms, per-class ms, flops, launches)."""
+    B, H, W, T = geom
+    d_labels, d_len, d_conf = outs
+
+    def step():
+        _lib.check(lib.ocrfa_recognize_device(handle, C.c_void_p(d_img.data_ptr()), None, B, H, W,
+                                              C.c_void_p(d_mask.data_ptr()), dec, bw, C.c_void_p(d_labels.data_ptr()),
+                                              C.c_void_p(d_len.data_ptr()), C.c_void_p(d_conf.data_ptr()),
+                                              C.c_void_p(ws.data_ptr()), ws_bytes, C.c_void_p(stream.cuda_stream)))
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(warmup):
+        step()
+    barrier()
+    launches0 = lib.ocrfa_launch_count(handle)
+    _lib.check(lib.ocrfa_profile_begin(handle, profile_mask))
+    barrier()
+    if flush_l2:
+        flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        with torch.cuda.stream(stream):
+            for i, (a, b) in enumerate(pairs):
+                flush_buf.fill_(i & 0xff)
+                a.record(stream)
+                step()
+                b.record(stream)
+        barrier()
+        dev_ms = sum(a.elapsed_time(b) for a, b in pairs)
+    else:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            step()
+        e1.record(stream)
+        barrier()
+        dev_ms = e0.elapsed_time(e1)
+    ms_cls = (C.c_double * 8)()
+    fl_cls = (C.c_double * 8)()
+    n_cls = (C.c_int64 * 8)()
+    _lib.check(lib.ocrfa_profile_end(handle, ms_cls, fl_cls, n_cls))
+    launches = int(lib.ocrfa_launch_count(handle) - launches0)
+    return dev_ms, list(ms_cls), list(fl_cls), list(n_cls), launches, step
+
+
 def run_gpu_arm(args):
     import ocrfa_b200 as ob
     from ocrfa_b200 import _lib
-    from ocrfa_b200.synth import synth_lines, synth_state_dict  # synthetic data generator (not timed)
+    from ocrfa_b200.recognition import CERTIFY_MARGIN, _ignore_mask
+    from ocrfa_b200.synth import synth_lines_global, synth_state_dict  # synthetic data generator (not timed)
 
     rank, local_rank, world = dist_env()
     if not torch.cuda.is_available():
@@ -207,112 +281,78 @@ def run_gpu_arm(args):
     chars = ob.default_character()
     conv = ob.CTCLabelConverter(chars)
     Cn = len(conv.character)
+    sd = {k: torch.from_numpy(v) for k, v in synth_state_dict(0).items()}
     model = ob.Model(1, 512, 512, Cn, precision=args.precision)
-    model.load_state_dict({k: torch.from_numpy(v) for k, v in synth_state_dict(0).items()})
+    model.load_state_dict(sd)
     handle = model._ensure_handle(dev)
     T = lib.ocrfa_out_timesteps(H, W)
 
-    # synthetic lines: a small seeded pool of text-like lines tiled to the batch (content does not change the work)
-    pool = synth_lines(min(B, 32), H, W, seed=1234 + rank)
-    imgs_np = np.ascontiguousarray(np.tile(pool, ((B + len(pool) - 1) // len(pool), 1, 1))[:B])
+    # this rank's lines: [rank * B, (rank + 1) * B) of the global synthetic set
+    imgs_np = synth_lines_global(rank * B, (rank + 1) * B, H, W, LINE_SEED)
     h_img = torch.from_numpy(imgs_np).pin_memory()
     d_img = h_img.to(dev)
-    mask_np = np.zeros(Cn, dtype=np.uint8)
-    from ocrfa_b200.recognition import _ignore_mask
     ign = [chars.index(ch) + 1 for ch in ob.default_ignore_char()]
     mask_np = _ignore_mask(Cn, ign)
     d_mask = torch.from_numpy(mask_np).to(dev)
     bw = beam if decoder == "beamsearch" else 1
-    ws_bytes = lib.ocrfa_recognize_workspace_bytes(handle, B, H, W, bw)
-    ws = model.workspace(ws_bytes, dev)
+    dec = 1 if decoder == "beamsearch" else 0
+    slots = [Slot(lib, handle, B, H, W, T, bw, dev) for _ in range(2)]
+    ws, ws_bytes, stream = slots[0].ws, slots[0].ws_bytes, slots[0].stream  # a non-default stream: CUDA-graph replay is possible
     d_labels = torch.empty((B, T), dtype=torch.int32, device=dev)
     d_len = torch.empty(B, dtype=torch.int32, device=dev)
     d_conf = torch.empty(B, dtype=torch.float64, device=dev)
-    stream = torch.cuda.current_stream(dev)
-    dec = 1 if decoder == "beamsearch" else 0
+    # A step whose working set (activation workspace + weights) fits the 126 MB L2 would be timed on a warm cache: such
+    # configurations (c1) get an explicit flush - a 256 MB fill - before every timed step, and the step is bracketed by
+    # its own event pair so that the flush is not in the sum. The big configurations stream > 1 GB per step.
+    flush_l2 = int(ws_bytes) + 220 * (1 << 20) < 512 * (1 << 20)
+    warmup = max(3, args.warmup)
 
-    def step_device():
-        _lib.check(lib.ocrfa_recognize_device(handle, C.c_void_p(d_img.data_ptr()), None, B, H, W,
-                                              C.c_void_p(d_mask.data_ptr()), dec, bw, C.c_void_p(d_labels.data_ptr()),
-                                              C.c_void_p(d_len.data_ptr()), C.c_void_p(d_conf.data_ptr()),
-                                              C.c_void_p(ws.data_ptr()), ws_bytes, C.c_void_p(stream.cuda_stream)))
-
-    def barrier():
-        torch.cuda.synchronize(dev)
-        if world > 1:
-            import torch.distributed as dist
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    for _ in range(max(3, args.warmup)):
-        step_device()
-    barrier()
-
-    # ---- timed region 1: device-resident inputs, CUDA events on the launching stream; tcgen05 class profiled
+    # ---- timed region 1: device-resident inputs; the tcgen05 implicit-GEMM class is bracketed by events (eager launches)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    launches0 = lib.ocrfa_launch_count(handle)
-    _lib.check(lib.ocrfa_profile_begin(handle, 1 << 1))
-    # A step whose working set (activation workspace + 108 MB of weights) fits the 126 MB L2 would be timed on a warm
-    # cache: such configurations (c1) get an explicit flush - a 256 MB fill - before every timed step, and the step is
-    # bracketed by its own event pair so that the flush is not in the sum. The big configurations stream > 1 GB per step.
-    flush_l2 = int(ws_bytes) + 110 * (1 << 20) < 512 * (1 << 20)
-    barrier()
+    dev_ms, ms_cls, fl_cls, n_cls, launches, step_device = measure_device(
+        lib, _lib, handle, (B, H, W, T), d_img, d_mask, dec, bw, ws, ws_bytes, (d_labels, d_len, d_conf), stream, args.steps,
+        warmup, dev, world, 1 << 1, flush_l2)
+
+    # ---- timed region 2: end to end through the host-buffer C-ABI call, two batches in flight (two streams, two
+    # workspaces, pinned host buffers): H2D of batch i+1 and D2H of batch i-1 overlap the kernels of batch i
+    def submit(slot):
+        _lib.check(lib.ocrfa_recognize_host_ex(
+            handle, C.c_void_p(h_img.data_ptr()), None, B, H, W, mask_np.ctypes.data_as(C.c_void_p), dec, bw,
+            C.c_void_p(slot.labels.data_ptr()), C.c_void_p(slot.lens.data_ptr()), C.c_void_p(slot.conf.data_ptr()),
+            C.c_void_p(slot.margin.data_ptr()), _lib.FLAG_ASYNC, C.c_void_p(slot.ws.data_ptr()), slot.ws_bytes,
+            C.c_void_p(slot.stream.cuda_stream)))
+
+    for s in slots:  # warm-up: first sight of each slot's pointers captures its CUDA graph
+        submit(s)
+        submit(s)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
     if flush_l2:
         flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-        pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-        with torch.cuda.stream(stream):
-            for i, (a, b) in enumerate(pairs):
-                flush_buf.fill_(i & 0xff)
-                a.record(stream)
-                step_device()
-                b.record(stream)
-        barrier()
-        dev_ms = sum(a.elapsed_time(b) for a, b in pairs)
-    else:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for _ in range(args.steps):
-            step_device()
-        e1.record(stream)
-        barrier()
-        dev_ms = e0.elapsed_time(e1)
-    ms_cls = (C.c_double * 8)()
-    fl_cls = (C.c_double * 8)()
-    n_cls = (C.c_int64 * 8)()
-    _lib.check(lib.ocrfa_profile_end(handle, ms_cls, fl_cls, n_cls))
-    launches = int(lib.ocrfa_launch_count(handle) - launches0)
-
-    # ---- timed region 2: end to end through the host-buffer C-ABI call (H2D + kernels + D2H + sync per step)
-    h_labels = torch.empty((B, T), dtype=torch.int32).pin_memory()
-    h_len = torch.empty(B, dtype=torch.int32).pin_memory()
-    h_conf = torch.empty(B, dtype=torch.float64).pin_memory()
-
-    def step_host():
-        _lib.check(lib.ocrfa_recognize_host(handle, C.c_void_p(h_img.data_ptr()), None, B, H, W,
-                                            mask_np.ctypes.data_as(C.c_void_p), dec, bw, C.c_void_p(h_labels.data_ptr()),
-                                            C.c_void_p(h_len.data_ptr()), C.c_void_p(h_conf.data_ptr()),
-                                            C.c_void_p(ws.data_ptr()), ws_bytes, C.c_void_p(stream.cuda_stream)))
-
-    step_host()
-    barrier()
-    if flush_l2:
         host_s = 0.0
         for i in range(args.steps):
             flush_buf.fill_(i & 0xff)
             torch.cuda.synchronize(dev)
             t0 = time.perf_counter()
-            step_host()
-            torch.cuda.synchronize(dev)
+            submit(slots[0])
+            slots[0].stream.synchronize()
             host_s += time.perf_counter() - t0
     else:
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            step_host()
+        for i in range(args.steps):
+            s = slots[i & 1]
+            s.stream.synchronize()  # the batch that used this slot two submissions ago has been read back
+            submit(s)
         torch.cuda.synchronize(dev)
         host_s = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
+    e2e_labels = slots[(args.steps - 1) & 1].labels.clone() if not flush_l2 else slots[0].labels.clone()
+    e2e_lens = slots[(args.steps - 1) & 1].lens.clone() if not flush_l2 else slots[0].lens.clone()
+    margins = (slots[(args.steps - 1) & 1].margin if not flush_l2 else slots[0].margin).numpy().copy()
 
     # ---- extra pass (not timed): per-class kernel time shares for the record
     _lib.check(lib.ocrfa_profile_begin(handle, 0xff))
@@ -321,18 +361,22 @@ def run_gpu_arm(args):
     fl_all = (C.c_double * 8)()
     n_all = (C.c_int64 * 8)()
     _lib.check(lib.ocrfa_profile_end(handle, ms_all, fl_all, n_all))
+    torch.cuda.synchronize(dev)
+    same_paths = bool(torch.equal(d_labels.cpu() * (torch.arange(T) < d_len.cpu()[:, None]),
+                                  e2e_labels * (torch.arange(T) < e2e_lens[:, None])))
 
-    # ---- max over ranks; gather a checksum of the decoded labels (NCCL only after the timed regions)
+    # ---- max over ranks; gather the decoded labels (NCCL only after the timed regions)
     times = torch.tensor([dev_ms, host_s * 1e3], dtype=torch.float64, device=dev)
-    label_sum = (d_labels.to(torch.int64) * (torch.arange(T, device=dev) < d_len[:, None])).sum().reshape(1)
+    valid = torch.arange(T, device=dev) < d_len[:, None]
+    lab_masked = torch.where(valid, d_labels, torch.zeros_like(d_labels))
     if world > 1:
         import torch.distributed as dist
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-        gathered = [torch.zeros_like(label_sum) for _ in range(world)]
-        dist.all_gather(gathered, label_sum)
-        label_sums = [int(g.item()) for g in gathered]
+        gathered = [torch.zeros_like(lab_masked) for _ in range(world)]
+        dist.all_gather(gathered, lab_masked)
+        all_labels = torch.cat(gathered).cpu()
     else:
-        label_sums = [int(label_sum.item())]
+        all_labels = lab_masked.cpu()
     dev_ms_max, host_ms_max = float(times[0].item()), float(times[1].item())
 
     if rank == 0:
@@ -347,40 +391,92 @@ def run_gpu_arm(args):
         shares = {n: {"ms_per_step": round(float(ms_all[i]), 4), "launches": int(n_all[i]),
                       "share": round(float(ms_all[i]) / tot_all, 4)} for i, n in enumerate(names) if n_all[i]}
         flops_line = FLOPS_PER_LINE.get((H, W))
+        products = 3 if args.precision == "f16x3" else 1
+
+        # multi-GPU equivalence (the reference's analogue is DataParallel's gather,
+        # utils.py:692): rank 0 recomputes every rank's lines itself and compares with the gathered labels
+        equivalence = None
+        if world > 1:
+            mism = 0
+            for r in range(1, world):
+                other = torch.from_numpy(synth_lines_global(r * B, (r + 1) * B, H, W, LINE_SEED)).to(dev)
+                _lib.check(lib.ocrfa_recognize_device(handle, C.c_void_p(other.data_ptr()), None, B, H, W,
+                                                      C.c_void_p(d_mask.data_ptr()), dec, bw, C.c_void_p(d_labels.data_ptr()),
+                                                      C.c_void_p(d_len.data_ptr()), C.c_void_p(d_conf.data_ptr()),
+                                                      C.c_void_p(ws.data_ptr()), ws_bytes, C.c_void_p(stream.cuda_stream)))
+                torch.cuda.synchronize(dev)
+                v2 = torch.arange(T, device=dev) < d_len[:, None]
+                mine = torch.where(v2, d_labels, torch.zeros_like(d_labels)).cpu()
+                mism += int((mine != all_labels[r * B:(r + 1) * B]).any(dim=1).sum())
+            equivalence = {"lines": world * B, "ranks": world, "lines_differing_from_single_gpu": mism,
+                           "how": "rank 0 recomputed the lines of every other rank and compared them with the all-gathered labels"}
+        label_checksum = int((all_labels.to(torch.int64) * (1 + torch.arange(T))).sum().item())
+
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {"bf16": "bf16", "f16x3": "f16x3 (fp16 hi/lo split operands, 3 tensor-core products per MAC, fp32 accumulate)",
-                      "f16": "f16 (fp16 operands/activations, fp32 accumulate: the bf16 kernels, 3 more mantissa bits)",
-                      "fp32": "f32"}[args.precision], "data": "synthetic",
-            "config": {"workload": f"{args.config}: {B} lines of {H}x{W} per rank per step, {decoder}"
-                                   + (f" beam={beam}" if decoder != "greedy" else "") + ", reference default model (ResNet-29 + 2xBiLSTM + Linear185), random-init weights",
+            "dtype": DTYPE_TEXT[args.precision], "data": "synthetic",
+            "config": {"workload": workload_text(args.config),
+                       "lines": f"rank r reads lines [r*{B}, (r+1)*{B}) of a synthetic set whose line g is synth_lines(seed={LINE_SEED}+g)",
                        "l2": ("explicit flush: a 256 MB fill before every timed step (the working set of this configuration "
                               "would fit the 126 MB L2), each step bracketed by its own CUDA event pair") if flush_l2 else
                              (f"per-step working set ({int(ws_bytes) / 2**30:.1f} GB activation workspace streamed every step + "
-                              "108 MB of weights) exceeds the 126 MB L2; no explicit flush"),
+                              "the weights) exceeds the 126 MB L2; no explicit flush"),
+                       "timing": "value: eager launches with CUDA events around every tcgen05 GEMM launch (the roofline's kernel "
+                                 "time comes from the same region); e2e: CUDA-graph replay, two batches in flight",
                        "parallelism": f"dp{world} (independent ranks, no collective on the path)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * H * W + Cn),
-                    "d2h_bytes_per_step": int(B * T * 4 + B * 4 + B * 8), "ms_per_step": host_ms_max / args.steps},
+                    "d2h_bytes_per_step": int(B * T * 4 + B * 4 + B * 8 + B * 4), "ms_per_step": host_ms_max / args.steps,
+                    "in_flight": 1 if flush_l2 else 2, "same_labels_as_device_path": same_paths},
             "gpu_launches": launches,
-            "roofline": {"kernel": ("igemm_tc_kernel<Split> (tcgen05 implicit GEMM, fp16 hi/lo split: executes 3 products per algorithmic MAC)"
-                                    if args.precision == "f16x3" else
+            "roofline": {"kernel": ("igemm_x3_kernel (tcgen05 cta_group::2 implicit GEMM on fp16 hi/lo split operands: 28 convs, 4 of them "
+                                    "halo-staged and 2 of those with the following max pool fused, + the LSTM input projections and the "
+                                    "3 linear GEMMs)" if args.precision == "f16x3" else
                                     "igemm_tc_kernel<Pair> + igemm_halo_kernel (tcgen05 implicit GEMM, cta_group::2: 28 convs, 2 of them with the "
                                     "following max pool fused, + the 3 linear GEMMs; the LSTM input projection is fused into lstm_tc)"),
                          "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                          "frac": achieved / peaks["bf16_sustained"], "traffic": load_traffic(args.config, args.precision),
                          "launches_per_step": tc_n / max(1, args.steps), "kernel_ms_per_step": tc_ms / max(1, args.steps),
-                         "peak_source": peaks["source"] + ", sustained bf16",
-                         "note": "frac can read above 1.0: the denominator is cuBLAS bf16 8192^3 back to back for seconds (power-capped at "
-                                 "~1.2 GHz), while these launches alternate with latency-bound kernels (LSTM recurrence, decode) that leave "
-                                 "power headroom, so they run at a higher SM clock (see clocks.sm_mhz); against the burst figure "
-                                 f"({load_burst():.0f} TFLOP/s) the fraction is {achieved / load_burst():.3f}",
+                         "peak_source": peaks["source"] + ", sustained bf16 (cuBLAS 8192^3 back to back); burst "
+                                        f"{peaks['bf16_burst']:.0f} TFLOP/s -> frac {achieved / peaks['bf16_burst']:.3f}",
+                         "products_per_mac": products,
+                         "executed_tflops": achieved * products,
+                         "frac_of_mode_ceiling": achieved * products / peaks["bf16_sustained"],
+                         "note": ("achieved counts ALGORITHMIC FLOPs (2 per MAC of the reference's layers). The f16x3 arithmetic spends three "
+                                  "fp16 tensor-core products per MAC (hi.hi + lo.hi + hi.lo), so its ceiling is one third of the peak: "
+                                  "frac_of_mode_ceiling = executed_tflops / peak. " if products == 3 else "") +
+                                 "A fraction can read above 1.0 of the sustained peak: that denominator is power-capped at ~1.2 GHz, "
+                                 "these launches alternate with latency-bound kernels and run at the SM clock in `clocks`",
                          "whole_step_tflops": (flops_line * B / (dev_ms_max / args.steps * 1e-3) / 1e12) if flops_line else None},
             "kernel_shares": shares,
             "clocks": clocks,
-            "label_checksums": label_sums,
+            "label_checksum": label_checksum,
+            "certificates": {"margin_bound": CERTIFY_MARGIN, "certified_lines": int((margins >= CERTIFY_MARGIN).sum()), "lines": int(B),
+                             "meaning": "lines whose smallest top-2 logit gap exceeds the bound: every fp32-grade evaluation "
+                                        "decodes them to the same greedy string (ocrfa_ctc_margin)"} if dec == 0 else None,
         }
+        if equivalence is not None:
+            line["multi_gpu_equivalence"] = equivalence
         if world == 1 and not args.no_cpu_baseline:
+            # ---- parity of THIS precision, measured in this run: the oracle's greedy strings on a bounded sample
+            from oracle import recognizer_ref as R
+            n_par = min(B, args.parity_lines)
+            torch.set_num_threads(os.cpu_count() or 1)
+            x = R.align_collate_ref(list(imgs_np[:n_par]), H, W)
+            ref_logits = R.model_forward_ref(sd, x)
+            ign_ref = R.ignore_idx_ref(chars, ob.default_ignore_char())
+            ref_probs = R.probs_ref(ref_logits, ign_ref)
+            if decoder == "greedy":
+                ref_strs = R.greedy_decode_ref(ref_probs, conv.character)
+            else:
+                ref_strs = R.beam_decode_ref(ref_probs, conv.character, beam)
+            got = conv.labels_to_text(e2e_labels.numpy()[:n_par], e2e_lens.numpy()[:n_par])
+            same = sum(a == b for a, b in zip(got, ref_strs))
+            cert_ok = [a == b for a, b, m in zip(got, ref_strs, margins[:n_par]) if m >= CERTIFY_MARGIN]
+            line["parity"] = {"mode": args.precision, "decoder": decoder, "lines": n_par, "identical_strings": same,
+                              "certified_lines": len(cert_ok), "identical_among_certified": int(sum(cert_ok)),
+                              "against": "oracle (CPU port of the reference, torch fp32) on the first lines of this run's batch; "
+                                         "the >= 10k-line runs are profiles/r02_parity_10k_*.json"}
             sample = 32 if (H, W) == (32, 512) else (4 if H == 64 else min(B, 32))
             lps, threads, n, sec = cpu_lines_per_s(args.config, sample, 2, 1)
             line["cpu_baseline"] = {"value": lps, "unit": UNIT, "cores": threads, "kind": "port",
@@ -390,6 +486,28 @@ def run_gpu_arm(args):
             q_lps, _, _, _ = cpu_lines_per_s(args.config, sample, 2, 1, quantize=True)
             line["cpu_baseline"]["quantize_true"] = {"value": q_lps, "unit": UNIT,
                                                      "note": "same sample with torch dynamic int8 LSTM/Linear (utils.py:686-690)"}
+        if world == 1 and not args.no_other_precisions:
+            # ---- the other tensor-core precisions on the same workload, same run (a few steps each, device-resident inputs)
+            others = {}
+            for prec in ("bf16", "f16", "f16x3"):
+                if prec == args.precision:
+                    continue
+                m2 = ob.Model(1, 512, 512, Cn, precision=prec)
+                m2.load_state_dict(sd)
+                h2 = m2._ensure_handle(dev)
+                wsb2 = lib.ocrfa_recognize_workspace_bytes(h2, B, H, W, bw)
+                if wsb2 > ws_bytes:
+                    buf = torch.empty(int(wsb2) + 1024, dtype=torch.uint8, device=dev)
+                    ws2 = buf[(-buf.data_ptr()) % 1024:][:wsb2]
+                else:
+                    ws2 = ws[:wsb2]
+                ms2, _, _, _, _, _ = measure_device(lib, _lib, h2, (B, H, W, T), d_img, d_mask, dec, bw, ws2, wsb2,
+                                                    (d_labels, d_len, d_conf), stream, min(args.steps, 10), 3, dev, 1, 0, flush_l2)
+                k2 = min(args.steps, 10)
+                others[prec] = {"value": B * k2 / (ms2 * 1e-3), "unit": UNIT, "ms_per_step": ms2 / k2, "steps": k2,
+                                "dtype": DTYPE_TEXT[prec]}
+                del m2
+            line["other_precisions"] = others
         print(json.dumps(line), flush=True)
     if world > 1:
         import torch.distributed as dist
@@ -400,13 +518,16 @@ def run_gpu_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "f16", "f16x3", "fp32"],
-                    help="bf16: tcgen05 bf16 (headline); f16: same kernels with fp16 operands/activations; f16x3: tcgen05 fp16 hi/lo split, fp32-grade logits; fp32: CUDA-core parity mode")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default="f16x3", choices=["f16x3", "bf16", "f16", "fp32"],
+                    help="f16x3 (default): tcgen05 fp16 hi/lo split, fp32-grade logits, the mode held to the reference's strings; "
+                         "bf16: the BASELINE config's dtype; f16: the bf16 kernels with fp16 operands; fp32: CUDA-core parity mode")
+    ap.add_argument("--parity-lines", type=int, default=128, help="lines of the in-run parity check against the oracle")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU legs (parity sample and cpu_baseline)")
+    ap.add_argument("--no-other-precisions", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

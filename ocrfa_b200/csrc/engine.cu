@@ -809,6 +809,7 @@ int forward_impl(ocrfa_handle* h, const float* d_x, const uint8_t* d_u8, const i
         int r2 = make_rows64_tmap(&lp.tmX, lp.hx, lstm_hx_rows(mode, lp.m_tiles), lp.box_rows);
         if (r2 == 0) r2 = make_wgt_tmap(&lp.tmW, lw.d_whh, 1024, 4096, 64);
         if (r2 == 0) r2 = make_rows64_store_tmap(&lp.tmP, lp.hx, lstm_hx_rows(mode, lp.m_tiles), lp.box_rows);
+        if (r2 == 0 && !sp) r2 = make_hseq_store_tmap(&lp.tmH, (uint16_t*)hseq + (size_t)b0 * T * hs_row, T, nb, lp.box_rows);
         if (r2 == 0 && !sp)
           r2 = make_act_tmap(&lp.tmS, (const __nv_bfloat16*)seq_in + (size_t)b0 * T * 512, 512, T, 1, nb, 1, 1, lp.box_rows, 1);
         if (r2) return fail(OCRFA_ERR_CUDA, "LSTM tensor map failed: %d", r2);

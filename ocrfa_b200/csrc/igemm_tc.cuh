@@ -615,6 +615,22 @@ inline int make_rows64_store_tmap(CUtensorMap* tm, const void* base, long long r
   return rc == CUDA_SUCCESS ? 0 : -static_cast<int>(rc) - 1000;
 }
 
+// The LSTM layer output [rows][T * 1024] (16-bit elements) as the destination of the TMA publish: un-swizzled
+// {16 units, box_rows} boxes stored from the same dense shared-memory tile as the exchange copy; rows >= `rows` are
+// clipped by the map's bounds.
+inline int make_hseq_store_tmap(CUtensorMap* tm, const void* base, int T, int rows, int box_rows) {
+  PFN_tmapEncodeTiled enc = get_tmap_encode();
+  if (!enc) return -1;
+  cuuint64_t dims[2] = {(cuuint64_t)T * 1024, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)T * 1024 * 2};
+  cuuint32_t box[2] = {16, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult rc = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return rc == CUDA_SUCCESS ? 0 : -static_cast<int>(rc) - 1000;
+}
+
 inline cudaError_t igemm_x3_launch(const IgemmTcParams& p, int num_sms, cudaStream_t stream);  // igemm_x3.cuh
 
 inline cudaError_t igemm_tc_launch(const IgemmTcParams& p, int /*mode*/, int num_sms, cudaStream_t stream) {

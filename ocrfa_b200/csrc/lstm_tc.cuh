@@ -37,30 +37,29 @@ namespace ocrfa {
 
 constexpr int kLstmThreads = 192;
 // How a CTA publishes its slice of h_t to the group (fused-x modes):
-//   generic  per-thread 16-byte stores + CTA barrier + red.release.gpu. The release is MEMBAR.ALL.GPU + ERRBAR in SASS and
-//            waits for the 256 scattered stores: measured 1.4 k cycles per step (4.68 -> 3.94 us/step with the fence
-//            removed, which is not a correct program).
-//   TMA      the slice is staged in shared memory (4 KB), one elected thread issues a TMA tensor store, waits for the
-//            bulk group to COMPLETE (cp.async.bulk.wait_group 0: the writes are performed at L2, which is where the
-//            peers' TMA loads read them) and then bumps the counter with a relaxed red - no gpu-scope fence on the path.
-//            The staging buffer takes the room of one ring stage.
+//   generic  per-thread 16-byte stores + CTA barrier + red.release.gpu (the split-precision mode, and every mode with
+//            -DOCRFA_LSTM_GENERIC_PUBLISH). The release is MEMBAR.ALL.GPU + ERRBAR in SASS and waits for the CTA's
+//            scattered stores: measured 1.4 k cycles per step.
+//   TMA      the slice is staged in shared memory (4 KB, double buffered), one elected thread issues TWO TMA tensor
+//            stores from that tile - the exchange copy the peers wait for and the layer-output copy (h sequence) - each
+//            in its own bulk group, waits for the FIRST group to complete (cp.async.bulk.wait_group 1), and then bumps the
+//            counter with red.RELEASE.gpu: completion makes the bulk writes visible to the issuing thread, the gpu-scope
+//            release publishes them (cumulativity), the peers' acquire poll + fence.proxy.async.global order their TMA
+//            reads after it. Round 1 used a RELAXED red here on a physical argument (a completed bulk store is at L2);
+//            the stress run of tools/test_igemm.cu --lstm-stress caught it: 2 of 100 launches at the c2 geometry read a
+//            stale slice. With every global store of the step moved to the async proxy no generic store is outstanding
+//            when the release executes, which is what made the fenced path slow before.
 #ifndef OCRFA_LSTM_GENERIC_PUBLISH
 #define OCRFA_LSTM_TMA_PUBLISH 1
 #endif
 #ifdef OCRFA_LSTM_TMA_PUBLISH
 constexpr int kLstmRing = 5;          // A-ring stages of 16 KB
-#ifdef OCRFA_LSTM_TMA_PUBLISH_SPLIT      // also for the split-precision mode (hi and lo tiles): compiled in only on request
-constexpr int kLstmStageBytes = 8192; // until it has been through the GPU suite
-constexpr bool kLstmTmaPublishSplit = true;
-#else
-constexpr int kLstmStageBytes = 4096; // h slice staging: 128 rows x 16 units x 2 B
-constexpr bool kLstmTmaPublishSplit = false;
-#endif
+constexpr int kLstmStageBytes = 8192; // h slice staging: 2 x (128 rows x 16 units x 2 B), alternating by step parity
 #else
 constexpr int kLstmRing = 6;          // A-ring stages of 16 KB
 constexpr int kLstmStageBytes = 0;
-constexpr bool kLstmTmaPublishSplit = false;
 #endif
+constexpr bool kLstmTmaPublishSplit = false;  // the split-precision mode keeps the generic publish
 constexpr int kLstmTmemCols = 128;    // fused-x modes: 2 accumulators x 64 columns
 constexpr int kLstmTmemColsSplit = 512;  // split mode: 4 "main" chunk buffers (columns 0..255) + "corr" (column 256)
 constexpr int kLstmCorrCol = 256;
@@ -80,6 +79,7 @@ struct alignas(64) LstmTcParams {
   CUtensorMap tmW;  // resident weights [4096][1024] (bf16: [W_ih | W_hh]; split: [W_hi | W_lo]), box {64, 64}
   CUtensorMap tmS;  // bf16 mode: layer input [B][T][512] bf16 as the 5-D activation map, box {64,1,1,128,1}
   CUtensorMap tmP;  // TMA publish: the exchange buffer again, un-swizzled, box {16 units, box_rows}
+  CUtensorMap tmH;  // TMA publish: the layer output [B][T * 1024] as 2-D (T * 1024, B), un-swizzled, box {16 units, box_rows}
   const float* xproj;        // split mode: [B*T][4096] fp32 gate pre-activations (bias included)
   const float* bias;         // bf16 mode: [4096] b_ih + b_hh in the permuted order
   void* hseq;                // layer output: bf16 [B][T][1024] (fwd | bwd), or fp16 [B][T][hi 1024 | lo 1024]
@@ -118,10 +118,10 @@ __device__ __forceinline__ void tma_store_2d(const void* tmap, const void* smem_
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
 }
-__device__ __forceinline__ void tma_store_commit_and_wait_all() {
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all bulk groups of this thread except the most recent one have completed (their writes are visible to this thread)
+__device__ __forceinline__ void tma_store_wait_all_but_last() { asm volatile("cp.async.bulk.wait_group 1;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // ex2.approx-based gate activations (abs error ~1e-6, far below the bf16 rounding of h); saturate cleanly at +-inf.
 #ifdef OCRFA_LSTM_TANH_APPROX
@@ -201,6 +201,7 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_tc_persistent_kernel(con
     if (MODE == kLstmBf16FusedX) tma_prefetch_desc(&p.tmS);
 #ifdef OCRFA_LSTM_TMA_PUBLISH
     tma_prefetch_desc(&p.tmP);
+    tma_prefetch_desc(&p.tmH);
 #endif
   }
   constexpr uint32_t kTmemCols = MODE == kLstmF16Split ? kLstmTmemColsSplit : kLstmTmemCols;
@@ -467,30 +468,27 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_tc_persistent_kernel(con
       constexpr bool kTmaPublish = false;
 #endif
       if (kTmaPublish) {
-        // stage the CTA's [rows][16 units] slice (rows beyond the batch carry whatever the padding lanes computed: they
-        // land in exchange rows that never reach a valid result), hand it to the async proxy, one TMA store, wait for
-        // the bulk group to complete, relaxed counter update
-        uint4* sp4 = reinterpret_cast<uint4*>(hstage) + row * 2;
+        // stage the CTA's [rows][16 units] slice (rows beyond the batch carry whatever the padding lanes computed: the
+        // exchange rows they land in never reach a valid result, and the layer-output map ends at row B), hand it to the
+        // async proxy, two TMA stores in two bulk groups, wait for the exchange group, release the counter. The tile of
+        // step s-2 (same parity) is free: its groups completed before this thread's release of step s-1, which every
+        // thread's tfull wait of step s transitively follows (the group counter gates the MMAs that signal tfull).
+        uint8_t* hst = hstage + (s & 1) * 4096;
+        uint4* sp4 = reinterpret_cast<uint4*>(hst) + row * 2;
         sp4[0] = o0;
         sp4[1] = o1;
-        if (MODE == kLstmF16Split) {  // the lo halves: second staging tile, stored 8 slabs further
-          sp4[256] = l0;
-          sp4[257] = l1;
-        }
         fence_proxy_async_smem();
         if (et == 0) LSTM_TS(s, 11);
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (et == 0) {
           LSTM_TS(s, 13);
           const int slab_row0 = static_cast<int>(((hx_region + (s & 1)) * kHxSlabs + (j0 >> 6)) * 128);
-          tma_store_2d(&p.tmP, hstage, j0 & 63, slab_row0);
-          if (MODE == kLstmF16Split) tma_store_2d(&p.tmP, hstage + 4096, j0 & 63, slab_row0 + 8 * 128);
-          tma_store_commit_and_wait_all();
-#ifdef OCRFA_LSTM_PUBLISH_RELEASE
-          red_release_gpu_add(group_ctr, 1u);  // measurement switch: gpu-scope release after the bulk group has completed
-#else
-          red_relaxed_gpu_add(group_ctr, 1u);
-#endif
+          tma_store_2d(&p.tmP, hst, j0 & 63, slab_row0);
+          tma_store_commit();
+          tma_store_2d(&p.tmH, hst, t_cur * 1024 + dir * 512 + j0, m_tile * 128);
+          tma_store_commit();
+          tma_store_wait_all_but_last();
+          red_release_gpu_add(group_ctr, 1u);
           LSTM_TS(s, 14);
         }
       } else {
@@ -517,7 +515,7 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_tc_persistent_kernel(con
           LSTM_TS(s, 14);
         }
       }
-      if (valid) {
+      if (valid && !kTmaPublish) {
         uint16_t* hs = reinterpret_cast<uint16_t*>(p.hseq);
         if (MODE == kLstmF16Split) {
           uint16_t* hp = hs + (static_cast<size_t>(b) * T + t_cur) * 2048 + dir * 512 + j0;
@@ -545,6 +543,9 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_tc_persistent_kernel(con
         if (as == 0) aphase ^= 1u;
       }
     }
+#ifdef OCRFA_LSTM_TMA_PUBLISH
+    if (MODE != kLstmF16Split && et == 0) tma_store_wait_all();  // the last layer-output store reads shared memory
+#endif
   }
 #undef LSTM_TS
 

@@ -105,6 +105,16 @@ def synth_lines(n: int, h: int, w: int, seed: int = 1234) -> np.ndarray:
     return out
 
 
+def synth_lines_global(lo: int, hi: int, h: int, w: int, base_seed: int = 1234) -> np.ndarray:
+    """Lines lo..hi-1 of an unbounded synthetic set in which line g is a function of its GLOBAL index g alone (its own
+    PCG64 stream, seed base_seed + g): any sharding of the set over ranks reads the same lines, which is what lets a
+    multi-GPU run be compared with a single-GPU run of the same lines."""
+    out = np.empty((max(0, hi - lo), h, w), dtype=np.uint8)
+    for g in range(lo, hi):
+        out[g - lo] = synth_lines(1, h, w, seed=base_seed + g)[0]
+    return out
+
+
 def synth_score_maps(h: int, w: int, seed: int, n_words: int = 14) -> Tuple[np.ndarray, np.ndarray]:
     """CRAFT-like region / affinity maps: words are rows of Gaussian character blobs (some rotated, some touching the
     border, some tiny, some weak), affinity blobs sit between neighbouring characters."""

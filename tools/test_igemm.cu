@@ -463,6 +463,7 @@ static void run_lstm_case(int B, int T, int mode, int repeat = 0) {
   int rc = make_rows64_tmap(&lp.tmX, d_hx, hx_rows, lp.box_rows);
   if (rc == 0) rc = make_wgt_tmap(&lp.tmW, d_w, 1024, 4096, 64);
   if (rc == 0) rc = make_rows64_store_tmap(&lp.tmP, d_hx, hx_rows, lp.box_rows);
+  if (rc == 0 && !sp) rc = make_hseq_store_tmap(&lp.tmH, d_hseq, T, B, lp.box_rows);
   if (rc == 0 && !sp) rc = make_act_tmap(&lp.tmS, d_x, 512, T, 1, B, 1, 1, lp.box_rows, 1);
   if (rc) { printf("[lstm] tensor map failed %d\n", rc); g_fail++; return; }
   lp.xproj = sp ? d_xproj : nullptr; lp.bias = d_bias; lp.hseq = d_hseq; lp.hx = d_hx; lp.sync = d_sync;
