@@ -55,11 +55,14 @@ def synth_craft_state_dict(seed: int = 0) -> "OrderedDict[str, np.ndarray]":
 
 
 class CraftNet:
-    """The reference's `OCRFA` detector network, forward only, on the B200 kernels. precision: "bf16" | "f16"."""
+    """The reference's `OCRFA` detector network, forward only, on the B200 kernels. precision: "f16" (default) | "bf16"
+    (single-pass tensor-core modes) | "f16x3" (fp32-grade: fp16 hi/lo split operands, the recognizer's igemm_x3 kernel;
+    score maps within 1e-5 of the reference's fp32 output, so the thresholded components - and hence the boxes - are
+    the reference's)."""
 
     def __init__(self, precision: str = "f16"):
-        if precision not in ("bf16", "f16"):
-            raise ValueError("the CRAFT forward runs in the 16-bit tensor-core modes only: 'bf16' or 'f16'")
+        if precision not in ("bf16", "f16", "f16x3"):
+            raise ValueError("the CRAFT forward runs in the tensor-core modes only: 'f16', 'bf16' or 'f16x3'")
         self.precision = precision
         self._state: Optional[Dict[str, torch.Tensor]] = None
         self._handle: Optional[C.c_void_p] = None

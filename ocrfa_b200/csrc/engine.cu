@@ -120,6 +120,7 @@ struct ocrfa_handle {
   int graph_failures = 0;
   bool stem_1px = false;   // OCRFA_STEM_1PX (experiment switch), read once in ocrfa_create
   int x3_halo_max_cout = 128;  // OCRFA_X3_HALO_MAXC: f16x3 layers up to this Cout use the halo-staged form (0 = never)
+  int x3_kchain = 1;           // OCRFA_X3_CHAIN: K chunks of 64 per hi.hi accumulation in igemm_x3_kernel (1 or 2)
   uint64_t graph_tick = 0;
   Profiler prof;
   ocrfa_config cfg;
@@ -499,6 +500,7 @@ int run_conv_x3_halo(ocrfa_handle* h, const ConvW& cw, const Act& in, const Act*
   p.residual = residual; p.ldr = 2 * cw.cout; p.res_lo = cw.cout;
   p.out = out; p.ldo = 2 * cw.cout; p.out_lo = cw.cout; p.out_f32 = 0; p.relu = relu ? 1 : 0;
   p.out_scale = cw.out_scale;
+  p.kchain = h->x3_kchain;
   const double flops = 2.0 * (double)in.n * in.h * in.w * cw.cout * (9.0 * cw.cin + cw.ds_cin);
   LaunchScope ls(h, kClsIgemmTc, flops, st);
   CUDA_TRY(igemm_tc_launch(p, kModeStd, h->num_sms, st));
@@ -528,6 +530,7 @@ int run_conv_tc(ocrfa_handle* h, const ConvW& cw, const Act& in, const Act* ds_s
   if (split) {
     // fp16 hi/lo pixels: [hi(C) | lo(C)]
     p.out_scale = cw.out_scale;
+    p.kchain = h->x3_kchain;
     p.ldr = 2 * cw.cout; p.res_lo = cw.cout;
     if (!out_f32) { p.ldo = 2 * ldo; p.out_lo = ldo; }
   }
@@ -933,6 +936,7 @@ int ocrfa_create(const ocrfa_config* cfg, ocrfa_handle** out) {
   if (const char* hl = getenv("OCRFA_HALO")) h->halo_level = atoi(hl);
   h->stem_1px = getenv("OCRFA_STEM_1PX") != nullptr;
   if (const char* e = getenv("OCRFA_X3_HALO_MAXC")) h->x3_halo_max_cout = atoi(e);
+  if (const char* e = getenv("OCRFA_X3_CHAIN")) h->x3_kchain = atoi(e) == 2 ? 2 : 1;
   const char* g = getenv("OCRFA_GRAPHS");
   if (g && g[0] == '0') h->graphs_enabled = 0;
   *out = h;
@@ -941,8 +945,8 @@ int ocrfa_create(const ocrfa_config* cfg, ocrfa_handle** out) {
 
 int ocrfa_craft_create(int32_t precision, int32_t device, ocrfa_handle** out) {
   if (!out) return fail(OCRFA_ERR_ARG, "null argument");
-  if (precision != OCRFA_PRECISION_BF16 && precision != OCRFA_PRECISION_F16)
-    return fail(OCRFA_ERR_ARG, "the CRAFT forward runs in the 16-bit tensor-core modes only (bf16 / f16)");
+  if (precision != OCRFA_PRECISION_BF16 && precision != OCRFA_PRECISION_F16 && precision != OCRFA_PRECISION_F16X3)
+    return fail(OCRFA_ERR_ARG, "the CRAFT forward runs in the tensor-core modes only (bf16 / f16 / f16x3)");
   ocrfa_config cfg;
   cfg.input_channel = 1; cfg.output_channel = 512; cfg.hidden_size = 512; cfg.num_class = 2;
   cfg.precision = precision; cfg.device = device;
@@ -954,7 +958,7 @@ int ocrfa_craft_create(int32_t precision, int32_t device, ocrfa_handle** out) {
 
 size_t ocrfa_craft_workspace_bytes(const ocrfa_handle* h, int32_t N, int32_t H, int32_t W) {
   if (!h || N <= 0 || H <= 0 || W <= 0) return 0;
-  return craft_layout(N, H, W).total;
+  return craft_layout(N, H, W, h->split() ? 4 : 2).total;
 }
 
 int ocrfa_craft_forward(ocrfa_handle* h, const float* d_x, int32_t N, int32_t H, int32_t W, float* d_y, float* d_feature,

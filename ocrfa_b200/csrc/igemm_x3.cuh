@@ -35,6 +35,7 @@
 //     of the group travel with it. A stage then carries 36 MMAs: L2 -> SM bytes per MMA fall from 104 (Cout = 64) /
 //     62 (Cout = 128) bytes per tensor-pipe cycle - above what L2 delivers to 148 SMs at once - to 57 / 39. The
 //     following 2x2/2 max pool (max_pool1, max_pool2) can be fused into the epilogue.
+//   * IgemmTcParams::kchain (1 or 2): K chunks per hi.hi accumulation - the precision / speed knob described at its use.
 // Warp roles (12 warps, three warpgroups): warpgroup 0 = TMA producer (warp 0), MMA issuer + TMEM alloc (warp 1, leader
 // CTA) and two idle warps, trimmed to 56 registers with setmaxnreg; warpgroups 1-2 = eight epilogue warps raised to 224
 // registers, so the 128 fp32 accumulators + 64 values in flight from TMEM live in registers (at the 168 registers a
@@ -49,10 +50,11 @@ namespace ocrfa {
 constexpr int kX3Threads = 384;
 constexpr int kX3FirstEpiWarp = 4;
 constexpr int kX3CorrCol = 256;  // TMEM column of the corr accumulator (main starts at column 0)
+constexpr int kX3Staging = 8 * 2048;  // per epilogue warp: a 32-row x 64-byte transposition buffer (behind the stages)
 
 inline size_t igemm_x3_smem_bytes(int block_n, int* stages_out) {
   const size_t stage = 2 * static_cast<size_t>(kTcBlockM) * kTcBlockK * 2 + 2 * static_cast<size_t>(block_n / 2) * kTcBlockK * 2;
-  const size_t header = 1024 + kTcSmemHeader;
+  const size_t header = 1024 + kTcSmemHeader + kX3Staging;
   const size_t budget = 227 * 1024 - header;
   int stages = static_cast<int>(budget / stage);
   if (stages > kTcMaxStages) stages = kTcMaxStages;
@@ -63,7 +65,7 @@ inline size_t igemm_x3_smem_bytes(int block_n, int* stages_out) {
 // halo mode: a stage = two halo boxes ((th + 2) * tw pixels x 128 B) + six weight blocks
 inline size_t igemm_x3_halo_smem_bytes(int block_n, int tw, int th, int* stages_out) {
   const size_t stage = 2 * static_cast<size_t>(th + 2) * tw * 128 + 6 * static_cast<size_t>(block_n / 2) * kTcBlockK * 2;
-  const size_t header = 1024 + kTcSmemHeader;
+  const size_t header = 1024 + kTcSmemHeader + kX3Staging;
   const size_t budget = 227 * 1024 - header;
   int stages = static_cast<int>(budget / stage);
   if (stages > kTcMaxStages) stages = kTcMaxStages;
@@ -105,6 +107,113 @@ __device__ __forceinline__ void x3_store8_split(const IgemmTcParams& p, float (&
   *reinterpret_cast<uint4*>(op + p.out_lo) = l;
 }
 
+// Tile tail for 32 consecutive output channels of this warp's 32 pixels (lane = pixel): x out_scale, + bias, + residual,
+// ReLU, store. Every global access goes through a per-warp transposition buffer (32 rows x 64 B, pieces XOR-swizzled by
+// (row >> 1) & 3) so that one load / store instruction covers 8 pixels x 64 contiguous bytes: a 16-byte access per pixel
+// row costs one L1 wavefront per lane, and - unlike the single-pass kernels, whose epilogue overlaps the next tile's
+// MMAs - these warps are needed again for the next tile's first drain, so the tail is on the tensor pipe's critical path
+// (ncu, 512-channel layers before this change: tensor pipe 70 % active). pixk / vk: pixel index / validity of rows
+// 8k + (lane >> 2), k = 0..3 (warp shuffles of pix / valid, done once per tile).
+__device__ __forceinline__ void x3_finish32(const IgemmTcParams& p, float (&f)[32], uint8_t* stg, int lane, size_t pix,
+                                            bool valid, const size_t (&pixk)[4], const bool (&vk)[4], int col0) {
+  const bool fast = (col0 + 32 <= p.n_valid) && (!p.out_f32 || (p.ldo & 3) == 0);
+  if (!fast) {  // ragged last column group (Prediction's 185 classes): the plain per-pixel tail
+    if (valid) igemm_finish32(p, f, pix, col0);
+    return;
+  }
+  const float sc = p.out_scale;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) f[i] *= sc;
+  if (p.bias != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
+      f[i] += b4.x; f[i + 1] += b4.y; f[i + 2] += b4.z; f[i + 3] += b4.w;
+    }
+  }
+  const int swz_own = (lane >> 1) & 3;
+  const int pc = lane & 3;  // the 16-byte piece this lane moves in the transposed mapping
+  uint8_t* own = stg + lane * 64;
+  uint8_t* tr = stg + static_cast<uint32_t>(lane >> 2) * 64u + static_cast<uint32_t>((pc ^ ((lane >> 3) & 3)) << 4);
+  if (p.residual != nullptr) {
+    // fp16 hi | lo residual: both halves are added in fp32 (hi + lo is exact)
+    const __half* rbase = reinterpret_cast<const __half*>(p.residual) + col0 + pc * 8;
+#pragma unroll
+    for (int part = 0; part < 2; ++part) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        uint4 r4 = make_uint4(0u, 0u, 0u, 0u);
+        if (vk[k]) r4 = __ldg(reinterpret_cast<const uint4*>(rbase + pixk[k] * p.ldr + part * p.res_lo));
+        *reinterpret_cast<uint4*>(tr + k * 512) = r4;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint4 r4 = *reinterpret_cast<const uint4*>(own + ((j ^ swz_own) << 4));
+        const uint32_t w4[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 v = __half22float2(*reinterpret_cast<const __half2*>(&w4[e]));
+          f[8 * j + 2 * e] += v.x;
+          f[8 * j + 2 * e + 1] += v.y;
+        }
+      }
+      __syncwarp();
+    }
+  }
+  if (p.relu) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.0f);
+  }
+  if (p.out_f32) {
+#pragma unroll
+    for (int hp = 0; hp < 2; ++hp) {  // 16 floats = 64 bytes per pixel and pass
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<float4*>(own + ((j ^ swz_own) << 4)) =
+            make_float4(f[16 * hp + 4 * j], f[16 * hp + 4 * j + 1], f[16 * hp + 4 * j + 2], f[16 * hp + 4 * j + 3]);
+      __syncwarp();
+      float* obase = reinterpret_cast<float*>(p.out) + col0 + 16 * hp + pc * 4;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4 o = *reinterpret_cast<const float4*>(tr + k * 512);
+        if (vk[k]) *reinterpret_cast<float4*>(obase + pixk[k] * p.ldo) = o;
+      }
+      __syncwarp();
+    }
+    return;
+  }
+  float lo[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const float hv = __half2float(__float2half_rn(f[i]));
+    lo[i] = f[i] - hv;
+    f[i] = hv;
+  }
+#pragma unroll
+  for (int part = 0; part < 2; ++part) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint4 o;
+      __half2 t;
+      const float* src = part ? lo : f;
+      t = __floats2half2_rn(src[8 * j], src[8 * j + 1]);     o.x = *reinterpret_cast<uint32_t*>(&t);
+      t = __floats2half2_rn(src[8 * j + 2], src[8 * j + 3]); o.y = *reinterpret_cast<uint32_t*>(&t);
+      t = __floats2half2_rn(src[8 * j + 4], src[8 * j + 5]); o.z = *reinterpret_cast<uint32_t*>(&t);
+      t = __floats2half2_rn(src[8 * j + 6], src[8 * j + 7]); o.w = *reinterpret_cast<uint32_t*>(&t);
+      *reinterpret_cast<uint4*>(own + ((j ^ swz_own) << 4)) = o;
+    }
+    __syncwarp();
+    __half* obase = reinterpret_cast<__half*>(p.out) + col0 + pc * 8 + part * p.out_lo;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint4 o = *reinterpret_cast<const uint4*>(tr + k * 512);
+      if (vk[k]) *reinterpret_cast<uint4*>(obase + pixk[k] * p.ldo) = o;
+    }
+    __syncwarp();
+  }
+}
+
 __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_constant__ IgemmTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -138,6 +247,11 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
   // buffers used alternately
   const bool wide = block_n == 256;
   const bool alt = block_n <= 128;  // two alternating whole-tile buffers (a 192-column tile has room for one)
+  // K chunks of 64 per hi.hi accumulation. 1: four chained MMAs, the smallest truncation bias - but every chunk is a
+  // 128 x N fp32 read of TMEM, 341 / 4 = 85 B per tensor-pipe cycle and SM, which is what the TMEM read port delivers
+  // (measured: the eight epilogue warps busy 69 % of the kernel, tensor pipe 70 % active). 2: eight chained MMAs, half
+  // the TMEM traffic (the drain hides), bias -5.2e-8 instead of -3.1e-8 of the rms per layer.
+  const int kchain = p.kchain > 1 ? p.kchain : 1;
 
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
   const int total_tiles = ((m_tiles + 1) >> 1) * p.n_tiles;
@@ -261,6 +375,7 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
       for (int tile = worker; tile < total_tiles; tile += num_workers) {
         mbar_wait(corr_empty, cph ^ 1u, 2);  // the previous tile's corr has been read back
         cph ^= 1u;
+        int unit = 0;  // K chunks of 64 issued so far in this tile; `kchain` consecutive ones share one accumulation
         for (int kb = 0; kb < total_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase, 3);
           tc_fence_after();
@@ -283,32 +398,41 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
             umma_bf16_pair(d_corr, a_hi + static_cast<uint64_t>(2 * k), b_lo + static_cast<uint64_t>(2 * k), idesc, 1u);
           // a "main" buffer is free again once the epilogue warps have drained its previous contents - they do that
           // while the corr MMAs above keep the tensor pipe busy
+          const bool fresh = (unit % kchain) == 0;                                   // first K chunk of an accumulation
+          const bool closes = (unit % kchain) == kchain - 1 || unit == total_chunks - 1;  // last one: hand it to the epilogue
+          ++unit;
           if (wide) {
 #pragma unroll
             for (int hb = 0; hb < 2; ++hb) {
-              mbar_wait(&main_empty[hb], mph[hb] ^ 1u, 4);
-              mph[hb] ^= 1u;
-              tc_fence_after();
+              if (fresh) {
+                mbar_wait(&main_empty[hb], mph[hb] ^ 1u, 4);
+                mph[hb] ^= 1u;
+                tc_fence_after();
+              }
               // rows hb*64 .. hb*64+63 of each CTA's 128-row weight tile: 8 swizzle atoms = 8192 B further
               const uint64_t b_half = b_hi + static_cast<uint64_t>(hb * (8192 >> 4));
 #pragma unroll
               for (int k = 0; k < kTcBlockK / 16; ++k)
                 umma_bf16_pair(d_main + static_cast<uint32_t>(hb) * 128u, a_hi + static_cast<uint64_t>(2 * k),
-                               b_half + static_cast<uint64_t>(2 * k), idesc_half, k > 0 ? 1u : 0u);
+                               b_half + static_cast<uint64_t>(2 * k), idesc_half, (k > 0 || !fresh) ? 1u : 0u);
               if (hb == 1 && j == nsub - 1) umma_commit_pair(&empty_bar[stage]);  // frees the slot in both CTAs once these MMAs have read it
-              umma_commit_pair(&main_full[hb]);                  // this half of the hi.hi chunk is complete (both CTAs)
+              if (closes) umma_commit_pair(&main_full[hb]);      // this half of the hi.hi accumulation is complete (both CTAs)
             }
           } else {
-            mbar_wait(&main_empty[mb], mph[mb] ^ 1u, 4);
-            mph[mb] ^= 1u;
-            tc_fence_after();
+            if (fresh) {
+              mbar_wait(&main_empty[mb], mph[mb] ^ 1u, 4);
+              mph[mb] ^= 1u;
+              tc_fence_after();
+            }
 #pragma unroll
             for (int k = 0; k < kTcBlockK / 16; ++k)
               umma_bf16_pair(d_main + static_cast<uint32_t>(mb) * 128u, a_hi + static_cast<uint64_t>(2 * k),
-                             b_hi + static_cast<uint64_t>(2 * k), idesc, k > 0 ? 1u : 0u);
+                             b_hi + static_cast<uint64_t>(2 * k), idesc, (k > 0 || !fresh) ? 1u : 0u);
             if (j == nsub - 1) umma_commit_pair(&empty_bar[stage]);
-            umma_commit_pair(&main_full[mb]);
-            if (alt) mb ^= 1;
+            if (closes) {
+              umma_commit_pair(&main_full[mb]);
+              if (alt) mb ^= 1;
+            }
           }
           }  // sub-blocks
           if (++stage == stages) { stage = 0; phase ^= 1u; }
@@ -329,6 +453,7 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
     const int half_cols = block_n >> 1;  // multiple of 32
     uint32_t cph = 0, mph[2] = {0u, 0u};
     int mb = wide ? half : 0;
+    uint8_t* stg = stage_base + static_cast<size_t>(stages) * stage_bytes + static_cast<size_t>(warp - kX3FirstEpiWarp) * 2048;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const uint32_t t_main = t_lane + (wide ? static_cast<uint32_t>(half) * 128u : static_cast<uint32_t>(half * half_cols));
     for (int tile = worker; tile < total_tiles; tile += num_workers) {
@@ -343,12 +468,21 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
       const int w = iw * p.tw + ww, h = ih * p.th + hh, n = in * p.tn + nn;
       const bool valid = (w < p.w_out) && (h < p.h_out) && (n < p.n_img);
       const size_t pix = (static_cast<size_t>(n) * p.h_out + h) * p.w_out + w;
+      // transposed store mapping: instruction k covers rows 8k + (lane >> 2)
+      size_t pixk[4];
+      bool vk[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        pixk[k] = __shfl_sync(0xffffffffu, static_cast<unsigned long long>(pix), 8 * k + (lane >> 2));
+        vk[k] = __shfl_sync(0xffffffffu, valid ? 1 : 0, 8 * k + (lane >> 2)) != 0;
+      }
       float2 racc[64];  // register accumulator group g (32 columns) = racc[16 g .. 16 g + 15]
 #pragma unroll
       for (int i = 0; i < 64; ++i) racc[i] = make_float2(0.f, 0.f);
-      for (int ch = 0; ch <= total_chunks; ++ch) {
-        // ch < total_chunks: hi.hi chunk from "main"; ch == total_chunks: the tile's lo.hi + hi.lo sum from "corr"
-        const bool last = ch == total_chunks;
+      const int drains = (total_chunks + kchain - 1) / kchain;
+      for (int ch = 0; ch <= drains; ++ch) {
+        // ch < drains: one hi.hi accumulation (kchain K chunks) from "main"; ch == drains: the tile's lo.hi + hi.lo sum from "corr"
+        const bool last = ch == drains;
         if (last) { mbar_wait(corr_full, cph, 5); cph ^= 1u; }
         else { mbar_wait(&main_full[mb], mph[mb], 6); mph[mb] ^= 1u; }
         tc_fence_after();
@@ -415,11 +549,11 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
       for (int g = 0; g < 4; ++g) {
         const int tcol = wide ? (g >> 1) * 128 + half * 64 + (g & 1) * 32 : half * half_cols + g * 32;
         const int col0 = n_tile * block_n + tcol;
-        if (g * 32 < half_cols && valid && col0 < p.n_valid) {
+        if (g * 32 < half_cols && col0 < p.n_valid) {  // warp-uniform: x3_finish32 is a warp-collective
           float f[32];
 #pragma unroll
           for (int i = 0; i < 16; ++i) { f[2 * i] = racc[g * 16 + i].x; f[2 * i + 1] = racc[g * 16 + i].y; }
-          igemm_finish32(p, f, pix, col0);
+          x3_finish32(p, f, stg, lane, pix, valid, pixk, vk, col0);
         }
       }
     }

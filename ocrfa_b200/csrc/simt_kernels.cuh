@@ -732,4 +732,86 @@ __global__ void nhwc16_to_nchw_f32_kernel(const uint16_t* __restrict__ in, int l
   out[gid] = f16 ? f16bits_to_f32(v) : __uint_as_float(v << 16);
 }
 
+// ---------------------------------------------------------------------------------------------
+// The same glue for the fp32-grade (f16x3) CRAFT forward: activations are fp16 hi/lo pairs, pixel = [hi(ld) | lo(ld)]
+// with ld = channels of the buffer (a channel slice [c0, c0 + c) of a concat buffer has its hi halves at c0 and its lo
+// halves at ld + c0); values are reconstructed as hi + lo in fp32, combined, and split again.
+// ---------------------------------------------------------------------------------------------
+__global__ void nchw3_to_nhwc8_split_kernel(const float* __restrict__ x, __half* __restrict__ out, int n, int h, int w) {
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long hw = (long long)h * w;
+  if (pix >= (long long)n * hw) return;
+  const long long b = pix / hw, r = pix - b * hw;
+  const float* xp = x + b * 3 * hw + r;
+  const float v[8] = {__ldg(xp), __ldg(xp + hw), __ldg(xp + 2 * hw), 0.f, 0.f, 0.f, 0.f, 0.f};
+  store_split8(out + pix * 16, 8, 0, v);
+}
+
+__global__ void pool_split_kernel(const __half* __restrict__ in, int ld_in, __half* __restrict__ out, int ld_out, int n,
+                                  int h_in, int w_in, int c, int k, int stride, int pad, int relu) {
+  const int cv = c / 8;
+  const int h_out = (h_in + 2 * pad - k) / stride + 1, w_out = (w_in + 2 * pad - k) / stride + 1;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (long long)n * h_out * w_out * cv) return;
+  const int cg = gid % cv;
+  const long long pix = gid / cv;
+  const int wo = pix % w_out, ho = (pix / w_out) % h_out;
+  const int b = pix / ((long long)w_out * h_out);
+  float m[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) m[i] = -INFINITY;
+  for (int r = 0; r < k; ++r)
+    for (int s2 = 0; s2 < k; ++s2) {
+      const int hi = ho * stride + r - pad, wi = wo * stride + s2 - pad;
+      if (hi < 0 || hi >= h_in || wi < 0 || wi >= w_in) continue;
+      float v[8];
+      load_split8(in + (((long long)b * h_in + hi) * w_in + wi) * 2 * ld_in, ld_in, cg * 8, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], v[i]);
+    }
+  if (relu) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], 0.f);
+  }
+  store_split8(out + pix * 2 * ld_out, ld_out, cg * 8, m);
+}
+
+__global__ void upsample2x_bilinear_split_kernel(const __half* __restrict__ in, __half* __restrict__ out, int ld_out, int n,
+                                                 int h_in, int w_in, int c) {
+  const int cv = c / 8;
+  const int h_out = 2 * h_in, w_out = 2 * w_in;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (long long)n * h_out * w_out * cv) return;
+  const int cg = gid % cv;
+  const long long pix = gid / cv;
+  const int wo = pix % w_out, ho = (pix / w_out) % h_out;
+  const int b = pix / ((long long)w_out * h_out);
+  const float fy = fmaxf(0.f, (ho + 0.5f) * 0.5f - 0.5f), fx = fmaxf(0.f, (wo + 0.5f) * 0.5f - 0.5f);
+  const int y0 = (int)fy, x0 = (int)fx;
+  const int y1 = min(y0 + 1, h_in - 1), x1 = min(x0 + 1, w_in - 1);
+  const float ly1 = fy - y0, lx1 = fx - x0, ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+  float v00[8], v01[8], v10[8], v11[8], o[8];
+  load_split8(in + (((long long)b * h_in + y0) * w_in + x0) * 2 * c, c, cg * 8, v00);
+  load_split8(in + (((long long)b * h_in + y0) * w_in + x1) * 2 * c, c, cg * 8, v01);
+  load_split8(in + (((long long)b * h_in + y1) * w_in + x0) * 2 * c, c, cg * 8, v10);
+  load_split8(in + (((long long)b * h_in + y1) * w_in + x1) * 2 * c, c, cg * 8, v11);
+#pragma unroll
+  for (int i = 0; i < 8; ++i)  // PyTorch's order: h0 * (w0 * v00 + w1 * v01) + h1 * (w0 * v10 + w1 * v11), no contraction
+    o[i] = __fadd_rn(__fmul_rn(ly0, __fadd_rn(__fmul_rn(lx0, v00[i]), __fmul_rn(lx1, v01[i]))),
+                     __fmul_rn(ly1, __fadd_rn(__fmul_rn(lx0, v10[i]), __fmul_rn(lx1, v11[i]))));
+  store_split8(out + pix * 2 * ld_out, ld_out, cg * 8, o);
+}
+
+__global__ void nhwc_split_to_nchw_f32_kernel(const __half* __restrict__ in, int ld_in, float* __restrict__ out, int n, int h,
+                                              int w, int c) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long hw = (long long)h * w;
+  if (gid >= (long long)n * c * hw) return;
+  const long long r = gid % hw;
+  const int ch = (gid / hw) % c;
+  const long long b = gid / (hw * c);
+  const __half* px = in + (b * hw + r) * 2 * ld_in;
+  out[gid] = __half2float(px[ch]) + __half2float(px[ld_in + ch]);
+}
+
 }  // namespace ocrfa

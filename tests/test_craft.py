@@ -81,3 +81,45 @@ def test_gpu_craft_larger_image_vs_oracle(craft_sd):
     assert ey <= 4e-3 and ef <= 4e-3
     y1, _ = net(torch.from_numpy(x[1:2]).cuda())
     assert torch.equal(y1[0], y[1])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["a", "b"])
+def test_gpu_craft_f16x3_forward_is_fp32_grade(craft_sd, case):
+    """The fp32-grade mode (fp16 hi/lo split operands on igemm_x3_kernel, split glue kernels) against the reference
+    module's fp32 output: 1e-5 of the range of the score maps / feature map (f16: 1.5e-3, bf16: 1e-2)."""
+    from ocrfa_b200.craft import CraftNet
+
+    g = load_golden("craft_64x96")
+    net = CraftNet(precision="f16x3")
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in craft_sd.items()})
+    y, feat = net(torch.from_numpy(g[f"x_{case}"]).cuda())
+    y, feat = y.cpu().numpy(), feat.cpu().numpy()
+    assert y.shape == g[f"y_{case}"].shape and feat.shape == g[f"feature_{case}"].shape
+    ey = np.abs(y - g[f"y_{case}"]).max() / np.abs(g[f"y_{case}"]).max()
+    ef = np.abs(feat - g[f"feature_{case}"]).max() / np.abs(g[f"feature_{case}"]).max()
+    print(f"craft f16x3 {case}: score-map error {ey:.3g}, feature error {ef:.3g} (relative to range)")
+    assert ey <= 1e-5 and ef <= 1e-5
+
+
+@pytest.mark.gpu
+def test_gpu_real_forward_boxes_equal_the_reference_boxes(craft_sd):
+    """SURVEY section 8f row 4, end to end with the REAL forward: `get_textbox` (resize + normalise on the GPU, CRAFT
+    forward in f16x3, thresholds / connected components / dilation on the GPU, minAreaRect on the row extents, coordinate
+    adjustment) returns exactly the boxes the reference's `get_textbox` returns with its own fp32 forward of the same
+    weights on the same pages (tests/golden/craft_boxes.npz, oracle/gen_golden_craft_boxes.py; reference:
+    detectors.py:24-115, utils.py:48-98, 106-175). The score maps agree to 1e-5 of their range and the thresholds sit
+    in gaps of the reference's maps at least 4e-5 of the range wide, so no pixel can change sides."""
+    import ocrfa_b200 as ob
+    from ocrfa_b200.craft import CraftNet
+
+    g = load_golden("craft_boxes")
+    net = CraftNet(precision="f16x3")
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in craft_sd.items()})
+    for i, (h, w, canvas, mag, _) in enumerate(g["cases"].tolist()):
+        tt, lt, low = g[f"c{i}_thr"].tolist()
+        res = ob.get_textbox(net, g[f"c{i}_page"], int(canvas), float(mag), tt, lt, low, False, "cuda")
+        got = np.array(res[0], dtype=np.int32).reshape(-1, 8)
+        want = g[f"c{i}_boxes"]
+        print(f"case {i}: {len(got)} boxes (reference {len(want)})")
+        assert got.shape == want.shape and np.array_equal(got, want)

@@ -4,8 +4,10 @@
     python tools/sweep_1m.py [--lines 1000000]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 tools/sweep_1m.py
 
-Every rank generates ITS shard on its own GPU (torch.Generator(device).manual_seed(1234 + rank): light background,
-dark vertical strokes, noise - SURVEY.md section 8d), recognises it in inner batches of 256 through
+Every rank generates ITS shard on its own GPU. The set is defined in global chunks of 8192 lines - chunk c comes from
+torch.Generator(device).manual_seed(1234 + c): light background, dark vertical strokes, noise -
+so a line is a function of its GLOBAL index and any sharding reads the same lines: the label checksum of a 1-GPU and an
+8-GPU run of the same set must be equal. Each rank recognises its shard in inner batches of 256 through
 ocrfa_recognize_device (device-resident inputs, CUDA events, no collective on the path), and only then the decoded
 labels are all-gathered over NCCL (ocrfa_b200.distributed.gather_decoded) and the slowest rank's device time is taken.
 Rank 0 prints one JSON line. Not a unit of the product: a driver for the throughput sweep.
@@ -50,11 +52,27 @@ def synth_lines_device(n: int, h: int, w: int, gen: torch.Generator, dev: torch.
     return out
 
 
+GLOBAL_CHUNK = 8192
+
+
+def synth_lines_device_global(lo: int, hi: int, h: int, w: int, dev: torch.device) -> torch.Tensor:
+    """Lines lo..hi-1 of the global set (see the module docstring)."""
+    out = torch.empty((max(hi - lo, 0), h, w), dtype=torch.uint8, device=dev)
+    gen = torch.Generator(device=dev)
+    for c in range(lo // GLOBAL_CHUNK, (max(hi, lo + 1) - 1) // GLOBAL_CHUNK + 1):
+        gen.manual_seed(1234 + c)
+        chunk = synth_lines_device(GLOBAL_CHUNK, h, w, gen, dev, chunk=GLOBAL_CHUNK)
+        a, b = max(lo, c * GLOBAL_CHUNK), min(hi, (c + 1) * GLOBAL_CHUNK)
+        if b > a:
+            out[a - lo:b - lo] = chunk[a - c * GLOBAL_CHUNK:b - c * GLOBAL_CHUNK]
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--lines", type=int, default=1_000_000)
     ap.add_argument("--batch", type=int, default=256)
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "f16", "f16x3", "fp32"])
+    ap.add_argument("--precision", default="f16x3", choices=["f16x3", "bf16", "f16", "fp32"])
     args = ap.parse_args()
     rank, local_rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     torch.cuda.set_device(local_rank)
@@ -74,9 +92,7 @@ def main():
     T = lib.ocrfa_out_timesteps(H, W)
     lo, hi = shard_range(args.lines, rank, world)
     n_local = hi - lo
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(1234 + rank)
-    lines = synth_lines_device(max(n_local, 1), H, W, gen, dev)
+    lines = synth_lines_device_global(lo, max(hi, lo + 1), H, W, dev)
     d_mask = torch.from_numpy(_ignore_mask(Cn, [chars.index(ch) + 1 for ch in ob.default_ignore_char()])).to(dev)
     ws_bytes = lib.ocrfa_recognize_workspace_bytes(handle, B, H, W, 1)
     ws = model.workspace(ws_bytes, dev)
@@ -88,7 +104,8 @@ def main():
     labs = torch.zeros((max(n_local, 1), T), dtype=torch.int32, device=dev)
     lens = torch.zeros(max(n_local, 1), dtype=torch.int32, device=dev)
     confs = torch.zeros(max(n_local, 1), dtype=torch.float64, device=dev)
-    stream = torch.cuda.current_stream(dev)
+    stream = torch.cuda.Stream(dev)  # a capturable stream: the step replays as a CUDA graph
+    torch.cuda.set_stream(stream)
 
     def run(a: int, b: int):
         nb = b - a
@@ -119,7 +136,7 @@ def main():
         checksum = int((g_lab.to(torch.int64) * (torch.arange(T, device=g_lab.device) < g_len[:, None])).sum().item())
         print(json.dumps({"metric": "text lines/sec (device-timed, max over ranks)", "value": args.lines / (ms * 1e-3),
                           "unit": "lines/s", "n_gpus": world, "lines": args.lines, "ms_total": ms, "scaling": "strong",
-                          "dtype": args.precision, "data": "synthetic (generated on device, per-rank seed)",
+                          "dtype": args.precision, "data": "synthetic (generated on device; line g is a function of its global index)",
                           "config": {"workload": f"c5: {args.lines} lines of {H}x{W}, contiguous shards, inner batch {B}, greedy"},
                           "gathered_lines": int(g_lab.shape[0]), "label_checksum": checksum, "sample": sample}), flush=True)
     if world > 1:

@@ -320,6 +320,7 @@ static void run_split_case(const Case& c, bool halo = false, bool pool = false) 
   p.residual = d_res; p.ldr = 2 * g.cout; p.res_lo = g.cout;
   p.out = d_out; p.out_f32 = c.out_f32; p.relu = c.relu;
   p.out_scale = std::ldexp(1.f, -kexp);
+  if (const char* e = getenv("OCRFA_X3_CHAIN")) p.kchain = atoi(e);
   if (c.out_f32) { p.ldo = g.cout; } else { p.ldo = 2 * g.cout; p.out_lo = g.cout; }
   CK(igemm_tc_launch(p, kModeStd, g_sms, 0));
   cudaError_t e = cudaDeviceSynchronize();
