@@ -50,7 +50,12 @@ namespace ocrfa {
 constexpr int kX3Threads = 384;
 constexpr int kX3FirstEpiWarp = 4;
 constexpr int kX3CorrCol = 256;  // TMEM column of the corr accumulator (main starts at column 0)
-constexpr int kX3Staging = 8 * 2048;  // per epilogue warp: a 32-row x 64-byte transposition buffer (behind the stages)
+// Tile tail through a per-warp transposition buffer (x3_finish32 below). Measured and NOT kept: the 512-channel layer
+// went 1.39-1.47 -> 1.54 ms with it. Stores are fire-and-forget - the warp does not wait for the L1 wavefronts of its
+// 16-byte-per-lane accesses - while the transposition adds dependent shared-memory round trips and registers to the
+// one phase in which the epilogue warps cannot drain. The code stays as the record of the experiment.
+constexpr bool kX3TransposedTail = false;
+constexpr int kX3Staging = kX3TransposedTail ? 8 * 2048 : 0;  // per epilogue warp: 32 rows x 64 bytes (behind the stages)
 
 inline size_t igemm_x3_smem_bytes(int block_n, int* stages_out) {
   const size_t stage = 2 * static_cast<size_t>(kTcBlockM) * kTcBlockK * 2 + 2 * static_cast<size_t>(block_n / 2) * kTcBlockK * 2;
@@ -469,12 +474,14 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
       const bool valid = (w < p.w_out) && (h < p.h_out) && (n < p.n_img);
       const size_t pix = (static_cast<size_t>(n) * p.h_out + h) * p.w_out + w;
       // transposed store mapping: instruction k covers rows 8k + (lane >> 2)
-      size_t pixk[4];
-      bool vk[4];
+      size_t pixk[4] = {0, 0, 0, 0};
+      bool vk[4] = {false, false, false, false};
+      if (kX3TransposedTail) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        pixk[k] = __shfl_sync(0xffffffffu, static_cast<unsigned long long>(pix), 8 * k + (lane >> 2));
-        vk[k] = __shfl_sync(0xffffffffu, valid ? 1 : 0, 8 * k + (lane >> 2)) != 0;
+        for (int k = 0; k < 4; ++k) {
+          pixk[k] = __shfl_sync(0xffffffffu, static_cast<unsigned long long>(pix), 8 * k + (lane >> 2));
+          vk[k] = __shfl_sync(0xffffffffu, valid ? 1 : 0, 8 * k + (lane >> 2)) != 0;
+        }
       }
       float2 racc[64];  // register accumulator group g (32 columns) = racc[16 g .. 16 g + 15]
 #pragma unroll
@@ -553,7 +560,8 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
           float f[32];
 #pragma unroll
           for (int i = 0; i < 16; ++i) { f[2 * i] = racc[g * 16 + i].x; f[2 * i + 1] = racc[g * 16 + i].y; }
-          x3_finish32(p, f, stg, lane, pix, valid, pixk, vk, col0);
+          if (kX3TransposedTail) x3_finish32(p, f, stg, lane, pix, valid, pixk, vk, col0);
+          else if (valid) igemm_finish32(p, f, pix, col0);
         }
       }
     }

@@ -283,7 +283,7 @@ class OCR:
 
     def __init__(self, gpu=True, recog_network="standard", download_enabled=True, detector=True, recognizer=True,
                  model_storage_directory=None, user_network_directory=None, detect_network="craft", verbose=True,
-                 quantize=True, cudnn_benchmark=False, *, precision="f16x3", detector_precision="f16", verify_md5=True,
+                 quantize=True, cudnn_benchmark=False, *, precision="f16x3", detector_precision="f16x3", verify_md5=True,
                  display_order=True):
         self.verbose = verbose
         self.download_enabled = download_enabled

@@ -239,7 +239,7 @@ def test_gpu_readtext_with_the_craft_forward(reader):
 
 @pytest.mark.gpu
 def test_gpu_default_precision_reader_reads_the_same_boxes(reader, tmp_path, synth_sd):
-    """The constructor's defaults (f16x3 recognizer - fp32-grade tensor-core arithmetic - and f16 detector): the same
+    """The constructor's defaults (f16x3 recognizer and detector: fp32-grade tensor-core arithmetic): the same
     boxes AND the same strings as the fp32 (CUDA-core) reader; display_order=True additionally applies the RTL display
     order (ocr.py:474-478) to every string."""
     import torch
@@ -250,7 +250,7 @@ def test_gpu_default_precision_reader_reads_the_same_boxes(reader, tmp_path, syn
     torch.save({k: torch.from_numpy(v) for k, v in ob.synth_craft_state_dict(0).items()},
                os.path.join(tmp_path, "craft_mlt_25k.pth"))
     fast = ob.OCR(model_storage_directory=str(tmp_path), verify_md5=False)
-    assert fast.precision == "f16x3" and fast.detector_precision == "f16" and fast.model_lang == "arabic"
+    assert fast.precision == "f16x3" and fast.detector_precision == "f16x3" and fast.model_lang == "arabic"
     assert fast.display_order and fast.bidi_backend in ("python-bidi", "ocrfa_b200.bidi")
     g = load_golden("reader")
     page = load_golden("crops")["page"]
