@@ -45,8 +45,9 @@ extern "C" {
 /* arithmetic of the contraction layers */
 #define OCRFA_PRECISION_FP32 0 /* CUDA-core fp32: logits within 1e-3 of the reference's fp32 path */
 #define OCRFA_PRECISION_BF16 1 /* tcgen05 bf16 inputs, fp32 accumulate: logits within 2e-2 */
-#define OCRFA_PRECISION_F16X3 2 /* tcgen05 fp16 hi/lo split operands, 3 products per term, fp32 accumulate: fp32-grade
-                                   logits (within 1e-3 of the reference) at 1/3 of the tensor-core rate */
+#define OCRFA_PRECISION_F16X3 2 /* the host mirror's DEFAULT. tcgen05 on fp16 hi/lo split operands, 3 products per term,
+                                   the dominant one summed per 64-wide K chunk in fp32 registers: fp32-grade logits
+                                   (1.2e-6 of their rms from exact arithmetic, the reference's own fp32 run: 0.6e-6) */
 #define OCRFA_PRECISION_F16 3 /* tcgen05 fp16 inputs/activations, fp32 accumulate: the bf16 kernels with 3 more mantissa bits
                                 (same rate and bytes); activations saturate at +-65504 */
 
@@ -71,7 +72,9 @@ void ocrfa_destroy(ocrfa_handle* h);
  * detectors.py:43-47): a second kind of handle. Load the detector's state dict with ocrfa_load_weight, call
  * ocrfa_finalize_weights, then ocrfa_craft_forward = OCRFA.forward: d_x float32 [N,3,H,W] (mean/variance normalised,
  * H and W multiples of 32 as resize_aspect_ratio produces) -> d_y float32 [N,H/2,W/2,2] (text, link score maps, the
- * reference's y.permute(0,2,3,1)) and, when not NULL, d_feature float32 [N,32,H/2,W/2]. precision: BF16 or F16. */
+ * reference's y.permute(0,2,3,1)) and, when not NULL, d_feature float32 [N,32,H/2,W/2]. precision: BF16, F16 (single-pass
+ * tensor-core modes) or F16X3 (fp32-grade: score maps within 1.4e-6 of their range of the reference's fp32 output, so the
+ * thresholded components and hence the boxes are the reference's). */
 int ocrfa_craft_create(int32_t precision, int32_t device, ocrfa_handle** out);
 size_t ocrfa_craft_workspace_bytes(const ocrfa_handle* h, int32_t N, int32_t H, int32_t W);
 int ocrfa_craft_forward(ocrfa_handle* h, const float* d_x, int32_t N, int32_t H, int32_t W, float* d_y, float* d_feature,

@@ -86,6 +86,12 @@ inline int plan_conv(IgemmTcParams* p, const ConvGeom& g, const void* in, int ci
   p->n_img = g.n; p->h_out = ho; p->w_out = wo;
   p->block_n = choose_block_n(g.cout);
   if (split) p->block_n = ceil_div(p->block_n, 64) * 64;  // the split epilogue halves a tile in 32-column groups
+  if (split) {
+    if (const char* e = std::getenv("OCRFA_X3_BLOCKN")) {  // experiment switch: cap the N tile of the fp32-grade kernel
+      const int cap = std::atoi(e);
+      if ((cap == 64 || cap == 128) && p->block_n > cap && g.cout % cap == 0) p->block_n = cap;
+    }
+  }
   // latency shapes (a handful of M tiles, e.g. one 32x128 line): narrower N tiles spread the layer over more SMs -
   // the K loop of a single 128 x 256 tile at K = 4608 is ~20 us on one SM while the other SMs idle
   {

@@ -324,6 +324,9 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // bring-up profiling: stamps of the leader CTA of pair 0, slot = running stage / chunk index of the CTA
+  long long* dbg = (blockIdx.x == 0) ? p.dbg : nullptr;
+#define X3_TS(idx, col) do { if (dbg && (idx) < 256) dbg[(idx) * 8 + (col)] = clock64(); } while (0)
   if (warp < kX3FirstEpiWarp) {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 0) {
@@ -377,12 +380,15 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
       int stage = 0;
       uint32_t phase = 0, cph = 0, mph[2] = {0u, 0u};
       int mb = 0;
+      int gstage = 0;  // running stage index of this CTA (profiling stamps)
       for (int tile = worker; tile < total_tiles; tile += num_workers) {
         mbar_wait(corr_empty, cph ^ 1u, 2);  // the previous tile's corr has been read back
         cph ^= 1u;
         int unit = 0;  // K chunks of 64 issued so far in this tile; `kchain` consecutive ones share one accumulation
         for (int kb = 0; kb < total_kb; ++kb) {
+          X3_TS(gstage, 0);
           mbar_wait(&full_bar[stage], phase, 3);
+          X3_TS(gstage, 1);
           tc_fence_after();
           const uint32_t sa0 = smem_u32(stage_base + static_cast<size_t>(stage) * stage_bytes);
           const int nsub = kb_table[3 * kb + 1].y;
@@ -409,11 +415,13 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
           if (wide) {
 #pragma unroll
             for (int hb = 0; hb < 2; ++hb) {
+              if (hb == 0) X3_TS(gstage, 2);
               if (fresh) {
                 mbar_wait(&main_empty[hb], mph[hb] ^ 1u, 4);
                 mph[hb] ^= 1u;
                 tc_fence_after();
               }
+              X3_TS(gstage, 3 + hb);
               // rows hb*64 .. hb*64+63 of each CTA's 128-row weight tile: 8 swizzle atoms = 8192 B further
               const uint64_t b_half = b_hi + static_cast<uint64_t>(hb * (8192 >> 4));
 #pragma unroll
@@ -440,6 +448,7 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
             }
           }
           }  // sub-blocks
+          ++gstage;
           if (++stage == stages) { stage = 0; phase ^= 1u; }
         }
         umma_commit_pair(corr_full);
@@ -458,6 +467,7 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
     const int half_cols = block_n >> 1;  // multiple of 32
     uint32_t cph = 0, mph[2] = {0u, 0u};
     int mb = wide ? half : 0;
+    int gchunk = 0;  // running drain index of this CTA (profiling stamps)
     uint8_t* stg = stage_base + static_cast<size_t>(stages) * stage_bytes + static_cast<size_t>(warp - kX3FirstEpiWarp) * 2048;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const uint32_t t_main = t_lane + (wide ? static_cast<uint32_t>(half) * 128u : static_cast<uint32_t>(half * half_cols));
@@ -487,11 +497,13 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
 #pragma unroll
       for (int i = 0; i < 64; ++i) racc[i] = make_float2(0.f, 0.f);
       const int drains = (total_chunks + kchain - 1) / kchain;
+      const bool ts_warp = wide && lane == 0 && q == 0;  // profiling: one lane of the first warp of each column half
       for (int ch = 0; ch <= drains; ++ch) {
         // ch < drains: one hi.hi accumulation (kchain K chunks) from "main"; ch == drains: the tile's lo.hi + hi.lo sum from "corr"
         const bool last = ch == drains;
         if (last) { mbar_wait(corr_full, cph, 5); cph ^= 1u; }
         else { mbar_wait(&main_full[mb], mph[mb], 6); mph[mb] ^= 1u; }
+        if (ts_warp && !last) X3_TS(gchunk, 5 + half);
         tc_fence_after();
         // two TMEM loads (64 columns) in flight per wait
 #pragma unroll
@@ -527,6 +539,8 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
           uint64_t* bar = last ? corr_empty : &main_empty[mb];
           if (leader) mbar_arrive(bar); else mbar_arrive_remote(bar, 0u);
         }
+        if (ts_warp && !last && half == 0) X3_TS(gchunk, 7);
+        if (!last) ++gchunk;
         if (!last && alt) mb ^= 1;
       }
       if (p.pool) {
@@ -567,6 +581,7 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
     }
   }
 
+#undef X3_TS
   tc_fence_before();
   cluster_sync_all();  // the peer's smem/TMEM stay live until the leader's MMAs are done
   if (warp == 1) {

@@ -321,6 +321,8 @@ static void run_split_case(const Case& c, bool halo = false, bool pool = false) 
   p.out = d_out; p.out_f32 = c.out_f32; p.relu = c.relu;
   p.out_scale = std::ldexp(1.f, -kexp);
   if (const char* e = getenv("OCRFA_X3_CHAIN")) p.kchain = atoi(e);
+  long long* d_dbg = nullptr;
+  if (getenv("X3_DBG")) { CK(cudaMalloc(&d_dbg, 256 * 8 * 8)); CK(cudaMemset(d_dbg, 0, 256 * 8 * 8)); p.dbg = d_dbg; }
   if (c.out_f32) { p.ldo = g.cout; } else { p.ldo = 2 * g.cout; p.out_lo = g.cout; }
   CK(igemm_tc_launch(p, kModeStd, g_sms, 0));
   cudaError_t e = cudaDeviceSynchronize();
@@ -384,6 +386,20 @@ static void run_split_case(const Case& c, bool halo = false, bool pool = false) 
            sum_d / cmp_elems / rr, p.pair, p.num_stages);
   }
   if (bad) g_fail++;
+  if (d_dbg) {
+    // stamps of pair 0's leader CTA: issuer columns 0 wait-full begin, 1 full, 2 corr issued, 3 / 4 main half 0 / 1 may
+    // issue; epilogue (first warp of each column half) 5 / 6 main_full seen by half 0 / 1, 7 half 0 drained + arrived
+    std::vector<long long> ts(256 * 8);
+    CK(cudaMemcpy(ts.data(), d_dbg, ts.size() * 8, cudaMemcpyDeviceToHost));
+    for (int i = 80; i < 92; ++i) {
+      const long long b0 = ts[i * 8 + 0];
+      printf("    stage %d: wait_full=%lld corr_issued=%lld me0_ok=%lld me1_ok=%lld | full0_seen=%lld full1_seen=%lld drained0=%lld | next stage at %lld\n",
+             i, ts[i * 8 + 1] - b0, ts[i * 8 + 2] - b0, ts[i * 8 + 3] - b0, ts[i * 8 + 4] - b0, ts[i * 8 + 5] - b0, ts[i * 8 + 6] - b0,
+             ts[i * 8 + 7] - b0, ts[(i + 1) * 8 + 0] - b0);
+    }
+    cudaFree(d_dbg);
+    p.dbg = nullptr;
+  }
   if (c.perf_iters > 0 && !bad) {
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
