@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
 
   // bring-up profiling: stamps of the leader CTA of pair 0, slot = running stage / chunk index of the CTA
   long long* dbg = (blockIdx.x == 0) ? p.dbg : nullptr;
-#define X3_TS(idx, col) do { if (dbg && (idx) < 256) dbg[(idx) * 8 + (col)] = clock64(); } while (0)
+#define X3_TS(idx, col) do { if (dbg && (idx) < 256 && ((threadIdx.x & 31) == 0)) dbg[(idx) * 8 + (col)] = clock64(); } while (0)
   if (warp < kX3FirstEpiWarp) {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 0) {
@@ -372,7 +372,12 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer (leader CTA only) =====================
-    if (leader && elect_one()) {
+    // The WHOLE warp walks the loop with warp-uniform values and only the tcgen05.mma / commit instructions are
+    // predicated on the elected lane: inside a one-thread branch every descriptor lives in a vector register and each
+    // UTCHMMA pays for four R2UR moves - measured ~60 cycles per issue, 960 of a stage's 1 536 tensor cycles with 16
+    // MMAs per stage, i.e. the issuing thread, not the tensor pipe, set the pace (stage period 1 600 / 2 200 cycles).
+    if (leader) {
+      const bool elected = elect_one();
       const uint32_t idesc = make_idesc_f16(2 * kTcBlockM, static_cast<uint32_t>(block_n));
       const uint32_t idesc_half = make_idesc_f16(2 * kTcBlockM, 128u);
       const uint32_t d_main = tmem_base;
@@ -391,7 +396,7 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
           X3_TS(gstage, 1);
           tc_fence_after();
           const uint32_t sa0 = smem_u32(stage_base + static_cast<size_t>(stage) * stage_bytes);
-          const int nsub = kb_table[3 * kb + 1].y;
+          const int nsub = halo ? kb_table[3 * kb + 1].y : 1;
           for (int j = 0; j < nsub; ++j) {
           // sub-block j: the rows of tap dy = j start j * tap_bytes into the halo boxes; its weight blocks are (hi, lo) pair j
           const uint32_t sa = sa0 + static_cast<uint32_t>(j) * tap_bytes;
@@ -400,13 +405,15 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
           const uint64_t a_lo = make_sw128_kmajor_desc(sa + a_slot);
           const uint64_t b_hi = make_sw128_kmajor_desc(sb);
           const uint64_t b_lo = make_sw128_kmajor_desc(sb + b_bytes);
+          if (elected) {
 #pragma unroll
-          for (int k = 0; k < kTcBlockK / 16; ++k)
-            umma_bf16_pair(d_corr, a_lo + static_cast<uint64_t>(2 * k), b_hi + static_cast<uint64_t>(2 * k), idesc,
-                           (kb > 0 || j > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < kTcBlockK / 16; ++k)
+              umma_bf16_pair(d_corr, a_lo + static_cast<uint64_t>(2 * k), b_hi + static_cast<uint64_t>(2 * k), idesc,
+                             (kb > 0 || j > 0 || k > 0) ? 1u : 0u);
 #pragma unroll
-          for (int k = 0; k < kTcBlockK / 16; ++k)
-            umma_bf16_pair(d_corr, a_hi + static_cast<uint64_t>(2 * k), b_lo + static_cast<uint64_t>(2 * k), idesc, 1u);
+            for (int k = 0; k < kTcBlockK / 16; ++k)
+              umma_bf16_pair(d_corr, a_hi + static_cast<uint64_t>(2 * k), b_lo + static_cast<uint64_t>(2 * k), idesc, 1u);
+          }
           // a "main" buffer is free again once the epilogue warps have drained its previous contents - they do that
           // while the corr MMAs above keep the tensor pipe busy
           const bool fresh = (unit % kchain) == 0;                                   // first K chunk of an accumulation
@@ -424,12 +431,14 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
               X3_TS(gstage, 3 + hb);
               // rows hb*64 .. hb*64+63 of each CTA's 128-row weight tile: 8 swizzle atoms = 8192 B further
               const uint64_t b_half = b_hi + static_cast<uint64_t>(hb * (8192 >> 4));
+              if (elected) {
 #pragma unroll
-              for (int k = 0; k < kTcBlockK / 16; ++k)
-                umma_bf16_pair(d_main + static_cast<uint32_t>(hb) * 128u, a_hi + static_cast<uint64_t>(2 * k),
-                               b_half + static_cast<uint64_t>(2 * k), idesc_half, (k > 0 || !fresh) ? 1u : 0u);
-              if (hb == 1 && j == nsub - 1) umma_commit_pair(&empty_bar[stage]);  // frees the slot in both CTAs once these MMAs have read it
-              if (closes) umma_commit_pair(&main_full[hb]);      // this half of the hi.hi accumulation is complete (both CTAs)
+                for (int k = 0; k < kTcBlockK / 16; ++k)
+                  umma_bf16_pair(d_main + static_cast<uint32_t>(hb) * 128u, a_hi + static_cast<uint64_t>(2 * k),
+                                 b_half + static_cast<uint64_t>(2 * k), idesc_half, (k > 0 || !fresh) ? 1u : 0u);
+                if (hb == 1 && j == nsub - 1) umma_commit_pair(&empty_bar[stage]);  // frees the slot in both CTAs once these MMAs have read it
+                if (closes) umma_commit_pair(&main_full[hb]);      // this half of the hi.hi accumulation is complete (both CTAs)
+              }
             }
           } else {
             if (fresh) {
@@ -437,21 +446,21 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
               mph[mb] ^= 1u;
               tc_fence_after();
             }
+            if (elected) {
 #pragma unroll
-            for (int k = 0; k < kTcBlockK / 16; ++k)
-              umma_bf16_pair(d_main + static_cast<uint32_t>(mb) * 128u, a_hi + static_cast<uint64_t>(2 * k),
-                             b_hi + static_cast<uint64_t>(2 * k), idesc, (k > 0 || !fresh) ? 1u : 0u);
-            if (j == nsub - 1) umma_commit_pair(&empty_bar[stage]);
-            if (closes) {
-              umma_commit_pair(&main_full[mb]);
-              if (alt) mb ^= 1;
+              for (int k = 0; k < kTcBlockK / 16; ++k)
+                umma_bf16_pair(d_main + static_cast<uint32_t>(mb) * 128u, a_hi + static_cast<uint64_t>(2 * k),
+                               b_hi + static_cast<uint64_t>(2 * k), idesc, (k > 0 || !fresh) ? 1u : 0u);
+              if (j == nsub - 1) umma_commit_pair(&empty_bar[stage]);
+              if (closes) umma_commit_pair(&main_full[mb]);
             }
+            if (closes && alt) mb ^= 1;
           }
           }  // sub-blocks
           ++gstage;
           if (++stage == stages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit_pair(corr_full);
+        if (elected) umma_commit_pair(corr_full);
       }
     }
   }
