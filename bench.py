@@ -16,8 +16,9 @@ JSON line keys: value = whole-job lines/s with inputs resident in HBM (CUDA even
 ranks); e2e = the same through ocrfa_recognize_host_ex with pinned HOST buffers, H2D + D2H inside the timed region,
 two batches in flight on two streams; roofline = the tcgen05 implicit-GEMM kernels, algorithmic FLOPs / CUDA-event
 kernel time in the timed region vs MEASURED_PEAKS.json; cpu_baseline = the oracle (port of the reference's CPU path)
-on a bounded sample, rank 0, N=1 only. `--impl reference` times that CPU path alone (the reference is Python and cannot
-travel to the GPU box, so the oracle port pinned against it in tests/test_oracle_golden.py is what runs).
+on a bounded sample, rank 0, N=1 only. `--impl reference` times that CPU path alone: the reference's OWN
+recognizer_predict when a copy of its package is present (/root/reference in the dev container; oracle/_ref/, git-ignored
+build output of __graft_entry__.build(), on the GPU box), else the oracle port pinned against it in tests/test_oracle_golden.py.
 """
 from __future__ import annotations
 
@@ -141,7 +142,11 @@ def dist_env():
 # CPU arm: the oracle port of the reference's CPU path (recognizer_predict on torch CPU fp32)
 # ------------------------------------------------------------------------------------------------------------------
 def cpu_lines_per_s(cfg_name: str, sample_lines: int, repeats: int, warmup: int, quantize: bool = False):
+    """lines/s of the reference's CPU path on a bounded sample. When a copy of the reference package is present
+    (/root/reference here, oracle/_ref/ on the GPU box: see __graft_entry__.build) the reference's OWN get_recognizer +
+    recognizer_predict run (kind "reference"); otherwise the oracle port of the same calls (kind "port")."""
     from oracle import recognizer_ref as R
+    from oracle import _refimport
     from ocrfa_b200.synth import synth_lines, synth_state_dict
     import ocrfa_b200.charset as cs
 
@@ -149,14 +154,44 @@ def cpu_lines_per_s(cfg_name: str, sample_lines: int, repeats: int, warmup: int,
     n = min(sample_lines, B)
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    sd = {k: torch.from_numpy(v) for k, v in synth_state_dict(0).items()}
-    chars = ["[blank]"] + list(cs.default_character())
-    ign = R.ignore_idx_ref(cs.default_character(), cs.default_ignore_char())
+    sd_np = synth_state_dict(0)
+    character = cs.default_character()
+    ign = R.ignore_idx_ref(character, cs.default_ignore_char())
     imgs = synth_lines(n, H, W, seed=777)
+    bw = beam if decoder != "greedy" else 5
+    kind = "port"
+    one_pass = None
+    if _refimport.reference_available():
+        try:
+            import tempfile
+            from collections import OrderedDict
+            from PIL import Image
 
-    def one_pass():
-        x = R.align_collate_ref(list(imgs), H, W)
-        return R.recognizer_predict_ref(sd, x, chars, ign, decoder, beam if decoder != "greedy" else 5, quantize=quantize)
+            utils, _ = _refimport.import_reference()
+            with tempfile.TemporaryDirectory() as td:
+                path = os.path.join(td, "synthetic.pth")
+                torch.save(OrderedDict(("module." + k, torch.from_numpy(v)) for k, v in sd_np.items()), path)
+                model, converter = utils.get_recognizer("generation1", {"input_channel": 1, "output_channel": 512, "hidden_size": 512},
+                                                        character, {}, {}, path, device="cpu", quantize=quantize)
+            model.eval()
+            collate = utils.AlignCollate(imgH=H, imgW=W, keep_ratio_with_pad=True)
+            pil = [Image.fromarray(im, "L") for im in imgs]
+
+            def one_pass():  # AlignCollate + recognizer_predict, utils.py:567-662
+                x = collate(pil)
+                return utils.recognizer_predict(model, converter, [x], int(W / 10), ign, {}, decoder, bw, "cpu")
+
+            kind = "reference"
+        except Exception as exc:  # a broken copy must not take the bench down: time the port instead
+            print(f"[bench] reference import failed ({exc!r}); timing the oracle port", file=sys.stderr)
+            one_pass = None
+    if one_pass is None:
+        sd = {k: torch.from_numpy(v) for k, v in sd_np.items()}
+        chars = ["[blank]"] + list(character)
+
+        def one_pass():
+            x = R.align_collate_ref(list(imgs), H, W)
+            return R.recognizer_predict_ref(sd, x, chars, ign, decoder, bw, quantize=quantize)
 
     for _ in range(warmup):
         one_pass()
@@ -165,7 +200,7 @@ def cpu_lines_per_s(cfg_name: str, sample_lines: int, repeats: int, warmup: int,
         t0 = time.perf_counter()
         one_pass()
         times.append(time.perf_counter() - t0)
-    return n / (sum(times) / len(times)), threads, n, sum(times) / len(times)
+    return n / (sum(times) / len(times)), threads, n, sum(times) / len(times), kind
 
 
 def run_reference_arm(args):
@@ -174,15 +209,16 @@ def run_reference_arm(args):
         return
     B, H, W, decoder, beam = CONFIGS[args.config]
     sample = min(B, 32 if (H, W) == (32, 512) else (4 if H == 64 else B))
-    lps, threads, n, sec = cpu_lines_per_s(args.config, sample, max(1, args.steps), max(1, min(args.warmup, 1)))
+    lps, threads, n, sec, kind = cpu_lines_per_s(args.config, sample, max(1, args.steps), max(1, min(args.warmup, 1)))
+    what = ("the reference's own get_recognizer + AlignCollate + recognizer_predict (src/ocrfa/utils.py:567-695), copied to oracle/_ref by build()"
+            if kind == "reference" else "oracle port of recognizer_predict; no copy of the Python reference on this box")
     line = {
         "impl": "reference", "metric": METRIC, "value": lps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_text(args.config), "sample": f"{n} lines per step on the host CPU"},
-        "cpu_baseline": {"value": lps, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{n} lines of {H}x{W} per step, torch CPU fp32, {threads} threads (oracle port of "
-                                   "recognizer_predict; the Python reference cannot travel to the GPU box)"},
+        "cpu_baseline": {"value": lps, "unit": UNIT, "cores": threads, "kind": kind,
+                         "sample": f"{n} lines of {H}x{W} per step, torch CPU fp32, {threads} threads ({what})"},
         "e2e": {"value": lps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -478,12 +514,13 @@ def run_gpu_arm(args):
                               "against": "oracle (CPU port of the reference, torch fp32) on the first lines of this run's batch; "
                                          "the >= 10k-line runs are profiles/r02_parity_10k_*.json"}
             sample = 32 if (H, W) == (32, 512) else (4 if H == 64 else min(B, 32))
-            lps, threads, n, sec = cpu_lines_per_s(args.config, sample, 2, 1)
-            line["cpu_baseline"] = {"value": lps, "unit": UNIT, "cores": threads, "kind": "port",
+            lps, threads, n, sec, kind = cpu_lines_per_s(args.config, sample, 2, 1)
+            line["cpu_baseline"] = {"value": lps, "unit": UNIT, "cores": threads, "kind": kind,
                                     "sample": f"{n} lines of {H}x{W}, best-effort mean of 2 passes after 1 warm-up, torch CPU fp32 "
-                                              f"{threads} threads (oracle port of recognizer_predict, {decoder})"}
+                                              f"{threads} threads ({'the reference itself' if kind == 'reference' else 'oracle port'}: "
+                                              f"recognizer_predict, {decoder})"}
             # the reference's literal CPU default, OCR(gpu=False, quantize=True): dynamic int8 LSTM / Linear layers
-            q_lps, _, _, _ = cpu_lines_per_s(args.config, sample, 2, 1, quantize=True)
+            q_lps, _, _, _, _ = cpu_lines_per_s(args.config, sample, 2, 1, quantize=True)
             line["cpu_baseline"]["quantize_true"] = {"value": q_lps, "unit": UNIT,
                                                      "note": "same sample with torch dynamic int8 LSTM/Linear (utils.py:686-690)"}
         if world == 1 and not args.no_other_precisions:

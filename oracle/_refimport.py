@@ -2,8 +2,9 @@
 
 Four third-party modules the reference imports at module scope are absent here (skimage, bidi, shapely,
 pyclipper). None is touched by the recognition path, so empty stand-ins are registered
-before `src.ocrfa` is imported. /root/reference does not exist on the GPU box: only oracle/gen_golden.py
-(which writes the committed fixtures under tests/golden/) may call this.
+before `src.ocrfa` is imported. Callers: the oracle/gen_golden*.py scripts (which write the committed fixtures under
+tests/golden/) and bench.py's CPU legs (`--impl reference`, `cpu_baseline`), which time the reference's own
+recognizer_predict when a copy of the tree is present and fall back to the oracle port otherwise.
 """
 from __future__ import annotations
 
@@ -11,7 +12,22 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("OCRFA_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _resolve_root() -> str:
+    """/root/reference in the dev container; on the GPU box the copy `__graft_entry__.build()` leaves under
+    oracle/_ref/ (git-ignored build output: it travels with the snapshot, it is never committed)."""
+    env = os.environ.get("OCRFA_REFERENCE_ROOT")
+    if env:
+        return env
+    for cand in ("/root/reference", os.path.join(_HERE, "_ref")):
+        if os.path.isdir(os.path.join(cand, "src", "ocrfa")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _resolve_root()
 
 
 def reference_available() -> bool:
