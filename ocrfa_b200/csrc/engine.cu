@@ -120,7 +120,7 @@ struct ocrfa_handle {
   int graph_failures = 0;
   bool stem_1px = false;   // OCRFA_STEM_1PX (experiment switch), read once in ocrfa_create
   int x3_halo_max_cout = 128;  // OCRFA_X3_HALO_MAXC: f16x3 layers up to this Cout use the halo-staged form (0 = never)
-  int x3_kchain = 1;           // OCRFA_X3_CHAIN: K chunks of 64 per hi.hi accumulation in igemm_x3_kernel (1 or 2)
+  int x3_kchain = 2;           // K chunks of 64 per hi.hi accumulation in the recognizer's convolutions (igemm_x3.cuh); OCRFA_X3_CHAIN=1: one
   uint64_t graph_tick = 0;
   Profiler prof;
   ocrfa_config cfg;

@@ -96,9 +96,13 @@ inline int plan_conv(IgemmTcParams* p, const ConvGeom& g, const void* in, int ci
   // the K loop of a single 128 x 256 tile at K = 4608 is ~20 us on one SM while the other SMs idle
   {
     const int m_items = ceil_div(p->tiles_w * p->tiles_h * p->tiles_n, 2);  // CTA pairs take two M tiles
+    const int wide_n = p->block_n;
     while (p->block_n > 64 && p->block_n % 128 == 0 && g.cout % (p->block_n / 2) == 0 &&
            m_items * ceil_div(g.cout, p->block_n) * 2 <= kPlanSmCount / 2)
       p->block_n /= 2;
+    // fp32-grade kernel: a layer with 256-column tiles is narrowed to 64 columns or not at all (igemm_x3.cuh pairs the
+    // K chunks of a column by its 64-column group, which a 128-column tile cannot do)
+    if (split && wide_n == 256 && p->block_n == 128) p->block_n = 256;
   }
   p->n_tiles = ceil_div(g.cout, p->block_n);
   p->n_valid = g.cout;

@@ -78,6 +78,7 @@ struct alignas(64) IgemmTcParams {
   int halo;      // split (igemm_x3.cuh): 1 = halo-staged 3x3/s1/p1: tmA boxes are {64, tw, 1, th + 2, 1}, tn = 1, tw % 8 = 0
   int pool;      // split + halo: 1 = fused 2x2 stride-2 max pool, output is [N][H/2][W/2][ldo]
   int kchain;    // split: K chunks of 64 per hi.hi accumulation (1 or 2; 0 = 1), see igemm_x3.cuh
+  float comp;    // split: hi.hi chunk sums are multiplied by 1 + comp when they are added up (0 = the default), see igemm_x3.cuh
   long long* dbg;  // split, bring-up profiling only: [256][8] SM-clock stamps of pair 0's leader CTA (tools/test_igemm.cu), or null
   const float* bias;              // [n_valid] fp32 or nullptr
   const void* residual;           // NHWC bf16 (split: fp16 hi/lo) or nullptr

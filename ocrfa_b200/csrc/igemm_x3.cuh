@@ -36,6 +36,14 @@
 //     62 (Cout = 128) bytes per tensor-pipe cycle - above what L2 delivers to 148 SMs at once - to 57 / 39. The
 //     following 2x2/2 max pool (max_pool1, max_pool2) can be fused into the epilogue.
 //   * IgemmTcParams::kchain (1 or 2): K chunks per hi.hi accumulation - the precision / speed knob described at its use.
+//   * truncation compensation (IgemmTcParams::comp, default 2^-24): the tensor core adds into its fp32 accumulator by
+//     TRUNCATION toward zero, so every chunk sum is a little short and a layer's output is a little smaller than the
+//     exactly rounded one - coherently, layer after layer: measured on the recognizer, the visual features come out
+//     scaled by 1 - 8.9e-7 (tools/error_budget.py `shrink`), which is 88 % of this mode's whole error against float64.
+//     The tile's register sum x is therefore finished as fma(x, 2^-24, x) = the next fp32 number away from zero: with
+//     it the shrink is +0.07e-7, the feature error falls from 10.1e-7 to 3.8e-7 of rms (the reference's own fp32
+//     evaluation: 4.5e-7) and the logit error from 11.4e-7 to 3.7e-7 (reference: 6.2e-7). One packed FFMA per two
+//     accumulators per tile.
 // Warp roles (12 warps, three warpgroups): warpgroup 0 = TMA producer (warp 0), MMA issuer + TMEM alloc (warp 1, leader
 // CTA) and two idle warps, trimmed to 56 registers with setmaxnreg; warpgroups 1-2 = eight epilogue warps raised to 224
 // registers, so the 128 fp32 accumulators + 64 values in flight from TMEM live in registers (at the 168 registers a
@@ -49,6 +57,8 @@ namespace ocrfa {
 
 constexpr int kX3Threads = 384;
 constexpr int kX3FirstEpiWarp = 4;
+constexpr float kX3Comp = 0x1p-24f;  // default of IgemmTcParams::comp: see "truncation compensation" in the header comment (experiment switch: OCRFA_X3_COMP)
+constexpr float kX3Comp2 = 0x1.4p-23f;  // ... with kchain = 2 (eight chained MMAs per accumulation): 2.5 x 2^-24
 constexpr int kX3CorrCol = 256;  // TMEM column of the corr accumulator (main starts at column 0)
 // Tile tail through a per-warp transposition buffer (x3_finish32 below). Measured and NOT kept: the 512-channel layer
 // went 1.39-1.47 -> 1.54 ms with it. Stores are fire-and-forget - the warp does not wait for the L1 wavefronts of its
@@ -257,6 +267,12 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
   // (measured: the eight epilogue warps busy 69 % of the kernel, tensor pipe 70 % active). 2: eight chained MMAs, half
   // the TMEM traffic (the drain hides), bias -5.2e-8 instead of -3.1e-8 of the rms per layer.
   const int kchain = p.kchain > 1 ? p.kchain : 1;
+  const bool stagger = wide && kchain == 2;  // the two column halves close on alternate stages (see the MMA issuer)
+  // kchain = 2 pairs the K chunks of an output column as (0,1)(2,3).. when its 64-column group is even and as
+  // (0)(1,2)(3,4).. when it is odd - a function of the COLUMN, not of the tile shape, so a layer whose 256-column tiles
+  // are staggered gives bit-identical sums when the planner narrows its tiles to 64 columns for a small batch (128-column
+  // tiles of such a layer would need both pairings at once: igemm_x3_launch rejects them)
+  const bool odd_groups = kchain == 2 && block_n == 64 && p.n_valid >= 256;
 
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
   const int total_tiles = ((m_tiles + 1) >> 1) * p.n_tiles;
@@ -390,6 +406,7 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
         mbar_wait(corr_empty, cph ^ 1u, 2);  // the previous tile's corr has been read back
         cph ^= 1u;
         int unit = 0;  // K chunks of 64 issued so far in this tile; `kchain` consecutive ones share one accumulation
+        const int ph = odd_groups ? ((tile % p.n_tiles) & 1) : 0;
         for (int kb = 0; kb < total_kb; ++kb) {
           X3_TS(gstage, 0);
           mbar_wait(&full_bar[stage], phase, 3);
@@ -397,6 +414,52 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
           tc_fence_after();
           const uint32_t sa0 = smem_u32(stage_base + static_cast<size_t>(stage) * stage_bytes);
           const int nsub = halo ? kb_table[3 * kb + 1].y : 1;
+          if (stagger) {
+            // 256-column tiles with kchain = 2: each column half accumulates TWO K chunks, and the halves close on
+            // alternate stages. Issue order per stage: [the half that closes] -> corr -> [the half that starts]. A half
+            // handed to the epilogue at the start of stage s is not written again before the end of stage s + 1
+            // (2 560 tensor-pipe cycles later), and only one half (64 KB per CTA, ~1 000 cycles of the 64 B/cycle TMEM
+            // read port) is being drained at a time - the drain no longer paces the tensor pipe.
+            const int u = unit++;
+            const int hc = (u & 1) ? 0 : 1;  // half 0 closes on odd chunks, half 1 on even ones
+            const uint64_t a_hi = make_sw128_kmajor_desc(sa0);
+            const uint64_t a_lo = make_sw128_kmajor_desc(sa0 + a_slot);
+            const uint64_t b_hi = make_sw128_kmajor_desc(sa0 + 2u * a_slot);
+            const uint64_t b_lo = make_sw128_kmajor_desc(sa0 + 2u * a_slot + b_bytes);
+            if (u == 0) {  // the closing half also starts here (a one-chunk accumulation)
+              mbar_wait(&main_empty[hc], mph[hc] ^ 1u, 4);
+              mph[hc] ^= 1u;
+              tc_fence_after();
+            }
+            if (elected) {
+              const uint64_t b_half = b_hi + static_cast<uint64_t>(hc * (8192 >> 4));
+#pragma unroll
+              for (int k = 0; k < kTcBlockK / 16; ++k)
+                umma_bf16_pair(d_main + static_cast<uint32_t>(hc) * 128u, a_hi + static_cast<uint64_t>(2 * k),
+                               b_half + static_cast<uint64_t>(2 * k), idesc_half, (k > 0 || u > 0) ? 1u : 0u);
+              umma_commit_pair(&main_full[hc]);
+#pragma unroll
+              for (int k = 0; k < kTcBlockK / 16; ++k)
+                umma_bf16_pair(d_corr, a_lo + static_cast<uint64_t>(2 * k), b_hi + static_cast<uint64_t>(2 * k), idesc,
+                               (kb > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+              for (int k = 0; k < kTcBlockK / 16; ++k)
+                umma_bf16_pair(d_corr, a_hi + static_cast<uint64_t>(2 * k), b_lo + static_cast<uint64_t>(2 * k), idesc, 1u);
+            }
+            const int hs = hc ^ 1;  // starts a new accumulation: its previous one must have been drained
+            mbar_wait(&main_empty[hs], mph[hs] ^ 1u, 4);
+            mph[hs] ^= 1u;
+            tc_fence_after();
+            if (elected) {
+              const uint64_t b_half = b_hi + static_cast<uint64_t>(hs * (8192 >> 4));
+#pragma unroll
+              for (int k = 0; k < kTcBlockK / 16; ++k)
+                umma_bf16_pair(d_main + static_cast<uint32_t>(hs) * 128u, a_hi + static_cast<uint64_t>(2 * k),
+                               b_half + static_cast<uint64_t>(2 * k), idesc_half, k > 0 ? 1u : 0u);
+              umma_commit_pair(&empty_bar[stage]);
+              if (u == total_chunks - 1) umma_commit_pair(&main_full[hs]);
+            }
+          } else
           for (int j = 0; j < nsub; ++j) {
           // sub-block j: the rows of tap dy = j start j * tap_bytes into the halo boxes; its weight blocks are (hi, lo) pair j
           const uint32_t sa = sa0 + static_cast<uint32_t>(j) * tap_bytes;
@@ -416,8 +479,8 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
           }
           // a "main" buffer is free again once the epilogue warps have drained its previous contents - they do that
           // while the corr MMAs above keep the tensor pipe busy
-          const bool fresh = (unit % kchain) == 0;                                   // first K chunk of an accumulation
-          const bool closes = (unit % kchain) == kchain - 1 || unit == total_chunks - 1;  // last one: hand it to the epilogue
+          const bool fresh = unit == 0 || ((unit + ph) % kchain) == 0;                     // first K chunk of an accumulation
+          const bool closes = ((unit + ph) % kchain) == kchain - 1 || unit == total_chunks - 1;  // last one: hand it to the epilogue
           ++unit;
           if (wide) {
 #pragma unroll
@@ -505,7 +568,9 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
       float2 racc[64];  // register accumulator group g (32 columns) = racc[16 g .. 16 g + 15]
 #pragma unroll
       for (int i = 0; i < 64; ++i) racc[i] = make_float2(0.f, 0.f);
-      const int drains = (total_chunks + kchain - 1) / kchain;
+      // staggered halves (see the issuer): half 0 closes on odd chunks and on the last one, half 1 on even chunks and on the last one
+      const int drains = stagger ? (half == 0 ? (total_chunks + 1) / 2 : (total_chunks + 1) / 2 + ((total_chunks & 1) ? 0 : 1))
+                                 : (total_chunks + (odd_groups ? (n_tile & 1) : 0) + kchain - 1) / kchain;
       const bool ts_warp = wide && lane == 0 && q == 0;  // profiling: one lane of the first warp of each column half
       for (int ch = 0; ch <= drains; ++ch) {
         // ch < drains: one hi.hi accumulation (kchain K chunks) from "main"; ch == drains: the tile's lo.hi + hi.lo sum from "corr"
@@ -551,6 +616,12 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
         if (ts_warp && !last && half == 0) X3_TS(gchunk, 7);
         if (!last) ++gchunk;
         if (!last && alt) mb ^= 1;
+      }
+      // truncation compensation (see kX3Comp): x + x * comp in one rounding - 1 + comp itself is not an fp32 number
+      {
+        const float2 comp2 = make_float2(p.comp, p.comp);
+#pragma unroll
+        for (int i = 0; i < 64; ++i) racc[i] = __ffma2_rn(racc[i], comp2, racc[i]);
       }
       if (p.pool) {
         // fused 2x2/2 max pool (halo mode): the window of a pixel lives in lanes {l, l^1, l^tw, l^tw^1} of this warp; the
@@ -600,7 +671,14 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
   }
 }
 
-inline cudaError_t igemm_x3_launch(const IgemmTcParams& p, int num_sms, cudaStream_t stream) {
+inline float igemm_x3_default_comp(int kchain) {
+  const char* e = getenv("OCRFA_X3_COMP");  // read per launch: tools/error_budget.py scans it inside one process
+  return e ? static_cast<float>(atof(e)) : (kchain == 2 ? kX3Comp2 : kX3Comp);
+}
+
+inline cudaError_t igemm_x3_launch(const IgemmTcParams& p_in, int num_sms, cudaStream_t stream) {
+  IgemmTcParams p = p_in;
+  if (p.comp == 0.0f) p.comp = igemm_x3_default_comp(p.kchain);
   static bool attr_set_dev[kMaxDevices] = {};
   bool& attr_set = attr_set_dev[current_device_slot()];
   int stages = 0;
@@ -610,6 +688,7 @@ inline cudaError_t igemm_x3_launch(const IgemmTcParams& p, int num_sms, cudaStre
   if (p.pool && (!p.halo || p.residual != nullptr || p.out_f32 || p.tw > 16 || (p.h_out & 1) || (p.w_out & 1) || (p.n_valid & 31)))
     return cudaErrorInvalidValue;
   if ((p.block_n & 63) != 0 || p.block_n > 256) return cudaErrorInvalidValue;  // the epilogue halves the tile in 32-column groups
+  if (p.kchain == 2 && p.block_n == 128 && p.n_valid >= 256) return cudaErrorInvalidValue;  // see `odd_groups` in the kernel
   int total_kb = 0;
   for (int t = 0; t < p.num_taps; ++t) total_kb += p.taps[t].src ? p.kchunks2 : p.kchunks;
   if (p.halo) total_kb = 3 * p.kchunks + p.kchunks2;

@@ -62,6 +62,7 @@ constexpr int kLstmStageBytes = 0;
 constexpr bool kLstmTmaPublishSplit = false;  // the split-precision mode keeps the generic publish
 constexpr int kLstmTmemCols = 128;    // fused-x modes: 2 accumulators x 64 columns
 constexpr int kLstmTmemColsSplit = 512;  // split mode: 4 "main" chunk buffers (columns 0..255) + "corr" (column 256)
+constexpr float kLstmComp = 0x1p-24f;  // default of LstmTcParams::comp, same rule as kX3Comp in igemm_x3.cuh (experiment switch: OCRFA_LSTM_COMP)
 constexpr int kLstmCorrCol = 256;
 constexpr int kLstmGroupCtas = 32;    // CTAs per (direction, m_tile) group = 512 hidden units / 16
 constexpr int kLstmWSlabs = 16;       // resident weight slabs (8 KB each) = 128 KB
@@ -87,6 +88,7 @@ struct alignas(64) LstmTcParams {
   unsigned int* sync;        // [2 * m_tiles] group counters, zero before launch
   long long* dbg;            // optional [64 steps][16] SM-clock timestamps of CTA 0 (bring-up profiling), or null
   float acc_scale;           // split mode: 2^-k undoing the power-of-two pre-scale of W_hh
+  float comp;                // split mode: truncation compensation, sums become x + x * comp (0 = the default), see igemm_x3.cuh
   int B, T, m_tiles;
   int box_rows;              // batch rows per TMA slab: 128, or B rounded up to 8 when one M tile holds the whole batch
                              // (a step is paced by the bytes each SM ingests: 64 lines load half of them)
@@ -395,7 +397,10 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_tc_persistent_kernel(con
           }
         }
 #pragma unroll
-        for (int j = 0; j < 32; ++j) { v0[j] = __float_as_uint(racc[j]); v1[j] = __float_as_uint(racc[32 + j]); }
+        for (int j = 0; j < 32; ++j) {
+          v0[j] = __float_as_uint(fmaf(racc[j], p.comp, racc[j]));
+          v1[j] = __float_as_uint(fmaf(racc[32 + j], p.comp, racc[32 + j]));
+        }
       } else {
       mbar_wait(&tfull[as], aphase, 15);
       if (et == 0) LSTM_TS(s, 8);
@@ -563,7 +568,12 @@ inline size_t lstm_tc_smem_bytes() {
 }
 
 // Cooperative launch (all CTAs co-resident). `sync` must hold 2*m_tiles zeroed counters.
-inline cudaError_t lstm_tc_launch(const LstmTcParams& p, int mode, cudaStream_t stream) {
+inline cudaError_t lstm_tc_launch(const LstmTcParams& p_in, int mode, cudaStream_t stream) {
+  LstmTcParams p = p_in;
+  if (p.comp == 0.0f) {
+    const char* e = getenv("OCRFA_LSTM_COMP");
+    p.comp = e ? static_cast<float>(atof(e)) : kLstmComp;
+  }
   static bool attr_set_dev[kMaxDevices][3] = {};
   bool* attr_set = attr_set_dev[current_device_slot()];
   const size_t smem = lstm_tc_smem_bytes();
@@ -575,7 +585,7 @@ inline cudaError_t lstm_tc_launch(const LstmTcParams& p, int mode, cudaStream_t 
     if (e != cudaSuccess) return e;
     attr_set[mode] = true;
   }
-  void* args[] = {const_cast<LstmTcParams*>(&p)};
+  void* args[] = {&p};
   return cudaLaunchCooperativeKernel(fn, dim3(64 * p.m_tiles), dim3(kLstmThreads), args, smem, stream);
 }
 

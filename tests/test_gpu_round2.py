@@ -277,10 +277,11 @@ def test_two_ranks_equal_one_rank_on_hardware(env, tmp_path):
     assert len(set(results[1]["strings"])) > 100  # the lines really differ from one another
 
 
-def _run_harness(args, timeout):
+def _run_harness(args, timeout, env=None):
     exe = os.path.join(ROOT, "build", "test_igemm")
     assert os.path.exists(exe), "build/test_igemm missing: run __graft_entry__.build()"
-    out = subprocess.run([exe] + args, capture_output=True, text=True, timeout=timeout)
+    out = subprocess.run([exe] + args, capture_output=True, text=True, timeout=timeout,
+                         env=dict(os.environ, **env) if env else None)
     print(out.stdout[-4000:])
     assert out.returncode == 0 and "ALL OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
     return out.stdout
@@ -295,7 +296,10 @@ def test_lstm_publish_stress():
     assert out.count("launches differ from the first (0 values) ok") == 6
 
 
-def test_f16x3_kernel_harness():
+@pytest.mark.parametrize("chain", [1, 2])
+def test_f16x3_kernel_harness(chain):
     """Every conv / GEMM geometry of the path through igemm_x3_kernel (per-tap and halo-staged forms, fused 1x1 source,
-    residual, fused pool) against a float64 CUDA reference of the same operand values (tools/test_igemm.cu --split)."""
-    _run_harness(["--split"], 600)
+    residual, fused pool) against a float64 CUDA reference of the same operand values (tools/test_igemm.cu --split), with
+    one K chunk per hi.hi accumulation (the linear GEMMs and the detector) and with two (the recognizer's convolutions:
+    alternating buffers, and on 256-column tiles the staggered column halves)."""
+    _run_harness(["--split"], 600, env={"OCRFA_X3_CHAIN": str(chain)})

@@ -44,8 +44,12 @@ def head64(sd64, v):
 def stats(x, truth):
     d = np.asarray(x, np.float64) - truth
     scale = float(np.sqrt((truth ** 2).mean()))
+    # shrink: the least-squares delta of x = (1 + delta) * truth; rms_rel_unshrunk: what is left without that component
+    delta = float((d * truth).sum() / (truth ** 2).sum())
+    rest = d - delta * truth
     return {"rms_rel": float(np.sqrt((d ** 2).mean())) / scale, "max_rel": float(np.abs(d).max()) / scale,
-            "mean_rel": float(d.mean()) / scale}
+            "mean_rel": float(d.mean()) / scale, "shrink": delta,
+            "rms_rel_unshrunk": float(np.sqrt((rest ** 2).mean())) / scale}
 
 
 def main():
@@ -54,6 +58,7 @@ def main():
     ap.add_argument("--height", type=int, default=32)
     ap.add_argument("--width", type=int, default=512)
     ap.add_argument("--precisions", default="fp32,f16x3")
+    ap.add_argument("--comps", default="", help="comma list of OCRFA_X3_COMP values to scan in the f16x3 mode")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "error_budget.json"))
     args = ap.parse_args()
     torch.set_num_threads(os.cpu_count() or 1)
@@ -74,13 +79,18 @@ def main():
     dev = torch.device("cuda", 0)
     xd = torch.from_numpy(x).to(dev)
     fd = torch.from_numpy(ft32).to(dev)
-    for prec in args.precisions.split(","):
+    runs = [(p, None) for p in args.precisions.split(",")] + [("f16x3", c) for c in args.comps.split(",") if c]
+    for prec, comp in runs:
+        if comp is not None:
+            cx, _, cl = comp.partition("/")  # "8e-8" or "8e-8/6e-8": igemm_x3 / LSTM recurrence
+            os.environ["OCRFA_X3_COMP"] = cx
+            os.environ["OCRFA_LSTM_COMP"] = cl or cx
         m = ob.Model(1, 512, 512, 185, precision=prec)
         m.load_state_dict(sd32)
         ft = m.features(xd).cpu().numpy()
         lg = m(xd, None).cpu().numpy()
         hd = m.sequence(fd, args.height, args.width).cpu().numpy()
-        out[prec] = {"features": stats(ft, ft64), "logits": stats(lg, lg64), "head": stats(hd, hd64),
+        out[prec if comp is None else "f16x3@" + comp] = {"features": stats(ft, ft64), "logits": stats(lg, lg64), "head": stats(hd, hd64),
                      "features_vs_ref32": stats(ft, ft32.astype(np.float64)),
                      "logits_vs_ref32": stats(lg, lg32.astype(np.float64)),
                      "head_vs_ref32": stats(hd, hd32.astype(np.float64))}
