@@ -267,6 +267,7 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
   // (measured: the eight epilogue warps busy 69 % of the kernel, tensor pipe 70 % active). 2: eight chained MMAs, half
   // the TMEM traffic (the drain hides), bias -5.2e-8 instead of -3.1e-8 of the rms per layer.
   const int kchain = p.kchain > 1 ? p.kchain : 1;
+  const int kmask = kchain - 1;  // kchain is 1 or 2: (x % kchain) == (x & kmask), without the integer division in the issue loop
   const bool stagger = wide && kchain == 2;  // the two column halves close on alternate stages (see the MMA issuer)
   // kchain = 2 pairs the K chunks of an output column as (0,1)(2,3).. when its 64-column group is even and as
   // (0)(1,2)(3,4).. when it is odd - a function of the COLUMN, not of the tile shape, so a layer whose 256-column tiles
@@ -342,9 +343,13 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
 
   // bring-up profiling: stamps of the leader CTA of pair 0, slot = running stage / chunk index of the CTA
   long long* dbg = (blockIdx.x == 0) ? p.dbg : nullptr;
+#ifdef OCRFA_X3_PROFILE  // tools/test_igemm.cu builds with it; the product library carries no stamps
 #define X3_TS(idx, col) do { if (dbg && (idx) < 256 && ((threadIdx.x & 31) == 0)) dbg[(idx) * 8 + (col)] = clock64(); } while (0)
+#else
+#define X3_TS(idx, col) do { } while (0)
+#endif
   if (warp < kX3FirstEpiWarp) {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");  // 64 / 224 would use the register file to the last register: tried, the launch fails
   if (warp == 0) {
     // ===================================== TMA producer (both CTAs) =========================
     if (elect_one()) {
@@ -468,6 +473,37 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
           const uint64_t a_lo = make_sw128_kmajor_desc(sa + a_slot);
           const uint64_t b_hi = make_sw128_kmajor_desc(sb);
           const uint64_t b_lo = make_sw128_kmajor_desc(sb + b_bytes);
+          if (alt) {
+            // tiles of <= 128 columns: an MMA is shorter than the latency of a dependent accumulate, so the two chains
+            // (corr, main) are issued interleaved - same order inside each chain, i.e. the same sums. The buffer the
+            // main chain writes was handed back two accumulations ago.
+            const bool fresh = unit == 0 || ((unit + ph) & kmask) == 0;
+            const bool closes = ((unit + ph) & kmask) == kmask || unit == total_chunks - 1;
+            ++unit;
+            X3_TS(gstage, 2);
+            if (fresh) {
+              mbar_wait(&main_empty[mb], mph[mb] ^ 1u, 4);
+              mph[mb] ^= 1u;
+              tc_fence_after();
+            }
+            X3_TS(gstage, 3);
+            if (elected) {
+#pragma unroll
+              for (int k = 0; k < kTcBlockK / 16; ++k) {
+                umma_bf16_pair(d_corr, a_lo + static_cast<uint64_t>(2 * k), b_hi + static_cast<uint64_t>(2 * k), idesc,
+                               (kb > 0 || j > 0 || k > 0) ? 1u : 0u);
+                umma_bf16_pair(d_main + static_cast<uint32_t>(mb) * 128u, a_hi + static_cast<uint64_t>(2 * k),
+                               b_hi + static_cast<uint64_t>(2 * k), idesc, (k > 0 || !fresh) ? 1u : 0u);
+              }
+              if (closes) umma_commit_pair(&main_full[mb]);
+#pragma unroll
+              for (int k = 0; k < kTcBlockK / 16; ++k)
+                umma_bf16_pair(d_corr, a_hi + static_cast<uint64_t>(2 * k), b_lo + static_cast<uint64_t>(2 * k), idesc, 1u);
+              if (j == nsub - 1) umma_commit_pair(&empty_bar[stage]);
+            }
+            if (closes) mb ^= 1;
+            continue;
+          }
           if (elected) {
 #pragma unroll
             for (int k = 0; k < kTcBlockK / 16; ++k)
@@ -479,8 +515,8 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
           }
           // a "main" buffer is free again once the epilogue warps have drained its previous contents - they do that
           // while the corr MMAs above keep the tensor pipe busy
-          const bool fresh = unit == 0 || ((unit + ph) % kchain) == 0;                     // first K chunk of an accumulation
-          const bool closes = ((unit + ph) % kchain) == kchain - 1 || unit == total_chunks - 1;  // last one: hand it to the epilogue
+          const bool fresh = unit == 0 || ((unit + ph) & kmask) == 0;                     // first K chunk of an accumulation
+          const bool closes = ((unit + ph) & kmask) == kmask || unit == total_chunks - 1;  // last one: hand it to the epilogue
           ++unit;
           if (wide) {
 #pragma unroll
@@ -504,11 +540,13 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
               }
             }
           } else {
+            X3_TS(gstage, 2);
             if (fresh) {
               mbar_wait(&main_empty[mb], mph[mb] ^ 1u, 4);
               mph[mb] ^= 1u;
               tc_fence_after();
             }
+            X3_TS(gstage, 3);
             if (elected) {
 #pragma unroll
               for (int k = 0; k < kTcBlockK / 16; ++k)
@@ -570,8 +608,8 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
       for (int i = 0; i < 64; ++i) racc[i] = make_float2(0.f, 0.f);
       // staggered halves (see the issuer): half 0 closes on odd chunks and on the last one, half 1 on even chunks and on the last one
       const int drains = stagger ? (half == 0 ? (total_chunks + 1) / 2 : (total_chunks + 1) / 2 + ((total_chunks & 1) ? 0 : 1))
-                                 : (total_chunks + (odd_groups ? (n_tile & 1) : 0) + kchain - 1) / kchain;
-      const bool ts_warp = wide && lane == 0 && q == 0;  // profiling: one lane of the first warp of each column half
+                                 : (total_chunks + (odd_groups ? (n_tile & 1) : 0) + kmask) >> kmask;
+      const bool ts_warp = lane == 0 && q == 0 && (wide || half == 0);  // profiling: one lane of the first warp of each column half
       for (int ch = 0; ch <= drains; ++ch) {
         // ch < drains: one hi.hi accumulation (kchain K chunks) from "main"; ch == drains: the tile's lo.hi + hi.lo sum from "corr"
         const bool last = ch == drains;

@@ -391,7 +391,8 @@ static void run_split_case(const Case& c, bool halo = false, bool pool = false) 
     // issue; epilogue (first warp of each column half) 5 / 6 main_full seen by half 0 / 1, 7 half 0 drained + arrived
     std::vector<long long> ts(256 * 8);
     CK(cudaMemcpy(ts.data(), d_dbg, ts.size() * 8, cudaMemcpyDeviceToHost));
-    for (int i = 80; i < 92; ++i) {
+    const int i0 = atoi(getenv("X3_DBG")) > 1 ? atoi(getenv("X3_DBG")) : 80;  // X3_DBG=<first stage to print>
+    for (int i = i0; i < i0 + 12; ++i) {
       const long long b0 = ts[i * 8 + 0];
       printf("    stage %d: wait_full=%lld corr_issued=%lld me0_ok=%lld me1_ok=%lld | full0_seen=%lld full1_seen=%lld drained0=%lld | next stage at %lld\n",
              i, ts[i * 8 + 1] - b0, ts[i * 8 + 2] - b0, ts[i * 8 + 3] - b0, ts[i * 8 + 4] - b0, ts[i * 8 + 5] - b0, ts[i * 8 + 6] - b0,
@@ -828,6 +829,7 @@ int main(int argc, char** argv) {
     for (const Case& c : pc) if (!strcmp(only, c.name)) run_case(c);
     if (!strcmp(only, "lstm_persistent")) run_lstm_case(256, 129, kLstmBf16FusedX);
     if (!strcmp(only, "lstm_split")) run_lstm_case(256, 129, kLstmF16Split);
+    if (!strcmp(only, "split_lat")) run_split_case({"lat_l3_c512", {1, 4, 33, 512, 512, 3, 3, 1, 1, 1}, 1, 1, 1, 0, 0, 0, 0, 0, 20});
     if (!strcmp(only, "split_l3")) run_split_case({"perf_l3_c512", {256, 4, 129, 512, 512, 3, 3, 1, 1, 1}, 1, 1, 1, 0, 0, 0, 0, 0, 2});
     printf("%s (%d failing cases)\n", g_fail ? "FAILED" : "ALL OK", g_fail);
     return g_fail ? 1 : 0;
