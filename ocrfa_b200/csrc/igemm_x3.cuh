@@ -229,6 +229,10 @@ __device__ __forceinline__ void x3_finish32(const IgemmTcParams& p, float (&f)[3
   }
 }
 
+// KIND (compile-time, so that the MMA warp - 56 registers - carries one issue path): 0 = 256-column tiles, 1 = tiles of
+// <= 128 columns per tap, 2 = the same halo-staged, 3 = other widths (192: one buffer)
+enum X3Kind : int { kX3Wide = 0, kX3Narrow = 1, kX3NarrowHalo = 2, kX3Other = 3 };
+template <int KIND>
 __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_constant__ IgemmTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -253,15 +257,15 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
   const int b_rows = block_n >> 1;
   const uint32_t a_bytes = kTcBlockM * kTcBlockK * 2;
   const uint32_t b_bytes = static_cast<uint32_t>(b_rows) * kTcBlockK * 2;
-  const bool halo = p.halo != 0;
+  constexpr bool halo = KIND == kX3NarrowHalo;
   const uint32_t tap_bytes = static_cast<uint32_t>(p.tw) * 128u;  // halo: one image row of the box
   const uint32_t a_slot = halo ? static_cast<uint32_t>(p.th + 2) * tap_bytes : a_bytes;  // room of one A box (hi or lo)
   const uint32_t stage_bytes = 2u * a_slot + (halo ? 6u : 2u) * b_bytes;
   // wide: a 256-column tile whose hi.hi product is issued as two N = 128 halves (buffer h = columns {h*64 + 0..63,
   // 128 + h*64 + 0..63} of the tile: an N = 128 pair MMA takes 64 weight rows from each CTA); otherwise two whole-tile
   // buffers used alternately
-  const bool wide = block_n == 256;
-  const bool alt = block_n <= 128;  // two alternating whole-tile buffers (a 192-column tile has room for one)
+  constexpr bool wide = KIND == kX3Wide;
+  constexpr bool alt = KIND == kX3Narrow || KIND == kX3NarrowHalo;  // two alternating whole-tile buffers (a 192-column tile has room for one)
   // K chunks of 64 per hi.hi accumulation. 1: four chained MMAs, the smallest truncation bias - but every chunk is a
   // 128 x N fp32 read of TMEM, 341 / 4 = 85 B per tensor-pipe cycle and SM, which is what the TMEM read port delivers
   // (measured: the eight epilogue warps busy 69 % of the kernel, tensor pipe 70 % active). 2: eight chained MMAs, half
@@ -404,7 +408,7 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
       const uint32_t d_main = tmem_base;
       const uint32_t d_corr = tmem_base + static_cast<uint32_t>(kX3CorrCol);
       int stage = 0;
-      uint32_t phase = 0, cph = 0, mph[2] = {0u, 0u};
+      uint32_t phase = 0, cph = 0, mph = 0;  // mph: one parity bit per "main" buffer
       int mb = 0;
       int gstage = 0;  // running stage index of this CTA (profiling stamps)
       for (int tile = worker; tile < total_tiles; tile += num_workers) {
@@ -432,8 +436,8 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
             const uint64_t b_hi = make_sw128_kmajor_desc(sa0 + 2u * a_slot);
             const uint64_t b_lo = make_sw128_kmajor_desc(sa0 + 2u * a_slot + b_bytes);
             if (u == 0) {  // the closing half also starts here (a one-chunk accumulation)
-              mbar_wait(&main_empty[hc], mph[hc] ^ 1u, 4);
-              mph[hc] ^= 1u;
+              mbar_wait(&main_empty[hc], ((mph >> hc) & 1u) ^ 1u, 4);
+              mph ^= 1u << hc;
               tc_fence_after();
             }
             if (elected) {
@@ -452,8 +456,8 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
                 umma_bf16_pair(d_corr, a_hi + static_cast<uint64_t>(2 * k), b_lo + static_cast<uint64_t>(2 * k), idesc, 1u);
             }
             const int hs = hc ^ 1;  // starts a new accumulation: its previous one must have been drained
-            mbar_wait(&main_empty[hs], mph[hs] ^ 1u, 4);
-            mph[hs] ^= 1u;
+            mbar_wait(&main_empty[hs], ((mph >> hs) & 1u) ^ 1u, 4);
+            mph ^= 1u << hs;
             tc_fence_after();
             if (elected) {
               const uint64_t b_half = b_hi + static_cast<uint64_t>(hs * (8192 >> 4));
@@ -482,8 +486,8 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
             ++unit;
             X3_TS(gstage, 2);
             if (fresh) {
-              mbar_wait(&main_empty[mb], mph[mb] ^ 1u, 4);
-              mph[mb] ^= 1u;
+              mbar_wait(&main_empty[mb], ((mph >> mb) & 1u) ^ 1u, 4);
+              mph ^= 1u << mb;
               tc_fence_after();
             }
             X3_TS(gstage, 3);
@@ -523,8 +527,8 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
             for (int hb = 0; hb < 2; ++hb) {
               if (hb == 0) X3_TS(gstage, 2);
               if (fresh) {
-                mbar_wait(&main_empty[hb], mph[hb] ^ 1u, 4);
-                mph[hb] ^= 1u;
+                mbar_wait(&main_empty[hb], ((mph >> hb) & 1u) ^ 1u, 4);
+                mph ^= 1u << hb;
                 tc_fence_after();
               }
               X3_TS(gstage, 3 + hb);
@@ -542,8 +546,8 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
           } else {
             X3_TS(gstage, 2);
             if (fresh) {
-              mbar_wait(&main_empty[mb], mph[mb] ^ 1u, 4);
-              mph[mb] ^= 1u;
+              mbar_wait(&main_empty[mb], ((mph >> mb) & 1u) ^ 1u, 4);
+              mph ^= 1u << mb;
               tc_fence_after();
             }
             X3_TS(gstage, 3);
@@ -575,7 +579,7 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
     const int half = (warp - kX3FirstEpiWarp) >> 2;
     const int row = q * 32 + lane;
     const int half_cols = block_n >> 1;  // multiple of 32
-    uint32_t cph = 0, mph[2] = {0u, 0u};
+    uint32_t cph = 0, mph = 0;  // mph: one parity bit per "main" buffer
     int mb = wide ? half : 0;
     int gchunk = 0;  // running drain index of this CTA (profiling stamps)
     uint8_t* stg = stage_base + static_cast<size_t>(stages) * stage_bytes + static_cast<size_t>(warp - kX3FirstEpiWarp) * 2048;
@@ -614,7 +618,7 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
         // ch < drains: one hi.hi accumulation (kchain K chunks) from "main"; ch == drains: the tile's lo.hi + hi.lo sum from "corr"
         const bool last = ch == drains;
         if (last) { mbar_wait(corr_full, cph, 5); cph ^= 1u; }
-        else { mbar_wait(&main_full[mb], mph[mb], 6); mph[mb] ^= 1u; }
+        else { mbar_wait(&main_full[mb], (mph >> mb) & 1u, 6); mph ^= 1u << mb; }
         if (ts_warp && !last) X3_TS(gchunk, 5 + half);
         tc_fence_after();
         // two TMEM loads (64 columns) in flight per wait
@@ -731,9 +735,16 @@ inline cudaError_t igemm_x3_launch(const IgemmTcParams& p_in, int num_sms, cudaS
   for (int t = 0; t < p.num_taps; ++t) total_kb += p.taps[t].src ? p.kchunks2 : p.kchunks;
   if (p.halo) total_kb = 3 * p.kchunks + p.kchunks2;
   if (total_kb > (kTcSmemHeader - 256) / 48) return cudaErrorInvalidValue;  // group schedule: 48 B per group
+  const int kind = p.block_n == 256 ? kX3Wide : p.block_n <= 128 ? (p.halo ? kX3NarrowHalo : kX3Narrow) : kX3Other;
+  if (p.halo && kind != kX3NarrowHalo) return cudaErrorInvalidValue;
+  void (*fn)(IgemmTcParams) = kind == kX3Wide ? igemm_x3_kernel<kX3Wide> : kind == kX3Narrow ? igemm_x3_kernel<kX3Narrow>
+                              : kind == kX3NarrowHalo ? igemm_x3_kernel<kX3NarrowHalo> : igemm_x3_kernel<kX3Other>;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return e;
+    for (void (*f)(IgemmTcParams) : {igemm_x3_kernel<kX3Wide>, igemm_x3_kernel<kX3Narrow>, igemm_x3_kernel<kX3NarrowHalo>,
+                                     igemm_x3_kernel<kX3Other>}) {
+      cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e != cudaSuccess) return e;
+    }
     attr_set = true;
   }
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
@@ -749,7 +760,7 @@ inline cudaError_t igemm_x3_launch(const IgemmTcParams& p_in, int num_sms, cudaS
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, igemm_x3_kernel, p);
+  return cudaLaunchKernelEx(&cfg, fn, p);
 }
 
 }  // namespace ocrfa
