@@ -46,8 +46,11 @@ extern "C" {
 #define OCRFA_PRECISION_FP32 0 /* CUDA-core fp32: logits within 1e-3 of the reference's fp32 path */
 #define OCRFA_PRECISION_BF16 1 /* tcgen05 bf16 inputs, fp32 accumulate: logits within 2e-2 */
 #define OCRFA_PRECISION_F16X3 2 /* the host mirror's DEFAULT. tcgen05 on fp16 hi/lo split operands, 3 products per term,
-                                   the dominant one summed per 64-wide K chunk in fp32 registers: fp32-grade logits
-                                   (1.2e-6 of their rms from exact arithmetic, the reference's own fp32 run: 0.6e-6) */
+                                   the dominant one summed per K chunk in fp32 registers and compensated for the tensor
+                                   core's truncating accumulate: fp32-grade logits (0.5e-6 of their rms from exact
+                                   arithmetic; the reference's own fp32 run: 0.6e-6). Results do not depend on how lines
+                                   are batched. Experiment switches (read at ocrfa_create / per launch): OCRFA_X3_CHAIN=1
+                                   (one 64-wide K chunk per accumulation instead of two), OCRFA_X3_COMP / OCRFA_LSTM_COMP */
 #define OCRFA_PRECISION_F16 3 /* tcgen05 fp16 inputs/activations, fp32 accumulate: the bf16 kernels with 3 more mantissa bits
                                 (same rate and bytes); activations saturate at +-65504 */
 

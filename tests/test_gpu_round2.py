@@ -92,6 +92,40 @@ def test_f16x3_strings_against_the_oracle_on_1024_config2_lines(env, synth_sd):
     assert n_same >= n_total - 1
 
 
+def test_f16x3_error_against_float64_is_at_the_reference_fp32_level(env, synth_sd):
+    """The truncation compensation of igemm_x3.cuh / lstm_tc.cuh, pinned: on 16 lines of 32x256 the oracle's graph is
+    evaluated in float64 (truth) and in fp32 (what the reference computes); the f16x3 logits must be no further from
+    the truth than 1.25 x the reference's own fp32 run, and the visual features must not be scaled - the least-squares
+    factor of features = (1 + shrink) * truth stays within +-3e-7 (measured on B200: 0.75 x, +0.3e-7; without the
+    compensation: 1.8 x, -8.9e-7, tools/error_budget.py)."""
+    import torch.nn.functional as F
+    from ocrfa_b200.synth import synth_lines
+    from oracle import recognizer_ref as R
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd32 = {k: torch.from_numpy(np.asarray(v)) if not torch.is_tensor(v) else v for k, v in synth_sd.items()}
+    sd64 = {k: v.double() for k, v in sd32.items()}
+    imgs = synth_lines(16, 32, 256, seed=777001)
+    x = R.align_collate_ref(list(imgs), 32, 256)
+    with torch.no_grad():
+        f64 = R.resnet_ref(sd64, torch.from_numpy(x).double()).permute(0, 3, 1, 2).mean(dim=3)
+        s64 = R.bilstm_ref(sd64, R.bilstm_ref(sd64, f64, "SequenceModeling.0."), "SequenceModeling.1.")
+        lg64 = F.linear(s64, sd64["Prediction.weight"], sd64["Prediction.bias"]).numpy()
+    ft64 = f64.numpy()
+    lg32 = np.asarray(R.model_forward_ref(sd32, x), np.float64)
+    m = _model(env, "f16x3")
+    xd = torch.from_numpy(x).to(env["dev"])
+    ft = m.features(xd).cpu().numpy().astype(np.float64)
+    lg = m(xd, None).cpu().numpy().astype(np.float64)
+    rms = lambda d: float(np.sqrt((d ** 2).mean()))
+    e_ref, e_x3 = rms(lg32 - lg64), rms(lg - lg64)
+    shrink = float(((ft - ft64) * ft64).sum() / (ft64 ** 2).sum())
+    print(f"logit error vs float64 (of rms): reference fp32 {e_ref / rms(lg64):.3g}, f16x3 {e_x3 / rms(lg64):.3g}; "
+          f"feature shrink {shrink:+.3g}")
+    assert e_x3 <= 1.25 * e_ref
+    assert abs(shrink) <= 3e-7
+
+
 def test_single_pass_precisions_have_a_floor_at_config2_size(env, synth_sd):
     """bf16 / f16 (single-pass tensor-core modes) against the oracle at the config-2 shape: their agreement is bounded
     from below, not just printed. Measured on 10 240 lines (profiles/r01_parity_10k_32x512_all_modes.json): per-timestep
