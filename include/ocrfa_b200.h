@@ -245,6 +245,22 @@ int ocrfa_ctc_beam_spans(const float* d_probs, const int32_t* d_span_row0, const
                          int32_t t_max, int32_t C, int32_t beam_width, const uint8_t* d_collapse_ignore,
                          int32_t* d_labels, int32_t* d_len, void* d_ws, size_t ws_bytes, void* stream);
 
+/* The ranked candidate list of the final beam state, for the dictionary lookup of word beam search
+ * (BeamState.wordsearch, src/ocrfa/utils.py:853-872, reached from ctcBeamSearch(..., dict_list != []), :1036-1037, which
+ * decode_wordbeamsearch calls per word, :1138-1147 and :1158-1172): the same search as ocrfa_ctc_beam / _spans
+ * (`beam_width` labelings survive every timestep), but after the last timestep ALL labelings of the state are ranked
+ * (prTotal descending, creation order on ties = the reference's stable sort) and the first n_cand (the reference uses
+ * maxCandidate = 20) are returned, each collapsed like the best labeling is (ignored indices and adjacent duplicates of
+ * the raw labeling dropped). d_span_row0 / d_span_len may both be NULL: item i then covers rows [i*t_max, (i+1)*t_max).
+ * d_cand_labels [n_items, n_cand, t_max] int32, d_cand_len [n_items, n_cand], d_cand_count [n_items] (how many
+ * candidates exist, <= n_cand; an item with no timestep has one empty candidate). beam_width and n_cand in [1, 64].
+ * Scratch = ocrfa_beam_candidates_workspace_bytes. The dictionary membership test stays with the caller (strings). */
+size_t ocrfa_beam_candidates_workspace_bytes(int32_t n_items, int32_t t_max, int32_t C, int32_t beam_width, int32_t n_cand);
+int ocrfa_ctc_beam_candidates(const float* d_probs, const int32_t* d_span_row0, const int32_t* d_span_len, int32_t n_items,
+                              int32_t t_max, int32_t C, int32_t beam_width, int32_t n_cand,
+                              const uint8_t* d_collapse_ignore, int32_t* d_cand_labels, int32_t* d_cand_len,
+                              int32_t* d_cand_count, void* d_ws, size_t ws_bytes, void* stream);
+
 /* Whole recognizer_predict step for one batch with HOST buffers: H2D of the uint8 lines, preprocess, forward,
  * decode (decoder 0 = greedy, 1 = beamsearch), D2H of labels/lengths/confidences, stream synchronised on return.
  * h_ignore_mask [num_class] may be NULL. h_labels [B,T] int32, h_len [B] int32, h_conf [B] float64. */

@@ -25,7 +25,8 @@ SYMBOLS = (
     "ocrfa_craft_create", "ocrfa_craft_workspace_bytes", "ocrfa_craft_forward",
     "ocrfa_det_preprocess_u8", "ocrfa_bgr2gray_u8", "ocrfa_det_workspace_bytes", "ocrfa_det_components",
     "ocrfa_forward", "ocrfa_forward_features", "ocrfa_forward_sequence", "ocrfa_forward_u8", "ocrfa_ctc_greedy", "ocrfa_ctc_collapse", "ocrfa_argmax_rows",
-    "ocrfa_beam_workspace_bytes", "ocrfa_ctc_beam", "ocrfa_ctc_beam_spans", "ocrfa_recognize_host",
+    "ocrfa_beam_workspace_bytes", "ocrfa_ctc_beam", "ocrfa_ctc_beam_spans", "ocrfa_beam_candidates_workspace_bytes",
+    "ocrfa_ctc_beam_candidates", "ocrfa_recognize_host",
     "ocrfa_recognize_device", "ocrfa_recognize_host_ex", "ocrfa_recognize_device_ex", "ocrfa_ctc_margin", "ocrfa_recognize_workspace_bytes", "ocrfa_profile_begin", "ocrfa_profile_end",
     "ocrfa_launch_count",
 )
@@ -77,6 +78,9 @@ def load():
     lib.ocrfa_beam_workspace_bytes.restype = sz
     lib.ocrfa_ctc_beam.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, vp, sz, vp]
     lib.ocrfa_ctc_beam_spans.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, sz, vp]
+    lib.ocrfa_beam_candidates_workspace_bytes.argtypes = [i32, i32, i32, i32, i32]
+    lib.ocrfa_beam_candidates_workspace_bytes.restype = sz
+    lib.ocrfa_ctc_beam_candidates.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, sz, vp]
     lib.ocrfa_recognize_host.argtypes = [vp, vp, vp, i32, i32, i32, vp, i32, i32, vp, vp, vp, vp, sz, vp]
     lib.ocrfa_recognize_device.argtypes = [vp, vp, vp, i32, i32, i32, vp, i32, i32, vp, vp, vp, vp, sz, vp]
     lib.ocrfa_recognize_host_ex.argtypes = [vp, vp, vp, i32, i32, i32, vp, i32, i32, vp, vp, vp, vp, C.c_uint32, vp, sz, vp]

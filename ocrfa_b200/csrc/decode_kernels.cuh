@@ -207,6 +207,14 @@ struct BeamParams {
   int emax;              // bw * (C + 1)
   int hs;                // hash slots (power of two >= 2 * emax)
   int ht32;              // 1: 32-bit hash slots
+  // candidate mode only (ctc_beam_kernel<true>, BeamState.wordsearch, utils.py:853-872): `bw` is then the WIDTH of the
+  // state arrays and of a trellis row = max(keep, n_out); `keep` labelings survive every step but the last, which ranks
+  // `bw` of them; the first n_out are rebuilt and collapsed into cand_labels [B][n_out][T] / cand_len [B][n_out],
+  // cand_count [B] = how many exist
+  int keep, n_out;
+  int32_t* cand_labels;
+  int32_t* cand_len;
+  int32_t* cand_count;
 };
 
 enum : int { kOpSame = 0, kOpAppend = 1, kOpReplace = 2 };
@@ -259,6 +267,9 @@ __host__ __device__ inline size_t beam_smem_bytes(int C, int bw, int emax, int h
 //      reference's sequence of float32 `+=` (utils.py:1004-1026), so the sums are bit-identical;
 //   3. the best `bw` labelings (prTotal descending, creation order ascending on ties = Python's stable sort) are
 //      picked with warp redux operations over register-resident keys.
+// kCand = false: the best labeling only (decode_beamsearch, dictionary-free word beam search). kCand = true: the ranked
+// candidate list of the final beam state, for the dictionary lookup of BeamState.wordsearch.
+template <bool kCand>
 __global__ void __launch_bounds__(32) ctc_beam_kernel(const BeamParams p) {
   extern __shared__ __align__(16) uint8_t dsm[];
   const int lane = threadIdx.x;
@@ -475,6 +486,8 @@ __global__ void __launch_bounds__(32) ctc_beam_kernel(const BeamParams p) {
     const int nxt = cur ^ 1;
     uint32_t* trow = trel + (size_t)t * bw;
     int n_new = 0;
+    // labelings ranked by this step: all `bw` of them, except that candidate mode keeps only `keep` before the last step
+    const int sel = (kCand && t != Tb - 1) ? p.keep : bw;
     auto emit = [&](int j, int r) {
       // labeling represented by entry j becomes beam r of the next step
       const uint32_t meta = s.e_meta[j];
@@ -500,7 +513,7 @@ __global__ void __launch_bounds__(32) ctc_beam_kernel(const BeamParams p) {
       // the rounds only pick the winners (two warp reductions each); the state of the surviving beams is written
       // afterwards by bw lanes in parallel instead of one lane per round
       int my_j0 = -1, my_j1 = -1;  // winners of rounds lane and lane + 32 (bw <= 64)
-      for (int r = 0; r < bw; ++r) {
+      for (int r = 0; r < sel; ++r) {
         uint32_t lmax = 0u;
 #pragma unroll
         for (int m = 0; m < kBeamRegChunks; ++m) lmax = key[m] > lmax ? key[m] : lmax;
@@ -522,7 +535,7 @@ __global__ void __launch_bounds__(32) ctc_beam_kernel(const BeamParams p) {
       if (my_j1 >= 0) emit(my_j1, lane + 32);
     } else {
       // many candidates (flat distributions): scan shared memory each round
-      for (int r = 0; r < bw; ++r) {
+      for (int r = 0; r < sel; ++r) {
         uint32_t lmax = 0u;
         for (int j = lane; j < E; j += 32)
           if (s.e_rep[j] == j) { const uint32_t kx = __float_as_uint(s.a_tot[j]) + 1u; lmax = kx > lmax ? kx : lmax; }
@@ -558,6 +571,7 @@ __global__ void __launch_bounds__(32) ctc_beam_kernel(const BeamParams p) {
     tsrc = stg;
   }
   __syncwarp();
+  if constexpr (!kCand) {
   if (lane == 0) {
     int len = 0;
     if (nb > 0) {
@@ -582,6 +596,37 @@ __global__ void __launch_bounds__(32) ctc_beam_kernel(const BeamParams p) {
       if (!ign && !(i > 0 && s.raw[i - 1] == l)) lo[n++] = l;
     }
     p.len_out[b] = n;
+  }
+  } else {
+    // ranks 0 .. n_cand-1 of the final state, best first (sortedBeams[:maxCandidate], utils.py:855-857); with no
+    // timestep at all the state is the initial empty labeling
+    const int n_cand = min(nb, p.n_out);
+    if (lane == 0) {
+      p.cand_count[b] = n_cand;
+      for (int r0 = 0; r0 < n_cand; ++r0) {
+        int len = 0;
+        int r = r0;
+        for (int t = Tb - 1; t >= 0; --t) {
+          const uint32_t e = tsrc[(size_t)t * bw + r];
+          s.chain[t] = e;
+          r = static_cast<int>(e & 0xffu);
+        }
+        for (int t = 0; t < Tb; ++t) {
+          const uint32_t e = s.chain[t];
+          const int op = (e >> 8) & 0xff, c = static_cast<int>(e >> 16);
+          if (op == kOpAppend) s.raw[len++] = static_cast<int16_t>(c);
+          else if (op == kOpReplace) s.raw[len - 1] = static_cast<int16_t>(c);
+        }
+        int32_t* lo = p.cand_labels + ((size_t)b * p.n_out + r0) * T;
+        int n = 0;
+        for (int i = 0; i < len; ++i) {
+          const int l = s.raw[i];
+          const bool ign = (l == 0) || (p.collapse_ignore && p.collapse_ignore[l]);
+          if (!ign && !(i > 0 && s.raw[i - 1] == l)) lo[n++] = l;
+        }
+        p.cand_len[(size_t)b * p.n_out + r0] = n;
+      }
+    }
   }
 }
 

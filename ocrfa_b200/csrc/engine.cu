@@ -1306,34 +1306,70 @@ int ocrfa_ctc_beam(const float* d_probs, int32_t B, int32_t T, int32_t C, int32_
                      stream);
 }
 
-static int beam_launch(const float* d_probs, const int32_t* d_span_row0, const int32_t* d_span_len, int32_t B, int32_t T,
-                       int32_t C, int32_t beam_width, const uint8_t* d_collapse_ignore, int32_t* d_labels, int32_t* d_len,
-                       void* d_ws, size_t ws_bytes, void* stream) {
+// One launch path for both instantiations. n_cand == 0: the best labeling per item (d_labels [B][T], d_len [B]);
+// n_cand > 0: the ranked candidate list (d_labels [B][n_cand][T], d_len [B][n_cand], d_count [B]).
+static int beam_launch_impl(const float* d_probs, const int32_t* d_span_row0, const int32_t* d_span_len, int32_t B, int32_t T,
+                            int32_t C, int32_t beam_width, int32_t n_cand, const uint8_t* d_collapse_ignore,
+                            int32_t* d_labels, int32_t* d_len, int32_t* d_count, void* d_ws, size_t ws_bytes, void* stream) {
   if (!d_probs || !d_labels || !d_len || !d_ws || B <= 0 || T <= 0 || C < 2 || C > 32767)
     return fail(OCRFA_ERR_ARG, "bad argument");
   if (beam_width < 1 || beam_width > 64) return fail(OCRFA_ERR_ARG, "beam_width must be in [1, 64]");
-  if (ws_bytes < beam_ws_bytes(B, T, C, beam_width)) return fail(OCRFA_ERR_WORKSPACE, "beam workspace too small");
+  if (n_cand < 0 || n_cand > 64 || (n_cand > 0 && !d_count)) return fail(OCRFA_ERR_ARG, "n_cand must be in [1, 64]");
+  const int width = n_cand > beam_width ? n_cand : beam_width;  // state arrays / trellis row (== beam_width when n_cand == 0)
+  if (ws_bytes < beam_ws_bytes(B, T, C, width)) return fail(OCRFA_ERR_WORKSPACE, "beam workspace too small");
   BeamParams p;
   p.probs = d_probs; p.labels_out = d_labels; p.len_out = d_len; p.trellis = (uint32_t*)d_ws;
   p.collapse_ignore = d_collapse_ignore;
   p.span_row0 = d_span_row0; p.span_len = d_span_len;
-  p.B = B; p.T = T; p.C = C; p.bw = beam_width;
-  p.emax = beam_width * (C + 1);
+  p.B = B; p.T = T; p.C = C; p.bw = width;
+  p.emax = width * (C + 1);
   int hs = 64;
   while (hs < 2 * p.emax) hs <<= 1;
   p.hs = hs;
-  p.ht32 = beam_smem_bytes(C, beam_width, p.emax, hs, T, 1) <= 227 * 1024 ? 1 : 0;
-  const size_t smem = beam_smem_bytes(C, beam_width, p.emax, hs, T, p.ht32);
+  p.ht32 = beam_smem_bytes(C, width, p.emax, hs, T, 1) <= 227 * 1024 ? 1 : 0;
+  p.keep = beam_width; p.n_out = n_cand;
+  p.cand_labels = d_labels; p.cand_len = d_len; p.cand_count = d_count;
+  const size_t smem = beam_smem_bytes(C, width, p.emax, hs, T, p.ht32);
   if (smem > 227 * 1024) return fail(OCRFA_ERR_ARG, "beam_width * num_class too large for shared memory (%zu B)", smem);
-  static size_t attr_smem_dev[kMaxDevices] = {};
-  size_t& attr_smem = attr_smem_dev[current_device_slot()];
-  if (smem > attr_smem) {
-    CUDA_TRY(cudaFuncSetAttribute(ctc_beam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_smem = smem;
+  static size_t attr_smem_dev[2][kMaxDevices] = {};
+  size_t& attr_smem = attr_smem_dev[n_cand > 0 ? 1 : 0][current_device_slot()];
+  if (n_cand > 0) {
+    if (smem > attr_smem) {
+      CUDA_TRY(cudaFuncSetAttribute(ctc_beam_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_smem = smem;
+    }
+    ctc_beam_kernel<true><<<B, 32, smem, (cudaStream_t)stream>>>(p);
+  } else {
+    if (smem > attr_smem) {
+      CUDA_TRY(cudaFuncSetAttribute(ctc_beam_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_smem = smem;
+    }
+    ctc_beam_kernel<false><<<B, 32, smem, (cudaStream_t)stream>>>(p);
   }
-  ctc_beam_kernel<<<B, 32, smem, (cudaStream_t)stream>>>(p);
   CUDA_TRY(cudaGetLastError());
   return 0;
+}
+
+static int beam_launch(const float* d_probs, const int32_t* d_span_row0, const int32_t* d_span_len, int32_t B, int32_t T,
+                       int32_t C, int32_t beam_width, const uint8_t* d_collapse_ignore, int32_t* d_labels, int32_t* d_len,
+                       void* d_ws, size_t ws_bytes, void* stream) {
+  return beam_launch_impl(d_probs, d_span_row0, d_span_len, B, T, C, beam_width, 0, d_collapse_ignore, d_labels, d_len,
+                          nullptr, d_ws, ws_bytes, stream);
+}
+
+size_t ocrfa_beam_candidates_workspace_bytes(int32_t n_items, int32_t t_max, int32_t C, int32_t beam_width, int32_t n_cand) {
+  if (n_items <= 0 || t_max <= 0 || C <= 0 || beam_width <= 0 || n_cand <= 0) return 0;
+  return beam_ws_bytes(n_items, t_max, C, n_cand > beam_width ? n_cand : beam_width);
+}
+
+int ocrfa_ctc_beam_candidates(const float* d_probs, const int32_t* d_span_row0, const int32_t* d_span_len, int32_t n_items,
+                              int32_t t_max, int32_t C, int32_t beam_width, int32_t n_cand,
+                              const uint8_t* d_collapse_ignore, int32_t* d_cand_labels, int32_t* d_cand_len,
+                              int32_t* d_cand_count, void* d_ws, size_t ws_bytes, void* stream) {
+  if ((d_span_row0 == nullptr) != (d_span_len == nullptr)) return fail(OCRFA_ERR_ARG, "span arrays come in pairs");
+  if (n_cand < 1) return fail(OCRFA_ERR_ARG, "n_cand must be in [1, 64]");
+  return beam_launch_impl(d_probs, d_span_row0, d_span_len, n_items, t_max, C, beam_width, n_cand, d_collapse_ignore,
+                          d_cand_labels, d_cand_len, d_cand_count, d_ws, ws_bytes, stream);
 }
 
 }  // extern "C"

@@ -524,6 +524,130 @@ def wordbeam_decode_ref(probs: np.ndarray, character: Sequence[str], beam_width:
 
 
 # --------------------------------------------------------------------------------------------------------------
+# a9, the converter's options: language separators and dictionaries  (src/ocrfa/utils.py:773-820, :853-872, :1058-1081,
+# :1152-1172). Inert in the default Farsi setup (separator_list = {}, no dictionary files), restated for completeness.
+# --------------------------------------------------------------------------------------------------------------
+def converter_ignore_idx_ref(separator_list: Dict[str, Sequence[str]]) -> List[int]:
+    """utils.py:1058-1062: blank plus one index per separator character - the separators are ASSUMED to be the first
+    characters of the charset (the indices count them, they are not looked up)."""
+    n = sum(len(sep) for sep in separator_list.values())
+    return [0] + [i + 1 for i in range(n)]
+
+
+def _run_edges(pos: Sequence[int], mode: str) -> List[int]:
+    """consecutive(), utils.py:773-782: first / last element of every run of consecutive integers in `pos`."""
+    out: List[int] = []
+    for k, v in enumerate(pos):
+        starts = k == 0 or v != pos[k - 1] + 1
+        ends = k == len(pos) - 1 or pos[k + 1] != v + 1
+        if (mode == "first" and starts) or (mode == "last" and ends):
+            out.append(int(v))
+    return out
+
+
+def word_segmentation_ref(argmax_row: np.ndarray, separator_idx=None, separator_idx_list=None):
+    """word_segmentation, utils.py:785-820 (decode_wordbeamsearch calls it with its DEFAULT tables, :1153): a start
+    separator class (odd index) marks with the LAST timestep of each of its runs, an end separator (even index) with the
+    FIRST; a start followed by the matching end yields [lang, [t0, t1]] (t1 < t0 when nothing lies between them), text
+    outside such pairs yields ['', [t0, t1]]."""
+    if separator_idx_list is None:
+        separator_idx_list = [1, 2, 3, 4]
+    if separator_idx is None:
+        separator_idx = {"th": [1, 2], "en": [3, 4]}
+    row = np.asarray(argmax_row).tolist()
+    marks = []
+    for sep in separator_idx_list:
+        pos = [t for t, k in enumerate(row) if k == sep]
+        marks += [(t, sep) for t in _run_edges(pos, "first" if sep % 2 == 0 else "last")]
+    marks.sort(key=lambda m: m[0])  # stable, like sorted(..., key=position)
+    result = []
+    start_idx = 0
+    open_lang, open_at = "", None
+    for t, sep in marks:
+        for lang, (s_idx, e_idx) in separator_idx.items():
+            if sep == s_idx:
+                open_lang, open_at = lang, t
+            elif sep == e_idx:
+                if open_lang == lang:
+                    if open_at > start_idx:
+                        result.append(["", [start_idx, open_at - 1]])
+                    start_idx = t + 1
+                    result.append([lang, [open_at + 1, t - 1]])
+                open_lang = ""
+    if start_idx <= len(row) - 1:
+        result.append(["", [start_idx, len(row) - 1]])
+    return result
+
+
+def beam_candidates_ref(mat: np.ndarray, beam_width: int, max_candidate: int = 20, blank: int = 0):
+    """The ranked raw labelings of the final beam state (sortedBeams[:maxCandidate] of BeamState.wordsearch,
+    utils.py:855-857): beam_labels_ref's search, all final labelings by prTotal under the stable descending sort."""
+    mat = np.asarray(mat, dtype=np.float32)
+    T, C = mat.shape if mat.ndim == 2 else (0, 0)
+    thr = np.float32(0.5 / C) if C else np.float32(0)
+    one, zero = np.float32(1.0), np.float32(0.0)
+    last: Dict[Tuple[int, ...], List[np.float32]] = {(): [one, zero, one]}
+    for t in range(T):
+        curr: Dict[Tuple[int, ...], List[np.float32]] = {}
+        order = sorted(last.keys(), key=lambda k: last[k][0], reverse=True)[:beam_width]
+        row = mat[t]
+        cand = np.nonzero(row >= thr)[0].tolist()
+        for lab in order:
+            p_tot, p_nb, p_b = last[lab]
+            nb = p_nb * row[lab[-1]] if lab else zero
+            bl = p_tot * row[blank]
+            e = curr.setdefault(lab, [zero, zero, zero])
+            e[1] = e[1] + nb
+            e[2] = e[2] + bl
+            e[0] = e[0] + (bl + nb)
+            for c in cand:
+                new = _extend_label(lab, c, blank)
+                pr = row[c] * (p_b if (lab and lab[-1] == c) else p_tot)
+                e2 = curr.setdefault(new, [zero, zero, zero])
+                e2[1] = e2[1] + pr
+                e2[0] = e2[0] + pr
+        last = curr
+    return sorted(last.keys(), key=lambda k: last[k][0], reverse=True)[:max_candidate]
+
+
+def wordsearch_ref(mat: np.ndarray, character: Sequence[str], beam_width: int, ignore: Sequence[int],
+                   dict_list: Sequence[str]) -> str:
+    """ctcBeamSearch's two endings, utils.py:1029-1038: the best labeling when the dictionary is empty, else the first
+    of the 20 best candidates whose text is a dictionary word (the best one when none is)."""
+    cands = beam_candidates_ref(mat, beam_width, 20 if len(dict_list) else 1)
+    texts = ["".join(character[k] for k in beam_collapse_ref(lab, ignore)) for lab in cands]
+    if not len(dict_list):
+        return texts[0]
+    for text in texts:
+        if text in dict_list:
+            return text
+    return texts[0]
+
+
+def wordbeam_decode_full_ref(probs: np.ndarray, character: Sequence[str], beam_width: int = 5,
+                             ignore: Sequence[int] = (0,), separator_list=None, dict_list=None) -> List[str]:
+    """decode_wordbeamsearch with every option, utils.py:1124-1173. Without separators `dict_list` is one word list and
+    the words of a line are joined with spaces; with separators it maps language -> word list, segments come from
+    word_segmentation_ref and are concatenated as they are."""
+    separator_list = separator_list or {}
+    am = np.argmax(probs, axis=2)
+    out = []
+    for i in range(probs.shape[0]):
+        if len(separator_list) == 0:
+            space_idx = list(character).index(" ")
+            words = [wordsearch_ref(probs[i, span, :], character, beam_width, ignore, dict_list or [])
+                     for span in word_spans_ref(am[i], space_idx)]
+            out.append(" ".join(words))
+        else:
+            text = ""
+            for lang, (t0, t1) in word_segmentation_ref(am[i]):
+                words = [] if lang == "" else dict_list[lang]
+                text += wordsearch_ref(probs[i, t0:t1 + 1, :], character, beam_width, ignore, words)
+            out.append(text)
+    return out
+
+
+# --------------------------------------------------------------------------------------------------------------
 # recognizer_predict restated end to end  (src/ocrfa/utils.py:605-662)
 # --------------------------------------------------------------------------------------------------------------
 def recognizer_predict_ref(sd, x: np.ndarray, character: Sequence[str], ignore_idx: Sequence[int],
