@@ -295,6 +295,42 @@ def measure_device(lib, _lib, handle, geom, d_img, d_mask, dec, bw, ws, ws_bytes
     return dev_ms, list(ms_cls), list(fl_cls), list(n_cls), launches, step
 
 
+def other_configs(args, lib, _lib, handle, d_mask, dev, synth_lines_global):
+    """Device-timed lines/s of the configurations other than args.config on the same handle. A failure is recorded in
+    the row instead of costing the run its headline line."""
+    rows = {}
+    for name in sorted(CONFIGS):
+        if name == args.config:
+            continue
+        B, H, W, decoder, beam = CONFIGS[name]
+        try:
+            T = lib.ocrfa_out_timesteps(H, W)
+            bw = beam if decoder == "beamsearch" else 1
+            dec = 1 if decoder == "beamsearch" else 0
+            d_img = torch.from_numpy(synth_lines_global(0, B, H, W, LINE_SEED)).to(dev)
+            slot = Slot(lib, handle, B, H, W, T, bw, dev)
+            outs = (torch.empty((B, T), dtype=torch.int32, device=dev), torch.empty(B, dtype=torch.int32, device=dev),
+                    torch.empty(B, dtype=torch.float64, device=dev))
+            flush_l2 = int(slot.ws_bytes) + 220 * (1 << 20) < 512 * (1 << 20)
+            k = min(args.steps, 10)
+            ms, _, _, _, launches, _ = measure_device(lib, _lib, handle, (B, H, W, T), d_img, d_mask, dec, bw, slot.ws,
+                                                      slot.ws_bytes, outs, slot.stream, k, 3, dev, 1, 0, flush_l2)
+            lens = outs[1].cpu().numpy().astype(np.int64)
+            labels = outs[0].cpu().numpy().astype(np.int64)
+            valid = np.arange(T)[None, :] < lens[:, None]
+            fl = FLOPS_PER_LINE.get((H, W))
+            rows[name] = {"workload": workload_text(name), "value": B * k / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / k,
+                          "steps": k, "warmup": 3, "gpu_launches": launches,
+                          "l2": "256 MB fill before every timed step" if flush_l2 else "working set exceeds L2",
+                          "whole_step_tflops": (fl * B / (ms / k * 1e-3) / 1e12) if fl else None,
+                          "label_checksum": int((labels * valid).sum() % (1 << 31))}
+            del d_img, slot, outs
+            torch.cuda.empty_cache()
+        except Exception as exc:  # noqa: BLE001
+            rows[name] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+    return rows
+
+
 def run_gpu_arm(args):
     import ocrfa_b200 as ob
     from ocrfa_b200 import _lib
@@ -545,6 +581,10 @@ def run_gpu_arm(args):
                                 "dtype": DTYPE_TEXT[prec]}
                 del m2
             line["other_precisions"] = others
+        if world == 1 and not args.no_other_configs and args.precision != "fp32":
+            # ---- BASELINE.json's other single-GPU configurations in the same run and precision (a few steps each,
+            # device-resident inputs, the same timing rules): informative rows, the headline stays `value`
+            line["other_configs"] = other_configs(args, lib, _lib, handle, d_mask, dev, synth_lines_global)
         print(json.dumps(line), flush=True)
     if world > 1:
         import torch.distributed as dist
@@ -565,6 +605,7 @@ def main():
     ap.add_argument("--parity-lines", type=int, default=128, help="lines of the in-run parity check against the oracle")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU legs (parity sample and cpu_baseline)")
     ap.add_argument("--no-other-precisions", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the c1 / c3 / c4 rows of the default run")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
