@@ -1550,8 +1550,6 @@ int ocrfa_recognize_host_ex(ocrfa_handle* h, const uint8_t* h_img, const int32_t
   uint8_t* d_img = ws + R.img;
   int32_t* d_w = (int32_t*)(ws + R.widths);
   uint8_t* d_mask = ws + R.mask;
-  float* d_logits = (float*)(ws + R.logits);
-  float* d_probs = (float*)(ws + R.probs);
   int32_t* d_labels = (int32_t*)(ws + R.labels);
   int32_t* d_len = (int32_t*)(ws + R.len);
   double* d_conf = (double*)(ws + R.conf);

@@ -346,8 +346,8 @@ __global__ void __launch_bounds__(kX3Threads, 1) igemm_x3_kernel(const __grid_co
   const uint32_t tmem_base = *tmem_slot;
 
   // bring-up profiling: stamps of the leader CTA of pair 0, slot = running stage / chunk index of the CTA
-  long long* dbg = (blockIdx.x == 0) ? p.dbg : nullptr;
 #ifdef OCRFA_X3_PROFILE  // tools/test_igemm.cu builds with it; the product library carries no stamps
+  long long* dbg = (blockIdx.x == 0) ? p.dbg : nullptr;
 #define X3_TS(idx, col) do { if (dbg && (idx) < 256 && ((threadIdx.x & 31) == 0)) dbg[(idx) * 8 + (col)] = clock64(); } while (0)
 #else
 #define X3_TS(idx, col) do { } while (0)
