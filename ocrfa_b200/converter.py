@@ -218,16 +218,7 @@ class CTCLabelConverter:
         am_h = am.cpu().numpy()
         per_line: List[List[str]] = [[] for _ in range(B)]
         if len(self.separator_list) == 0:
-            space = self.dict[" "]
-            # span bookkeeping (host integer work on B*T flags, as in the reference)
-            pad = np.zeros((B, T + 2), dtype=np.int8)
-            pad[:, 1:-1] = am_h != space
-            d = np.diff(pad, axis=1)
-            starts = np.argwhere(d == 1)   # (line, t0) sorted by line then t0
-            ends = np.argwhere(d == -1)    # (line, t1 + 1)
-            lines = starts[:, 0].tolist()
-            row0 = (starts[:, 0] * T + starts[:, 1]).astype(np.int64)
-            slen = (ends[:, 1] - starts[:, 1]).astype(np.int64)
+            lines, row0, slen = word_spans(am_h, self.dict[" "])
             dicts = [self.dict_list] * len(lines)
             joiner = " "
         else:
@@ -244,6 +235,21 @@ class CTCLabelConverter:
         for line, w in zip(lines, self._search_spans(m, row0, slen, beamWidth, dicts)):
             per_line[line].append(w)
         return [joiner.join(ws_) for ws_ in per_line]
+
+
+def word_spans(argmax: np.ndarray, space_idx: int):
+    """utils.py:1132-1136 for a whole batch: the maximal runs of timesteps whose argmax is not the space class. `argmax`
+    is [B, T]; returns (line of every span, its first row in the [B*T, C] view of the probabilities, its length), spans
+    ordered by line then time (host integer work on B*T flags, as in the reference)."""
+    B, T = argmax.shape
+    pad = np.zeros((B, T + 2), dtype=np.int8)
+    pad[:, 1:-1] = argmax != space_idx
+    d = np.diff(pad, axis=1)
+    starts = np.argwhere(d == 1)   # (line, t0) sorted by line then t0
+    ends = np.argwhere(d == -1)    # (line, t1 + 1)
+    row0 = (starts[:, 0] * T + starts[:, 1]).astype(np.int64)
+    slen = (ends[:, 1] - starts[:, 1]).astype(np.int64)
+    return starts[:, 0].tolist(), row0, slen
 
 
 def _run_edges(pos: np.ndarray, last: bool) -> List[int]:

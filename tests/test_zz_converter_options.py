@@ -173,3 +173,34 @@ def test_gpu_candidate_list_against_the_oracle():
             got = [h_lab[b, k, :h_len[b, k]].tolist() for k in range(h_cnt[b])]
             assert got == want, (bw, K, b)
             assert lab1[b, :len1[b]].tolist() == got[0]
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU: host span bookkeeping of the drop-in against the oracle's independent restatement, random inputs
+# ------------------------------------------------------------------------------------------------------------------
+def test_word_spans_match_the_oracle_on_random_rows():
+    from ocrfa_b200.converter import word_spans
+
+    rng = np.random.default_rng(5)
+    for T in (1, 2, 7, 33):
+        am = rng.integers(0, 4, size=(9, T))
+        am[0, :] = 2          # a line of spaces only: no span
+        am[1, :] = 1          # no space at all: one span
+        lines, row0, slen = word_spans(am, 2)
+        want = [(i, span[0], len(span)) for i in range(am.shape[0]) for span in R.word_spans_ref(am[i], 2)]
+        assert [(b, int(r) - b * T, int(n)) for b, r, n in zip(lines, row0, slen)] == want
+        assert 0 not in lines and lines.count(1) == 1
+
+
+def test_word_segmentation_dropin_equals_oracle_on_random_rows():
+    from ocrfa_b200.converter import word_segmentation
+
+    rng = np.random.default_rng(6)
+    for _ in range(300):
+        T = int(rng.integers(1, 40))
+        row = np.repeat(rng.integers(0, 7, size=T), rng.integers(1, 4, size=T))[:T]
+        assert word_segmentation(row) == R.word_segmentation_ref(row)
+    custom = {"fa": [5, 6]}
+    row = np.array([0, 5, 5, 1, 2, 6, 6, 3, 5, 6])
+    assert word_segmentation(row, custom, [5, 6]) == R.word_segmentation_ref(row, custom, [5, 6]) == \
+        [["", [0, 1]], ["fa", [3, 4]], ["", [6, 7]], ["fa", [9, 8]]]
