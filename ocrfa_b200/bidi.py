@@ -8,6 +8,9 @@ implements - the Unicode Bidirectional Algorithm, UAX #9 - for the text this pat
 
   * P2-P3  paragraph level from the first strong character (L -> 0, R / AL -> 1, none -> 0), or `base_dir`
   * W1-W7  weak types (NSM, EN after AL -> AN, AL -> R, ES / CS between numbers, ET next to EN, EN after L -> L)
+  * N0     paired brackets (BD14-BD16: a 63-deep stack over the characters that are still ON; a pair takes the embedding
+           direction when it encloses it, the opposite one only when the text before the pair agrees; marks that followed
+           a changed bracket follow it) - `paired_brackets=False` skips the rule
   * N1-N2  neutral types (B, S, WS, ON) from the surrounding strong text, numbers counting as R
   * I1-I2  implicit levels
   * L1     trailing whitespace back to the paragraph level
@@ -15,13 +18,23 @@ implements - the Unicode Bidirectional Algorithm, UAX #9 - for the text this pat
   * L4     mirrored characters at odd levels
 
 Not restated: explicit embeddings / overrides / isolates (X1-X10, no such format character exists in the recognizer's
-184-character charset, utils.py:414-415: its classes are AL, L, EN, AN, ES, ET, CS, NSM, ON, WS), the paired-bracket
-rule N0 (added to UAX #9 in Unicode 6.3; the pure-Python python-bidi 0.4 line does not have it either) and L3 (combining
-marks stay where the reversal puts them, as in python-bidi). A string with an explicit formatting character raises.
+184-character charset, utils.py:414-415: its classes are AL, L, EN, AN, ES, ET, CS, NSM, ON, WS) and L3 (combining marks
+stay where the reversal puts them, as in python-bidi). A string with an explicit formatting character raises.
 
-PARITY UNPINNED: without the package there is no reference output to generate fixtures from; tests/test_bidi.py holds
-this restatement to hand-derived UAX #9 cases only. When python-bidi is importable `ocrfa_b200.reader` calls it instead
-(the reference's own dependency wins); `OCR.bidi_backend` says which one ran.
+Which python-bidi: the reference does not pin one. The releases since 0.5 wrap the Rust `unicode-bidi` crate (current
+UAX #9, N0 included) - what `pip install python-bidi` resolves to - while the pure-Python 0.4 line predates N0; the
+default here is the current algorithm, `paired_brackets=False` gives the older one. The two differ only on text with
+brackets (()[]{} in the charset) around mixed-direction content.
+
+PARITY: pinned against an independent implementation of the same published algorithm, not against python-bidi itself
+(absent here). tests/golden/bidi_icu.npz holds ICU 71's display strings and levels for 6 000 seeded cases over the charset
+plus Hebrew letters, tabs, further bracket pairs and both forced paragraph directions (oracle/gen_golden_bidi.py, ICU
+borrowed from the Nsight Compute installation through ctypes); tests/test_bidi.py requires identical results on all of
+them, and a differential run of 420 000 random cases during development found no difference either. One family is left
+out of the fixture: a combining mark directly after a paired bracket whose type N0 changes - UAX #9 (since Unicode 8.0)
+lets the mark follow the bracket, ICU keeps it neutral; this module follows the published rule (hand-derived tests).
+When python-bidi is importable `ocrfa_b200.reader` calls it instead (the reference's own dependency wins);
+`OCR.bidi_backend` says which one ran.
 """
 from __future__ import annotations
 
@@ -55,8 +68,69 @@ def base_level(text: str) -> int:
     return 0
 
 
-def resolve_levels(text: str, base_dir: Optional[str] = None) -> List[int]:
-    """Embedding level of every character after W1-W7, N1-N2, I1-I2 and L1 (one paragraph, no explicit formatting)."""
+# BidiBrackets.txt: the mirrored pairs above whose members are opening / closing punctuation (gc = Ps / Pe); quotation
+# marks such as the guillemets (Pi / Pf) and the relations (Sm) mirror but do not pair
+_BRACKET_CLOSE = {a: b for a, b in zip(_MIRROR_PAIRS[0::2], _MIRROR_PAIRS[1::2])
+                  if unicodedata.category(a) == "Ps" and unicodedata.category(b) == "Pe"}
+_BRACKET_OPEN = {b: a for a, b in _BRACKET_CLOSE.items()}
+
+
+def _bracket_pairs(text: str, types: List[str]) -> List[tuple]:
+    """BD16: (opening, closing) positions of the paired brackets, ordered by opening position. Only characters whose
+    type is still ON take part; a stack deeper than 63 abandons the search."""
+    stack: List[tuple] = []
+    pairs: List[tuple] = []
+    for i, ch in enumerate(text):
+        if types[i] != "ON":
+            continue
+        if ch in _BRACKET_CLOSE:
+            if len(stack) == 63:
+                return []
+            stack.append((_BRACKET_CLOSE[ch], i))
+        elif ch in _BRACKET_OPEN:
+            for k in range(len(stack) - 1, -1, -1):
+                if stack[k][0] == ch:
+                    pairs.append((stack[k][1], i))
+                    del stack[k:]
+                    break
+    pairs.sort()
+    return pairs
+
+
+def _resolve_paired_brackets(text: str, types: List[str], orig: List[str], e: str, sos: str) -> None:
+    """N0: a bracket pair takes the embedding direction `e` when it encloses a strong type of that direction (numbers
+    count as R); when it encloses only the opposite direction it takes the opposite direction if the text before the
+    opening bracket establishes it, else `e`; a pair around no strong type is left to N1-N2. Marks that followed a
+    changed bracket (NSM before W1) follow it."""
+    o = "L" if e == "R" else "R"
+
+    def strong(t: str) -> Optional[str]:
+        return "R" if t in ("R", "AN", "EN") else ("L" if t == "L" else None)
+
+    for a, b in _bracket_pairs(text, types):
+        inside = {strong(types[k]) for k in range(a + 1, b)}
+        if e in inside:
+            new = e
+        elif o in inside:
+            before = sos
+            for k in range(a - 1, -1, -1):
+                if strong(types[k]):
+                    before = strong(types[k])
+                    break
+            new = o if before == o else e
+        else:
+            continue
+        for pos in (a, b):
+            types[pos] = new
+            k = pos + 1
+            while k < len(types) and orig[k] == "NSM":
+                types[k] = new
+                k += 1
+
+
+def resolve_levels(text: str, base_dir: Optional[str] = None, paired_brackets: bool = True) -> List[int]:
+    """Embedding level of every character after W1-W7, N0-N2, I1-I2 and L1 (one paragraph, no explicit formatting).
+    paired_brackets=False skips N0 (UAX #9 before Unicode 6.3; python-bidi 0.4.x)."""
     types = [unicodedata.bidirectional(ch) for ch in text]
     for t in types:
         if t in _EXPLICIT:
@@ -116,6 +190,10 @@ def resolve_levels(text: str, base_dir: Optional[str] = None) -> List[int]:
         if types[i] in ("L", "R"):
             prev_strong = types[i]
 
+    # N0: paired brackets
+    if paired_brackets:
+        _resolve_paired_brackets(text, types, orig, _direction(base), sor)
+
     # N1-N2: runs of neutrals take the direction both neighbours agree on (numbers count as R), else the embedding's
     ext = [sor] + types + [eor]
     start = None
@@ -158,11 +236,11 @@ def resolve_levels(text: str, base_dir: Optional[str] = None) -> List[int]:
     return levels
 
 
-def get_display(text: str, base_dir: Optional[str] = None) -> str:
+def get_display(text: str, base_dir: Optional[str] = None, paired_brackets: bool = True) -> str:
     """Logical -> visual order of one paragraph (the `bidi.algorithm.get_display(text)` call of ocr.py:477)."""
     if not text:
         return text
-    levels = resolve_levels(text, base_dir)
+    levels = resolve_levels(text, base_dir, paired_brackets)
     chars = list(text)
     # L4 first (it depends on the resolved level, not on the position)
     for i, lv in enumerate(levels):
